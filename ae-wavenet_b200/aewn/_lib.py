@@ -1,0 +1,88 @@
+"""ctypes binding of libaewn.so -- mirrors include/aewn.h one to one.
+
+The library is REQUIRED: there is no CPU or eager-PyTorch fallback for the hot path.  Importing this module never
+touches the GPU; the first kernel call fails loudly if the shared object is missing or a launch fails.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaewn.so")
+
+MAX_ACTS, MAX_SEGS, MAX_NTILES = 3, 3, 4
+WGRAD_MAX_ACTS, WGRAD_MAX_ITEMS = 6, 32
+
+EPI_LINEAR, EPI_GATE_FWD, EPI_GATE_BWD = 0, 1, 2
+F_ACCUM, F_RELU, F_MASKPOS = 1, 2, 4
+ERR_TIMEOUT = -1003
+
+
+class Act(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("t_extent", C.c_int), ("channels", C.c_int), ("batch", C.c_int),
+                ("row_pitch", C.c_longlong), ("batch_stride", C.c_longlong)]
+
+
+class Seg(C.Structure):
+    _fields_ = [("act", C.c_int), ("shift", C.c_int), ("channels", C.c_int), ("w_koff", C.c_int)]
+
+
+class NTile(C.Structure):
+    _fields_ = [("w_row", C.c_int), ("n", C.c_int), ("n_valid", C.c_int), ("mode", C.c_int), ("flags", C.c_int),
+                ("seg_mask", C.c_int), ("t_lo", C.c_int), ("t_hi", C.c_int), ("t_zero_lo", C.c_int),
+                ("out", C.c_void_p), ("out2", C.c_void_p), ("out3", C.c_void_p),
+                ("out_bs", C.c_longlong), ("out_cs", C.c_longlong), ("out_toff", C.c_int),
+                ("add", C.c_void_p), ("add2", C.c_void_p), ("add_bs", C.c_longlong), ("add_cs", C.c_longlong),
+                ("add_toff", C.c_int), ("bias", C.c_void_p)]
+
+
+class TGemmDesc(C.Structure):
+    _fields_ = [("acts", Act * MAX_ACTS), ("n_acts", C.c_int), ("segs", Seg * MAX_SEGS), ("n_segs", C.c_int),
+                ("w", C.c_void_p), ("w_rows", C.c_int), ("w_kpad", C.c_int),
+                ("ntiles", NTile * MAX_NTILES), ("n_ntiles", C.c_int), ("batch", C.c_int),
+                ("t_begin", C.c_int), ("t_end", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int),
+                ("dbg_lbo", C.c_int), ("dbg_sbo", C.c_int)]
+
+
+class WGradItem(C.Structure):
+    _fields_ = [("g_act", C.c_int), ("x_act", C.c_int), ("g_row", C.c_int), ("x_row", C.c_int),
+                ("m_valid", C.c_int), ("n", C.c_int), ("n_valid", C.c_int), ("shift", C.c_int),
+                ("t_lo", C.c_int), ("t_hi", C.c_int), ("n_split", C.c_int),
+                ("out", C.c_void_p), ("out_rs", C.c_longlong), ("out_cs", C.c_longlong)]
+
+
+class WGradDesc(C.Structure):
+    _fields_ = [("acts", Act * WGRAD_MAX_ACTS), ("n_acts", C.c_int), ("items", WGradItem * WGRAD_MAX_ITEMS),
+                ("n_items", C.c_int), ("batch", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int)]
+
+
+_lib = None
+
+# every symbol include/aewn.h declares (tests/test_capi.py checks the shared object exports all of them)
+SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_tgemm", "aewn_wgrad",
+           "aewn_base_embed_fwd", "aewn_base_embed_bwd", "aewn_fill", "aewn_relu_mask_bwd",
+           "aewn_vq_fwd", "aewn_vq_commit_bwd", "aewn_ema_update", "aewn_crr_fwd", "aewn_crr_bwd_data",
+           "aewn_pack_rows"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make` or `python -c 'import __graft_entry__ as g; g.build()'`."
+                " The aewn hot path has no CPU / eager fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.aewn_last_error_string.restype = C.c_char_p
+        _lib.aewn_launch_count.restype = C.c_longlong
+        _lib.aewn_version.restype = C.c_int
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().aewn_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"aewn: {what} failed (code {rc}): {msg}")
+
+
+def launch_count():
+    return int(lib().aewn_launch_count())

@@ -1,0 +1,231 @@
+// wgrad: weight-gradient GEMM, contraction over (batch, time), on tcgen05 (TF32 in, FP32 accumulate in TMEM).
+//
+//   out[m, n] += sum_b sum_u G[b, g_row + m, u] * X[b, x_row + n, u + shift]          (dW lines)
+//
+// Both operands are K-major (time contiguous in the NCT tensors), so each K block is one TMA box {32 t x 128 rows}
+// for G and up to two for X, all SWIZZLE_128B.  Work unit = (item, split); a unit accumulates its slice of the
+// (batch x time) axis in TMEM and adds the 128 x n partial tile to `out` with red.global.add.f32.
+// Warp roles and pipelines are the same as tgemm.cu.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace aewn {
+
+constexpr int WG_BK = 32;
+constexpr int WG_STAGES = 4;
+constexpr int WG_BOX_BYTES = 128 * WG_BK * 4;        // 16 KB
+constexpr int WG_STAGE_BYTES = 3 * WG_BOX_BYTES;     // G box + 2 X boxes
+constexpr int WG_THREADS = 384;
+constexpr int WG_EPI_WARPS = 8;
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 256 + 1024;
+
+struct WgParams {
+  CUtensorMap map[AEWN_WGRAD_MAX_ACTS];
+  aewn_wgrad_item items[AEWN_WGRAD_MAX_ITEMS];
+  int unit_begin[AEWN_WGRAD_MAX_ITEMS + 1];  // prefix sum of n_split
+  int n_items;
+  int batch;
+  int* err;
+};
+
+struct WgUnit {
+  int item;
+  int kb_begin, kb_end;  // flattened (b, time-block) range
+  int blocks_per_b;
+};
+
+__device__ __forceinline__ WgUnit wg_decode(const WgParams& p, int unit) {
+  WgUnit u;
+  int it = 0;
+  while (it + 1 < p.n_items && unit >= p.unit_begin[it + 1]) ++it;
+  u.item = it;
+  const aewn_wgrad_item& im = p.items[it];
+  const int split = unit - p.unit_begin[it];
+  u.blocks_per_b = (im.t_hi - im.t_lo + WG_BK - 1) / WG_BK;
+  const long long total = static_cast<long long>(u.blocks_per_b) * p.batch;
+  u.kb_begin = static_cast<int>(total * split / im.n_split);
+  u.kb_end = static_cast<int>(total * (split + 1) / im.n_split);
+  return u;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + WG_STAGES;
+  uint64_t* tfull_bar = empty_bar + WG_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    *abort_flag = 0;
+    for (int i = 0; i < WG_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], WG_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_units = p.unit_begin[p.n_items];
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      bool ok = true;
+      for (int unit = blockIdx.x; unit < total_units && ok; unit += gridDim.x) {
+        const WgUnit u = wg_decode(p, unit);
+        if (u.kb_end <= u.kb_begin) continue;
+        const aewn_wgrad_item& im = p.items[u.item];
+        const int xboxes = (im.n + 127) >> 7;
+        for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
+          const int b = kb / u.blocks_per_b;
+          const int t = im.t_lo + (kb - b * u.blocks_per_b) * WG_BK;
+          if (!mbar_wait(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
+          uint8_t* sg = smem + stage * WG_STAGE_BYTES;
+          uint8_t* sx = sg + WG_BOX_BYTES;
+          mbar_expect_tx(&full_bar[stage], (1 + xboxes) * WG_BOX_BYTES);
+          tma_load_3d(sg, &p.map[im.g_act], &full_bar[stage], t, im.g_row, b);
+          for (int j = 0; j < xboxes; ++j)
+            tma_load_3d(sx + j * WG_BOX_BYTES, &p.map[im.x_act], &full_bar[stage], t + im.shift, im.x_row + j * 128, b);
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      bool ok = true;
+      for (int unit = blockIdx.x; unit < total_units && ok; unit += gridDim.x) {
+        const WgUnit u = wg_decode(p, unit);
+        if (u.kb_end <= u.kb_begin) continue;
+        const aewn_wgrad_item& im = p.items[u.item];
+        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256u;
+        const uint32_t idesc = make_idesc_tf32(128, im.n, 0, 0);
+        for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
+          if (!mbar_wait(&full_bar[stage], phase, abort_flag)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t g_addr = smem_u32(smem + stage * WG_STAGE_BYTES);
+          const uint32_t x_addr = g_addr + WG_BOX_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < WG_BK / 8; ++ks) {
+            const uint64_t adesc = make_smem_desc(g_addr + ks * 32, 16, 1024, kLayoutSW128);
+            const uint64_t bdesc = make_smem_desc(x_addr + ks * 32, 16, 1024, kLayoutSW128);
+            umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kb > u.kb_begin) || (ks > 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const WgUnit u = wg_decode(p, unit);
+      if (u.kb_end <= u.kb_begin) continue;
+      const aewn_wgrad_item& im = p.items[u.item];
+      if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 256u + (static_cast<uint32_t>(q * 32) << 16);
+      const int m = q * 32 + lane;
+      float* orow = im.out + static_cast<long long>(m) * im.out_rs;
+      for (int c0 = half * 32; c0 < im.n; c0 += 64) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        if (m < im.m_valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < im.n_valid) atomicAdd(orow + static_cast<long long>(c0 + j) * im.out_cs, __uint_as_float(v[j]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && *abort_flag && p.err) atomicExch(p.err, AEWN_ERR_TIMEOUT);
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace aewn
+
+using namespace aewn;
+
+extern "C" int aewn_wgrad(const aewn_wgrad_desc* d, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d) return set_err(AEWN_ERR_INVALID, "wgrad: null descriptor");
+  if (d->n_acts < 1 || d->n_acts > AEWN_WGRAD_MAX_ACTS || d->n_items < 1 || d->n_items > AEWN_WGRAD_MAX_ITEMS ||
+      d->batch <= 0)
+    return set_err(AEWN_ERR_INVALID, "wgrad: n_acts/n_items/batch out of range (%d/%d/%d)", d->n_acts, d->n_items,
+                   d->batch);
+  cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_err(e, "wgrad: cudaFuncSetAttribute");
+
+  // kernel parameters are limited to 4 KB: the item table rides in the parameter block
+  static_assert(sizeof(WgParams) <= 4000, "WgParams must fit the kernel parameter space");
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < d->n_acts; ++i) {
+    int rc = encode_act_map(&p.map[i], d->acts[i], 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (d->acts[i].batch < d->batch) return set_err(AEWN_ERR_INVALID, "wgrad: act %d batch smaller than problem batch", i);
+  }
+  int units = 0;
+  for (int i = 0; i < d->n_items; ++i) {
+    const aewn_wgrad_item& im = d->items[i];
+    if (im.g_act < 0 || im.g_act >= d->n_acts || im.x_act < 0 || im.x_act >= d->n_acts)
+      return set_err(AEWN_ERR_INVALID, "wgrad: item %d operand index out of range", i);
+    if (im.n < 16 || im.n > 256 || (im.n & 15) || im.n_valid < 1 || im.n_valid > im.n || im.m_valid < 1 ||
+        im.m_valid > 128)
+      return set_err(AEWN_ERR_INVALID, "wgrad: item %d tile shape invalid (m_valid=%d n=%d n_valid=%d)", i, im.m_valid,
+                     im.n, im.n_valid);
+    if (im.t_hi <= im.t_lo || im.n_split < 1 || !im.out)
+      return set_err(AEWN_ERR_INVALID, "wgrad: item %d needs t_hi>t_lo, n_split>=1, out", i);
+    p.items[i] = im;
+    p.unit_begin[i] = units;
+    units += im.n_split;
+  }
+  p.unit_begin[d->n_items] = units;
+  p.n_items = d->n_items;
+  p.batch = d->batch;
+  p.err = d->err;
+
+  int ctas = d->max_ctas > 0 ? d->max_ctas : sm_count();
+  if (ctas > units) ctas = units;
+  wgrad_kernel<<<ctas, WG_THREADS, WG_SMEM_BYTES, stream>>>(p);
+  count_launch();
+  return cuda_err(cudaGetLastError(), "wgrad launch");
+}

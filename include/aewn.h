@@ -1,0 +1,158 @@
+/*
+ * aewn.h -- C ABI of libaewn.so: the B200 (sm_100a) hot path of hrbigelow/ae-wavenet.
+ *
+ * The reference has no FFI layer: its hot path is reached through Python nn.Modules
+ * (wavenet.py:15-111 GatedResidualCondConv, wavenet.py:323-364 WaveNet.forward_train, wave_encoder.py:34-50
+ * ConvReLURes, vqema_bn.py:125-214 VQEMA.forward, vq_bn.py:28-61 VQ.forward).  The drop-in modules in
+ * ae-wavenet_b200/aewn call ONLY the entry points declared here (through ctypes).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller; nothing is allocated, freed or synchronised here;
+ *   - every call enqueues on `stream` and returns 0, or a negative AEWN_ERR_* / -cudaError code; never throws;
+ *   - activations are fp32, channel-major with time contiguous: elem(b, c, t) = ptr[b*batch_stride + c*row_pitch + t];
+ *     tensors consumed by TMA need ptr 16-byte aligned and row_pitch, batch_stride multiples of 4 elements;
+ *   - "absolute time": all tensors of one WaveNet stack share one time axis (tau = index into the first layer's
+ *     input); a dilated tap is a negative shift on that axis.
+ *   - kernels report device-side faults (e.g. a lost mbarrier arrival) through a caller-provided int32 error word
+ *     (`err`), which the caller may read after synchronising; waits inside kernels are bounded, they never hang.
+ */
+#ifndef AEWN_H_
+#define AEWN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* aewn_stream_t; /* cudaStream_t */
+
+#define AEWN_OK 0
+#define AEWN_ERR_INVALID (-1001)  /* bad argument (null pointer, misaligned pitch, size out of range) */
+#define AEWN_ERR_DRIVER (-1002)   /* cuTensorMapEncodeTiled / driver entry point unavailable */
+#define AEWN_ERR_TIMEOUT (-1003)  /* value written to the device error word when a bounded wait expires */
+
+int aewn_version(void);
+const char* aewn_last_error_string(void);
+/* number of kernels launched by this library in this process since load (bench.py's gpu_launches) */
+long long aewn_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Time-major GEMM with shifted segments ("tgemm"): the contraction engine behind every conv on the path.
+ *
+ *   acc[b, tau, n] = sum_s sum_k  act_s[b, k, tau + shift_s] * W[w_row + n, w_koff_s + k]
+ *
+ * One CTA tile = 128 time steps (UMMA M) x one "n-tile" (<= 256 output channels, UMMA N).  Activations are the
+ * MN-major A operand, loaded by TMA straight from the NCT tensors (out-of-range time/channel coordinates read as
+ * zero); W is a K-major matrix [rows][kpad] (kpad % 32 == 0, zero padded).  TF32 tcgen05.mma, FP32 accumulate in
+ * TMEM.  A dilated conv layer (wavenet.py:100-101) is 3 segments: x@-d, x@0, cond@0.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* ptr;
+  int t_extent;           /* valid time extent (TMA zero-fills beyond) */
+  int channels;           /* valid channel extent (TMA zero-fills beyond) */
+  int batch;
+  long long row_pitch;    /* elements between channels */
+  long long batch_stride; /* elements between batch items */
+} aewn_act;
+
+typedef struct {
+  int act;      /* index into acts[] */
+  int shift;    /* time shift: coordinate = tau + shift */
+  int channels; /* K rows consumed (rounded up to 32 inside; rows >= act.channels read as zero) */
+  int w_koff;   /* first K column of W for this segment (multiple of 32) */
+} aewn_seg;
+
+/* epilogue modes */
+#define AEWN_EPI_LINEAR 0   /* out = acc (+bias[n]) (+add[b,n,t]); flags below */
+#define AEWN_EPI_GATE_FWD 1 /* n == 256: cols [0,128) filt, [128,256) gate -> out=tanh, out2=sigmoid, out3=z */
+#define AEWN_EPI_GATE_BWD 2 /* n == 256: acc = g_z; add=tanh, add2=sigmoid -> out=g_filt, out2=g_gate */
+/* flags */
+#define AEWN_F_ACCUM 1 /* out += value (read-modify-write) */
+#define AEWN_F_RELU 2  /* out = max(value, 0) */
+
+typedef struct {
+  int w_row;      /* first W row of this n-tile */
+  int n;          /* tile width: multiple of 16, 16..256 */
+  int n_valid;    /* columns actually stored (<= n) */
+  int mode;       /* AEWN_EPI_* */
+  int flags;      /* AEWN_F_* */
+  int seg_mask;   /* bit s set = segment s contributes to this tile */
+  int t_lo, t_hi; /* store range on the absolute time axis; tiles outside are skipped */
+  int t_zero_lo;  /* GATE_BWD: stores for tau < t_zero_lo write 0 */
+  float* out;     /* pre-offset to the tile's first channel */
+  float* out2;
+  float* out3;
+  long long out_bs, out_cs; /* batch / channel strides (elements) of out, out2, out3 */
+  int out_toff;             /* out time index = tau + out_toff */
+  const float* add;         /* optional */
+  const float* add2;
+  long long add_bs, add_cs;
+  int add_toff;
+  const float* bias; /* optional, pre-offset, indexed by column */
+} aewn_ntile;
+
+#define AEWN_MAX_ACTS 3
+#define AEWN_MAX_SEGS 3
+#define AEWN_MAX_NTILES 4
+
+typedef struct {
+  aewn_act acts[AEWN_MAX_ACTS];
+  int n_acts;
+  aewn_seg segs[AEWN_MAX_SEGS];
+  int n_segs;
+  const float* w; /* K-major [w_rows][w_kpad] */
+  int w_rows;
+  int w_kpad;
+  aewn_ntile ntiles[AEWN_MAX_NTILES];
+  int n_ntiles;
+  int batch;
+  int t_begin, t_end; /* time range covered by tiles: tile i = [t_begin + 128 i, +128), t_begin % 32 == 0 */
+  int* err;           /* device error word (may be NULL) */
+  int max_ctas;       /* 0 = one per SM */
+  int dbg_lbo, dbg_sbo; /* 0 = defaults; descriptor probing only */
+} aewn_tgemm_desc;
+
+int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Weight-gradient GEMM ("wgrad"): contraction over (batch, time).
+ *
+ *   out[m * out_rs + n * out_cs] += sum_b sum_{u in [t_lo,t_hi)}  G[b, g_row + m, u] * X[b, x_row + n, u + shift]
+ *
+ * Both operands are K-major (time contiguous), TMA-loaded; TF32 tcgen05.mma; split-K over (b, time) with fp32
+ * red.global.add (callers zero `out` first; summation order is therefore not deterministic, like cuDNN wgrad).
+ * Implements dW of wavenet.py:25-34.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int g_act, x_act;   /* indices into acts[] */
+  int g_row, x_row;   /* first channel row of each operand */
+  int m_valid;        /* rows stored (<= 128) */
+  int n;              /* UMMA N: multiple of 16, 16..256 */
+  int n_valid;        /* columns stored */
+  int shift;          /* X time coordinate = u + shift */
+  int t_lo, t_hi;     /* u range (G's time axis) */
+  int n_split;        /* split-K factor for this item (>= 1) */
+  float* out;
+  long long out_rs, out_cs;
+} aewn_wgrad_item;
+
+#define AEWN_WGRAD_MAX_ACTS 6
+#define AEWN_WGRAD_MAX_ITEMS 32
+
+typedef struct {
+  aewn_act acts[AEWN_WGRAD_MAX_ACTS];
+  int n_acts;
+  aewn_wgrad_item items[AEWN_WGRAD_MAX_ITEMS];
+  int n_items;
+  int batch;
+  int* err;
+  int max_ctas;
+} aewn_wgrad_desc;
+
+int aewn_wgrad(const aewn_wgrad_desc* d, aewn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AEWN_H_ */
