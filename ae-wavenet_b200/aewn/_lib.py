@@ -9,11 +9,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libaewn.so")
 
-MAX_ACTS, MAX_SEGS, MAX_NTILES = 3, 3, 4
+MAX_ACTS, MAX_SEGS, MAX_NTILES = 4, 4, 4
 WGRAD_MAX_ACTS, WGRAD_MAX_ITEMS = 6, 32
 
 EPI_LINEAR, EPI_GATE_FWD, EPI_GATE_BWD = 0, 1, 2
-F_ACCUM, F_RELU, F_MASKPOS = 1, 2, 4
+F_ACCUM, F_RELU, F_MASKPOS, F_RELU_FIRST = 1, 2, 4, 8
 ERR_TIMEOUT = -1003
 
 
@@ -31,8 +31,9 @@ class NTile(C.Structure):
                 ("seg_mask", C.c_int), ("t_lo", C.c_int), ("t_hi", C.c_int), ("t_zero_lo", C.c_int),
                 ("out", C.c_void_p), ("out2", C.c_void_p), ("out3", C.c_void_p),
                 ("out_bs", C.c_longlong), ("out_cs", C.c_longlong), ("out_toff", C.c_int),
+                ("dup_toff", C.c_int), ("dup_t_hi", C.c_int), ("zero_count", C.c_void_p),
                 ("add", C.c_void_p), ("add2", C.c_void_p), ("add_bs", C.c_longlong), ("add_cs", C.c_longlong),
-                ("add_toff", C.c_int), ("bias", C.c_void_p)]
+                ("add_toff", C.c_int), ("add_t_lo", C.c_int), ("bias", C.c_void_p)]
 
 
 class TGemmDesc(C.Structure):

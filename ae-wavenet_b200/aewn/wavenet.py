@@ -1,0 +1,443 @@
+"""Drop-in replacements for the reference's wavenet.py classes, backed by libaewn.so (sm_100a).
+
+Same class names, constructor signatures, sub-module names/creation order (=> identical RNG stream, parameters()
+order and state_dict keys), buffers and caller-visible attributes as the reference:
+  GatedResidualCondConv  wavenet.py:15-111      Conditioning  :114-140     Upsampling :142-165
+  Conv1dWrap             wavenet.py:167-177     WaveNet       :179-364     RecLoss    :536-552
+The nn.Conv1d / nn.Linear sub-modules are parameter containers only: the dilated gated-residual stack and the
+base layer never call them -- they run in the CUDA kernels (ops.py).  There is no CPU fallback: calling forward on
+CPU tensors raises.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from . import _lib as L
+from .compat import vconv, xavier_init
+
+
+class _HP(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+LAYER_KEYS = ("conv_signal.weight", "conv_signal.bias", "conv_gate.weight", "conv_gate.bias", "proj_signal.weight",
+              "proj_gate.weight", "dil_skp.weight", "dil_res.weight")
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("aewn: the B200 hot path has no CPU implementation; move the module and its inputs to "
+                               "a CUDA device (the oracle under oracle/ is test infrastructure, not a fallback)")
+
+
+class GatedResidualCondConv(nn.Module):
+    """wavenet.py:15-111.  forward(x (B,R,T), cond (B,C,Tc)) -> (sig (B,R,T-d), skp (B,S,T-d-skip_lead))."""
+
+    def __init__(self, wavenet_vc, hps, n_cond, stride, dil, final_layer=False, parent_vc=None, name=None):
+        super().__init__()
+        self.wavenet_vc = wavenet_vc
+        self.final_layer = final_layer
+        self.dil = dil
+        self.conv_signal = nn.Conv1d(hps.n_res, hps.n_dil, hps.filter_sz, dilation=dil, bias=hps.bias)
+        self.conv_gate = nn.Conv1d(hps.n_res, hps.n_dil, hps.filter_sz, dilation=dil, bias=hps.bias)
+        self.proj_signal = nn.Conv1d(n_cond, hps.n_dil, kernel_size=1, bias=False)
+        self.proj_gate = nn.Conv1d(n_cond, hps.n_dil, kernel_size=1, bias=False)
+        self.dil_skp = nn.Conv1d(hps.n_dil, hps.n_skp, kernel_size=1, bias=False)
+        if not final_layer:
+            self.dil_res = nn.Conv1d(hps.n_dil, hps.n_res, kernel_size=1, bias=False)
+        if hps.filter_sz != 2:
+            raise ValueError("aewn: the fused GRCC kernels implement filter_sz == 2 (the reference's only setting)")
+        dil_filter_sz = (hps.filter_sz - 1) * dil + 1
+        self.vc = vconv.VirtualConv(filter_info=(dil_filter_sz - 1, 0), parent=parent_vc, name=name)
+        self.apply(xavier_init)
+
+    # -- geometry bookkeeping, wavenet.py:45-89 ------------------------------------------------------------------
+    def post_init(self):
+        self.register_buffer("leads", torch.empty(4, dtype=torch.long))
+        self.init_leads()
+        self.set_full()
+
+    def init_leads(self):
+        cond_lead, r_off = vconv.output_offsets(self.wavenet_vc["beg_grcc"], self.vc)
+        assert r_off == 0
+        if self.vc == self.wavenet_vc["end_grcc"]:
+            skip_lead = 0
+        else:
+            skip_lead, r_off = vconv.output_offsets(self.vc.child, self.wavenet_vc["end_grcc"])
+            assert r_off == 0
+        self.leads[0] = cond_lead
+        self.leads[1] = skip_lead
+        self.leads[2] = self.vc.l_wing_sz
+        self.leads[3] = 0
+        self._leads_host = [int(cond_lead), int(skip_lead), int(self.vc.l_wing_sz), 0]   # no D2H sync in forward
+        self.global_rf = self.vc.in_len()
+        self.local_rf = self.vc.filter_size()
+
+    def set_incremental(self):
+        self.cond, self.skip, self.lw = 3, 3, 2
+
+    def set_full(self):
+        self.cond, self.skip, self.lw = 0, 1, 2
+
+    def param_dict(self):
+        p = {}
+        for k in LAYER_KEYS:
+            mod, attr = k.split(".")
+            m = getattr(self, mod, None)
+            t = getattr(m, attr, None) if m is not None else None
+            if t is not None:
+                p[k] = t
+        return p
+
+    def forward(self, x, cond):
+        _require_cuda(x, cond)
+        lh = getattr(self, "_leads_host", None)
+        if lh is None:
+            lh = self._leads_host = [int(v) for v in self.leads.tolist()]
+        cl, sl = lh[self.cond], lh[self.skip]
+        p = self.param_dict()
+        keys = list(p.keys())
+        sig, skp = _LayerFn.apply(x, cond, self, cl, sl, keys, *[p[k] for k in keys])
+        return sig, skp
+
+
+class _LayerFn(torch.autograd.Function):
+    """One stand-alone GRCC layer on the kernel path (used when a caller invokes a layer module directly)."""
+
+    @staticmethod
+    def forward(ctx, x, cond, mod, cl, sl, keys, *weights):
+        d = mod.dil
+        B, R, T_in = x.shape
+        D, S, Cc = mod.conv_signal.out_channels, mod.dil_skp.out_channels, cond.shape[1]
+        T_out = T_in - d
+        if T_out <= sl or cond.shape[2] < cl + T_out:
+            raise RuntimeError("aewn: GatedResidualCondConv input shorter than its receptive field / conditioning")
+        geom = ops.StackGeom([d], T_in, skip_start=d + sl, last_is_final=mod.final_layer)
+        ws = ops.get_workspace(B, R, D, S, Cc, geom, x.device)
+        ws.generation += 1
+        with torch.no_grad():
+            ws.sig[0][:, :, :T_in] = x
+            if ops.needs_dup(d):
+                ws.xs[0][:, :, d:T_in] = x[:, :, :T_out]
+            ws.cond[:, :Cc, d:T_in] = cond[:, :, cl:cl + T_out]
+            p = dict(zip(keys, [w.detach() for w in weights]))
+            packs = [ops.LayerPack(p, R, D, S, Cc, mod.final_layer)]
+            ops.stack_forward(ws, geom, packs, relu_last=False, save=True)
+            skp = ws.skp[:, :, geom.RF:T_in].clone()
+            sig = x[:, :, d:].clone() if mod.final_layer else ws.sig[1][:, :, d:T_in].clone()
+        ctx.ws, ctx.geom, ctx.packs, ctx.p, ctx.keys = ws, geom, packs, p, keys
+        ctx.gen = ws.generation
+        ctx.dims = (B, R, D, S, Cc, T_in, d, cl, sl, cond.shape[2])
+        ctx.final = mod.final_layer
+        return sig, skp
+
+    @staticmethod
+    def backward(ctx, g_sig, g_skp):
+        ws, geom = ctx.ws, ctx.geom
+        if ws.generation != ctx.gen:
+            raise RuntimeError("aewn: workspace was reused by a later forward before this backward ran")
+        B, R, D, S, Cc, T_in, d, cl, sl, Tc = ctx.dims
+        bw = ws.bwd()
+        gs = bw["g_skp"]
+        gs.zero_()
+        gs[:, :, geom.RF:T_in] = g_skp
+        gl = None
+        if not ctx.final:
+            gl = bw["gx"][1]
+            gl.zero_()
+            gl[:, :, d:T_in] = g_sig
+        gx, g_cond, grads = ops.stack_backward(ws, geom, ctx.packs, [ctx.p], gs, need_gx0=True, g_sig_last=gl)
+        g_x = gx[:, :, :T_in].clone()
+        if ctx.final:
+            g_x[:, :, d:] += g_sig          # final layer: sig = x[:, :, lw:] (wavenet.py:105-106)
+        g_c = torch.zeros(B, Cc, Tc, device=g_x.device)
+        g_c[:, :, cl:cl + T_in - d] = g_cond[:, :, d:T_in]
+        return (g_x, g_c, None, None, None, None) + tuple(grads[0].get(k) for k in ctx.keys)
+
+
+class Conditioning(nn.Module):
+    """wavenet.py:114-140: concatenate up-sampled local conditioning with a learned speaker embedding."""
+
+    def __init__(self, n_speakers, n_embed, bias=True):
+        super().__init__()
+        self.n_speakers = n_speakers
+        self.speaker_embedding = nn.Linear(n_speakers, n_embed, bias)
+        self.register_buffer("eye", torch.eye(n_speakers))
+        self.apply(xavier_init)
+
+    def forward(self, lc, speaker_inds):
+        # Linear(one_hot(i)) == weight[:, i] + bias: a row gather instead of a one-hot matmul
+        gc = self.speaker_embedding.weight.t()[speaker_inds.long()]
+        if self.speaker_embedding.bias is not None:
+            gc = gc + self.speaker_embedding.bias
+        return torch.cat((lc, gc.unsqueeze(2).expand(-1, -1, lc.shape[2])), dim=1)
+
+
+class Upsampling(nn.Module):
+    """wavenet.py:142-165."""
+
+    def __init__(self, n_chan, filter_sz, stride, parent_vc, bias=True, name=None):
+        super().__init__()
+        end_padding = stride - 1
+        self.vc = vconv.VirtualConv(filter_info=filter_sz, stride=stride, padding=(end_padding, end_padding),
+                                    is_downsample=False, parent=parent_vc, name=name)
+        self.tconv = nn.ConvTranspose1d(n_chan, n_chan, filter_sz, stride, padding=filter_sz - stride, bias=bias)
+        self.apply(xavier_init)
+
+    def forward(self, lc):
+        return self.tconv(lc)
+
+
+class Conv1dWrap(nn.Conv1d):
+    """wavenet.py:167-177."""
+
+    def __init__(self, name, parent_vc, **kwargs):
+        super().__init__(**kwargs)
+        self.apply(xavier_init)
+        self.vc = vconv.VirtualConv(filter_info=kwargs["kernel_size"], stride=kwargs["stride"], name=name,
+                                    parent=parent_vc)
+
+
+_OLD_API_KEYS = ("filter_sz", "n_lc_out", "lc_upsample_strides", "lc_upsample_filt_sizes", "n_res", "n_dil", "n_skp",
+                 "n_post", "n_quant", "n_blocks", "n_block_layers", "n_global_embed", "n_speakers", "n_lc_in", "bias")
+
+
+class WaveNet(nn.Module):
+    """wavenet.py:179-364.  Accepts the current ctor ``WaveNet(hps, parent_vc=None)`` and the keyword form the stale
+    ``AutoEncoder`` still uses (autoencoder_model.py:83-87: ``WaveNet(**dec_params, parent_vc=..., n_lc_in=...)``)."""
+    __constants__ = ["conv_layers"]
+
+    def __init__(self, hps=None, parent_vc=None, **old_api):
+        super().__init__()
+        if hps is None:
+            unknown = set(old_api) - set(_OLD_API_KEYS)
+            if unknown:
+                raise TypeError(f"WaveNet() got unexpected keyword arguments {sorted(unknown)}")
+            hps = _HP(old_api)
+            hps.setdefault("bias", True)
+        elif old_api:
+            raise TypeError("WaveNet(): pass either hps or keyword hyper-parameters, not both")
+        self.n_blocks = hps.n_blocks
+        self.n_block_layers = hps.n_block_layers
+        self.n_skp = hps.n_skp
+        self.n_res = hps.n_res
+        self.n_quant = hps.n_quant
+        self.n_dil = hps.n_dil
+        self.bias = hps.bias
+        post_jitter_filt_sz = 3
+        self.lc_conv = Conv1dWrap(f"LC_Conv(filter_size={post_jitter_filt_sz})", parent_vc, in_channels=hps.n_lc_in,
+                                  out_channels=hps.n_lc_out, kernel_size=post_jitter_filt_sz, stride=1, bias=hps.bias)
+        self.vc = dict()
+        self.vc["beg"] = self.lc_conv.vc
+        cur_vc = self.vc["beg"]
+        self.lc_upsample = nn.Sequential()
+        for i, (filt_sz, stride) in enumerate(zip(hps.lc_upsample_filt_sizes, hps.lc_upsample_strides)):
+            mod = Upsampling(hps.n_lc_out, filt_sz, stride, cur_vc,
+                             name=f"Upsampling_{i}(filter_sz={filt_sz}, stride={stride})")
+            self.lc_upsample.add_module(str(i), mod)
+            cur_vc = mod.vc
+        self.vc["last_upsample"] = cur_vc
+        self.cond = Conditioning(hps.n_speakers, hps.n_global_embed)
+        self.base_layer = Conv1dWrap("Base Layer", cur_vc, in_channels=hps.n_quant, out_channels=hps.n_res,
+                                     kernel_size=1, stride=1, dilation=1, bias=self.bias)
+        self.base_layer.vc.do_trim_input = True
+        cur_vc = self.base_layer.vc
+        self.conv_layers = nn.ModuleList()
+        n_cond = hps.n_lc_out + hps.n_global_embed
+        self.n_cond = n_cond
+        for b in range(self.n_blocks):
+            for bl in range(self.n_block_layers):
+                dil = 2 ** bl
+                final_layer = (b + 1 == self.n_blocks and bl + 1 == self.n_block_layers)
+                grc = GatedResidualCondConv(self.vc, hps, n_cond=n_cond, stride=1, dil=dil, final_layer=final_layer,
+                                            parent_vc=cur_vc, name=f"GRCC_{b},{bl}(dil={dil})")
+                self.conv_layers.append(grc)
+                cur_vc = grc.vc
+        self.vc["beg_grcc"] = self.conv_layers[0].vc
+        self.vc["end_grcc"] = self.conv_layers[-1].vc
+        self.relu = nn.ReLU()
+        self.post1 = Conv1dWrap("Post1", cur_vc, in_channels=hps.n_skp, out_channels=hps.n_post, kernel_size=1,
+                                stride=1, bias=hps.bias)
+        self.post2 = Conv1dWrap("Post2", self.post1.vc, in_channels=hps.n_post, out_channels=hps.n_quant,
+                                kernel_size=1, stride=1, bias=hps.bias)
+        self.logsoftmax = nn.LogSoftmax(1)
+        self.vc["main"] = self.post2.vc
+        self.n_replicas = 1
+
+    # -- geometry, wavenet.py:261-311 ------------------------------------------------------------------------------
+    def set_parent_vc(self, parent_vc):
+        self.vc["beg"].parent = parent_vc
+        parent_vc.child = self.vc["beg"]
+
+    def post_init(self, n_win_batch=None):
+        if n_win_batch is None:     # stale caller (autoencoder_model.py:89): geometry is finalised later
+            n_win_batch = getattr(self, "n_win_batch", None)
+            if n_win_batch is None:
+                raise TypeError("WaveNet.post_init() needs n_win_batch (wavenet.py:266)")
+        one_gr = vconv.GridRange((0, int(1e12)), (0, 1), 1)
+        win_gr = vconv.GridRange((0, int(1e12)), (0, n_win_batch), 1)
+        vconv.compute_inputs(self.vc["end_grcc"], win_gr)
+        di = self.vc["beg_grcc"].input_gr
+        wi = self.vc["beg"].parent.input_gr
+        self.wav_cond_offset = [int(di.sub[0] - wi.sub[0]), int(di.sub[1] - wi.sub[0])]
+        vconv.compute_inputs(self.vc["end_grcc"], one_gr)
+        for layer in self.conv_layers:
+            layer.post_init()
+        self.base_global_rf = self.conv_layers[0].global_rf
+        self.n_win_batch = n_win_batch
+
+    def get_input_size(self, output_size):
+        win_gr = vconv.GridRange((0, int(1e12)), (0, output_size), 1)
+        vconv.compute_inputs(self.vc["end_grcc"], win_gr)
+        return self.vc["beg"].parent.in_len()
+
+    def set_n_replicas(self, n_replicas):
+        self.n_replicas = n_replicas
+
+    def set_incremental(self):
+        for layer in self.conv_layers:
+            layer.set_incremental()
+
+    def set_full(self):
+        for layer in self.conv_layers:
+            layer.set_full()
+
+    # -- forward ---------------------------------------------------------------------------------------------------
+    def forward(self, wav, lc_sparse, speaker_inds, jitter_index):
+        if self.training:
+            return self.forward_train(wav, lc_sparse, speaker_inds, jitter_index)
+        return self.forward_test(wav, lc_sparse, speaker_inds, jitter_index)
+
+    def conditioning(self, lc_sparse, speaker_inds, jitter_index):
+        """wavenet.py:330-343.  The jitter gather reproduces the reference exactly, including its quirk (SURVEY.md
+        F8): torch.take on the flat tensor with an index that carries only the batch offset."""
+        B, D1, T = lc_sparse.shape
+        flat_idx = jitter_index + (torch.arange(B, device=jitter_index.device) * jitter_index.shape[1]).unsqueeze(1)
+        lc_jitter = lc_sparse.reshape(-1)[flat_idx].unsqueeze(1).expand(-1, D1, -1)
+        lc_dense = self.lc_upsample(self.lc_conv(lc_jitter))
+        t0, t1 = int(self.trim_ups_out[0]), int(self.trim_ups_out[1])
+        return self.cond(lc_dense[:, :, t0:t1], speaker_inds)
+
+    def stack_geometry(self, T0):
+        dils = [layer.dil for layer in self.conv_layers]
+        return ops.StackGeom(dils, T0)
+
+    def forward_train(self, wav, lc_sparse, speaker_inds, jitter_index):
+        """wavenet.py:323-364."""
+        _require_cuda(wav, lc_sparse)
+        if isinstance(self.trim_ups_out, torch.Tensor) and self.trim_ups_out.is_cuda:
+            self.trim_ups_out = self.trim_ups_out.cpu()      # read on the host once, never per step
+        cond = self.conditioning(lc_sparse, speaker_inds, jitter_index)
+        keys, weights = [], []
+        for li, layer in enumerate(self.conv_layers):
+            for k, t in layer.param_dict().items():
+                keys.append((li, k))
+                weights.append(t)
+        bias = self.base_layer.bias
+        h = _DecoderCoreFn.apply(wav, cond, self, keys, self.base_layer.weight,
+                                 bias if bias is not None else wav.new_zeros(0), *weights)
+        post1 = self.post1(h)                               # h = relu(skp_sum), fused into the last layer's epilogue
+        return self.post2(self.relu(post1))
+
+    def forward_test(self, wav, lc_sparse, speaker_inds, jitter_index):
+        raise NotImplementedError(
+            "aewn: incremental sampling (wavenet.py:367-531) is outside this round's hot-path scope (SURVEY.md 8f rank "
+            "3); run generation with the reference module, or call the model in training mode for teacher-forced logits")
+
+
+class _DecoderCoreFn(torch.autograd.Function):
+    """Base layer (embedding gather) + the whole GRCC stack + ReLU of the skip sum, on the kernel path.
+    Inputs: wav (B, T_wav) float mu-law codes, cond (B, C, T0).  Output: relu(skp_sum) (B, S, W)."""
+
+    @staticmethod
+    def forward(ctx, wav, cond, net, keys, base_w, base_b, *weights):
+        o0, o1 = net.wav_cond_offset
+        T0 = o1 - o0
+        B, Cc = cond.shape[0], cond.shape[1]
+        if cond.shape[2] != T0:
+            raise RuntimeError(f"aewn: conditioning length {cond.shape[2]} != decoder input length {T0} "
+                               f"(wav_cond_offset={net.wav_cond_offset}); see SURVEY.md 9.5")
+        if wav.shape[1] < o1:
+            raise RuntimeError(f"aewn: wav has {wav.shape[1]} samples, wav_cond_offset needs {o1}")
+        R, D, S, Q = net.n_res, net.n_dil, net.n_skp, net.n_quant
+        geom = net.stack_geometry(T0)
+        if geom.W != net.n_win_batch:
+            raise RuntimeError(f"aewn: geometry mismatch, window {geom.W} != n_win_batch {net.n_win_batch}")
+        dev = wav.device
+        ws = ops.get_workspace(B, R, D, S, Cc, geom, dev)
+        ws.generation += 1
+        wav_c = wav.detach().float().contiguous()
+        with torch.no_grad():
+            ws.cond[:, :Cc, :T0] = cond
+            d0 = geom.dils[0]
+            dup = ws.xs[0] if ops.needs_dup(d0) else None
+            bw = base_w.detach().reshape(R, Q).contiguous()
+            L.check(L.lib().aewn_base_embed_fwd(
+                L.C.c_void_p(wav_c.data_ptr()), L.C.c_longlong(wav_c.stride(0)), L.C.c_int(o0),
+                L.C.c_void_p(bw.data_ptr()), L.C.c_void_p(base_b.data_ptr() if base_b.numel() else None),
+                L.C.c_void_p(ws.sig[0].data_ptr()), L.C.c_longlong(ws.sig[0].stride(0)),
+                L.C.c_longlong(ws.sig[0].stride(1)), L.C.c_void_p(dup.data_ptr() if dup is not None else None),
+                L.C.c_int(d0), L.C.c_int(T0), L.C.c_int(B), L.C.c_int(R), L.C.c_int(Q), L.C.c_int(T0),
+                L.C.c_void_p(ws.err.data_ptr()), ops._stream()), "aewn_base_embed_fwd")
+            params = [dict() for _ in range(geom.L)]
+            for (li, k), w in zip(keys, weights):
+                params[li][k] = w.detach()
+            packs = [ops.LayerPack(params[l], R, D, S, Cc, l == geom.L - 1) for l in range(geom.L)]
+            ops.stack_forward(ws, geom, packs, relu_last=True, save=True)
+            out = ws.skp[:, :, geom.RF:T0].clone()
+        ctx.ws, ctx.geom, ctx.packs, ctx.params, ctx.keys = ws, geom, packs, params, keys
+        ctx.gen = ws.generation
+        ctx.wav, ctx.o0 = wav_c, o0
+        ctx.dims = (B, R, D, S, Cc, Q, T0)
+        ctx.has_bias = base_b.numel() > 0
+        ctx.base_shape = base_w.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        ws, geom = ctx.ws, ctx.geom
+        if ws.generation != ctx.gen:
+            raise RuntimeError("aewn: workspace was reused by a later forward before this backward ran "
+                               "(one in-flight forward per configuration)")
+        B, R, D, S, Cc, Q, T0 = ctx.dims
+        lib = L.lib()
+        bw = ws.bwd()
+        gs = bw["g_skp"]
+        g_out = g_out if g_out.stride(2) == 1 else g_out.contiguous()
+        mask = ws.skp[:, :, geom.RF:]
+        gsv = gs[:, :, geom.RF:]
+        # g wrt the pre-ReLU skip sum, written straight onto the absolute time axis (margin [RF&~3, RF) stays 0)
+        L.check(lib.aewn_relu_mask_bwd(
+            L.C.c_void_p(g_out.data_ptr()), L.C.c_longlong(g_out.stride(0)), L.C.c_longlong(g_out.stride(1)),
+            L.C.c_void_p(mask.data_ptr()), L.C.c_longlong(mask.stride(0)), L.C.c_longlong(mask.stride(1)),
+            L.C.c_void_p(gsv.data_ptr()), L.C.c_longlong(gsv.stride(0)), L.C.c_longlong(gsv.stride(1)),
+            L.C.c_int(B), L.C.c_int(S), L.C.c_int(geom.W), ops._stream()), "aewn_relu_mask_bwd")
+        gx0, g_cond, grads = ops.stack_backward(ws, geom, ctx.packs, ctx.params, gs, need_gx0=True)
+        d_base = torch.zeros(R, Q, device=g_out.device)
+        d_bias = torch.zeros(R, device=g_out.device) if ctx.has_bias else None
+        L.check(lib.aewn_base_embed_bwd(
+            L.C.c_void_p(gx0.data_ptr()), L.C.c_longlong(gx0.stride(0)), L.C.c_longlong(gx0.stride(1)),
+            L.C.c_void_p(ctx.wav.data_ptr()), L.C.c_longlong(ctx.wav.stride(0)), L.C.c_int(ctx.o0),
+            L.C.c_void_p(d_base.data_ptr()), L.C.c_void_p(d_bias.data_ptr() if d_bias is not None else None),
+            L.C.c_int(B), L.C.c_int(R), L.C.c_int(Q), L.C.c_int(T0), ops._stream()), "aewn_base_embed_bwd")
+        wgrads = tuple(grads[li].get(k) for (li, k) in ctx.keys)
+        return (None, g_cond[:, :, :T0], None, None, d_base.reshape(ctx.base_shape), d_bias) + wgrads
+
+
+class RecLoss(nn.Module):
+    """wavenet.py:536-552."""
+
+    def __init__(self):
+        super().__init__()
+        self.logsoftmax = nn.LogSoftmax(1)
+
+    def forward(self, quant_pred, target_wav):
+        log_pred = self.logsoftmax(quant_pred)
+        log_pred_target = torch.gather(log_pred, 1, target_wav.long().unsqueeze(1))
+        rec_loss = -log_pred_target.mean()
+        self.metrics = {"rec": rec_loss}
+        return rec_loss

@@ -1,0 +1,174 @@
+// HBM-bound helper kernels of the decoder path: base-layer embedding gather (K3 in SURVEY.md 2b), its backward,
+// fills and the ReLU-mask product.  All are coalesced along the time axis (128-bit where alignment allows).
+#include "host_util.h"
+
+namespace aewn {
+
+// ---------------------------------------------------------------------------------------------------------------
+// base layer, wavenet.py:348-351:  one_hot(wav.long())[.., off0:off1] -> Conv1d(Q -> R, k=1)  ==  a column gather
+//   out[b, r, tau] = W[r, code(b, off0 + tau)] + bias[r]
+// CTA = (32 output channels) x (1024 time steps of one batch item); the 32 x Q weight slab sits in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BE_ROWS = 32;
+constexpr int BE_TT = 1024;
+
+__global__ void __launch_bounds__(256) base_embed_fwd_kernel(const float* __restrict__ wav, long long wav_pitch,
+                                                             int off0, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ out,
+                                                             long long out_bs, long long out_cs,
+                                                             float* __restrict__ dup, int dup_toff, int dup_t_hi,
+                                                             int R, int Q, int T, int* err) {
+  extern __shared__ float sw[];  // [BE_ROWS][Q + 1]
+  const int r0 = blockIdx.y * BE_ROWS;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * BE_TT;
+  const int qs = Q + 1;
+  for (int i = threadIdx.x; i < BE_ROWS * Q; i += blockDim.x) {
+    const int rr = i / Q, q = i - rr * Q;
+    sw[rr * qs + q] = (r0 + rr < R) ? w[static_cast<long long>(r0 + rr) * Q + q] + (bias ? bias[r0 + rr] : 0.0f) : 0.0f;
+  }
+  __syncthreads();
+  for (int tt = threadIdx.x; tt < BE_TT; tt += blockDim.x) {
+    const int t = t0 + tt;
+    if (t >= T) break;
+    int code = static_cast<int>(wav[static_cast<long long>(b) * wav_pitch + off0 + t]);  // == .long(): truncation
+    if (code < 0 || code >= Q) {
+      if (err) atomicExch(err, AEWN_ERR_INVALID);
+      code = code < 0 ? 0 : Q - 1;
+    }
+    float* o = out + static_cast<long long>(b) * out_bs + static_cast<long long>(r0) * out_cs + t;
+    const int dt = t + dup_toff;
+    const bool dup_ok = dup && dt >= 0 && dt < dup_t_hi;
+    float* od = dup ? dup + static_cast<long long>(b) * out_bs + static_cast<long long>(r0) * out_cs + dt : nullptr;
+#pragma unroll 8
+    for (int rr = 0; rr < BE_ROWS; ++rr) {
+      if (r0 + rr < R) {
+        const float v = sw[rr * qs + code];
+        o[static_cast<long long>(rr) * out_cs] = v;
+        if (dup_ok) od[static_cast<long long>(rr) * out_cs] = v;
+      }
+    }
+  }
+}
+
+// dW[r, q] += sum_{b, tau : code = q} g[b, r, tau];  dbias[r] += sum g[b, r, tau].
+// CTA = 8 channels x 2048 steps of one batch item; per-channel 256-bin shared-memory accumulators, flushed with
+// one global atomic per non-empty bin.
+constexpr int BB_ROWS = 8;
+constexpr int BB_TT = 2048;
+
+__global__ void __launch_bounds__(256) base_embed_bwd_kernel(const float* __restrict__ g, long long g_bs, long long g_cs,
+                                                             const float* __restrict__ wav, long long wav_pitch,
+                                                             int off0, float* __restrict__ dw,
+                                                             float* __restrict__ dbias, int R, int Q, int T) {
+  extern __shared__ float sacc[];  // [BB_ROWS][Q]
+  const int r0 = blockIdx.y * BB_ROWS;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * BB_TT;
+  for (int i = threadIdx.x; i < BB_ROWS * Q; i += blockDim.x) sacc[i] = 0.0f;
+  __syncthreads();
+  for (int tt = threadIdx.x; tt < BB_TT; tt += blockDim.x) {
+    const int t = t0 + tt;
+    if (t >= T) break;
+    int code = static_cast<int>(wav[static_cast<long long>(b) * wav_pitch + off0 + t]);
+    code = code < 0 ? 0 : (code >= Q ? Q - 1 : code);
+    const float* gp = g + static_cast<long long>(b) * g_bs + static_cast<long long>(r0) * g_cs + t;
+#pragma unroll
+    for (int rr = 0; rr < BB_ROWS; ++rr)
+      if (r0 + rr < R) atomicAdd(&sacc[rr * Q + code], gp[static_cast<long long>(rr) * g_cs]);
+  }
+  __syncthreads();
+  for (int rr = 0; rr < BB_ROWS; ++rr) {
+    if (r0 + rr >= R) break;
+    float rowsum = 0.0f;
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+      const float v = sacc[rr * Q + q];
+      if (v != 0.0f) atomicAdd(dw + static_cast<long long>(r0 + rr) * Q + q, v);
+      rowsum += v;
+    }
+    if (dbias) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rowsum += __shfl_xor_sync(0xffffffffu, rowsum, o);
+      if ((threadIdx.x & 31) == 0 && rowsum != 0.0f) atomicAdd(dbias + r0 + rr, rowsum);
+    }
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, long long n, float v) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+// out[b, c, t] = mask[b, c, t] > 0 ? g[b, c, t] : 0   (ReLU backward; wavenet.py:359-360, wave_encoder.py:39)
+__global__ void relu_mask_bwd_kernel(const float* __restrict__ g, long long g_bs, long long g_cs,
+                                     const float* __restrict__ mask, long long m_bs, long long m_cs,
+                                     float* __restrict__ out, long long o_bs, long long o_cs, int C, int T) {
+  const int b = blockIdx.z;
+  const int c = blockIdx.y;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    const float m = mask[static_cast<long long>(b) * m_bs + static_cast<long long>(c) * m_cs + t];
+    const float v = g[static_cast<long long>(b) * g_bs + static_cast<long long>(c) * g_cs + t];
+    out[static_cast<long long>(b) * o_bs + static_cast<long long>(c) * o_cs + t] = m > 0.0f ? v : 0.0f;
+  }
+}
+
+}  // namespace aewn
+
+using namespace aewn;
+
+extern "C" {
+
+int aewn_base_embed_fwd(const float* wav, long long wav_pitch, int off0, const float* w, const float* bias, float* out,
+                        long long out_bs, long long out_cs, float* dup, int dup_toff, int dup_t_hi, int batch, int R,
+                        int Q, int T, int* err, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!wav || !w || !out || batch <= 0 || R <= 0 || Q <= 0 || T <= 0 || Q > 1024)
+    return set_err(AEWN_ERR_INVALID, "base_embed_fwd: bad arguments");
+  dim3 grid((T + BE_TT - 1) / BE_TT, (R + BE_ROWS - 1) / BE_ROWS, batch);
+  const size_t smem = static_cast<size_t>(BE_ROWS) * (Q + 1) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(base_embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_err(e, "base_embed_fwd: cudaFuncSetAttribute");
+  }
+  base_embed_fwd_kernel<<<grid, 256, smem, stream>>>(wav, wav_pitch, off0, w, bias, out, out_bs, out_cs, dup, dup_toff,
+                                                     dup_t_hi, R, Q, T, err);
+  count_launch();
+  return cuda_err(cudaGetLastError(), "base_embed_fwd launch");
+}
+
+int aewn_base_embed_bwd(const float* g, long long g_bs, long long g_cs, const float* wav, long long wav_pitch, int off0,
+                        float* dw, float* dbias, int batch, int R, int Q, int T, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!g || !wav || !dw || batch <= 0 || R <= 0 || Q <= 0 || T <= 0 || Q > 1024)
+    return set_err(AEWN_ERR_INVALID, "base_embed_bwd: bad arguments");
+  dim3 grid((T + BB_TT - 1) / BB_TT, (R + BB_ROWS - 1) / BB_ROWS, batch);
+  const size_t smem = static_cast<size_t>(BB_ROWS) * Q * sizeof(float);
+  base_embed_bwd_kernel<<<grid, 256, smem, stream>>>(g, g_bs, g_cs, wav, wav_pitch, off0, dw, dbias, R, Q, T);
+  count_launch();
+  return cuda_err(cudaGetLastError(), "base_embed_bwd launch");
+}
+
+int aewn_fill(float* p, long long n, float value, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!p || n <= 0) return set_err(AEWN_ERR_INVALID, "fill: bad arguments");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fill_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p, n, value);
+  count_launch();
+  return cuda_err(cudaGetLastError(), "fill launch");
+}
+
+int aewn_relu_mask_bwd(const float* g, long long g_bs, long long g_cs, const float* mask, long long m_bs, long long m_cs,
+                       float* out, long long o_bs, long long o_cs, int batch, int C, int T, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!g || !mask || !out || batch <= 0 || C <= 0 || T <= 0) return set_err(AEWN_ERR_INVALID, "relu_mask_bwd: bad arguments");
+  int bx = (T + 255) / 256;
+  if (bx > 64) bx = 64;
+  dim3 grid(bx, C, batch);
+  relu_mask_bwd_kernel<<<grid, 256, 0, stream>>>(g, g_bs, g_cs, mask, m_bs, m_cs, out, o_bs, o_cs, C, T);
+  count_launch();
+  return cuda_err(cudaGetLastError(), "relu_mask_bwd launch");
+}
+
+}  // extern "C"

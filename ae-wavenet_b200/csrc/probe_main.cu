@@ -87,6 +87,7 @@ static aewn_ntile mk_tile(int w_row, int n, int n_valid, int mode, int flags, in
 }
 
 // ---------------------------------------------------------------- test 1: single segment, descriptor candidates
+static int g_shift = 0;
 static int test_basic(int lbo, int sbo, bool ints, double tol) {
   const int B = 2, C = 40, T = 300, N = 48, KP = 64;
   Act x(B, C, T, ints);
@@ -103,7 +104,7 @@ static int test_basic(int lbo, int sbo, bool ints, double tol) {
   memset(&d, 0, sizeof(d));
   d.acts[0] = x.desc();
   d.n_acts = 1;
-  d.segs[0] = {0, 0, C, 0};
+  d.segs[0] = {0, g_shift, C, 0};
   d.n_segs = 1;
   d.w = dw;
   d.w_rows = N;
@@ -134,7 +135,7 @@ static int test_basic(int lbo, int sbo, bool ints, double tol) {
     for (int n = 0; n < N; ++n)
       for (int t = 0; t < T; ++t) {
         double ref = 0;
-        for (int k = 0; k < C; ++k) ref += (double)x.at(b, k, t) * w[(size_t)n * KP + k];
+        for (int k = 0; k < C; ++k) ref += (double)x.at(b, k, t + g_shift) * w[(size_t)n * KP + k];
         double err = fabs(ref - out.at(b, n, t));
         if (err > maxerr) maxerr = err;
         if (err > tol && bad < 4) {
@@ -152,7 +153,7 @@ static int test_basic(int lbo, int sbo, bool ints, double tol) {
 
 // ---------------------------------------------------------------- test 2: layer-shaped problem (3 segs, 2+ n-tiles)
 static int test_layer(bool ints, double tol, int variant = 0) {
-  const int B = 2, R = 72, Cc = 11, T = 700, d_ = 5, N = 368;
+  const int B = 2, R = 72, Cc = 11, T = 700, d_ = 8, N = 368;
   const int KR = (R + 31) / 32 * 32, KC = (Cc + 31) / 32 * 32, KP = 2 * KR + KC;
   Act x(B, R, T, ints, NAN), cond(B, Cc, T, ints, NAN);
   std::vector<float> w((size_t)N * KP, 0.f);
@@ -350,7 +351,7 @@ static int test_gate() {
 
 // ---------------------------------------------------------------- test 4: wgrad
 static int test_wgrad(bool ints, double tol) {
-  const int B = 2, M = 130, N = 70, T = 500, shift = -5, t_lo = 13;
+  const int B = 2, M = 130, N = 70, T = 500, shift = -8, t_lo = 12;
   Act g(B, M, T, ints, NAN), x(B, N, T, ints, NAN);
   std::vector<float> out0((size_t)M * N * 2, 0.f);  // strided output: rs = 2N, cs = 2 (conv weight layout, tap 1)
   for (auto& v : out0) v = ints ? rnd_int(2) : rnd_f();
@@ -418,7 +419,7 @@ static int test_wgrad(bool ints, double tol) {
 
 // ---------------------------------------------------------------- timing at reference size (cfg2 layer 0)
 static void time_layer() {
-  const int B = 8, R = 368, Cc = 139, D = 256, T = 18430, d_ = 1;
+  const int B = 8, R = 368, Cc = 139, D = 256, T = 18430, d_ = 4;
   const int pitch = (T + 31) / 32 * 32;
   const int KR = 384, KC = 160, KP = 2 * KR + KC;
   float *x, *cond, *w1, *th, *sg, *z, *w2, *sig, *skp;
@@ -491,7 +492,10 @@ static void time_layer() {
   CK(cudaEventCreate(&e1));
   for (int which = 0; which < 2; ++which) {
     aewn_tgemm_desc* g = which == 0 ? &g1 : &g2;
-    for (int i = 0; i < 3; ++i) aewn_tgemm(g, 0);
+    for (int i = 0; i < 3; ++i) {
+      int rc = aewn_tgemm(g, 0);
+      if (rc) printf("  tgemm rc=%d (%s)\n", rc, aewn_last_error_string());
+    }
     CK(cudaDeviceSynchronize());
     const int reps = 10;
     CK(cudaEventRecord(e0));
@@ -546,7 +550,10 @@ static void time_layer() {
   wd.n_items = ni;
   wd.batch = B;
   wd.err = g_err;
-  for (int i = 0; i < 2; ++i) aewn_wgrad(&wd, 0);
+  for (int i = 0; i < 2; ++i) {
+    int rc = aewn_wgrad(&wd, 0);
+    if (rc) printf("  wgrad rc=%d (%s)\n", rc, aewn_last_error_string());
+  }
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
   for (int i = 0; i < 5; ++i) aewn_wgrad(&wd, 0);
@@ -565,6 +572,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&g_err, 4));
     CK(cudaMemset(g_err, 0, 4));
     const char* t = argv[1];
+    if (!strcmp(t, "shift")) { g_shift = atoi(argv[2]); return test_basic(0, 0, true, 1e-3); }
     if (!strcmp(t, "layer")) return test_layer(true, 1e-3);
     if (!strcmp(t, "layer1")) { test_layer(true, 1e9, 1); return 0; }
     if (!strcmp(t, "layer2")) { test_layer(true, 1e9, 2); return 0; }

@@ -66,12 +66,21 @@ __device__ __forceinline__ TgItem tg_decode(const TgParams& p, int item) {
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
+// Common conventions: lane = time step tau; stores happen for tau in [t_lo, t_hi); values for tau < t_zero_lo are
+// forced to 0 so that the aligned-down margin of every tensor stays finite (TMA reads it, 0 * garbage must be 0).
 __device__ __forceinline__ void epi_linear(const aewn_ntile& nt, uint32_t taddr, int half, int b, int tau) {
   const bool in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
+  const bool live = tau >= nt.t_zero_lo;
   float* outp = nt.out + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
+  const int dup_t = tau + nt.dup_toff;
+  const bool dup_ok = nt.out2 && in_range && dup_t >= 0 && dup_t < nt.dup_t_hi;
+  float* dupp = nt.out2 ? nt.out2 + static_cast<long long>(b) * nt.out_bs + dup_t : nullptr;
   const float* addp = nt.add ? nt.add + static_cast<long long>(b) * nt.add_bs + (tau + nt.add_toff) : nullptr;
   const bool accum = (nt.flags & AEWN_F_ACCUM) != 0;
   const bool relu = (nt.flags & AEWN_F_RELU) != 0;
+  const bool relu_first = (nt.flags & AEWN_F_RELU_FIRST) != 0;
+  const bool maskpos = (nt.flags & AEWN_F_MASKPOS) != 0;
+  unsigned int zeros = 0;
   for (int c0 = half * 32; c0 < nt.n; c0 += 64) {
     uint32_t v[32];
     tmem_ld32(taddr + c0, v);
@@ -85,15 +94,39 @@ __device__ __forceinline__ void epi_linear(const aewn_ntile& nt, uint32_t taddr,
       for (int j = 0; j < 32; ++j)
         if (c0 + j < nt.n_valid) r[j] += __ldg(nt.bias + c0 + j);
     }
+    if (relu_first) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.0f);
+      if (nt.out3) {  // keep relu(pre) so the backward pass has the exact activation mask (wave_encoder.py:39)
+        float* o3 = nt.out3 + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (in_range && c0 + j < nt.n_valid) o3[static_cast<long long>(c0 + j) * nt.out_cs] = live ? r[j] : 0.0f;
+      }
+    }
+    // global loads are hoisted into their own fully unrolled loops (select, not branch) so that all 32 are in
+    // flight together; a fused load+use loop serialises on memory latency (measured: 25x slower epilogue)
     if (addp) {
+      const bool add_ok = in_range && live && tau >= nt.add_t_lo;
+      float a[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (in_range && c0 + j < nt.n_valid) r[j] += __ldg(addp + static_cast<long long>(c0 + j) * nt.add_cs);
+        a[j] = (add_ok && c0 + j < nt.n_valid) ? __ldg(addp + static_cast<long long>(c0 + j) * nt.add_cs)
+                                               : (maskpos ? 1.0f : 0.0f);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = maskpos ? (a[j] > 0.0f ? r[j] : 0.0f) : r[j] + a[j];
+    }
+    if (!live) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = 0.0f;
     }
     if (accum) {
+      float prev[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (in_range && c0 + j < nt.n_valid) r[j] += outp[static_cast<long long>(c0 + j) * nt.out_cs];
+        prev[j] = (in_range && c0 + j < nt.n_valid) ? __ldcg(outp + static_cast<long long>(c0 + j) * nt.out_cs) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] += prev[j];
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -101,14 +134,22 @@ __device__ __forceinline__ void epi_linear(const aewn_ntile& nt, uint32_t taddr,
         float x = r[j];
         if (relu) x = fmaxf(x, 0.0f);
         outp[static_cast<long long>(c0 + j) * nt.out_cs] = x;
+        if (dup_ok) dupp[static_cast<long long>(c0 + j) * nt.out_cs] = x;
+        zeros += (x == 0.0f) ? 1u : 0u;
       }
     }
+  }
+  if (nt.zero_count) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(nt.zero_count, static_cast<unsigned long long>(zeros));
   }
 }
 
 // wavenet.py:102  z = tanh(filt) * sigmoid(gate); columns [0,128) = filt, [128,256) = gate of the same channels.
 __device__ __forceinline__ void epi_gate_fwd(const aewn_ntile& nt, uint32_t taddr, int half, int b, int tau) {
   const bool in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
+  const bool live = tau >= nt.t_zero_lo;
   const long long off = static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
   for (int c0 = half * 32; c0 < 128; c0 += 64) {
     uint32_t vf[32], vg[32];
@@ -123,8 +164,8 @@ __device__ __forceinline__ void epi_gate_fwd(const aewn_ntile& nt, uint32_t tadd
         f += __ldg(nt.bias + c0 + j);
         g += __ldg(nt.bias + 128 + c0 + j);
       }
-      const float th = fast_tanh(f);
-      const float sg = fast_sigmoid(g);
+      const float th = live ? fast_tanh(f) : 0.0f;
+      const float sg = live ? fast_sigmoid(g) : 0.0f;
       if (in_range && c0 + j < nt.n_valid) {
         const long long o = off + static_cast<long long>(c0 + j) * nt.out_cs;
         if (nt.out) nt.out[o] = th;
@@ -141,6 +182,10 @@ __device__ __forceinline__ void epi_gate_bwd(const aewn_ntile& nt, uint32_t tadd
   const bool live = tau >= nt.t_zero_lo;
   const long long ooff = static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
   const long long aoff = static_cast<long long>(b) * nt.add_bs + (tau + nt.add_toff);
+  const int dup_t = tau + nt.dup_toff;
+  const bool dup_ok = nt.out3 && in_range && dup_t >= 0 && dup_t < nt.dup_t_hi;
+  const long long doff = static_cast<long long>(b) * nt.out_bs + dup_t;
+  const long long g_delta = nt.out2 - nt.out;  // g_gate rows follow g_filt rows in the same tensor
   for (int c0 = half * 32; c0 < nt.n; c0 += 64) {
     uint32_t v[32];
     tmem_ld32(taddr + c0, v);
@@ -157,9 +202,16 @@ __device__ __forceinline__ void epi_gate_bwd(const aewn_ntile& nt, uint32_t tadd
       if (in_range && c0 + j < nt.n_valid) {
         const float gz = live ? __uint_as_float(v[j]) : 0.0f;
         const float gs = gz * sg[j];
+        const float gf = live ? gs * (1.0f - th[j] * th[j]) : 0.0f;
+        const float gg = live ? gs * th[j] * (1.0f - sg[j]) : 0.0f;
         const long long o = ooff + static_cast<long long>(c0 + j) * nt.out_cs;
-        nt.out[o] = live ? gs * (1.0f - th[j] * th[j]) : 0.0f;
-        nt.out2[o] = live ? gs * th[j] * (1.0f - sg[j]) : 0.0f;
+        nt.out[o] = gf;
+        nt.out2[o] = gg;
+        if (dup_ok) {
+          const long long od = doff + static_cast<long long>(c0 + j) * nt.out_cs;
+          nt.out3[od] = gf;
+          nt.out3[od + g_delta] = gg;
+        }
       }
     }
   }
@@ -326,11 +378,9 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
     return set_err(AEWN_ERR_INVALID, "tgemm: need batch>0, t_end>t_begin, t_begin%%32==0 (b=%d t=[%d,%d))", d->batch,
                    d->t_begin, d->t_end);
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  {
     cudaError_t e = cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
     if (e != cudaSuccess) return cuda_err(e, "tgemm: cudaFuncSetAttribute");
-    attr_set = true;
   }
 
   TgParams p;
@@ -348,6 +398,9 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
     const aewn_seg& sg = d->segs[s];
     if (sg.act < 0 || sg.act >= d->n_acts || sg.channels <= 0 || (sg.w_koff & 31) || sg.w_koff < 0)
       return set_err(AEWN_ERR_INVALID, "tgemm: bad segment %d", s);
+    if (sg.shift & 3)
+      return set_err(AEWN_ERR_INVALID, "tgemm: segment %d shift %d is not a multiple of 4 (TMA 16-byte origin rule)", s,
+                     sg.shift);
     p.seg[s].map = sg.act;
     p.seg[s].shift = sg.shift;
     p.seg[s].kblocks = (sg.channels + TG_BK - 1) / TG_BK;

@@ -214,6 +214,9 @@ extern "C" int aewn_wgrad(const aewn_wgrad_desc* d, aewn_stream_t stream_) {
                      im.n, im.n_valid);
     if (im.t_hi <= im.t_lo || im.n_split < 1 || !im.out)
       return set_err(AEWN_ERR_INVALID, "wgrad: item %d needs t_hi>t_lo, n_split>=1, out", i);
+    if ((im.t_lo & 3) || (im.shift & 3))
+      return set_err(AEWN_ERR_INVALID, "wgrad: item %d t_lo=%d / shift=%d must be multiples of 4 (TMA 16-byte origin rule)",
+                     i, im.t_lo, im.shift);
     p.items[i] = im;
     p.unit_begin[i] = units;
     units += im.n_split;

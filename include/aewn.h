@@ -12,7 +12,10 @@
  *   - activations are fp32, channel-major with time contiguous: elem(b, c, t) = ptr[b*batch_stride + c*row_pitch + t];
  *     tensors consumed by TMA need ptr 16-byte aligned and row_pitch, batch_stride multiples of 4 elements;
  *   - "absolute time": all tensors of one WaveNet stack share one time axis (tau = index into the first layer's
- *     input); a dilated tap is a negative shift on that axis.
+ *     input); a dilated tap is a negative shift on that axis.  TMA box origins must be 16-byte aligned
+ *     (measured on B200: an unaligned inner coordinate raises "illegal instruction"), so every segment shift and
+ *     every tile origin is a multiple of 4 elements; taps with dilation 1 or 2 read a pre-shifted duplicate that the
+ *     producing kernel writes with its `dup` store.
  *   - kernels report device-side faults (e.g. a lost mbarrier arrival) through a caller-provided int32 error word
  *     (`err`), which the caller may read after synchronising; waits inside kernels are bounded, they never hang.
  */
@@ -58,18 +61,22 @@ typedef struct {
 
 typedef struct {
   int act;      /* index into acts[] */
-  int shift;    /* time shift: coordinate = tau + shift */
+  int shift;    /* time shift: coordinate = tau + shift; must be a multiple of 4 (TMA 16-byte rule) */
   int channels; /* K rows consumed (rounded up to 32 inside; rows >= act.channels read as zero) */
   int w_koff;   /* first K column of W for this segment (multiple of 32) */
 } aewn_seg;
 
 /* epilogue modes */
-#define AEWN_EPI_LINEAR 0   /* out = acc (+bias[n]) (+add[b,n,t]); flags below */
+#define AEWN_EPI_LINEAR 0   /* out = acc (+bias[n]) (+add[b,n,t]); flags below; optional dup store to out2 */
 #define AEWN_EPI_GATE_FWD 1 /* n == 256: cols [0,128) filt, [128,256) gate -> out=tanh, out2=sigmoid, out3=z */
-#define AEWN_EPI_GATE_BWD 2 /* n == 256: acc = g_z; add=tanh, add2=sigmoid -> out=g_filt, out2=g_gate */
+#define AEWN_EPI_GATE_BWD 2 /* acc = g_z; add=tanh, add2=sigmoid -> out=g_filt, out2=g_gate; optional dup store of
+                               g_filt to out3 and of g_gate to out3 + (out2 - out) */
 /* flags */
-#define AEWN_F_ACCUM 1 /* out += value (read-modify-write) */
-#define AEWN_F_RELU 2  /* out = max(value, 0) */
+#define AEWN_F_ACCUM 1      /* out += value (read-modify-write) */
+#define AEWN_F_RELU 2       /* value = max(value, 0) after bias/add */
+#define AEWN_F_MASKPOS 4    /* `add` is a mask source, not an addend: value = add[b,n,t] > 0 ? value : 0 */
+#define AEWN_F_RELU_FIRST 8 /* value = max(acc + bias, 0) + add  (wave_encoder.py:39-43 order); out3 (optional)
+                               receives max(acc + bias, 0), the activation mask source for the backward pass */
 
 typedef struct {
   int w_row;      /* first W row of this n-tile */
@@ -79,21 +86,25 @@ typedef struct {
   int flags;      /* AEWN_F_* */
   int seg_mask;   /* bit s set = segment s contributes to this tile */
   int t_lo, t_hi; /* store range on the absolute time axis; tiles outside are skipped */
-  int t_zero_lo;  /* GATE_BWD: stores for tau < t_zero_lo write 0 */
+  int t_zero_lo;  /* stores for tau < t_zero_lo write 0 (keeps the aligned-down margin of a tensor finite) */
   float* out;     /* pre-offset to the tile's first channel */
   float* out2;
   float* out3;
   long long out_bs, out_cs; /* batch / channel strides (elements) of out, out2, out3 */
   int out_toff;             /* out time index = tau + out_toff */
+  int dup_toff;             /* dup store time index = tau + dup_toff (skipped when outside [0, dup_t_hi)) */
+  int dup_t_hi;
+  unsigned long long* zero_count; /* optional: += number of stored values equal to 0 (wave_encoder.py:46) */
   const float* add;         /* optional */
   const float* add2;
   long long add_bs, add_cs;
   int add_toff;
+  int add_t_lo;             /* LINEAR: the addend / mask applies only for tau >= add_t_lo */
   const float* bias; /* optional, pre-offset, indexed by column */
 } aewn_ntile;
 
-#define AEWN_MAX_ACTS 3
-#define AEWN_MAX_SEGS 3
+#define AEWN_MAX_ACTS 4
+#define AEWN_MAX_SEGS 4
 #define AEWN_MAX_NTILES 4
 
 typedef struct {
@@ -130,8 +141,8 @@ typedef struct {
   int m_valid;        /* rows stored (<= 128) */
   int n;              /* UMMA N: multiple of 16, 16..256 */
   int n_valid;        /* columns stored */
-  int shift;          /* X time coordinate = u + shift */
-  int t_lo, t_hi;     /* u range (G's time axis) */
+  int shift;          /* X time coordinate = u + shift; multiple of 4 */
+  int t_lo, t_hi;     /* u range (G's time axis); t_lo multiple of 4 */
   int n_split;        /* split-K factor for this item (>= 1) */
   float* out;
   long long out_rs, out_cs;
@@ -151,6 +162,42 @@ typedef struct {
 } aewn_wgrad_desc;
 
 int aewn_wgrad(const aewn_wgrad_desc* d, aewn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Decoder base layer (wavenet.py:348-351): one_hot(wav.long())[..., off0:off0+T] -> Conv1d(Q->R, k=1) evaluated as
+ * a column gather  out[b, r, tau] = w[r, code(b, off0 + tau)] + bias[r]  (no one-hot tensor is materialised).
+ * `dup` (optional) receives the same values at time index tau + dup_toff (pre-shifted copy for a dilation-1/2 tap).
+ * A code outside [0, Q) sets *err = AEWN_ERR_INVALID (the reference raises in F.one_hot).
+ * ------------------------------------------------------------------------------------------------------------ */
+int aewn_base_embed_fwd(const float* wav, long long wav_pitch, int off0, const float* w, const float* bias, float* out,
+                        long long out_bs, long long out_cs, float* dup, int dup_toff, int dup_t_hi, int batch, int R,
+                        int Q, int T, int* err, aewn_stream_t stream);
+/* dw[r, q] += sum_{b,tau: code == q} g[b, r, tau];  dbias[r] += sum g[b, r, tau]  (dbias may be NULL) */
+int aewn_base_embed_bwd(const float* g, long long g_bs, long long g_cs, const float* wav, long long wav_pitch, int off0,
+                        float* dw, float* dbias, int batch, int R, int Q, int T, aewn_stream_t stream);
+int aewn_fill(float* p, long long n, float value, aewn_stream_t stream);
+/* out = mask > 0 ? g : 0   (ReLU backward) */
+int aewn_relu_mask_bwd(const float* g, long long g_bs, long long g_cs, const float* mask, long long m_bs, long long m_cs,
+                       float* out, long long o_bs, long long o_cs, int batch, int C, int T, aewn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused VQ step (vqema_bn.py:133-188, vq_bn.py:38-41): nearest code per (b, n) vector of ze (B, d, N).
+ *   metric 0: squared L2 (vq_bn.py:39);  metric 1: scaled L2 |z-e| / (|z| + |e|) (vqema_bn.py:67-76)
+ * Outputs: min_ind (B*N) int64, min_dist (B*N), zq (B, d, N) gathered codes; optional hist[K] += counts
+ * (util.int_hist accumulate, vqema_bn.py:156), z_sum[K][d] / n_sum[K] (overwritten: per-code sums / counts,
+ * vqema_bn.py:172-188), ze_norm (B*N).  Distances are IEEE fp32 in a fixed order (see vq.cu); first index wins ties.
+ * ------------------------------------------------------------------------------------------------------------ */
+int aewn_vq_fwd(const float* ze, long long ze_bs, long long ze_cs, const float* emb, int metric, long long* min_ind,
+                float* min_dist, float* zq, long long zq_bs, long long zq_cs, float* hist, float* z_sum, float* n_sum,
+                float* ze_norm, int batch, int d, int N, int K, aewn_stream_t stream);
+/* g_ze (+)= g_min_dist[b,n] * d(min_dist)/d(ze)   (commitment-loss gradient) */
+int aewn_vq_commit_bwd(const float* ze, long long ze_bs, long long ze_cs, const float* emb, const long long* min_ind,
+                       const float* g_min_dist, int metric, float* g_ze, long long g_bs, long long g_cs, int accumulate,
+                       int batch, int d, int N, aewn_stream_t stream);
+/* EMA update (vqema_bn.py:190-195) when z_sum != NULL; codebook refresh emb = numer/denom (vqema_bn.py:216-222) when
+ * emb != NULL. */
+int aewn_ema_update(float* ema_numer, float* ema_denom, const float* z_sum, const float* n_sum, float gamma, float* emb,
+                    int K, int d, aewn_stream_t stream);
 
 #ifdef __cplusplus
 }
