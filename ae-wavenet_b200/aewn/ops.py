@@ -414,3 +414,143 @@ def stack_backward(ws, geom, packs, params, g_skp, need_gx0=True, g_sig_last=Non
         grads[l] = gr
         g_sig = gx
     return g_sig, g_cond, grads
+
+
+# ------------------------------------------------------------------------------------------------- generic convs
+def to_buf(x, pad_t=0):
+    """Copy a (B, C, T) tensor into a fresh TMA-legal (B, C, Tp) buffer (Tp % 32 == 0, zero tail)."""
+    B, Cc, T = x.shape
+    buf = new_buf(B, Cc, ceil_to(T + pad_t + 4, 32), x.device)
+    buf[:, :, :T] = x
+    return buf
+
+
+_ones_cache = {}
+
+
+def ones_row(B, Tp, device):
+    """(B, 1, Tp) all-ones activation: contracting a gradient against it yields the bias gradient inside wgrad."""
+    key = (B, Tp, str(device))
+    t = _ones_cache.get(key)
+    if t is None:
+        if len(_ones_cache) > 16:
+            _ones_cache.clear()
+        t = _ones_cache[key] = torch.ones(B, 1, Tp, device=device)
+    return t
+
+
+_err_cache = {}
+
+
+def err_word(device):
+    key = str(device)
+    t = _err_cache.get(key)
+    if t is None:
+        t = _err_cache[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return t
+
+
+def pack_taps(weight, kc):
+    """(N, C, k) conv weight -> K-major [N][k * kc] with tap j in columns [j*kc, j*kc + C)."""
+    N, Cc, k = weight.shape
+    return torch.cat([_pad_k(weight[:, :, j], kc) for j in range(k)], 1).contiguous()
+
+
+class _TapConvFn(torch.autograd.Function):
+    """y[b, n, u] = epi( sum_j sum_c W[n, c, j] * x[b, c, u*stride + j] + bias[n] ),  u in [0, T_out)
+    with epi = identity | relu | relu-then-add-residual (wave_encoder.py:39-43).  k <= 4 taps.  Forward, data
+    gradient and weight gradient all run on the tcgen05 engines; PyTorch only stages the tap-shifted copies that
+    TMA's 16-byte origin rule requires (taps 1..3 of a stride-1 conv are not 16-byte aligned shifts)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, mode, res_lw, zero_count):
+        # mode: 0 linear, 1 relu, 2 relu-first + residual x[:, :, res_lw : res_lw + T_out]
+        B, Cc, T = x.shape
+        N, _, k = weight.shape
+        assert k <= L.MAX_SEGS
+        T_out = (T - k) // stride + 1
+        dev = x.device
+        err = err_word(dev)
+        kc = ceil_to(Cc, 32)
+        with torch.no_grad():
+            xd = x.detach()
+            taps = [to_buf(xd[:, :, j::stride][:, :, :T_out]) for j in range(k)]
+            Tp = taps[0].shape[2]
+            wp = pack_taps(weight.detach(), kc)
+            out = new_buf(B, N, Tp, dev)
+            relu_out = new_buf(B, N, Tp, dev) if mode == 2 else None
+            flags = {0: 0, 1: L.F_RELU, 2: L.F_RELU_FIRST}[mode]
+            tiles = []
+            for (c0, n) in chunks(N):
+                tiles.append(ntile(c0, n, out[:, c0:], flags=flags, t_lo=0, t_hi=T_out,
+                                   bias=bias.detach()[c0:] if bias is not None else None,
+                                   add=taps[res_lw][:, c0:] if mode == 2 else None,
+                                   out3=relu_out[:, c0:] if mode == 2 else None, zero_count=zero_count))
+            tgemm([act_of(t, T_out) for t in taps], [(j, 0, Cc, j * kc) for j in range(k)], wp, tiles, B, 0, T_out, err)
+        ctx.save_for_backward(weight)
+        ctx.taps, ctx.out, ctx.relu_out = taps, out, relu_out
+        ctx.cfg = (B, Cc, T, N, k, T_out, stride, mode, res_lw, bias is not None)
+        return out[:, :, :T_out].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (weight,) = ctx.saved_tensors
+        B, Cc, T, N, k, T_out, stride, mode, res_lw, has_bias = ctx.cfg
+        dev = g.device
+        err = err_word(dev)
+        lib = L.lib()
+        Tp = ctx.out.shape[2]
+        # g_pre = g * (activation > 0)
+        if mode == 0:
+            gp = to_buf(g)
+        else:
+            gp = new_buf(B, N, Tp, dev)
+            mask = ctx.out if mode == 1 else ctx.relu_out
+            gc = g if g.stride(2) == 1 else g.contiguous()
+            L.check(lib.aewn_relu_mask_bwd(
+                C.c_void_p(gc.data_ptr()), C.c_longlong(gc.stride(0)), C.c_longlong(gc.stride(1)),
+                C.c_void_p(mask.data_ptr()), C.c_longlong(mask.stride(0)), C.c_longlong(mask.stride(1)),
+                C.c_void_p(gp.data_ptr()), C.c_longlong(gp.stride(0)), C.c_longlong(gp.stride(1)),
+                C.c_int(B), C.c_int(N), C.c_int(T_out), _stream()), "aewn_relu_mask_bwd")
+        # weight / bias gradients:  dW[n, c, j] = sum_{b,u} gp[b, n, u] * tap_j[b, c, u]
+        dw = torch.zeros_like(weight)
+        db = torch.zeros(N, device=dev) if has_bias else None
+        acts = [act_of(gp, T_out)] + [act_of(t, T_out) for t in ctx.taps]
+        if has_bias:
+            acts.append(act_of(ones_row(B, Tp, dev), T_out))
+        items = []
+        for i in range((N + 127) // 128):
+            base = dict(g_act=0, g_row=128 * i, m_valid=min(128, N - 128 * i), t_lo=0, t_hi=T_out)
+            for j in range(k):
+                for (c0, n) in chunks(Cc):
+                    items.append(dict(base, x_act=1 + j, x_row=c0, n_valid=n, out=dw,
+                                      out_off=(128 * i) * Cc * k + c0 * k + j, out_rs=Cc * k, out_cs=k))
+            if has_bias:
+                items.append(dict(base, x_act=1 + k, x_row=0, n_valid=1, out=db, out_off=128 * i, out_rs=1, out_cs=1))
+        wgrad(acts, items, B, err)
+        # data gradient, one phase r of the input at a time:  g_x[s*u + r] = sum_m W[:, :, r + s*m]^T gp[u - m]
+        g_x = torch.zeros(B, Cc, T, device=dev)
+        kn = ceil_to(N, 32)
+        for r in range(min(stride, k)):
+            js = list(range(r, k, stride))
+            n_u = (T - r + stride - 1) // stride
+            shifted = []
+            for m in range(len(js)):
+                sb = new_buf(B, N, ceil_to(n_u + 4, 32), dev)
+                hi = min(n_u, T_out + m)
+                if hi > m:
+                    sb[:, :, m:hi] = gp[:, :, :hi - m]
+                shifted.append(sb)
+            wt = torch.cat([_pad_k(weight.detach()[:, :, j].t(), kn) for j in js], 1).contiguous()
+            gph = new_buf(B, Cc, ceil_to(n_u + 4, 32), dev)
+            tiles = [ntile(c0, n, gph[:, c0:], t_lo=0, t_hi=n_u) for (c0, n) in chunks(Cc)]
+            tgemm([act_of(sb, n_u) for sb in shifted], [(m, 0, N, m * kn) for m in range(len(js))], wt, tiles, B, 0, n_u,
+                  err)
+            g_x[:, :, r::stride] = gph[:, :, :n_u]
+        if mode == 2:
+            g_x[:, :, res_lw:res_lw + T_out] += g
+        return g_x, dw, db, None, None, None, None
+
+
+def tap_conv(x, weight, bias=None, stride=1, mode=0, res_lw=0, zero_count=None):
+    return _TapConvFn.apply(x, weight, bias, stride, mode, res_lw, zero_count)

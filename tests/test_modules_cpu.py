@@ -1,0 +1,83 @@
+"""Drop-in surface checks that need no GPU: constructor parity (same RNG stream => bit-identical initial weights as the
+reference), state_dict keys, geometry attributes, stale-caller compatibility and the no-CPU-fallback rule."""
+import hashlib
+import json
+import os
+
+import pytest
+import torch
+
+
+class HP(dict):
+    __getattr__ = dict.__getitem__
+
+
+from test_geometry import ARCH_BASIC  # noqa: E402
+
+
+def test_wavenet_init_is_bit_identical_to_reference(golden_dir):
+    import aewn
+    from aewn import geometry as vc
+    ref = json.load(open(os.path.join(golden_dir, "init_digest_basic.json")))
+    torch.manual_seed(2507)
+    parent = vc.VirtualConv(filter_info=1, stride=320, parent=None, name="LC-grid")
+    wn = aewn.WaveNet(HP(ARCH_BASIC), parent_vc=parent)
+    vc.compute_inputs(wn.vc["end_grcc"], vc.GridRange((0, 10 ** 7), (0, 1024), 1))
+    wn.trim_ups_out = torch.tensor([0, wn.vc["beg_grcc"].in_len()], dtype=torch.long)
+    wn.post_init(1024)
+    sd = wn.state_dict()
+    floats = {k: v for k, v in sd.items() if v.dtype == torch.float32}
+    assert sorted(floats) == sorted(ref)
+    for k, v in floats.items():
+        assert hashlib.sha256(v.numpy().tobytes()).hexdigest() == ref[k], k
+    assert [k for k in sd if k.endswith("leads")] == [f"conv_layers.{i}.leads" for i in range(20)]
+    assert "conv_layers.19.dil_res.weight" not in sd and "conv_layers.18.dil_res.weight" in sd
+    assert sum(p.numel() for p in wn.parameters()) == 13508490
+
+
+def test_old_keyword_constructor_is_accepted():
+    """autoencoder_model.py:83-87 still calls WaveNet(**dec_params, parent_vc=..., n_lc_in=...)."""
+    import aewn
+    from aewn import geometry as vc
+    kw = {k: v for k, v in ARCH_BASIC.items() if k != "bias"}
+    parent = vc.VirtualConv(filter_info=1, stride=320, parent=None, name="p")
+    with torch.device("meta"):
+        wn = aewn.WaveNet(parent_vc=parent, **kw)
+    assert len(wn.conv_layers) == 20 and wn.bias is True
+    with pytest.raises(TypeError):
+        aewn.WaveNet(parent_vc=parent, bogus=1, **kw)
+
+
+def test_no_cpu_fallback():
+    import aewn
+    from aewn import geometry as vc
+    small = dict(ARCH_BASIC, n_res=16, n_dil=16, n_skp=16, n_post=16, n_lc_out=8, n_blocks=1, n_block_layers=2)
+    parent = vc.VirtualConv(filter_info=1, stride=320, parent=None, name="p")
+    wn = aewn.WaveNet(HP(small), parent_vc=parent)
+    vc.compute_inputs(wn.vc["end_grcc"], vc.GridRange((0, 10 ** 7), (0, 8), 1))
+    wn.trim_ups_out = torch.tensor([0, wn.vc["beg_grcc"].in_len()], dtype=torch.long)
+    wn.post_init(8)
+    wn.train()
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        wn(torch.zeros(1, 4000), torch.zeros(1, 64, 20), torch.zeros(1, dtype=torch.long),
+           torch.arange(20).unsqueeze(0))
+
+
+def test_encoder_and_vq_state_dicts(golden_dir):
+    from aewn import geometry as vc, wave_encoder, vqema_bn, vq_bn
+    g = torch.load(os.path.join(golden_dir, "encoder_small.pt"))
+    torch.manual_seed(2507)
+    enc = wave_encoder.Encoder(13, 64, vc.VirtualConv(filter_info=400, stride=160, name="MFCC"))
+    sd = enc.state_dict()
+    assert list(sd) == list(g["state_dict"])
+    assert all(torch.equal(sd[k], g["state_dict"][k]) for k in sd)
+    gv = torch.load(os.path.join(golden_dir, "vq.pt"))
+    torch.manual_seed(2507)
+    bn = vqema_bn.VQEMA(96, 32, 0.25, 0.99, 4096, True)
+    assert torch.equal(bn.emb, gv["vqema"]["emb"]) and torch.equal(bn.linear.weight, gv["vqema"]["lin_w"])
+    assert torch.equal(bn.ema_numer, gv["vqema"]["ema_numer0"])
+    torch.manual_seed(2508)
+    vq = vq_bn.VQ(96, 64, 0.25, 512)
+    assert torch.equal(vq.emb.detach(), gv["vq"]["emb"])
+    with pytest.raises(RuntimeError):
+        vqema_bn.VQEMA(96, 32, 0.25, 1.0, 64, True)
