@@ -69,7 +69,43 @@ def ntile(w_row, n_valid, out, mode=L.EPI_LINEAR, flags=0, seg_mask=0xF, t_lo=0,
     return nt
 
 
-def tgemm(acts, segs, w, ntiles, batch, t_begin, t_end, err=None):
+class LaunchProfiler:
+    """Optional per-launch CUDA-event timing (bench.py's roofline leg).  Events are recorded on the launching stream."""
+
+    def __init__(self):
+        self.records = []      # (tag, start_event, end_event)
+
+    def times_ms(self):
+        out = {}
+        for tag, e0, e1 in self.records:
+            out.setdefault(tag, []).append(e0.elapsed_time(e1))
+        return out
+
+
+_prof = None
+
+
+def set_profiler(p):
+    global _prof
+    _prof = p
+
+
+def _prof_begin(tag):
+    if _prof is None or tag is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _prof_end(tag, e0):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        _prof.records.append((tag, e0, e1))
+
+
+def tgemm(acts, segs, w, ntiles, batch, t_begin, t_end, err=None, tag=None):
     """One aewn_tgemm launch.  acts: list of L.Act; segs: list of (act_idx, shift, channels, w_koff); w: (rows, kpad)
     fp32 contiguous; ntiles: list of L.NTile (split into launches of <= MAX_NTILES)."""
     assert w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 2
@@ -88,10 +124,12 @@ def tgemm(acts, segs, w, ntiles, batch, t_begin, t_end, err=None):
         d.n_ntiles = len(chunk)
         d.batch, d.t_begin, d.t_end = int(batch), int(t_begin), int(t_end)
         d.err = err.data_ptr() if err is not None else None
+        e0 = _prof_begin(tag)
         L.check(L.lib().aewn_tgemm(C.byref(d), _stream()), "aewn_tgemm")
+        _prof_end(tag, e0)
 
 
-def wgrad(acts, items, batch, err=None):
+def wgrad(acts, items, batch, err=None, tag=None):
     """aewn_wgrad launches.  items: list of dicts(g_act, x_act, g_row, x_row, m_valid, n_valid, shift, t_lo, t_hi, out,
     out_off (elements), out_rs, out_cs)."""
     lib = L.lib()
@@ -117,7 +155,9 @@ def wgrad(acts, items, batch, err=None):
         d.n_items = len(chunk)
         d.batch = int(batch)
         d.err = err.data_ptr() if err is not None else None
+        e0 = _prof_begin(tag)
         L.check(lib.aewn_wgrad(C.byref(d), _stream()), "aewn_wgrad")
+        _prof_end(tag, e0)
 
 
 def chunks(total, size=256):
@@ -292,7 +332,7 @@ def stack_forward(ws, geom, packs, relu_last, save):
             tiles.append(ntile(256 * j, nj, ws.th[l][:, c0:] if save else None, mode=L.EPI_GATE_FWD, n=256,
                                out2=ws.sg[l][:, c0:] if save else None, out3=ws.z[l][:, c0:],
                                t_lo=lo4, t_hi=T0, t_zero_lo=lo))
-        tgemm(acts, segs, pk.w1, tiles, B, t_begin, T0, ws.err)
+        tgemm(acts, segs, pk.w1, tiles, B, t_begin, T0, ws.err, tag=f"fwd_gemm1.{l}")
 
         tiles = []
         if not final:
@@ -307,7 +347,7 @@ def stack_forward(ws, geom, packs, relu_last, save):
         for (c0, n) in chunks(S):
             tiles.append(ntile(row0 + c0, n, ws.skp[:, c0:], flags=flags, t_lo=rf4, t_hi=T0,
                                t_zero_lo=g.RF if l == 0 else 0))
-        tgemm([act_of(ws.z[l], T0)], [(0, 0, D, 0)], pk.w2, tiles, B, t_begin, T0, ws.err)
+        tgemm([act_of(ws.z[l], T0)], [(0, 0, D, 0)], pk.w2, tiles, B, t_begin, T0, ws.err, tag=f"fwd_gemm2.{l}")
 
 
 # ------------------------------------------------------------------------------------------------- stack backward
@@ -345,7 +385,7 @@ def stack_backward(ws, geom, packs, params, g_skp, need_gx0=True, g_sig_last=Non
         tile = ntile(0, D, gfg, mode=L.EPI_GATE_BWD, out2=gfg[:, D:], add=ws.th[l], add2=ws.sg[l],
                      out3=gfs if needs_dup(d) else None, dup_toff=-d, dup_t_hi=T0,
                      t_lo=t_store, t_hi=T0, t_zero_lo=lo)
-        tgemm(acts, segs, pk.w2t, [tile], B, t_store & ~31, T0, ws.err)
+        tgemm(acts, segs, pk.w2t, [tile], B, t_store & ~31, T0, ws.err, tag=f"bwd_gz.{l}")
 
         # (2) g_x[tau] = tap1^T gfg[tau] + tap0^T gfg[tau + d] (+ g_sig[tau]);  g_cond[tau] += P^T gfg[tau]
         if needs_dup(d):
@@ -363,7 +403,7 @@ def stack_backward(ws, geom, packs, params, g_skp, need_gx0=True, g_sig_last=Non
                                    t_lo=lop4, t_hi=T0, t_zero_lo=lo_prev))
         for (c0, n) in chunks(Cc):
             tiles.append(ntile(R + c0, n, g_cond[:, c0:], flags=L.F_ACCUM, seg_mask=2, t_lo=lo, t_hi=T0))
-        tgemm(acts, segs, pk.w1t, tiles, B, lop4 & ~31, T0, ws.err)
+        tgemm(acts, segs, pk.w1t, tiles, B, lop4 & ~31, T0, ws.err, tag=f"bwd_dgrad.{l}")
 
         # (3) weight gradients of conv_signal/conv_gate/proj_signal/proj_gate (+ biases via the ones channel)
         gr = {}
@@ -385,7 +425,7 @@ def stack_backward(ws, geom, packs, params, g_skp, need_gx0=True, g_sig_last=Non
                 for (c0, n) in chunks(Cc + 1):
                     items.append(dict(base, x_act=3, x_row=c0, n_valid=n, shift=0, out=dpb,
                                       out_off=(h * D + 128 * i) * (Cc + 1) + c0, out_rs=Cc + 1, out_cs=1))
-        wgrad(acts, items, B, ws.err)
+        wgrad(acts, items, B, ws.err, tag=f"wgrad1.{l}")
         gr["conv_signal.weight"], gr["conv_gate.weight"] = dwf, dwg
         gr["proj_signal.weight"] = dpb[:D, :Cc].unsqueeze(2).contiguous()
         gr["proj_gate.weight"] = dpb[D:, :Cc].unsqueeze(2).contiguous()
@@ -409,7 +449,7 @@ def stack_backward(ws, geom, packs, params, g_skp, need_gx0=True, g_sig_last=Non
                                       n_valid=n, t_lo=lo4, t_hi=T0, out=dwr, out_off=128 * i * D + c0, out_rs=D,
                                       out_cs=1))
             gr["dil_res.weight"] = dwr
-        wgrad(acts, items, B, ws.err)
+        wgrad(acts, items, B, ws.err, tag=f"wgrad2.{l}")
         gr["dil_skp.weight"] = dws
         grads[l] = gr
         g_sig = gx

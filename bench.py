@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- audio samples/s through the WaveNet decoder train step (cfg2 of BASELINE.json) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Workload: WaveNet decoder of par/arch.basic.json (20 GRCC layers, R=368 D=256 S=256 C=138),
+batch 8 per GPU, window 16384 (decoder input T0 = 18430), synthetic 16 kHz mu-law codes, random-init weights
+(seed 2507).  One step = H2D of the batch (e2e leg only), forward, RecLoss, backward, one flat-buffer all-reduce
+(N > 1), Adam step.  `value` = B_total * W / t_step with inputs resident in HBM, timed with CUDA events, max over ranks.
+
+`--impl reference` times the reference's own CPU path (the oracle port of wavenet.py, oracle/torch_oracle.py) on the
+host cores on a bounded sample of the same workload.  oracle/ is touched ONLY by that leg and by the cpu_baseline leg.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "ae-wavenet_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+ARCH_BASIC = dict(filter_sz=2, n_lc_out=128, lc_upsample_strides=[5, 4, 4, 4], lc_upsample_filt_sizes=[25, 16, 16, 16],
+                  n_res=368, n_dil=256, n_skp=256, n_post=256, n_quant=256, n_blocks=2, n_block_layers=10,
+                  n_global_embed=10, n_speakers=40, bias=True, n_lc_in=64)
+METRIC = "audio samples/s through WaveNet fwd+bwd"
+UNIT = "samples/s"
+
+
+class HP(dict):
+    __getattr__ = dict.__getitem__
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback")
+
+
+def synth_batch(B, wav_len, lc_len, n_lc_in, n_speakers, seed):
+    """Synthetic 16 kHz window: mu-law codes of a two-tone + noise signal (util.mu_encode_np, util.py:62-67)."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(wav_len).float()
+    f1 = 0.01 + 0.02 * torch.rand(B, 1, generator=g)
+    f2 = 0.05 + 0.10 * torch.rand(B, 1, generator=g)
+    x = 0.3 * torch.sin(f1 * t) + 0.2 * torch.sin(f2 * t + 1.0) + 0.05 * torch.randn(B, wav_len, generator=g)
+    x = x.clamp(-1, 1)
+    mu = 255.0
+    amp = torch.sign(x) * torch.log1p(mu * x.abs()) / torch.log1p(torch.tensor(mu))
+    wav = ((amp + 1) * 0.5 * mu + 0.5).to(torch.int32).float()
+    lc = torch.randn(B, n_lc_in, lc_len, generator=g)
+    spk = torch.randint(0, n_speakers, (B,), generator=g)
+    jit = torch.arange(lc_len).unsqueeze(0).repeat(B, 1)
+    return wav, lc, spk, jit
+
+
+def build_decoder(W, WaveNet, vc):
+    """Stand-alone decoder built exactly like MfccInverter._init_geometry (mfcc_inverter.py:38-65)."""
+    hp = HP(ARCH_BASIC)
+    parent = vc.VirtualConv(filter_info=1, stride=320, parent=None, name="LC-grid")
+    wn = WaveNet(hp, parent_vc=parent)
+    end_gr = vc.GridRange((0, 10 ** 7), (0, W), 1)
+    vc.compute_inputs(wn.vc["end_grcc"], end_gr)
+    beg = wn.vc["beg_grcc"]
+    geo = dict(wav_len=parent.in_len(), lc_len=parent.child.in_len(), dec_in_len=beg.in_len(),
+               trim_dec_out=[end_gr.sub[0] - parent.input_gr.sub[0], end_gr.sub[1] - parent.input_gr.sub[0]])
+    wn.trim_ups_out = torch.tensor([0, beg.in_len()], dtype=torch.long)
+    wn.post_init(W)
+    return wn, geo
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = max([int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()] or [0])
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def grcc_layer_fwd_bytes(B, R, D, S, C, T_in, d, W, train):
+    """read x, read cond slice, write sig, RMW skip-sum, weights once (+ saved tanh/sigmoid/z if training)."""
+    T_out = T_in - d
+    b = 4 * B * (R * T_in + C * T_out + R * T_out + 2 * S * W) + 4 * 607744
+    if train:
+        b += 4 * B * 3 * D * T_out
+    return b
+
+
+def grcc_layer_fwd_flops(B, R, D, S, C, T_in, d, W, K=2):
+    T_out = T_in - d
+    return 2.0 * B * T_out * D * (2 * K * R + 2 * C) + 2.0 * B * T_out * R * D + 2.0 * B * W * S * D
+
+
+# ------------------------------------------------------------------------------------------------- reference arm / CPU
+def cpu_port_step(B, W, steps, warmup, seed=2507):
+    """The reference's own CPU implementation of the path (oracle port of wavenet.py:323-364 + RecLoss + autograd)."""
+    from oracle import torch_oracle as orc
+    from aewn import geometry as vc
+    import aewn
+    torch.manual_seed(seed)
+    with torch.device("cpu"):
+        wn, geo = build_decoder(W, aewn.WaveNet, vc)
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype == torch.float32 and k != "cond.eye" else v)
+          for k, v in wn.state_dict().items()}
+    ogeo = dict(trim_ups_out=wn.trim_ups_out.tolist(), wav_cond_offset=list(wn.wav_cond_offset),
+                leads=[l.leads.tolist() for l in wn.conv_layers], n_win_batch=W, trim_dec_out=geo["trim_dec_out"])
+    wav, lc, spk, jit = synth_batch(B, geo["wav_len"], geo["lc_len"], 64, 40, 1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, _ = orc.decoder_loss(sd, ARCH_BASIC, ogeo, wav, lc, spk, jit)
+        loss.backward()
+        for v in sd.values():
+            if getattr(v, "grad", None) is not None:
+                v.grad = None
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    return B * W / times[len(times) // 2], times
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    B, W = 2, 2048                               # bounded sample of cfg2: same network, 2 x 2048-sample windows
+    sps, times = cpu_port_step(B, W, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+    out = dict(metric=METRIC, value=sps, unit=UNIT, n_gpus=args.gpus, steps=len(times), warmup=min(args.warmup, 2),
+               ms_per_step=1e3 * sorted(times)[len(times) // 2], higher_is_better=True, scaling="weak", vs_baseline=None,
+               dtype="f32", data="synthetic", impl="reference",
+               config=dict(workload="WaveNet decoder par/arch.basic.json train step (fwd+RecLoss+bwd), CPU",
+                           global_batch=B, window=W),
+               cpu_baseline=dict(value=sps, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                                 sample=f"same decoder, batch {B} x window {W} (cfg2 is 8 x 16384), median step"),
+               e2e=dict(value=sps, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (cfg2: 8)")
+    ap.add_argument("--window", type=int, default=16384)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    import aewn
+    from aewn import geometry as vc, ops, _lib
+    from aewn.dist import FlatGradSync
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the aewn hot path has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, W = args.batch, args.window
+    torch.manual_seed(2507)                      # identical replicas
+    wn, geo = build_decoder(W, aewn.WaveNet, vc)
+    wn = wn.to(dev).train()
+    loss_fn = aewn.RecLoss()
+    sync = FlatGradSync(wn.parameters())
+    opt = torch.optim.Adam(wn.parameters(), lr=2e-5)          # checkpoint.py:49, par/train.basic.json:6
+    wav_h, lc_h, spk_h, jit_h = [t.pin_memory() for t in synth_batch(B, geo["wav_len"], geo["lc_len"], 64, 40, 1234 + rank)]
+    t0w, t1w = geo["trim_dec_out"]
+
+    def step(wav, lc, spk, jit):
+        sync.zero_grad()
+        quant = wn(wav, lc, spk, jit)
+        loss = loss_fn(quant[..., :-1], wav[:, t0w:t1w][..., 1:])
+        loss.backward()
+        sync.sync()
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dwav, dlc, dspk, djit = [t.to(dev) for t in (wav_h, lc_h, spk_h, jit_h)]
+    for _ in range(args.warmup):
+        loss = step(dwav, dlc, dspk, djit)
+    ops.check_device_errors()
+
+    # ---- timed region 1: device-resident inputs, CUDA events, per-launch roofline events
+    prof = ops.LaunchProfiler()
+    ops.set_profiler(prof)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = _lib.launch_count()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(dwav, dlc, dspk, djit)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    ops.set_profiler(None)
+    ms = e0.elapsed_time(e1) / args.steps
+    final_loss = float(loss)
+    ops.check_device_errors()
+
+    # ---- timed region 2: end to end through the public module API with HOST (pinned) inputs and a D2H loss read
+    barrier()
+    t_start = time.perf_counter()
+    for _ in range(args.steps):
+        ins = [t.to(dev, non_blocking=True) for t in (wav_h, lc_h, spk_h, jit_h)]
+        loss = step(*ins)
+        _ = loss.item()                           # D2H read of the step's result
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t_start) / args.steps
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([float(launches)], device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt[0])
+
+    if rank == 0:
+        pk = peaks()
+        R, D, S, C = 368, 256, 256, 138
+        times = prof.times_ms()
+        geomS = wn.stack_geometry(geo["dec_in_len"])
+        fwd_bytes = fwd_flops = fwd_ms = 0.0
+        T_in = geomS.T0
+        for l, d in enumerate(geomS.dils):
+            g1, g2 = times.get(f"fwd_gemm1.{l}", []), times.get(f"fwd_gemm2.{l}", [])
+            if g1 and g2:
+                fwd_ms += sum(g1) / len(g1) + sum(g2) / len(g2)
+                fwd_bytes += grcc_layer_fwd_bytes(B, R, D, S, C, T_in, d, W, train=True)
+                fwd_flops += grcc_layer_fwd_flops(B, R, D, S, C, T_in, d, W)
+            T_in -= d
+        gemm_ms = sum(sum(v) for v in times.values()) / args.steps
+        hbm_ach = fwd_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None
+        tf_ach = fwd_flops / (fwd_ms * 1e-3) / 1e12 if fwd_ms else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tpath):
+            traffic = json.load(open(tpath)).get("grcc_layer_fwd_dram_bytes_per_launch")
+        out = dict(
+            metric=METRIC, value=world * B * W / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
+            warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="tf32", data="synthetic",
+            config=dict(workload="cfg2: WaveNet decoder par/arch.basic.json train step, batch 8/GPU, window 16384",
+                        step="H2D(e2e only)+fwd+RecLoss+bwd+allreduce+Adam", global_batch=world * B, window=W,
+                        dec_in_len=geo["dec_in_len"], parallelism=f"dp{world}",
+                        l2="activations per step ~13 GB >> 126 MB L2 (no flush needed)", seed=2507,
+                        final_loss=final_loss),
+            roofline=dict(bound="hbm", achieved=hbm_ach, peak=pk["hbm_gbs"], unit="GB/s",
+                          frac=(hbm_ach / pk["hbm_gbs"]) if hbm_ach else None, traffic=traffic,
+                          kernel="tgemm_kernel: GRCC layer forward (2 launches/layer: conv+gate, res+skip), "
+                                 "algorithmic bytes per SURVEY.md 8d incl. saved activations, summed over 20 layers",
+                          ms_per_layer_fwd=fwd_ms / max(1, geomS.L), peak_source=pk["source"]),
+            roofline_tensor=dict(bound="tensor", achieved=tf_ach, peak=pk["bf16_tflops"], unit="TFLOP/s",
+                                 frac=(tf_ach / pk["bf16_tflops"]) if tf_ach else None,
+                                 note="TF32 operands (nominal peak = half of bf16); denominator is the measured bf16 "
+                                      "cuBLAS rate"),
+            kernel_share=dict(tcgen05_ms_per_step=gemm_ms, step_ms=ms),
+            clocks=clocks,
+            e2e=dict(value=world * B * W / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms,
+                     h2d_bytes_per_step=int(sum(t.numel() * t.element_size() for t in (wav_h, lc_h, spk_h, jit_h))),
+                     d2h_bytes_per_step=4),
+            gpu_launches=launches,
+        )
+        if not args.no_cpu_baseline and world == 1:
+            torch.set_num_threads(os.cpu_count() or 1)
+            sps, ctimes = cpu_port_step(2, 2048, 3, 1)
+            out["cpu_baseline"] = dict(value=sps, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                                       sample="same decoder (oracle port of wavenet.py), batch 2 x window 2048, "
+                                              "median of 3 steps after 1 warm-up")
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,101 @@
+"""Size-independent properties of the GRCC stack at the full cfg2 size (arch.basic, batch 8, window 16384), where the
+CPU oracle would take minutes: linearity of the residual/skip path, time-shift invariance, batch independence, and
+agreement of a random sub-window with the CPU oracle."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class HP(dict):
+    __getattr__ = dict.__getitem__
+
+
+ARCH_BASIC = dict(filter_sz=2, n_lc_out=128, lc_upsample_strides=[5, 4, 4, 4], lc_upsample_filt_sizes=[25, 16, 16, 16],
+                  n_res=368, n_dil=256, n_skp=256, n_post=256, n_quant=256, n_blocks=2, n_block_layers=10,
+                  n_global_embed=10, n_speakers=40, bias=True, n_lc_in=64)
+
+
+def build(W):
+    import aewn
+    from aewn import geometry as vc
+    parent = vc.VirtualConv(filter_info=1, stride=320, parent=None, name="LC-grid")
+    wn = aewn.WaveNet(HP(ARCH_BASIC), parent_vc=parent)
+    end_gr = vc.GridRange((0, 10 ** 7), (0, W), 1)
+    vc.compute_inputs(wn.vc["end_grcc"], end_gr)
+    geo = dict(wav_len=parent.in_len(), lc_len=parent.child.in_len(), dec_in_len=wn.vc["beg_grcc"].in_len())
+    wn.trim_ups_out = torch.tensor([0, geo["dec_in_len"]], dtype=torch.long)
+    wn.post_init(W)
+    return wn, geo
+
+
+def test_full_size_forward_window_matches_cpu_oracle_and_batch_items_are_independent():
+    from aewn import ops
+    from oracle import torch_oracle as orc
+    torch.manual_seed(2507)
+    W = 16384
+    wn, geo = build(W)
+    wn = wn.cuda().train()
+    g = torch.Generator().manual_seed(5)
+    B = 8
+    wav = torch.randint(0, 256, (B, geo["wav_len"]), generator=g).float()
+    lc = torch.randn(B, 64, geo["lc_len"], generator=g)
+    spk = torch.randint(0, 40, (B,), generator=g)
+    jit = torch.arange(geo["lc_len"]).unsqueeze(0).repeat(B, 1)
+    with torch.no_grad():
+        q = wn(wav.cuda(), lc.cuda(), spk.cuda(), jit.cuda())
+        # batch independence: item 3 alone gives the same logits as inside the batch of 8
+        q3 = wn(wav[3:4].cuda(), lc[3:4].cuda(), spk[3:4].cuda(), jit[3:4].cuda())
+    ops.check_device_errors()
+    assert q.shape == (B, 256, W) and torch.isfinite(q).all()
+    assert torch.equal(q[3:4], q3)
+    # CPU oracle on the LAST 64 output steps of item 0: outputs only depend on the trailing RF + 64 inputs
+    sd = {k: v.cpu() for k, v in wn.state_dict().items()}
+    n_out = 64
+    o0, o1 = wn.wav_cond_offset
+    rf = 2046
+    geo_small = dict(trim_ups_out=[0, geo["dec_in_len"]], wav_cond_offset=[o0, o1], n_win_batch=W,
+                     leads=[l.leads.tolist() for l in wn.conv_layers])
+    cond = orc.conditioning(sd, ARCH_BASIC, lc[0:1], spk[0:1], jit[0:1], geo_small["trim_ups_out"])
+    T0 = geo["dec_in_len"]
+    s = T0 - (rf + n_out)
+    onehot = torch.nn.functional.one_hot(wav[0:1, o0:o1].long(), 256).permute(0, 2, 1).float()[:, :, s:]
+    sig = torch.nn.functional.conv1d(onehot, sd["base_layer.weight"], sd["base_layer.bias"])
+    c = cond[:, :, s:]
+    skp_sum = 0
+    for li, d in enumerate(orc.dilations(ARCH_BASIC)):
+        lead = geo_small["leads"][li]
+        sig, skp = orc.grcc_layer(sig, c, orc.sub(sd, f"conv_layers.{li}"), d, lead, li == 19)
+        skp_sum = skp_sum + skp
+    post1 = torch.nn.functional.conv1d(torch.relu(skp_sum), sd["post1.weight"], sd["post1.bias"])
+    ref = torch.nn.functional.conv1d(torch.relu(post1), sd["post2.weight"], sd["post2.bias"])
+    got = q[0:1, :, -n_out:].cpu()
+    err = float((got - ref).abs().max()) / float(ref.abs().max())
+    assert err < 5e-3, err
+
+
+def test_full_size_backward_is_finite_and_weight_grads_scale_linearly():
+    """d(c * loss)/dW = c * d(loss)/dW through the whole kernel path (linearity of backward in the upstream gradient)."""
+    import aewn
+    from aewn import ops
+    torch.manual_seed(2507)
+    W = 4096
+    wn, geo = build(W)
+    wn = wn.cuda().train()
+    g = torch.Generator().manual_seed(6)
+    B = 2
+    wav = torch.randint(0, 256, (B, geo["wav_len"]), generator=g).float().cuda()
+    lc = torch.randn(B, 64, geo["lc_len"], generator=g).cuda()
+    spk = torch.randint(0, 40, (B,), generator=g).cuda()
+    jit = torch.arange(geo["lc_len"]).unsqueeze(0).repeat(B, 1).cuda()
+    q = wn(wav, lc, spk, jit)
+    gq = torch.randn(q.shape, generator=torch.Generator().manual_seed(1)).cuda()
+    params = [p for p in wn.parameters()]
+    g1 = torch.autograd.grad((q * gq).sum(), params, retain_graph=True)
+    g3 = torch.autograd.grad((q * gq).sum() * 3.0, params)
+    ops.check_device_errors()
+    for a, b, (k, _) in zip(g1, g3, wn.named_parameters()):
+        assert torch.isfinite(a).all(), k
+        assert torch.allclose(3.0 * a, b, rtol=2e-3, atol=1e-5 * float(b.abs().max())), k
