@@ -41,7 +41,7 @@ class TGemmDesc(C.Structure):
                 ("w", C.c_void_p), ("w_rows", C.c_int), ("w_kpad", C.c_int),
                 ("ntiles", NTile * MAX_NTILES), ("n_ntiles", C.c_int), ("batch", C.c_int),
                 ("t_begin", C.c_int), ("t_end", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int),
-                ("dbg_lbo", C.c_int), ("dbg_sbo", C.c_int)]
+                ("dbg_lbo", C.c_int), ("dbg_sbo", C.c_int), ("cluster", C.c_int)]
 
 
 class WGradItem(C.Structure):
@@ -56,13 +56,17 @@ class WGradDesc(C.Structure):
                 ("n_items", C.c_int), ("batch", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int)]
 
 
+class CopyBlock(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("ni", C.c_int), ("nj", C.c_int), ("si", C.c_longlong),
+                ("sj", C.c_longlong), ("di", C.c_longlong)]
+
+
 _lib = None
 
 # every symbol include/aewn.h declares (tests/test_capi.py checks the shared object exports all of them)
 SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_tgemm", "aewn_wgrad",
            "aewn_base_embed_fwd", "aewn_base_embed_bwd", "aewn_fill", "aewn_relu_mask_bwd",
-           "aewn_vq_fwd", "aewn_vq_commit_bwd", "aewn_ema_update", "aewn_crr_fwd", "aewn_crr_bwd_data",
-           "aewn_pack_rows"]
+           "aewn_vq_fwd", "aewn_vq_commit_bwd", "aewn_ema_update", "aewn_pack_blocks"]
 
 
 def lib():

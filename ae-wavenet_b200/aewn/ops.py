@@ -105,10 +105,11 @@ def _prof_end(tag, e0):
         _prof.records.append((tag, e0, e1))
 
 
-def tgemm(acts, segs, w, ntiles, batch, t_begin, t_end, err=None, tag=None):
-    """One aewn_tgemm launch.  acts: list of L.Act; segs: list of (act_idx, shift, channels, w_koff); w: (rows, kpad)
-    fp32 contiguous; ntiles: list of L.NTile (split into launches of <= MAX_NTILES)."""
+def build_tgemm(acts, segs, w, ntiles, batch, t_begin, t_end, err=None, tag=None):
+    """Descriptors of one logical tgemm (split into launches of <= MAX_NTILES n-tiles).  acts: list of L.Act; segs: list
+    of (act_idx, shift, channels, w_koff); w: (rows, kpad) fp32 contiguous.  Returns [("tgemm", desc, tag, keepalive)]."""
     assert w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 2
+    out = []
     for i in range(0, len(ntiles), L.MAX_NTILES):
         chunk = ntiles[i:i + L.MAX_NTILES]
         d = L.TGemmDesc()
@@ -124,16 +125,15 @@ def tgemm(acts, segs, w, ntiles, batch, t_begin, t_end, err=None, tag=None):
         d.n_ntiles = len(chunk)
         d.batch, d.t_begin, d.t_end = int(batch), int(t_begin), int(t_end)
         d.err = err.data_ptr() if err is not None else None
-        e0 = _prof_begin(tag)
-        L.check(L.lib().aewn_tgemm(C.byref(d), _stream()), "aewn_tgemm")
-        _prof_end(tag, e0)
+        out.append(("tgemm", d, tag))
+    return out
 
 
-def wgrad(acts, items, batch, err=None, tag=None):
-    """aewn_wgrad launches.  items: list of dicts(g_act, x_act, g_row, x_row, m_valid, n_valid, shift, t_lo, t_hi, out,
-    out_off (elements), out_rs, out_cs)."""
-    lib = L.lib()
+def build_wgrad(acts, items, batch, err=None, tag=None):
+    """Descriptors of one logical wgrad.  items: list of dicts(g_act, x_act, g_row, x_row, m_valid, n_valid, shift, t_lo,
+    t_hi, out, out_off (elements), out_rs, out_cs)."""
     sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    out = []
     for i in range(0, len(items), L.WGRAD_MAX_ITEMS):
         chunk = items[i:i + L.WGRAD_MAX_ITEMS]
         d = L.WGradDesc()
@@ -155,9 +155,29 @@ def wgrad(acts, items, batch, err=None, tag=None):
         d.n_items = len(chunk)
         d.batch = int(batch)
         d.err = err.data_ptr() if err is not None else None
+        out.append(("wgrad", d, tag))
+    return out
+
+
+def run_launches(launches):
+    """Enqueue prebuilt descriptors on the current stream (ctypes call only: ~2 us of host time per launch)."""
+    lib = L.lib()
+    st = _stream()
+    for kind, d, tag in launches:
         e0 = _prof_begin(tag)
-        L.check(lib.aewn_wgrad(C.byref(d), _stream()), "aewn_wgrad")
+        if kind == "tgemm":
+            L.check(lib.aewn_tgemm(C.byref(d), st), "aewn_tgemm")
+        else:
+            L.check(lib.aewn_wgrad(C.byref(d), st), "aewn_wgrad")
         _prof_end(tag, e0)
+
+
+def tgemm(acts, segs, w, ntiles, batch, t_begin, t_end, err=None, tag=None):
+    run_launches(build_tgemm(acts, segs, w, ntiles, batch, t_begin, t_end, err, tag))
+
+
+def wgrad(acts, items, batch, err=None, tag=None):
+    run_launches(build_wgrad(acts, items, batch, err, tag))
 
 
 def chunks(total, size=256):
@@ -165,57 +185,11 @@ def chunks(total, size=256):
     return [(o, min(size, total - o)) for o in range(0, total, size)]
 
 
-# ------------------------------------------------------------------------------------------------- weight packing
+# ------------------------------------------------------------------------------------------------- stack geometry
 def _pad_k(m, k):
     return torch.nn.functional.pad(m, (0, k - m.shape[1]))
 
 
-class LayerPack:
-    """K-major, zero-padded operand matrices of one GRCC layer (rebuilt from the live parameters each step).
-
-    w1  [256*J][2*KR + KC]  rows: per 128-channel block j, 128 filt rows then 128 gate rows (GATE_FWD pairs column c
-                            with column 128+c);  columns: tap0 | tap1 | cond proj | bias (the bias rides on an
-                            all-ones conditioning channel, so no epilogue bias add and d(bias) falls out of wgrad)
-    w2  [R + S][KD]         rows: dil_res (absent in the final layer) then dil_skp
-    w2t [D][KR + KS]        [Wr^T | Ws^T]            (g_z   = Wr^T g_sig + Ws^T g_skp)
-    w1t [R + C][2*K2]       [tap0^T | tap1^T] over (g_f;g_g), cond rows only under the tap-1 (unshifted) block
-    """
-
-    def __init__(self, p, R, D, S, Cc, final_layer):
-        dev = p["conv_signal.weight"].device
-        KR, KC, KD, KS, K2 = ceil_to(R, 32), ceil_to(Cc + 1, 32), ceil_to(D, 32), ceil_to(S, 32), ceil_to(2 * D, 32)
-        self.KR, self.KC, self.KD, self.KS, self.K2 = KR, KC, KD, KS, K2
-        J = (D + 127) // 128
-        self.J = J
-
-        def full(wc, pj, bias):
-            b = bias if bias is not None else torch.zeros(D, device=dev)
-            return torch.cat([_pad_k(wc[:, :, 0], KR), _pad_k(wc[:, :, 1], KR),
-                              _pad_k(torch.cat([pj[:, :, 0], b[:, None]], 1), KC)], 1)
-
-        ff = full(p["conv_signal.weight"], p["proj_signal.weight"], p.get("conv_signal.bias"))
-        gg = full(p["conv_gate.weight"], p["proj_gate.weight"], p.get("conv_gate.bias"))
-        w1 = torch.zeros(256 * J, ff.shape[1], device=dev)
-        for j in range(J):
-            nj = min(128, D - 128 * j)
-            w1[256 * j:256 * j + nj] = ff[128 * j:128 * j + nj]
-            w1[256 * j + 128:256 * j + 128 + nj] = gg[128 * j:128 * j + nj]
-        self.w1 = w1
-        ws = p["dil_skp.weight"][:, :, 0]
-        if final_layer:
-            self.w2 = _pad_k(ws, KD).contiguous()
-            self.w2t = torch.cat([torch.zeros(D, KR, device=dev), _pad_k(ws.t(), KS)], 1).contiguous()
-        else:
-            wr = p["dil_res.weight"][:, :, 0]
-            self.w2 = _pad_k(torch.cat([wr, ws], 0), KD).contiguous()
-            self.w2t = torch.cat([_pad_k(wr.t(), KR), _pad_k(ws.t(), KS)], 1).contiguous()
-        wf, wg = p["conv_signal.weight"], p["conv_gate.weight"]
-        tap = [_pad_k(torch.cat([wf[:, :, k].t(), wg[:, :, k].t()], 1), K2) for k in (0, 1)]        # (R, K2) each
-        pc = _pad_k(torch.cat([p["proj_signal.weight"][:, :, 0].t(), p["proj_gate.weight"][:, :, 0].t()], 1), K2)
-        self.w1t = torch.cat([torch.cat(tap, 1), torch.cat([torch.zeros(Cc, K2, device=dev), pc], 1)], 0).contiguous()
-
-
-# ------------------------------------------------------------------------------------------------- stack geometry
 class StackGeom:
     """Integer geometry of a GRCC stack on the absolute time axis."""
 
@@ -243,21 +217,43 @@ class StackGeom:
     def lead_in(self, l):
         return self.lead[l - 1] if l > 0 else 0
 
+    def is_final(self, l):
+        return l == self.L - 1 and self.last_is_final
+
 
 def needs_dup(d):
     """TMA box origins must be multiples of 4 elements: taps with d % 4 != 0 read a pre-shifted duplicate."""
     return d % 4 != 0
 
 
-class StackWorkspace:
-    """Persistent device buffers of one (B, widths, T0) configuration.  Reused across steps (never NaN: see new_buf)."""
+LAYER_KEYS = ("conv_signal.weight", "conv_signal.bias", "conv_gate.weight", "conv_gate.bias", "proj_signal.weight",
+              "proj_gate.weight", "dil_skp.weight", "dil_res.weight")
 
-    def __init__(self, B, R, D, S, Cc, geom, device):
-        g = geom
-        Tp = g.Tp
-        # sig[l] = input of layer l; sig[L] = output of the last layer when it has a residual branch
-        self.sig = [new_buf(B, R, Tp, device) for _ in range(g.L + (0 if g.last_is_final else 1))]
+
+class StackPlan:
+    """Everything one (batch, widths, geometry, parameter set) configuration needs, built ONCE and replayed every step:
+    persistent zero-initialised workspaces, K-major packed weight buffers plus the block-copy table that
+    refreshes them from the live parameters with one launch, prebuilt launch descriptors for forward and backward, and
+    one flat gradient buffer.  Per step the host only issues ~7 ctypes calls per layer.
+
+    Packed operand matrices of layer l:
+      w1  [256*J][2*KR + KC]  per 128-channel block: 128 filt rows then 128 gate rows; columns tap0 | tap1 | cond | bias
+      w2  [R + S][KD]         dil_res rows (absent in the final layer) then dil_skp rows
+      w2t [D][KR + KS]        [Wr^T | Ws^T]
+      w1t [R + C][2*K2]       [tap0^T | tap1^T] over (g_f ; g_g); cond rows only under the unshifted block
+    """
+
+    def __init__(self, B, R, D, S, Cc, geom, params, device, relu_last):
+        g = self.geom = geom
+        self.B, self.R, self.D, self.S, self.Cc = B, R, D, S, Cc
+        self.device = device
+        self.relu_last = relu_last
         self.generation = 0
+        self.param_ptrs = self._ptrs(params)
+        self.has_bias = "conv_signal.bias" in params[0]
+        Tp = g.Tp
+        n_sig = g.L + (0 if g.last_is_final else 1)
+        self.sig = [new_buf(B, R, Tp, device) for _ in range(n_sig)]       # sig[l] = input of layer l
         self.xs = {l: new_buf(B, R, Tp, device) for l in range(g.L) if needs_dup(g.dils[l])}
         self.th = [new_buf(B, D, Tp, device) for _ in range(g.L)]
         self.sg = [new_buf(B, D, Tp, device) for _ in range(g.L)]
@@ -266,194 +262,294 @@ class StackWorkspace:
         self.cond = new_buf(B, Cc + 1, Tp, device)
         self.cond[:, Cc, :] = 1.0                                            # the bias channel
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.KR, self.KC, self.KD = ceil_to(R, 32), ceil_to(Cc + 1, 32), ceil_to(D, 32)
+        self.KS, self.K2 = ceil_to(S, 32), ceil_to(2 * D, 32)
+        self.J = (D + 127) // 128
+        self._build_packs(params)
+        self.fwd_train = self._build_forward(save=True)
+        self.fwd_infer = None
         self._bwd = None
-        self.B, self.R, self.D, self.S, self.Cc = B, R, D, S, Cc
-        self.device = device
+
+    # ---------------------------------------------------------------------------------------------- parameters
+    @staticmethod
+    def _ptrs(params):
+        return tuple(p[k].data_ptr() for p in params for k in LAYER_KEYS if k in p)
+
+    def matches(self, params):
+        return self._ptrs(params) == self.param_ptrs
+
+    def _build_packs(self, params):
+        g, R, D, S, Cc, dev = self.geom, self.R, self.D, self.S, self.Cc, self.device
+        KR, KC, KD, KS, K2, J = self.KR, self.KC, self.KD, self.KS, self.K2, self.J
+        KP = 2 * KR + KC
+        self.w1, self.w2, self.w2t, self.w1t = [], [], [], []
+        blocks = []
+
+        def blk(src, s_off, dst, d_row, d_col, ni, nj, si, sj):
+            blocks.append((src.data_ptr() + 4 * s_off, dst.data_ptr() + 4 * (d_row * dst.shape[1] + d_col), ni, nj, si,
+                           sj, dst.shape[1]))
+
+        for l in range(g.L):
+            p = params[l]
+            final = g.is_final(l)
+            w1 = torch.zeros(256 * J, KP, device=dev)
+            w2 = torch.zeros((0 if final else R) + S, KD, device=dev)
+            w2t = torch.zeros(D, KR + KS, device=dev)
+            w1t = torch.zeros(R + Cc, 2 * K2, device=dev)
+            wf, wg = p["conv_signal.weight"], p["conv_gate.weight"]          # (D, R, 2)
+            pf, pg = p["proj_signal.weight"], p["proj_gate.weight"]          # (D, Cc, 1)
+            for j in range(J):
+                nj_ = min(128, D - 128 * j)
+                for h, (wc, pj, bk) in enumerate(((wf, pf, "conv_signal.bias"), (wg, pg, "conv_gate.bias"))):
+                    row = 256 * j + 128 * h
+                    blk(wc, 128 * j * R * 2 + 0, w1, row, 0, nj_, R, 2 * R, 2)          # tap 0
+                    blk(wc, 128 * j * R * 2 + 1, w1, row, KR, nj_, R, 2 * R, 2)         # tap 1
+                    blk(pj, 128 * j * Cc, w1, row, 2 * KR, nj_, Cc, Cc, 1)              # cond projection
+                    if bk in p:
+                        blk(p[bk], 128 * j, w1, row, 2 * KR + Cc, nj_, 1, 1, 1)         # bias on the ones channel
+            ws = p["dil_skp.weight"]                                                   # (S, D, 1)
+            if not final:
+                wr = p["dil_res.weight"]                                               # (R, D, 1)
+                blk(wr, 0, w2, 0, 0, R, D, D, 1)
+                blk(ws, 0, w2, R, 0, S, D, D, 1)
+                blk(wr, 0, w2t, 0, 0, D, R, 1, D)                                      # Wr^T
+            else:
+                blk(ws, 0, w2, 0, 0, S, D, D, 1)
+            blk(ws, 0, w2t, 0, KR, D, S, 1, D)                                         # Ws^T
+            for h, wc in enumerate((wf, wg)):
+                for k in (0, 1):                                                       # tap k transposed
+                    blk(wc, k, w1t, 0, k * K2 + h * D, R, D, 2, 2 * R)
+            for h, pj in enumerate((pf, pg)):
+                blk(pj, 0, w1t, R, K2 + h * D, Cc, D, 1, Cc)                           # P^T under the unshifted block
+            self.w1.append(w1)
+            self.w2.append(w2)
+            self.w2t.append(w2t)
+            self.w1t.append(w1t)
+        import numpy as np
+        dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("ni", "<i4"), ("nj", "<i4"), ("si", "<i8"), ("sj", "<i8"),
+                       ("di", "<i8")])
+        arr = np.array(blocks, dtype=dt)
+        assert dt.itemsize == C.sizeof(L.CopyBlock)
+        self.n_blocks = len(blocks)
+        self.block_table = torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(dev)
+
+    def repack(self):
+        L.check(L.lib().aewn_pack_blocks(C.c_void_p(self.block_table.data_ptr()), C.c_int(self.n_blocks), _stream()),
+                "aewn_pack_blocks")
+
+    # ---------------------------------------------------------------------------------------------- forward
+    def _build_forward(self, save):
+        g, B, R, D, S, Cc = self.geom, self.B, self.R, self.D, self.S, self.Cc
+        T0 = g.T0
+        out = []
+        for l, d in enumerate(g.dils):
+            final = g.is_final(l)
+            lo = g.lead[l]
+            lo4 = lo & ~3
+            t_begin = lo4 & ~31
+            x = self.sig[l]
+            xa, ca = act_of(x, T0), act_of(self.cond, T0)
+            if needs_dup(d):
+                acts = [act_of(self.xs[l], T0), xa, ca]
+                segs = [(0, 0, R, 0), (1, 0, R, self.KR), (2, 0, Cc + 1, 2 * self.KR)]
+            else:
+                acts = [xa, ca]
+                segs = [(0, -d, R, 0), (0, 0, R, self.KR), (1, 0, Cc + 1, 2 * self.KR)]
+            tiles = []
+            for j in range(self.J):
+                c0, nj = 128 * j, min(128, D - 128 * j)
+                tiles.append(ntile(256 * j, nj, self.th[l][:, c0:] if save else None, mode=L.EPI_GATE_FWD, n=256,
+                                   out2=self.sg[l][:, c0:] if save else None, out3=self.z[l][:, c0:],
+                                   t_lo=lo4, t_hi=T0, t_zero_lo=lo))
+            out += build_tgemm(acts, segs, self.w1[l], tiles, B, t_begin, T0, self.err, tag=f"fwd_gemm1.{l}")
+            tiles = []
+            if not final:
+                d_next = g.dils[l + 1] if l + 1 < g.L else 4
+                for (c0, n) in chunks(R):
+                    tiles.append(ntile(c0, n, self.sig[l + 1][:, c0:], add=x[:, c0:], t_lo=lo4, t_hi=T0, t_zero_lo=lo,
+                                       out2=self.xs[l + 1][:, c0:] if (l + 1 < g.L and needs_dup(d_next)) else None,
+                                       dup_toff=d_next, dup_t_hi=T0))
+            rf4 = g.RF & ~3
+            flags = (L.F_ACCUM if l > 0 else 0) | (L.F_RELU if (l == g.L - 1 and self.relu_last) else 0)
+            row0 = 0 if final else R
+            for (c0, n) in chunks(S):
+                tiles.append(ntile(row0 + c0, n, self.skp[:, c0:], flags=flags, t_lo=rf4, t_hi=T0,
+                                   t_zero_lo=g.RF if l == 0 else 0))
+            out += build_tgemm([act_of(self.z[l], T0)], [(0, 0, D, 0)], self.w2[l], tiles, B, t_begin, T0, self.err,
+                               tag=f"fwd_gemm2.{l}")
+        return out
+
+    def forward(self, save=True):
+        """Inputs already staged: sig[0] (and xs[0]) = base-layer output, cond.  Result: skp (B, S, Tp) valid on
+        [RF, T0), ReLU applied when relu_last (wavenet.py:359)."""
+        self.repack()
+        if save:
+            run_launches(self.fwd_train)
+        else:
+            if self.fwd_infer is None:
+                self.fwd_infer = self._build_forward(save=False)
+            run_launches(self.fwd_infer)
+
+    # ---------------------------------------------------------------------------------------------- backward
+    def _grad_layout(self):
+        """One flat fp32 buffer holding every weight gradient (reference layouts) + the (2D, Cc+1) proj/bias scratch."""
+        g, R, D, S, Cc = self.geom, self.R, self.D, self.S, self.Cc
+        off = 0
+        lay = []
+        for l in range(g.L):
+            e = {}
+            for k, shape in (("conv_signal.weight", (D, R, 2)), ("conv_gate.weight", (D, R, 2)),
+                             ("dpb", (2 * D, Cc + 1)), ("dil_skp.weight", (S, D, 1)), ("dil_res.weight", (R, D, 1))):
+                if k == "dil_res.weight" and g.is_final(l):
+                    continue
+                n = 1
+                for v in shape:
+                    n *= v
+                e[k] = (off, shape)
+                off += ceil_to(n, 4)
+            lay.append(e)
+        return lay, off
 
     def bwd(self):
-        if self._bwd is None:
-            B, R, D, S, Cc, dev = self.B, self.R, self.D, self.S, self.Cc, self.device
-            Tp = self.sig[0].shape[2]
-            self._bwd = dict(gfg=new_buf(B, 2 * D, Tp, dev), gfs=new_buf(B, 2 * D, Tp, dev),
-                             gx=[new_buf(B, R, Tp, dev), new_buf(B, R, Tp, dev)], g_skp=new_buf(B, S, Tp, dev))
-        return self._bwd
+        if self._bwd is not None:
+            return self._bwd
+        g, B, R, D, S, Cc, dev = self.geom, self.B, self.R, self.D, self.S, self.Cc, self.device
+        T0, Tp = g.T0, g.Tp
+        bw = dict(gfg=new_buf(B, 2 * D, Tp, dev), gfs=new_buf(B, 2 * D, Tp, dev),
+                  gx=[new_buf(B, R, Tp, dev), new_buf(B, R, Tp, dev)], g_skp=new_buf(B, S, Tp, dev),
+                  g_cond=new_buf(B, Cc, Tp, dev), g_last=None if g.last_is_final else new_buf(B, R, Tp, dev))
+        lay, total = self._grad_layout()
+        flat = torch.zeros(total, device=dev)
+        views = [{k: flat[o:o + int(torch.tensor(sh).prod())].view(sh) for k, (o, sh) in e.items()} for e in lay]
+        bw["flat"], bw["views"] = flat, views
+        gfg, gfs, g_skp, g_cond = bw["gfg"], bw["gfs"], bw["g_skp"], bw["g_cond"]
+        rf4 = g.RF & ~3
+        launches = []
+        g_sig = bw["g_last"]                     # gradient w.r.t. the output of the layer being processed
+        for l in range(g.L - 1, -1, -1):
+            d = g.dils[l]
+            final = g.is_final(l)
+            lo, lo_prev = g.lead[l], g.lead_in(l)
+            lo4, lop4 = lo & ~3, lo_prev & ~3
+            x = self.sig[l]
+            v = views[l]
+            # (1) g_z = Wr^T g_sig + Ws^T g_skp, then the gate derivative -> gfg = [g_f ; g_g]   (SURVEY.md 9.1)
+            if g_sig is not None:
+                acts = [act_of(g_sig, T0), act_of(g_skp, T0)]
+                segs = [(0, 0, R, 0), (1, 0, S, self.KR)]
+            else:
+                acts = [act_of(g_skp, T0)]
+                segs = [(0, 0, S, self.KR)]
+            t_store = min(lop4, lo4)
+            tile = ntile(0, D, gfg, mode=L.EPI_GATE_BWD, out2=gfg[:, D:], add=self.th[l], add2=self.sg[l],
+                         out3=gfs if needs_dup(d) else None, dup_toff=-d, dup_t_hi=T0,
+                         t_lo=t_store, t_hi=T0, t_zero_lo=lo)
+            launches += build_tgemm(acts, segs, self.w2t[l], [tile], B, t_store & ~31, T0, self.err, tag=f"bwd_gz.{l}")
+            # (2) g_x[tau] = tap1^T gfg[tau] + tap0^T gfg[tau + d] (+ g_sig[tau]);  g_cond[tau] += P^T gfg[tau]
+            if needs_dup(d):
+                acts = [act_of(gfs, T0 - d), act_of(gfg, T0)]
+                segs = [(0, 0, 2 * D, 0), (1, 0, 2 * D, self.K2)]
+            else:
+                acts = [act_of(gfg, T0)]
+                segs = [(0, d, 2 * D, 0), (0, 0, 2 * D, self.K2)]
+            gx = bw["gx"][l % 2]
+            tiles = []
+            for (c0, n) in chunks(R):
+                tiles.append(ntile(c0, n, gx[:, c0:], add=g_sig[:, c0:] if g_sig is not None else None, add_t_lo=lo,
+                                   t_lo=lop4, t_hi=T0, t_zero_lo=lo_prev))
+            for (c0, n) in chunks(Cc):
+                tiles.append(ntile(R + c0, n, g_cond[:, c0:], flags=L.F_ACCUM, seg_mask=2, t_lo=lo, t_hi=T0))
+            launches += build_tgemm(acts, segs, self.w1t[l], tiles, B, lop4 & ~31, T0, self.err, tag=f"bwd_dgrad.{l}")
+            # (3) weight gradients of conv_signal/conv_gate/proj_signal/proj_gate (+ biases via the ones channel)
+            x0_act = act_of(self.xs[l], T0) if needs_dup(d) else act_of(x, T0)
+            acts = [act_of(gfg, T0), x0_act, act_of(x, T0), act_of(self.cond, T0)]
+            sh0 = 0 if needs_dup(d) else -d
+            items = []
+            for h, key in ((0, "conv_signal.weight"), (1, "conv_gate.weight")):
+                dw = v[key]
+                for i in range((D + 127) // 128):
+                    mv = min(128, D - 128 * i)
+                    base = dict(g_act=0, g_row=h * D + 128 * i, m_valid=mv, t_lo=lo4, t_hi=T0)
+                    for (c0, n) in chunks(R):
+                        items.append(dict(base, x_act=1, x_row=c0, n_valid=n, shift=sh0, out=dw,
+                                          out_off=(128 * i) * R * 2 + c0 * 2 + 0, out_rs=2 * R, out_cs=2))
+                        items.append(dict(base, x_act=2, x_row=c0, n_valid=n, shift=0, out=dw,
+                                          out_off=(128 * i) * R * 2 + c0 * 2 + 1, out_rs=2 * R, out_cs=2))
+                    for (c0, n) in chunks(Cc + 1):
+                        items.append(dict(base, x_act=3, x_row=c0, n_valid=n, shift=0, out=v["dpb"],
+                                          out_off=(h * D + 128 * i) * (Cc + 1) + c0, out_rs=Cc + 1, out_cs=1))
+            launches += build_wgrad(acts, items, B, self.err, tag=f"wgrad1.{l}")
+            # (4) dWs = sum g_skp z^T (tau >= RF);  dWr = sum g_sig z^T (tau >= lead_l)
+            acts = [act_of(g_skp, T0), act_of(self.z[l], T0)]
+            items = []
+            for i in range((S + 127) // 128):
+                for (c0, n) in chunks(D):
+                    items.append(dict(g_act=0, x_act=1, g_row=128 * i, x_row=c0, m_valid=min(128, S - 128 * i),
+                                      n_valid=n, t_lo=rf4, t_hi=T0, out=v["dil_skp.weight"], out_off=128 * i * D + c0,
+                                      out_rs=D, out_cs=1))
+            if not final and g_sig is not None:
+                acts.append(act_of(g_sig, T0))
+                for i in range((R + 127) // 128):
+                    for (c0, n) in chunks(D):
+                        items.append(dict(g_act=2, x_act=1, g_row=128 * i, x_row=c0, m_valid=min(128, R - 128 * i),
+                                          n_valid=n, t_lo=lo4, t_hi=T0, out=v["dil_res.weight"],
+                                          out_off=128 * i * D + c0, out_rs=D, out_cs=1))
+            launches += build_wgrad(acts, items, B, self.err, tag=f"wgrad2.{l}")
+            g_sig = gx
+        bw["launches"] = launches
+        bw["gx0"] = g_sig
+        self._bwd = bw
+        return bw
+
+    def backward(self):
+        """Inputs staged by the caller: bwd()['g_skp'] (zero below RF) and, for a stand-alone non-final layer,
+        bwd()['g_last'].  Returns (g_x0 (B,R,Tp) valid on [0,T0), g_cond (B,Cc,Tp), per-layer dict of gradient views).
+        The returned tensors alias plan-owned buffers: callers clone what they hand to autograd."""
+        bw = self.bwd()
+        bw["flat"].zero_()
+        bw["g_cond"].zero_()
+        run_launches(bw["launches"])
+        D, Cc = self.D, self.Cc
+        grads = []
+        for l, v in enumerate(bw["views"]):
+            gr = {"conv_signal.weight": v["conv_signal.weight"], "conv_gate.weight": v["conv_gate.weight"],
+                  "proj_signal.weight": v["dpb"][:D, :Cc].unsqueeze(2), "proj_gate.weight": v["dpb"][D:, :Cc].unsqueeze(2),
+                  "dil_skp.weight": v["dil_skp.weight"]}
+            if self.has_bias:
+                gr["conv_signal.bias"], gr["conv_gate.bias"] = v["dpb"][:D, Cc], v["dpb"][D:, Cc]
+            if "dil_res.weight" in v:
+                gr["dil_res.weight"] = v["dil_res.weight"]
+            grads.append(gr)
+        return bw["gx0"], bw["g_cond"], grads
 
 
-_workspaces = {}
+_plans = {}
 
 
-def get_workspace(B, R, D, S, Cc, geom, device):
-    key = (B, R, D, S, Cc, geom.key(), str(device))
-    ws = _workspaces.get(key)
-    if ws is None:
-        if len(_workspaces) >= 2:   # bound the cache: configurations rarely alternate
-            _workspaces.clear()
+def get_plan(B, R, D, S, Cc, geom, params, device, relu_last):
+    """params: list (per layer) of dicts of the live parameter tensors."""
+    key = (B, R, D, S, Cc, geom.key(), str(device), bool(relu_last))
+    plan = _plans.get(key)
+    if plan is not None and not plan.matches(params):
+        plan = None                                  # parameters were re-allocated (e.g. .to(device)): rebuild
+    if plan is None:
+        if len(_plans) >= 2:                         # bound the cache: configurations rarely alternate
+            _plans.clear()
             torch.cuda.empty_cache()
-        ws = _workspaces[key] = StackWorkspace(B, R, D, S, Cc, geom, device)
-    return ws
+        plan = _plans[key] = StackPlan(B, R, D, S, Cc, geom, params, device, relu_last)
+    return plan
 
 
 def check_device_errors():
     """Synchronise and raise if any kernel reported a device-side fault (bounded-wait timeout, bad mu-law code)."""
     torch.cuda.synchronize()
-    for ws in _workspaces.values():
-        e = int(ws.err.item())
+    words = [p.err for p in _plans.values()] + list(_err_cache.values())
+    for w in words:
+        e = int(w.item())
         if e != 0:
-            ws.err.zero_()
+            w.zero_()
             raise RuntimeError(f"aewn: device-side error word = {e} "
                                f"({'bounded wait timed out' if e == L.ERR_TIMEOUT else 'invalid input'})")
-
-
-# ------------------------------------------------------------------------------------------------- stack forward
-def stack_forward(ws, geom, packs, relu_last, save):
-    """Run all GRCC layers.  Inputs already in the workspace: ws.sig[0] (and ws.xs[0]) = base-layer output, ws.cond.
-    Result: ws.skp (B, S, Tp), valid on [RF, T0) -- with ReLU applied when relu_last (wavenet.py:359).
-    save=False (inference) skips the tanh/sigmoid stores."""
-    g = geom
-    B, R, D, S, Cc = ws.B, ws.R, ws.D, ws.S, ws.Cc
-    T0 = g.T0
-    for l, d in enumerate(g.dils):
-        pk = packs[l]
-        final = (l == g.L - 1) and g.last_is_final
-        lo = g.lead[l]
-        lo4 = lo & ~3
-        t_begin = lo4 & ~31
-        x = ws.sig[l]
-        xa, ca = act_of(x, T0), act_of(ws.cond, T0)
-        if needs_dup(d):
-            acts = [act_of(ws.xs[l], T0), xa, ca]
-            segs = [(0, 0, R, 0), (1, 0, R, pk.KR), (2, 0, Cc + 1, 2 * pk.KR)]
-        else:
-            acts = [xa, ca]
-            segs = [(0, -d, R, 0), (0, 0, R, pk.KR), (1, 0, Cc + 1, 2 * pk.KR)]
-        tiles = []
-        for j in range(pk.J):
-            c0, nj = 128 * j, min(128, D - 128 * j)
-            tiles.append(ntile(256 * j, nj, ws.th[l][:, c0:] if save else None, mode=L.EPI_GATE_FWD, n=256,
-                               out2=ws.sg[l][:, c0:] if save else None, out3=ws.z[l][:, c0:],
-                               t_lo=lo4, t_hi=T0, t_zero_lo=lo))
-        tgemm(acts, segs, pk.w1, tiles, B, t_begin, T0, ws.err, tag=f"fwd_gemm1.{l}")
-
-        tiles = []
-        if not final:
-            d_next = g.dils[l + 1] if l + 1 < g.L else 4
-            for (c0, n) in chunks(R):
-                tiles.append(ntile(c0, n, ws.sig[l + 1][:, c0:], add=x[:, c0:], t_lo=lo4, t_hi=T0, t_zero_lo=lo,
-                                   out2=ws.xs[l + 1][:, c0:] if needs_dup(d_next) else None, dup_toff=d_next,
-                                   dup_t_hi=T0))
-        rf4 = g.RF & ~3
-        flags = (L.F_ACCUM if l > 0 else 0) | (L.F_RELU if (l == g.L - 1 and relu_last) else 0)
-        row0 = 0 if final else R
-        for (c0, n) in chunks(S):
-            tiles.append(ntile(row0 + c0, n, ws.skp[:, c0:], flags=flags, t_lo=rf4, t_hi=T0,
-                               t_zero_lo=g.RF if l == 0 else 0))
-        tgemm([act_of(ws.z[l], T0)], [(0, 0, D, 0)], pk.w2, tiles, B, t_begin, T0, ws.err, tag=f"fwd_gemm2.{l}")
-
-
-# ------------------------------------------------------------------------------------------------- stack backward
-def stack_backward(ws, geom, packs, params, g_skp, need_gx0=True, g_sig_last=None):
-    """Backward of stack_forward.  g_skp: (B, S, Tp) gradient w.r.t. the (pre-ReLU) skip sum, zero
-    below RF.  g_sig_last: (B, R, Tp) gradient w.r.t. the last layer's residual output (stand-alone layers only; zero
-    on [lead & ~3, lead)).  Returns (g_x0 buffer (B,R,Tp) valid on [0,T0), g_cond (B,Cc,Tp), per-layer grad dicts)."""
-    g = geom
-    B, R, D, S, Cc = ws.B, ws.R, ws.D, ws.S, ws.Cc
-    T0 = g.T0
-    dev = ws.device
-    bw = ws.bwd()
-    gfg, gfs = bw["gfg"], bw["gfs"]
-    g_cond = torch.zeros(B, Cc, g.Tp, device=dev)
-    rf4 = g.RF & ~3
-    grads = [None] * g.L
-    g_sig = g_sig_last                   # gradient w.r.t. the output of the layer being processed
-    for l in range(g.L - 1, -1, -1):
-        d = g.dils[l]
-        pk = packs[l]
-        p = params[l]
-        final = (l == g.L - 1) and g.last_is_final
-        lo, lo_prev = g.lead[l], g.lead_in(l)
-        lo4, lop4 = lo & ~3, lo_prev & ~3
-        x = ws.sig[l]
-
-        # (1) g_z = Wr^T g_sig + Ws^T g_skp, then the gate derivative -> gfg = [g_f ; g_g]
-        if g_sig is not None:
-            acts = [act_of(g_sig, T0), act_of(g_skp, T0)]
-            segs = [(0, 0, R, 0), (1, 0, S, pk.KR)]
-        else:
-            acts = [act_of(g_skp, T0)]
-            segs = [(0, 0, S, pk.KR)]
-        t_store = min(lop4, lo4)
-        tile = ntile(0, D, gfg, mode=L.EPI_GATE_BWD, out2=gfg[:, D:], add=ws.th[l], add2=ws.sg[l],
-                     out3=gfs if needs_dup(d) else None, dup_toff=-d, dup_t_hi=T0,
-                     t_lo=t_store, t_hi=T0, t_zero_lo=lo)
-        tgemm(acts, segs, pk.w2t, [tile], B, t_store & ~31, T0, ws.err, tag=f"bwd_gz.{l}")
-
-        # (2) g_x[tau] = tap1^T gfg[tau] + tap0^T gfg[tau + d] (+ g_sig[tau]);  g_cond[tau] += P^T gfg[tau]
-        if needs_dup(d):
-            acts = [act_of(gfs, T0 - d), act_of(gfg, T0)]
-            segs = [(0, 0, 2 * D, 0), (1, 0, 2 * D, pk.K2)]
-        else:
-            acts = [act_of(gfg, T0)]
-            segs = [(0, d, 2 * D, 0), (0, 0, 2 * D, pk.K2)]
-        tiles = []
-        gx = None
-        if l > 0 or need_gx0:
-            gx = bw["gx"][l % 2]
-            for (c0, n) in chunks(R):
-                tiles.append(ntile(c0, n, gx[:, c0:], add=g_sig[:, c0:] if g_sig is not None else None, add_t_lo=lo,
-                                   t_lo=lop4, t_hi=T0, t_zero_lo=lo_prev))
-        for (c0, n) in chunks(Cc):
-            tiles.append(ntile(R + c0, n, g_cond[:, c0:], flags=L.F_ACCUM, seg_mask=2, t_lo=lo, t_hi=T0))
-        tgemm(acts, segs, pk.w1t, tiles, B, lop4 & ~31, T0, ws.err, tag=f"bwd_dgrad.{l}")
-
-        # (3) weight gradients of conv_signal/conv_gate/proj_signal/proj_gate (+ biases via the ones channel)
-        gr = {}
-        dwf, dwg = torch.zeros_like(p["conv_signal.weight"]), torch.zeros_like(p["conv_gate.weight"])
-        dpb = torch.zeros(2 * D, Cc + 1, device=dev)
-        x0_act = act_of(ws.xs[l], T0) if needs_dup(d) else act_of(x, T0)
-        acts = [act_of(gfg, T0), x0_act, act_of(x, T0), act_of(ws.cond, T0)]
-        sh0 = 0 if needs_dup(d) else -d
-        items = []
-        for h, dw in ((0, dwf), (1, dwg)):
-            for i in range((D + 127) // 128):
-                mv = min(128, D - 128 * i)
-                base = dict(g_act=0, g_row=h * D + 128 * i, m_valid=mv, t_lo=lo4, t_hi=T0)
-                for (c0, n) in chunks(R):
-                    items.append(dict(base, x_act=1, x_row=c0, n_valid=n, shift=sh0, out=dw,
-                                      out_off=(128 * i) * R * 2 + c0 * 2 + 0, out_rs=2 * R, out_cs=2))
-                    items.append(dict(base, x_act=2, x_row=c0, n_valid=n, shift=0, out=dw,
-                                      out_off=(128 * i) * R * 2 + c0 * 2 + 1, out_rs=2 * R, out_cs=2))
-                for (c0, n) in chunks(Cc + 1):
-                    items.append(dict(base, x_act=3, x_row=c0, n_valid=n, shift=0, out=dpb,
-                                      out_off=(h * D + 128 * i) * (Cc + 1) + c0, out_rs=Cc + 1, out_cs=1))
-        wgrad(acts, items, B, ws.err, tag=f"wgrad1.{l}")
-        gr["conv_signal.weight"], gr["conv_gate.weight"] = dwf, dwg
-        gr["proj_signal.weight"] = dpb[:D, :Cc].unsqueeze(2).contiguous()
-        gr["proj_gate.weight"] = dpb[D:, :Cc].unsqueeze(2).contiguous()
-        if "conv_signal.bias" in p:
-            gr["conv_signal.bias"], gr["conv_gate.bias"] = dpb[:D, Cc].contiguous(), dpb[D:, Cc].contiguous()
-
-        # (4) dWr = sum g_sig z^T  (tau >= lead_l);  dWs = sum g_skp z^T  (tau >= RF)
-        dws = torch.zeros_like(p["dil_skp.weight"])
-        acts = [act_of(g_skp, T0), act_of(ws.z[l], T0)]
-        items = []
-        for i in range((S + 127) // 128):
-            for (c0, n) in chunks(D):
-                items.append(dict(g_act=0, x_act=1, g_row=128 * i, x_row=c0, m_valid=min(128, S - 128 * i), n_valid=n,
-                                  t_lo=rf4, t_hi=T0, out=dws, out_off=128 * i * D + c0, out_rs=D, out_cs=1))
-        if not final and g_sig is not None:
-            dwr = torch.zeros_like(p["dil_res.weight"])
-            acts.append(act_of(g_sig, T0))
-            for i in range((R + 127) // 128):
-                for (c0, n) in chunks(D):
-                    items.append(dict(g_act=2, x_act=1, g_row=128 * i, x_row=c0, m_valid=min(128, R - 128 * i),
-                                      n_valid=n, t_lo=lo4, t_hi=T0, out=dwr, out_off=128 * i * D + c0, out_rs=D,
-                                      out_cs=1))
-            gr["dil_res.weight"] = dwr
-        wgrad(acts, items, B, ws.err, tag=f"wgrad2.{l}")
-        gr["dil_skp.weight"] = dws
-        grads[l] = gr
-        g_sig = gx
-    return g_sig, g_cond, grads
 
 
 # ------------------------------------------------------------------------------------------------- generic convs

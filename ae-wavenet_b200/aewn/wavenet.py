@@ -23,8 +23,7 @@ class _HP(dict):
     __setattr__ = dict.__setitem__
 
 
-LAYER_KEYS = ("conv_signal.weight", "conv_signal.bias", "conv_gate.weight", "conv_gate.bias", "proj_signal.weight",
-              "proj_gate.weight", "dil_skp.weight", "dil_res.weight")
+LAYER_KEYS = ops.LAYER_KEYS
 
 
 def _require_cuda(*tensors):
@@ -117,46 +116,45 @@ class _LayerFn(torch.autograd.Function):
         if T_out <= sl or cond.shape[2] < cl + T_out:
             raise RuntimeError("aewn: GatedResidualCondConv input shorter than its receptive field / conditioning")
         geom = ops.StackGeom([d], T_in, skip_start=d + sl, last_is_final=mod.final_layer)
-        ws = ops.get_workspace(B, R, D, S, Cc, geom, x.device)
-        ws.generation += 1
+        p = dict(zip(keys, weights))
+        plan = ops.get_plan(B, R, D, S, Cc, geom, [p], x.device, relu_last=False)
+        plan.generation += 1
         with torch.no_grad():
-            ws.sig[0][:, :, :T_in] = x
+            plan.sig[0][:, :, :T_in] = x
             if ops.needs_dup(d):
-                ws.xs[0][:, :, d:T_in] = x[:, :, :T_out]
-            ws.cond[:, :Cc, d:T_in] = cond[:, :, cl:cl + T_out]
-            p = dict(zip(keys, [w.detach() for w in weights]))
-            packs = [ops.LayerPack(p, R, D, S, Cc, mod.final_layer)]
-            ops.stack_forward(ws, geom, packs, relu_last=False, save=True)
-            skp = ws.skp[:, :, geom.RF:T_in].clone()
-            sig = x[:, :, d:].clone() if mod.final_layer else ws.sig[1][:, :, d:T_in].clone()
-        ctx.ws, ctx.geom, ctx.packs, ctx.p, ctx.keys = ws, geom, packs, p, keys
-        ctx.gen = ws.generation
+                plan.xs[0][:, :, d:T_in] = x[:, :, :T_out]
+            plan.cond[:, :Cc, d:T_in] = cond[:, :, cl:cl + T_out]
+            plan.forward(save=True)
+            skp = plan.skp[:, :, geom.RF:T_in].clone()
+            sig = x[:, :, d:].clone() if mod.final_layer else plan.sig[1][:, :, d:T_in].clone()
+        ctx.plan, ctx.keys = plan, keys
+        ctx.gen = plan.generation
         ctx.dims = (B, R, D, S, Cc, T_in, d, cl, sl, cond.shape[2])
         ctx.final = mod.final_layer
         return sig, skp
 
     @staticmethod
     def backward(ctx, g_sig, g_skp):
-        ws, geom = ctx.ws, ctx.geom
-        if ws.generation != ctx.gen:
+        plan = ctx.plan
+        geom = plan.geom
+        if plan.generation != ctx.gen:
             raise RuntimeError("aewn: workspace was reused by a later forward before this backward ran")
         B, R, D, S, Cc, T_in, d, cl, sl, Tc = ctx.dims
-        bw = ws.bwd()
+        bw = plan.bwd()
         gs = bw["g_skp"]
         gs.zero_()
         gs[:, :, geom.RF:T_in] = g_skp
-        gl = None
         if not ctx.final:
-            gl = bw["gx"][1]
+            gl = bw["g_last"]
             gl.zero_()
             gl[:, :, d:T_in] = g_sig
-        gx, g_cond, grads = ops.stack_backward(ws, geom, ctx.packs, [ctx.p], gs, need_gx0=True, g_sig_last=gl)
+        gx, g_cond, grads = plan.backward()
         g_x = gx[:, :, :T_in].clone()
         if ctx.final:
             g_x[:, :, d:] += g_sig          # final layer: sig = x[:, :, lw:] (wavenet.py:105-106)
         g_c = torch.zeros(B, Cc, Tc, device=g_x.device)
         g_c[:, :, cl:cl + T_in - d] = g_cond[:, :, d:T_in]
-        return (g_x, g_c, None, None, None, None) + tuple(grads[0].get(k) for k in ctx.keys)
+        return (g_x, g_c, None, None, None, None) + tuple(grads[0][k].clone() for k in ctx.keys)
 
 
 class Conditioning(nn.Module):
@@ -368,29 +366,28 @@ class _DecoderCoreFn(torch.autograd.Function):
         if geom.W != net.n_win_batch:
             raise RuntimeError(f"aewn: geometry mismatch, window {geom.W} != n_win_batch {net.n_win_batch}")
         dev = wav.device
-        ws = ops.get_workspace(B, R, D, S, Cc, geom, dev)
-        ws.generation += 1
+        params = [dict() for _ in range(geom.L)]
+        for (li, k), w in zip(keys, weights):
+            params[li][k] = w
+        plan = ops.get_plan(B, R, D, S, Cc, geom, params, dev, relu_last=True)
+        plan.generation += 1
         wav_c = wav.detach().float().contiguous()
         with torch.no_grad():
-            ws.cond[:, :Cc, :T0] = cond
+            plan.cond[:, :Cc, :T0] = cond
             d0 = geom.dils[0]
-            dup = ws.xs[0] if ops.needs_dup(d0) else None
-            bw = base_w.detach().reshape(R, Q).contiguous()
+            dup = plan.xs[0] if ops.needs_dup(d0) else None
+            bw = base_w.detach().reshape(R, Q)
             L.check(L.lib().aewn_base_embed_fwd(
                 L.C.c_void_p(wav_c.data_ptr()), L.C.c_longlong(wav_c.stride(0)), L.C.c_int(o0),
                 L.C.c_void_p(bw.data_ptr()), L.C.c_void_p(base_b.data_ptr() if base_b.numel() else None),
-                L.C.c_void_p(ws.sig[0].data_ptr()), L.C.c_longlong(ws.sig[0].stride(0)),
-                L.C.c_longlong(ws.sig[0].stride(1)), L.C.c_void_p(dup.data_ptr() if dup is not None else None),
+                L.C.c_void_p(plan.sig[0].data_ptr()), L.C.c_longlong(plan.sig[0].stride(0)),
+                L.C.c_longlong(plan.sig[0].stride(1)), L.C.c_void_p(dup.data_ptr() if dup is not None else None),
                 L.C.c_int(d0), L.C.c_int(T0), L.C.c_int(B), L.C.c_int(R), L.C.c_int(Q), L.C.c_int(T0),
-                L.C.c_void_p(ws.err.data_ptr()), ops._stream()), "aewn_base_embed_fwd")
-            params = [dict() for _ in range(geom.L)]
-            for (li, k), w in zip(keys, weights):
-                params[li][k] = w.detach()
-            packs = [ops.LayerPack(params[l], R, D, S, Cc, l == geom.L - 1) for l in range(geom.L)]
-            ops.stack_forward(ws, geom, packs, relu_last=True, save=True)
-            out = ws.skp[:, :, geom.RF:T0].clone()
-        ctx.ws, ctx.geom, ctx.packs, ctx.params, ctx.keys = ws, geom, packs, params, keys
-        ctx.gen = ws.generation
+                L.C.c_void_p(plan.err.data_ptr()), ops._stream()), "aewn_base_embed_fwd")
+            plan.forward(save=True)
+            out = plan.skp[:, :, geom.RF:T0].clone()
+        ctx.plan, ctx.keys = plan, keys
+        ctx.gen = plan.generation
         ctx.wav, ctx.o0 = wav_c, o0
         ctx.dims = (B, R, D, S, Cc, Q, T0)
         ctx.has_bias = base_b.numel() > 0
@@ -399,16 +396,17 @@ class _DecoderCoreFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out):
-        ws, geom = ctx.ws, ctx.geom
-        if ws.generation != ctx.gen:
+        plan = ctx.plan
+        geom = plan.geom
+        if plan.generation != ctx.gen:
             raise RuntimeError("aewn: workspace was reused by a later forward before this backward ran "
                                "(one in-flight forward per configuration)")
         B, R, D, S, Cc, Q, T0 = ctx.dims
         lib = L.lib()
-        bw = ws.bwd()
+        bw = plan.bwd()
         gs = bw["g_skp"]
         g_out = g_out if g_out.stride(2) == 1 else g_out.contiguous()
-        mask = ws.skp[:, :, geom.RF:]
+        mask = plan.skp[:, :, geom.RF:]
         gsv = gs[:, :, geom.RF:]
         # g wrt the pre-ReLU skip sum, written straight onto the absolute time axis (margin [RF&~3, RF) stays 0)
         L.check(lib.aewn_relu_mask_bwd(
@@ -416,7 +414,7 @@ class _DecoderCoreFn(torch.autograd.Function):
             L.C.c_void_p(mask.data_ptr()), L.C.c_longlong(mask.stride(0)), L.C.c_longlong(mask.stride(1)),
             L.C.c_void_p(gsv.data_ptr()), L.C.c_longlong(gsv.stride(0)), L.C.c_longlong(gsv.stride(1)),
             L.C.c_int(B), L.C.c_int(S), L.C.c_int(geom.W), ops._stream()), "aewn_relu_mask_bwd")
-        gx0, g_cond, grads = ops.stack_backward(ws, geom, ctx.packs, ctx.params, gs, need_gx0=True)
+        gx0, g_cond, grads = plan.backward()
         d_base = torch.zeros(R, Q, device=g_out.device)
         d_bias = torch.zeros(R, device=g_out.device) if ctx.has_bias else None
         L.check(lib.aewn_base_embed_bwd(
@@ -424,8 +422,10 @@ class _DecoderCoreFn(torch.autograd.Function):
             L.C.c_void_p(ctx.wav.data_ptr()), L.C.c_longlong(ctx.wav.stride(0)), L.C.c_int(ctx.o0),
             L.C.c_void_p(d_base.data_ptr()), L.C.c_void_p(d_bias.data_ptr() if d_bias is not None else None),
             L.C.c_int(B), L.C.c_int(R), L.C.c_int(Q), L.C.c_int(T0), ops._stream()), "aewn_base_embed_bwd")
-        wgrads = tuple(grads[li].get(k) for (li, k) in ctx.keys)
-        return (None, g_cond[:, :, :T0], None, None, d_base.reshape(ctx.base_shape), d_bias) + wgrads
+        # gradient views alias the plan's flat buffer (overwritten by the next backward): autograd accumulates them
+        # into .grad right away; a caller that keeps them (torch.autograd.grad) gets private copies
+        wgrads = tuple(grads[li][k].clone() for (li, k) in ctx.keys)
+        return (None, g_cond[:, :, :T0].clone(), None, None, d_base.reshape(ctx.base_shape), d_bias) + wgrads
 
 
 class RecLoss(nn.Module):

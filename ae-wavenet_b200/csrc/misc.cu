@@ -113,6 +113,20 @@ __global__ void relu_mask_bwd_kernel(const float* __restrict__ g, long long g_bs
   }
 }
 
+// Weight repacking: a table of strided block copies  dst[i*di + j] = src[i*si + j*sj]  (i < ni, j < nj), one CTA per
+// block.  Turns the live PyTorch parameters (out, in, tap) into the K-major zero-padded operand matrices of the GEMM
+// engines with ONE launch per step (the table is built once; parameter and pack buffers have stable addresses).
+__global__ void pack_blocks_kernel(const aewn_copy_block* __restrict__ blocks, int n_blocks) {
+  for (int bi = blockIdx.x; bi < n_blocks; bi += gridDim.x) {
+    const aewn_copy_block b = blocks[bi];
+    const long long total = static_cast<long long>(b.ni) * b.nj;
+    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+      const long long i = e / b.nj, j = e - i * b.nj;
+      b.dst[i * b.di + j] = b.src[i * b.si + j * b.sj];
+    }
+  }
+}
+
 }  // namespace aewn
 
 using namespace aewn;
@@ -157,6 +171,15 @@ int aewn_fill(float* p, long long n, float value, aewn_stream_t stream_) {
   fill_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p, n, value);
   count_launch();
   return cuda_err(cudaGetLastError(), "fill launch");
+}
+
+int aewn_pack_blocks(const aewn_copy_block* blocks_dev, int n_blocks, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!blocks_dev || n_blocks <= 0) return set_err(AEWN_ERR_INVALID, "pack_blocks: bad arguments");
+  int grid = n_blocks < 148 * 8 ? n_blocks : 148 * 8;
+  pack_blocks_kernel<<<grid, 256, 0, stream>>>(blocks_dev, n_blocks);
+  count_launch();
+  return cuda_err(cudaGetLastError(), "pack_blocks launch");
 }
 
 int aewn_relu_mask_bwd(const float* g, long long g_bs, long long g_cs, const float* mask, long long m_bs, long long m_cs,

@@ -490,8 +490,9 @@ static void time_layer() {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  for (int which = 0; which < 2; ++which) {
-    aewn_tgemm_desc* g = which == 0 ? &g1 : &g2;
+  for (int which = 0; which < 6; ++which) {
+    aewn_tgemm_desc* g = (which & 1) == 0 ? &g1 : &g2;
+    g->cluster = which < 2 ? 1 : (which < 4 ? 2 : 4);
     for (int i = 0; i < 3; ++i) {
       int rc = aewn_tgemm(g, 0);
       if (rc) printf("  tgemm rc=%d (%s)\n", rc, aewn_last_error_string());
@@ -505,9 +506,9 @@ static void time_layer() {
     float ms;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= reps;
-    double flops = which == 0 ? 2.0 * B * (T - d_) * 512.0 * (2 * R + Cc) : 2.0 * B * ((T - d_) * 368.0 + 16384.0 * 256) * 256;
-    printf("  time %s: %.3f ms  -> %.1f TFLOP/s (useful)  device_err=%d\n", which == 0 ? "GEMM1+gate" : "GEMM2+res+skip", ms,
-           flops / ms * 1e-9, read_err());
+    double flops = (which & 1) == 0 ? 2.0 * B * (T - d_) * 512.0 * (2 * R + Cc) : 2.0 * B * ((T - d_) * 368.0 + 16384.0 * 256) * 256;
+    printf("  time %s cluster=%d: %.3f ms  -> %.1f TFLOP/s (useful)  device_err=%d\n",
+           (which & 1) == 0 ? "GEMM1+gate" : "GEMM2+res+skip", g->cluster, ms, flops / ms * 1e-9, read_err());
   }
 
   // wgrad for the layer: G = g_fg (512 rows), X = x@-d, x@0, cond

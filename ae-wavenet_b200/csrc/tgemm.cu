@@ -46,6 +46,8 @@ struct TgParams {
   int n_ttiles;
   int* err;
   uint32_t a_lbo, a_sbo;
+  int cluster;   // 1, 2 or 4: CTAs of a cluster work on adjacent time tiles of the same (batch, n-tile) and share W
+  int n_tgroups; // ceil(n_ttiles / cluster)
 };
 
 struct TgItem {
@@ -53,90 +55,144 @@ struct TgItem {
   bool active;
 };
 
-__device__ __forceinline__ TgItem tg_decode(const TgParams& p, int item) {
+// `item` indexes (batch, time-tile GROUP, n-tile); the CTAs of a cluster take consecutive tiles of the group.  The
+// activity test is evaluated on the whole group so that every CTA of a cluster walks the same item sequence (they
+// exchange multicast data and barrier arrivals); a CTA whose own tile lies outside the store range just stores nothing.
+__device__ __forceinline__ TgItem tg_decode(const TgParams& p, int item, int crank) {
   TgItem it;
   it.ni = item % p.n_ntiles;
   int r = item / p.n_ntiles;
-  int tt = r % p.n_ttiles;
-  it.b = r / p.n_ttiles;
-  it.tau0 = p.t_begin + tt * TG_BM;
+  int tg = r % p.n_tgroups;
+  it.b = r / p.n_tgroups;
+  const int g0 = p.t_begin + tg * p.cluster * TG_BM;
+  it.tau0 = g0 + crank * TG_BM;
   const aewn_ntile& nt = p.nt[it.ni];
-  it.active = (it.tau0 + TG_BM > nt.t_lo) && (it.tau0 < nt.t_hi);
+  it.active = (g0 + p.cluster * TG_BM > nt.t_lo) && (g0 < nt.t_hi);
   return it;
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
 // Common conventions: lane = time step tau; stores happen for tau in [t_lo, t_hi); values for tau < t_zero_lo are
 // forced to 0 so that the aligned-down margin of every tensor stays finite (TMA reads it, 0 * garbage must be 0).
-__device__ __forceinline__ void epi_linear(const aewn_ntile& nt, uint32_t taddr, int half, int b, int tau) {
+// Addend / accumulate source of a LINEAR tile, software-pipelined: the loads of column chunk i+1 are issued before
+// chunk i is processed, and those of the first chunk BEFORE the epilogue waits for the accumulator, so the global
+// load latency hides behind the MMAs instead of stalling each chunk (GEMM2 of a GRCC layer is epilogue-bound).
+struct LinSrc {
+  const float* p;   // element (b, first channel of tile, tau [+ toff])
+  long long cs;
+  bool ok;          // this lane may load
+  bool is_add;      // true: `add` operand (or mask);  false: previous value of `out` (accumulate)
+  float fill;
+};
+
+__device__ __forceinline__ LinSrc lin_src(const aewn_ntile& nt, int b, int tau) {
+  LinSrc s;
+  const bool in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
+  if (nt.add) {
+    s.p = nt.add + static_cast<long long>(b) * nt.add_bs + (tau + nt.add_toff);
+    s.cs = nt.add_cs;
+    s.ok = in_range && tau >= nt.t_zero_lo && tau >= nt.add_t_lo;
+    s.is_add = true;
+    s.fill = (nt.flags & AEWN_F_MASKPOS) ? 1.0f : 0.0f;
+  } else if (nt.flags & AEWN_F_ACCUM) {
+    s.p = nt.out + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
+    s.cs = nt.out_cs;
+    s.ok = in_range;
+    s.is_add = false;
+    s.fill = 0.0f;
+  } else {
+    s.p = nullptr;
+    s.cs = 0;
+    s.ok = false;
+    s.is_add = false;
+    s.fill = 0.0f;
+  }
+  return s;
+}
+
+__device__ __forceinline__ void lin_issue(const LinSrc& s, int n_valid, int c0, float (&a)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float* q = s.p + static_cast<long long>(c0 + j) * s.cs;
+    a[j] = (s.ok && c0 + j < n_valid) ? (s.is_add ? __ldg(q) : __ldcg(q)) : s.fill;
+  }
+}
+
+__device__ __forceinline__ void epi_linear(const aewn_ntile& nt, uint32_t taddr, int half, int b, int tau,
+                                           const LinSrc& src, float (&pre)[32]) {
   const bool in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
   const bool live = tau >= nt.t_zero_lo;
   float* outp = nt.out + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
   const int dup_t = tau + nt.dup_toff;
   const bool dup_ok = nt.out2 && in_range && dup_t >= 0 && dup_t < nt.dup_t_hi;
   float* dupp = nt.out2 ? nt.out2 + static_cast<long long>(b) * nt.out_bs + dup_t : nullptr;
-  const float* addp = nt.add ? nt.add + static_cast<long long>(b) * nt.add_bs + (tau + nt.add_toff) : nullptr;
   const bool accum = (nt.flags & AEWN_F_ACCUM) != 0;
   const bool relu = (nt.flags & AEWN_F_RELU) != 0;
   const bool relu_first = (nt.flags & AEWN_F_RELU_FIRST) != 0;
   const bool maskpos = (nt.flags & AEWN_F_MASKPOS) != 0;
+  const bool both = nt.add && accum;  // rare: addend prefetched, previous value loaded inline
   unsigned int zeros = 0;
   for (int c0 = half * 32; c0 < nt.n; c0 += 64) {
+    float nxt[32];
+    const bool have_next = src.p && (c0 + 64 < nt.n) && (c0 + 64 < nt.n_valid);
+    if (have_next) lin_issue(src, nt.n_valid, c0 + 64, nxt);
     uint32_t v[32];
     tmem_ld32(taddr + c0, v);
     tmem_ld_wait();
-    if (c0 >= nt.n_valid) continue;
-    float r[32];
+    if (c0 < nt.n_valid) {
+      float r[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
-    if (nt.bias) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c0 + j < nt.n_valid) r[j] += __ldg(nt.bias + c0 + j);
-    }
-    if (relu_first) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.0f);
-      if (nt.out3) {  // keep relu(pre) so the backward pass has the exact activation mask (wave_encoder.py:39)
-        float* o3 = nt.out3 + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
+      for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+      if (nt.bias) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (in_range && c0 + j < nt.n_valid) o3[static_cast<long long>(c0 + j) * nt.out_cs] = live ? r[j] : 0.0f;
+          if (c0 + j < nt.n_valid) r[j] += __ldg(nt.bias + c0 + j);
+      }
+      if (relu_first) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.0f);
+        if (nt.out3) {  // keep relu(pre) so the backward pass has the exact activation mask (wave_encoder.py:39)
+          float* o3 = nt.out3 + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (in_range && c0 + j < nt.n_valid) o3[static_cast<long long>(c0 + j) * nt.out_cs] = live ? r[j] : 0.0f;
+        }
+      }
+      if (src.p && src.is_add) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = maskpos ? (pre[j] > 0.0f ? r[j] : 0.0f) : r[j] + pre[j];
+      }
+      if (!live) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0.0f;
+      }
+      if (accum) {
+        if (both) {
+          float prev[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            prev[j] = (in_range && c0 + j < nt.n_valid) ? __ldcg(outp + static_cast<long long>(c0 + j) * nt.out_cs) : 0.0f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] += prev[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] += pre[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (in_range && c0 + j < nt.n_valid) {
+          float x = r[j];
+          if (relu) x = fmaxf(x, 0.0f);
+          outp[static_cast<long long>(c0 + j) * nt.out_cs] = x;
+          if (dup_ok) dupp[static_cast<long long>(c0 + j) * nt.out_cs] = x;
+          zeros += (x == 0.0f) ? 1u : 0u;
+        }
       }
     }
-    // global loads are hoisted into their own fully unrolled loops (select, not branch) so that all 32 are in
-    // flight together; a fused load+use loop serialises on memory latency (measured: 25x slower epilogue)
-    if (addp) {
-      const bool add_ok = in_range && live && tau >= nt.add_t_lo;
-      float a[32];
+    if (have_next) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        a[j] = (add_ok && c0 + j < nt.n_valid) ? __ldg(addp + static_cast<long long>(c0 + j) * nt.add_cs)
-                                               : (maskpos ? 1.0f : 0.0f);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = maskpos ? (a[j] > 0.0f ? r[j] : 0.0f) : r[j] + a[j];
-    }
-    if (!live) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = 0.0f;
-    }
-    if (accum) {
-      float prev[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        prev[j] = (in_range && c0 + j < nt.n_valid) ? __ldcg(outp + static_cast<long long>(c0 + j) * nt.out_cs) : 0.0f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] += prev[j];
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (in_range && c0 + j < nt.n_valid) {
-        float x = r[j];
-        if (relu) x = fmaxf(x, 0.0f);
-        outp[static_cast<long long>(c0 + j) * nt.out_cs] = x;
-        if (dup_ok) dupp[static_cast<long long>(c0 + j) * nt.out_cs] = x;
-        zeros += (x == 0.0f) ? 1u : 0u;
-      }
+      for (int j = 0; j < 32; ++j) pre[j] = nxt[j];
     }
   }
   if (nt.zero_count) {
@@ -237,7 +293,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
     *abort_flag = 0;
     for (int i = 0; i < TG_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], p.cluster);   // one tcgen05.commit arrival from every CTA that reads the stage's W
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -255,21 +311,33 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();   // peers' barriers must be initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total = p.batch * p.n_ttiles * p.n_ntiles;
+  const int crank = p.cluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cid = blockIdx.x / p.cluster;            // cluster index; all CTAs of a cluster walk the same items
+  const int n_clusters = gridDim.x / p.cluster;
+  const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1u);
+  const int total = p.batch * p.n_tgroups * p.n_ntiles;
 
+  // Register reallocation: warps 0-3 (TMA / MMA / TMEM-alloc roles, one warpgroup) shrink to 88 registers and the 8
+  // epilogue warps grow to 208, so 32-wide column chunks + prefetch buffers stay in registers
+  // (128*88 + 256*208 = 64512 <= 65536).  Each setmaxnreg dominates its role code (no merge of limits).
+  if (warp < 4) {
+  reg_dealloc<88>();
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       bool ok = true;
-      for (int item = blockIdx.x; item < total && ok; item += gridDim.x) {
-        const TgItem it = tg_decode(p, item);
+      for (int item = cid; item < total && ok; item += n_clusters) {
+        const TgItem it = tg_decode(p, item, crank);
         if (!it.active) continue;
         const aewn_ntile& nt = p.nt[it.ni];
-        const int wboxes = (nt.n + 127) >> 7;
+        // W rows are split into `cluster` slices of wrows each; CTA r loads slice r and multicasts it to all peers
+        const int wrows = 256 / p.cluster;
+        const int wslices = (nt.n + wrows - 1) / wrows;
         for (int s = 0; s < p.n_segs && ok; ++s) {
           if (!((nt.seg_mask >> s) & 1)) continue;
           const TgSeg sg = p.seg[s];
@@ -277,14 +345,20 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
             if (!mbar_wait(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
             uint8_t* sa = smem + stage * TG_STAGE_BYTES;
             uint8_t* sw = sa + TG_A_BYTES;
-            mbar_expect_tx(&full_bar[stage], TG_A_BYTES + wboxes * TG_WBOX_BYTES);
+            const int wboxes = (nt.n + 127) >> 7;
+            mbar_expect_tx(&full_bar[stage], TG_A_BYTES + (p.cluster == 1 ? wboxes * TG_WBOX_BYTES : wslices * wrows * 128));
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               tma_load_3d(sa + i * 4096, &p.a_map[sg.map], &full_bar[stage], it.tau0 + sg.shift + 32 * i, kb * TG_BK,
                           it.b);
-            for (int j = 0; j < wboxes; ++j)
-              tma_load_2d(sw + j * TG_WBOX_BYTES, &p.w_map, &full_bar[stage], sg.w_koff + kb * TG_BK,
-                          nt.w_row + j * 128);
+            if (p.cluster == 1) {
+              for (int j = 0; j < wboxes; ++j)
+                tma_load_2d(sw + j * TG_WBOX_BYTES, &p.w_map, &full_bar[stage], sg.w_koff + kb * TG_BK,
+                            nt.w_row + j * 128);
+            } else if (crank < wslices) {
+              tma_load_2d_mcast(sw + crank * wrows * 128, &p.w_map, &full_bar[stage], sg.w_koff + kb * TG_BK,
+                                nt.w_row + crank * wrows, cmask);
+            }
             if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -295,8 +369,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       bool ok = true;
-      for (int item = blockIdx.x; item < total && ok; item += gridDim.x) {
-        const TgItem it = tg_decode(p, item);
+      for (int item = cid; item < total && ok; item += n_clusters) {
+        const TgItem it = tg_decode(p, item, crank);
         if (!it.active) continue;
         const aewn_ntile& nt = p.nt[it.ni];
         if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) break;
@@ -320,7 +394,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
               const uint64_t bdesc = make_smem_desc(w_addr + ks * 32, 16, 1024, kLayoutSW128);
               umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kiter | ks) != 0u);
             }
-            umma_commit(&empty_bar[stage]);
+            if (p.cluster == 1) umma_commit(&empty_bar[stage]);
+            else umma_commit_mcast(&empty_bar[stage], cmask);
             ++kiter;
             if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
           }
@@ -330,20 +405,30 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    reg_alloc<208>();
     // ===================================================== epilogue
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     uint32_t acc = 0, acc_phase = 0;
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
-      const TgItem it = tg_decode(p, item);
+    for (int item = cid; item < total; item += n_clusters) {
+      const TgItem it = tg_decode(p, item, crank);
       if (!it.active) continue;
       const aewn_ntile& nt = p.nt[it.ni];
+      const int tau = it.tau0 + q * 32 + lane;
+      // issue the first chunk's addend / accumulate loads before waiting for the accumulator
+      LinSrc src;
+      src.p = nullptr;
+      float pre[32];
+      if (nt.mode == AEWN_EPI_LINEAR) {
+        src = lin_src(nt, it.b, tau);
+        if (src.p && half * 32 < nt.n_valid) lin_issue(src, nt.n_valid, half * 32, pre);
+      }
       if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) break;
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256u + (static_cast<uint32_t>(q * 32) << 16);
-      const int tau = it.tau0 + q * 32 + lane;
-      if (nt.mode == AEWN_EPI_LINEAR) epi_linear(nt, taddr, half, it.b, tau);
+      if (nt.mode == AEWN_EPI_LINEAR) epi_linear(nt, taddr, half, it.b, tau, src, pre);
       else if (nt.mode == AEWN_EPI_GATE_FWD) epi_gate_fwd(nt, taddr, half, it.b, tau);
       else epi_gate_bwd(nt, taddr, half, it.b, tau);
       tc_fence_before();
@@ -356,6 +441,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();   // no CTA may exit while a peer can still multicast into its smem
   if (threadIdx.x == 0 && *abort_flag && p.err) atomicExch(p.err, AEWN_ERR_TIMEOUT);
   if (warp == 2) {
     tc_fence_after();
@@ -391,7 +477,9 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
     if (d->acts[i].batch < d->batch) return set_err(AEWN_ERR_INVALID, "tgemm: act %d batch smaller than problem batch", i);
   }
   for (int i = d->n_acts; i < AEWN_MAX_ACTS; ++i) p.a_map[i] = p.a_map[0];
-  int rc = encode_w_map(&p.w_map, d->w, d->w_rows, d->w_kpad, 128);
+  int cluster = d->cluster > 0 ? d->cluster : 2;
+  if (cluster != 1 && cluster != 2 && cluster != 4) return set_err(AEWN_ERR_INVALID, "tgemm: cluster must be 1, 2 or 4");
+  int rc = encode_w_map(&p.w_map, d->w, d->w_rows, d->w_kpad, cluster == 1 ? 128 : 256 / cluster);
   if (rc) return rc;
 
   for (int s = 0; s < d->n_segs; ++s) {
@@ -440,10 +528,27 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
   p.a_lbo = d->dbg_lbo > 0 ? d->dbg_lbo : 4096;
   p.a_sbo = d->dbg_sbo > 0 ? d->dbg_sbo : 512;
 
-  const long long total = static_cast<long long>(p.batch) * p.n_ttiles * p.n_ntiles;
-  int ctas = d->max_ctas > 0 ? d->max_ctas : sm_count();
-  if (ctas > total) ctas = static_cast<int>(total);
-  tgemm_kernel<<<ctas, TG_THREADS, TG_SMEM_BYTES, stream>>>(p);
+  p.cluster = cluster;
+  p.n_tgroups = (p.n_ttiles + cluster - 1) / cluster;
+  const long long total = static_cast<long long>(p.batch) * p.n_tgroups * p.n_ntiles;   // items per cluster walk
+  int clusters = (d->max_ctas > 0 ? d->max_ctas : sm_count()) / cluster;
+  if (clusters > total) clusters = static_cast<int>(total);
+  if (clusters < 1) clusters = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * cluster);
+  cfg.blockDim = dim3(TG_THREADS);
+  cfg.dynamicSmemBytes = TG_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, tgemm_kernel, p);
   count_launch();
+  if (le != cudaSuccess) return cuda_err(le, "tgemm launch");
   return cuda_err(cudaGetLastError(), "tgemm launch");
 }

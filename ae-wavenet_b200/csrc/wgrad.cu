@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
 
   const int total_units = p.unit_begin[p.n_items];
 
+  if (warp < 4) {
+  reg_dealloc<88>();
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -140,7 +142,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    reg_alloc<208>();
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     uint32_t acc = 0, acc_phase = 0;

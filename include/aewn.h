@@ -122,6 +122,7 @@ typedef struct {
   int* err;           /* device error word (may be NULL) */
   int max_ctas;       /* 0 = one per SM */
   int dbg_lbo, dbg_sbo; /* 0 = defaults; descriptor probing only */
+  int cluster;        /* CTAs per cluster sharing W by TMA multicast: 0 = default (2), or 1, 2, 4 */
 } aewn_tgemm_desc;
 
 int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream);
@@ -176,6 +177,15 @@ int aewn_base_embed_fwd(const float* wav, long long wav_pitch, int off0, const f
 int aewn_base_embed_bwd(const float* g, long long g_bs, long long g_cs, const float* wav, long long wav_pitch, int off0,
                         float* dw, float* dbias, int batch, int R, int Q, int T, aewn_stream_t stream);
 int aewn_fill(float* p, long long n, float value, aewn_stream_t stream);
+/* Weight repacking: n_blocks strided block copies dst[i*di + j] = src[i*si + j*sj] (i < ni, j < nj); `blocks_dev` is a
+ * DEVICE array.  One launch turns the (out, in, tap) parameters of wavenet.py:25-34 into the K-major operand matrices. */
+typedef struct {
+  const float* src;
+  float* dst;
+  int ni, nj;
+  long long si, sj, di;
+} aewn_copy_block;
+int aewn_pack_blocks(const aewn_copy_block* blocks_dev, int n_blocks, aewn_stream_t stream);
 /* out = mask > 0 ? g : 0   (ReLU backward) */
 int aewn_relu_mask_bwd(const float* g, long long g_bs, long long g_cs, const float* mask, long long m_bs, long long m_cs,
                        float* out, long long o_bs, long long o_cs, int batch, int C, int T, aewn_stream_t stream);

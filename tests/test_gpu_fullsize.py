@@ -46,11 +46,12 @@ def test_full_size_forward_window_matches_cpu_oracle_and_batch_items_are_indepen
     jit = torch.arange(geo["lc_len"]).unsqueeze(0).repeat(B, 1)
     with torch.no_grad():
         q = wn(wav.cuda(), lc.cuda(), spk.cuda(), jit.cuda())
-        # batch independence: item 3 alone gives the same logits as inside the batch of 8
-        q3 = wn(wav[3:4].cuda(), lc[3:4].cuda(), spk[3:4].cuda(), jit[3:4].cuda())
+        # the forward path has no atomics: a second run is bit-identical (NB: batch items are NOT independent in the
+        # reference -- the jitter gather reads lc_sparse[0, b, :] for item b, SURVEY.md F8 -- so no such check here)
+        q2 = wn(wav.cuda(), lc.cuda(), spk.cuda(), jit.cuda())
     ops.check_device_errors()
     assert q.shape == (B, 256, W) and torch.isfinite(q).all()
-    assert torch.equal(q[3:4], q3)
+    assert torch.equal(q, q2)
     # CPU oracle on the LAST 64 output steps of item 0: outputs only depend on the trailing RF + 64 inputs
     sd = {k: v.cpu() for k, v in wn.state_dict().items()}
     n_out = 64
@@ -77,7 +78,8 @@ def test_full_size_forward_window_matches_cpu_oracle_and_batch_items_are_indepen
 
 
 def test_full_size_backward_is_finite_and_weight_grads_scale_linearly():
-    """d(c * loss)/dW = c * d(loss)/dW through the whole kernel path (linearity of backward in the upstream gradient)."""
+    """d(c * loss)/dW = c * d(loss)/dW through the whole kernel path (linearity of backward in the upstream gradient).
+    c = 4: a power of two commutes with TF32 operand rounding, so the only slack is fp32 atomic-add ordering."""
     import aewn
     from aewn import ops
     torch.manual_seed(2507)
@@ -94,8 +96,8 @@ def test_full_size_backward_is_finite_and_weight_grads_scale_linearly():
     gq = torch.randn(q.shape, generator=torch.Generator().manual_seed(1)).cuda()
     params = [p for p in wn.parameters()]
     g1 = torch.autograd.grad((q * gq).sum(), params, retain_graph=True)
-    g3 = torch.autograd.grad((q * gq).sum() * 3.0, params)
+    g3 = torch.autograd.grad((q * gq).sum() * 4.0, params)
     ops.check_device_errors()
     for a, b, (k, _) in zip(g1, g3, wn.named_parameters()):
         assert torch.isfinite(a).all(), k
-        assert torch.allclose(3.0 * a, b, rtol=2e-3, atol=1e-5 * float(b.abs().max())), k
+        assert torch.allclose(4.0 * a, b, rtol=1e-3, atol=1e-4 * float(b.abs().max())), k

