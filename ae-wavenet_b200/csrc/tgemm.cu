@@ -118,81 +118,94 @@ __device__ __forceinline__ void lin_issue(const LinSrc& s, int n_valid, int c0, 
   }
 }
 
-__device__ __forceinline__ void epi_linear(const aewn_ntile& nt, uint32_t taddr, int half, int b, int tau,
-                                           const LinSrc& src, float (&pre)[32]) {
-  const bool in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
-  const bool live = tau >= nt.t_zero_lo;
-  float* outp = nt.out + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
-  const int dup_t = tau + nt.dup_toff;
-  const bool dup_ok = nt.out2 && in_range && dup_t >= 0 && dup_t < nt.dup_t_hi;
-  float* dupp = nt.out2 ? nt.out2 + static_cast<long long>(b) * nt.out_bs + dup_t : nullptr;
-  const bool accum = (nt.flags & AEWN_F_ACCUM) != 0;
-  const bool relu = (nt.flags & AEWN_F_RELU) != 0;
-  const bool relu_first = (nt.flags & AEWN_F_RELU_FIRST) != 0;
-  const bool maskpos = (nt.flags & AEWN_F_MASKPOS) != 0;
-  const bool both = nt.add && accum;  // rare: addend prefetched, previous value loaded inline
-  unsigned int zeros = 0;
-  for (int c0 = half * 32; c0 < nt.n; c0 += 64) {
-    float nxt[32];
-    const bool have_next = src.p && (c0 + 64 < nt.n) && (c0 + 64 < nt.n_valid);
-    if (have_next) lin_issue(src, nt.n_valid, c0 + 64, nxt);
-    uint32_t v[32];
-    tmem_ld32(taddr + c0, v);
-    tmem_ld_wait();
-    if (c0 < nt.n_valid) {
-      float r[32];
+struct LinCtx {
+  bool in_range, live, accum, relu, relu_first, maskpos, both, dup_ok;
+  float* outp;
+  float* dupp;
+};
+
+// One 32-column chunk of a LINEAR tile.  `buf` holds the prefetched addend / previous-output values of this chunk.
+__device__ __forceinline__ void lin_chunk(const aewn_ntile& nt, const LinCtx& cx, const LinSrc& src, uint32_t taddr, int c0,
+                                          int b, int tau, const float (&buf)[32], unsigned int& zeros) {
+  uint32_t v[32];
+  tmem_ld32(taddr + c0, v);
+  tmem_ld_wait();
+  if (c0 >= nt.n_valid) return;
+  float r[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
-      if (nt.bias) {
+  for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+  if (nt.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < nt.n_valid) r[j] += __ldg(nt.bias + c0 + j);
-      }
-      if (relu_first) {
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < nt.n_valid) r[j] += __ldg(nt.bias + c0 + j);
+  }
+  if (cx.relu_first) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.0f);
-        if (nt.out3) {  // keep relu(pre) so the backward pass has the exact activation mask (wave_encoder.py:39)
-          float* o3 = nt.out3 + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
+    for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.0f);
+    if (nt.out3) {  // keep relu(pre) so the backward pass has the exact activation mask (wave_encoder.py:39)
+      float* o3 = nt.out3 + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (in_range && c0 + j < nt.n_valid) o3[static_cast<long long>(c0 + j) * nt.out_cs] = live ? r[j] : 0.0f;
-        }
-      }
-      if (src.p && src.is_add) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = maskpos ? (pre[j] > 0.0f ? r[j] : 0.0f) : r[j] + pre[j];
-      }
-      if (!live) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0.0f;
-      }
-      if (accum) {
-        if (both) {
-          float prev[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            prev[j] = (in_range && c0 + j < nt.n_valid) ? __ldcg(outp + static_cast<long long>(c0 + j) * nt.out_cs) : 0.0f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] += prev[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] += pre[j];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (in_range && c0 + j < nt.n_valid) {
-          float x = r[j];
-          if (relu) x = fmaxf(x, 0.0f);
-          outp[static_cast<long long>(c0 + j) * nt.out_cs] = x;
-          if (dup_ok) dupp[static_cast<long long>(c0 + j) * nt.out_cs] = x;
-          zeros += (x == 0.0f) ? 1u : 0u;
-        }
-      }
+      for (int j = 0; j < 32; ++j)
+        if (cx.in_range && c0 + j < nt.n_valid) o3[static_cast<long long>(c0 + j) * nt.out_cs] = cx.live ? r[j] : 0.0f;
     }
-    if (have_next) {
+  }
+  if (src.p && src.is_add) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) pre[j] = nxt[j];
+    for (int j = 0; j < 32; ++j) r[j] = cx.maskpos ? (buf[j] > 0.0f ? r[j] : 0.0f) : r[j] + buf[j];
+  }
+  if (!cx.live) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = 0.0f;
+  }
+  if (cx.accum) {
+    if (cx.both) {
+      float prev[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        prev[j] = (cx.in_range && c0 + j < nt.n_valid) ? __ldcg(cx.outp + static_cast<long long>(c0 + j) * nt.out_cs) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] += prev[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] += buf[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (cx.in_range && c0 + j < nt.n_valid) {
+      float x = r[j];
+      if (cx.relu) x = fmaxf(x, 0.0f);
+      cx.outp[static_cast<long long>(c0 + j) * nt.out_cs] = x;
+      if (cx.dup_ok) cx.dupp[static_cast<long long>(c0 + j) * nt.out_cs] = x;
+      zeros += (x == 0.0f) ? 1u : 0u;
+    }
+  }
+}
+
+// LINEAR epilogue of one tile.  Column chunks c0 = 32*half + 64*i; chunk i uses buffer A (i even) or B (i odd), and
+// as soon as a buffer is consumed the loads of chunk i+2 are issued into it: two chunks (2 x 32 x 128 B per warp) stay
+// in flight, the first two are issued by the caller BEFORE it waits for the accumulator.
+__device__ __forceinline__ void epi_linear(const aewn_ntile& nt, uint32_t taddr, int half, int b, int tau,
+                                           const LinSrc& src, float (&bufA)[32], float (&bufB)[32]) {
+  LinCtx cx;
+  cx.in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
+  cx.live = tau >= nt.t_zero_lo;
+  cx.outp = nt.out + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
+  const int dup_t = tau + nt.dup_toff;
+  cx.dup_ok = nt.out2 && cx.in_range && dup_t >= 0 && dup_t < nt.dup_t_hi;
+  cx.dupp = nt.out2 ? nt.out2 + static_cast<long long>(b) * nt.out_bs + dup_t : nullptr;
+  cx.accum = (nt.flags & AEWN_F_ACCUM) != 0;
+  cx.relu = (nt.flags & AEWN_F_RELU) != 0;
+  cx.relu_first = (nt.flags & AEWN_F_RELU_FIRST) != 0;
+  cx.maskpos = (nt.flags & AEWN_F_MASKPOS) != 0;
+  cx.both = nt.add && cx.accum;  // rare: addend prefetched, previous value loaded inline
+  unsigned int zeros = 0;
+  for (int c0 = half * 32; c0 < nt.n; c0 += 128) {
+    lin_chunk(nt, cx, src, taddr, c0, b, tau, bufA, zeros);
+    if (src.p && c0 + 128 < nt.n && c0 + 128 < nt.n_valid) lin_issue(src, nt.n_valid, c0 + 128, bufA);
+    if (c0 + 64 < nt.n) {
+      lin_chunk(nt, cx, src, taddr, c0 + 64, b, tau, bufB, zeros);
+      if (src.p && c0 + 192 < nt.n && c0 + 192 < nt.n_valid) lin_issue(src, nt.n_valid, c0 + 192, bufB);
     }
   }
   if (nt.zero_count) {
@@ -233,43 +246,69 @@ __device__ __forceinline__ void epi_gate_fwd(const aewn_ntile& nt, uint32_t tadd
 }
 
 // g_f = g_z * sg * (1 - th^2), g_g = g_z * th * sg * (1 - sg); acc columns = g_z of all D channels.
-__device__ __forceinline__ void epi_gate_bwd(const aewn_ntile& nt, uint32_t taddr, int half, int b, int tau) {
-  const bool in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
-  const bool live = tau >= nt.t_zero_lo;
-  const long long ooff = static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
-  const long long aoff = static_cast<long long>(b) * nt.add_bs + (tau + nt.add_toff);
-  const int dup_t = tau + nt.dup_toff;
-  const bool dup_ok = nt.out3 && in_range && dup_t >= 0 && dup_t < nt.dup_t_hi;
-  const long long doff = static_cast<long long>(b) * nt.out_bs + dup_t;
-  const long long g_delta = nt.out2 - nt.out;  // g_gate rows follow g_filt rows in the same tensor
-  for (int c0 = half * 32; c0 < nt.n; c0 += 64) {
-    uint32_t v[32];
-    tmem_ld32(taddr + c0, v);
-    tmem_ld_wait();
-    float th[32], sg[32];
+struct GateBwdCtx {
+  bool in_range, live, dup_ok;
+  long long ooff, aoff, doff, g_delta;
+};
+
+__device__ __forceinline__ void gbwd_issue(const aewn_ntile& nt, const GateBwdCtx& cx, int c0, float (&th)[32],
+                                           float (&sg)[32]) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const bool ok = in_range && live && (c0 + j < nt.n_valid);
-      th[j] = ok ? __ldg(nt.add + aoff + static_cast<long long>(c0 + j) * nt.add_cs) : 0.0f;
-      sg[j] = ok ? __ldg(nt.add2 + aoff + static_cast<long long>(c0 + j) * nt.add_cs) : 0.0f;
-    }
+  for (int j = 0; j < 32; ++j) {
+    const bool ok = cx.in_range && cx.live && (c0 + j < nt.n_valid);
+    th[j] = ok ? __ldg(nt.add + cx.aoff + static_cast<long long>(c0 + j) * nt.add_cs) : 0.0f;
+    sg[j] = ok ? __ldg(nt.add2 + cx.aoff + static_cast<long long>(c0 + j) * nt.add_cs) : 0.0f;
+  }
+}
+
+__device__ __forceinline__ void gbwd_chunk(const aewn_ntile& nt, const GateBwdCtx& cx, uint32_t taddr, int c0,
+                                           const float (&th)[32], const float (&sg)[32]) {
+  uint32_t v[32];
+  tmem_ld32(taddr + c0, v);
+  tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (in_range && c0 + j < nt.n_valid) {
-        const float gz = live ? __uint_as_float(v[j]) : 0.0f;
-        const float gs = gz * sg[j];
-        const float gf = live ? gs * (1.0f - th[j] * th[j]) : 0.0f;
-        const float gg = live ? gs * th[j] * (1.0f - sg[j]) : 0.0f;
-        const long long o = ooff + static_cast<long long>(c0 + j) * nt.out_cs;
-        nt.out[o] = gf;
-        nt.out2[o] = gg;
-        if (dup_ok) {
-          const long long od = doff + static_cast<long long>(c0 + j) * nt.out_cs;
-          nt.out3[od] = gf;
-          nt.out3[od + g_delta] = gg;
-        }
+  for (int j = 0; j < 32; ++j) {
+    if (cx.in_range && c0 + j < nt.n_valid) {
+      const float gz = cx.live ? __uint_as_float(v[j]) : 0.0f;
+      const float gs = gz * sg[j];
+      const float gf = cx.live ? gs * (1.0f - th[j] * th[j]) : 0.0f;
+      const float gg = cx.live ? gs * th[j] * (1.0f - sg[j]) : 0.0f;
+      const long long o = cx.ooff + static_cast<long long>(c0 + j) * nt.out_cs;
+      nt.out[o] = gf;
+      nt.out2[o] = gg;
+      if (cx.dup_ok) {
+        const long long od = cx.doff + static_cast<long long>(c0 + j) * nt.out_cs;
+        nt.out3[od] = gf;
+        nt.out3[od + cx.g_delta] = gg;
       }
     }
+  }
+}
+
+__device__ __forceinline__ GateBwdCtx gbwd_ctx(const aewn_ntile& nt, int b, int tau) {
+  GateBwdCtx cx;
+  cx.in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
+  cx.live = tau >= nt.t_zero_lo;
+  cx.ooff = static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
+  cx.aoff = static_cast<long long>(b) * nt.add_bs + (tau + nt.add_toff);
+  const int dup_t = tau + nt.dup_toff;
+  cx.dup_ok = nt.out3 && cx.in_range && dup_t >= 0 && dup_t < nt.dup_t_hi;
+  cx.doff = static_cast<long long>(b) * nt.out_bs + dup_t;
+  cx.g_delta = nt.out2 - nt.out;  // g_gate rows follow g_filt rows in the same tensor
+  return cx;
+}
+
+// tanh / sigmoid of the first chunk are loaded by the caller before it waits for the accumulator; those of chunk i+1
+// are issued before chunk i is processed.
+__device__ __forceinline__ void epi_gate_bwd(const aewn_ntile& nt, uint32_t taddr, int half, const GateBwdCtx& cx,
+                                             float (&thA)[32], float (&sgA)[32]) {
+  float thB[32], sgB[32];
+  for (int c0 = half * 32; c0 < nt.n; c0 += 128) {
+    const bool hasB = c0 + 64 < nt.n;
+    if (hasB) gbwd_issue(nt, cx, c0 + 64, thB, sgB);
+    gbwd_chunk(nt, cx, taddr, c0, thA, sgA);
+    if (c0 + 128 < nt.n) gbwd_issue(nt, cx, c0 + 128, thA, sgA);
+    if (hasB) gbwd_chunk(nt, cx, taddr, c0 + 64, thB, sgB);
   }
 }
 
@@ -325,7 +364,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   // epilogue warps grow to 208, so 32-wide column chunks + prefetch buffers stay in registers
   // (128*88 + 256*208 = 64512 <= 65536).  Each setmaxnreg dominates its role code (no merge of limits).
   if (warp < 4) {
-  reg_dealloc<88>();
+  reg_dealloc<40>();
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
@@ -407,7 +446,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
     }
   }
   } else {
-    reg_alloc<208>();
+    reg_alloc<232>();
     // ===================================================== epilogue
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
@@ -420,17 +459,22 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
       // issue the first chunk's addend / accumulate loads before waiting for the accumulator
       LinSrc src;
       src.p = nullptr;
-      float pre[32];
+      float pre[32], pre2[32];
+      GateBwdCtx gcx;
       if (nt.mode == AEWN_EPI_LINEAR) {
         src = lin_src(nt, it.b, tau);
         if (src.p && half * 32 < nt.n_valid) lin_issue(src, nt.n_valid, half * 32, pre);
+        if (src.p && half * 32 + 64 < nt.n_valid) lin_issue(src, nt.n_valid, half * 32 + 64, pre2);
+      } else if (nt.mode == AEWN_EPI_GATE_BWD) {
+        gcx = gbwd_ctx(nt, it.b, tau);
+        gbwd_issue(nt, gcx, half * 32, pre, pre2);
       }
       if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) break;
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256u + (static_cast<uint32_t>(q * 32) << 16);
-      if (nt.mode == AEWN_EPI_LINEAR) epi_linear(nt, taddr, half, it.b, tau, src, pre);
+      if (nt.mode == AEWN_EPI_LINEAR) epi_linear(nt, taddr, half, it.b, tau, src, pre, pre2);
       else if (nt.mode == AEWN_EPI_GATE_FWD) epi_gate_fwd(nt, taddr, half, it.b, tau);
-      else epi_gate_bwd(nt, taddr, half, it.b, tau);
+      else epi_gate_bwd(nt, taddr, half, gcx, pre, pre2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);

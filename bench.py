@@ -309,6 +309,9 @@ def main():
                 fwd_flops += grcc_layer_fwd_flops(B, R, D, S, C, T_in, d, W)
             T_in -= d
         gemm_ms = sum(sum(v) for v in times.values()) / args.steps
+        per_class = {}
+        for tag, v in times.items():
+            per_class[tag.split(".")[0]] = per_class.get(tag.split(".")[0], 0.0) + sum(v) / args.steps
         hbm_ach = fwd_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None
         tf_ach = fwd_flops / (fwd_ms * 1e-3) / 1e12 if fwd_ms else None
         traffic = None
@@ -333,7 +336,7 @@ def main():
                                  frac=(tf_ach / pk["bf16_tflops"]) if tf_ach else None,
                                  note="TF32 operands (nominal peak = half of bf16); denominator is the measured bf16 "
                                       "cuBLAS rate"),
-            kernel_share=dict(tcgen05_ms_per_step=gemm_ms, step_ms=ms),
+            kernel_share=dict(tcgen05_ms_per_step=gemm_ms, step_ms=ms, per_class_ms=per_class),
             clocks=clocks,
             e2e=dict(value=world * B * W / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms,
                      h2d_bytes_per_step=int(sum(t.numel() * t.element_size() for t in (wav_h, lc_h, spk_h, jit_h))),
