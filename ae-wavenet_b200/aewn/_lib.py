@@ -41,7 +41,7 @@ class TGemmDesc(C.Structure):
                 ("w", C.c_void_p), ("w_rows", C.c_int), ("w_kpad", C.c_int),
                 ("ntiles", NTile * MAX_NTILES), ("n_ntiles", C.c_int), ("batch", C.c_int),
                 ("t_begin", C.c_int), ("t_end", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int),
-                ("dbg_lbo", C.c_int), ("dbg_sbo", C.c_int), ("cluster", C.c_int)]
+                ("dbg_lbo", C.c_int), ("dbg_sbo", C.c_int), ("cluster", C.c_int), ("no_tma_store", C.c_int)]
 
 
 class WGradItem(C.Structure):
@@ -53,7 +53,8 @@ class WGradItem(C.Structure):
 
 class WGradDesc(C.Structure):
     _fields_ = [("acts", Act * WGRAD_MAX_ACTS), ("n_acts", C.c_int), ("items", WGradItem * WGRAD_MAX_ITEMS),
-                ("n_items", C.c_int), ("batch", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int)]
+                ("n_items", C.c_int), ("batch", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int),
+                ("pair_x", C.c_int)]
 
 
 class CopyBlock(C.Structure):

@@ -129,9 +129,22 @@ def build_tgemm(acts, segs, w, ntiles, batch, t_begin, t_end, err=None, tag=None
     return out
 
 
-def build_wgrad(acts, items, batch, err=None, tag=None):
+def pair_items(items_by_x):
+    """items_by_x: list of lists; each inner list holds the m-tile items that read the SAME X tile.  Returns a flat list in
+    which items (2i, 2i+1) share their X tile (wgrad pair_x mode: 2-CTA cluster, X multicast); odd groups are padded
+    with a partner that stores nothing (m_valid = 0)."""
+    out = []
+    for grp in items_by_x:
+        grp = list(grp)
+        if len(grp) % 2:
+            grp.append(dict(grp[-1], m_valid=0))
+        out += grp
+    return out
+
+
+def build_wgrad(acts, items, batch, err=None, tag=None, pair=False):
     """Descriptors of one logical wgrad.  items: list of dicts(g_act, x_act, g_row, x_row, m_valid, n_valid, shift, t_lo,
-    t_hi, out, out_off (elements), out_rs, out_cs)."""
+    t_hi, out, out_off (elements), out_rs, out_cs).  pair=True: items come in X-sharing pairs (see pair_items)."""
     sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
     out = []
     for i in range(0, len(items), L.WGRAD_MAX_ITEMS):
@@ -140,21 +153,24 @@ def build_wgrad(acts, items, batch, err=None, tag=None):
         for j, a in enumerate(acts):
             d.acts[j] = a
         d.n_acts = len(acts)
-        target_units = max(1, (5 * sms // 2) // len(chunk))
+        n_work = len(chunk) // 2 if pair else len(chunk)          # clusters (pairs) or CTAs per split
+        target_units = max(1, (5 * (sms // 2 if pair else sms) // 2) // max(1, n_work))
+        min_kb = min(batch * ((it["t_hi"] - it["t_lo"] + 31) // 32) for it in chunk)
+        n_split = max(1, min(target_units, min_kb // 48))         # uniform: split-major unit order (wgrad.cu)
         for j, it in enumerate(chunk):
             w = L.WGradItem()
             w.g_act, w.x_act, w.g_row, w.x_row = it["g_act"], it["x_act"], it["g_row"], it["x_row"]
             w.m_valid, w.n_valid = it["m_valid"], it["n_valid"]
             w.n = max(16, ceil_to(it["n_valid"], 16))
             w.shift, w.t_lo, w.t_hi = it.get("shift", 0), it["t_lo"], it["t_hi"]
-            kblocks = batch * ((it["t_hi"] - it["t_lo"] + 31) // 32)
-            w.n_split = max(1, min(target_units, kblocks // 48))
+            w.n_split = n_split
             w.out = it["out"].data_ptr() + 4 * int(it.get("out_off", 0))
             w.out_rs, w.out_cs = int(it["out_rs"]), int(it["out_cs"])
             d.items[j] = w
         d.n_items = len(chunk)
         d.batch = int(batch)
         d.err = err.data_ptr() if err is not None else None
+        d.pair_x = 1 if pair else 0
         out.append(("wgrad", d, tag))
     return out
 
@@ -464,37 +480,39 @@ class StackPlan:
             x0_act = act_of(self.xs[l], T0) if needs_dup(d) else act_of(x, T0)
             acts = [act_of(gfg, T0), x0_act, act_of(x, T0), act_of(self.cond, T0)]
             sh0 = 0 if needs_dup(d) else -d
-            items = []
-            for h, key in ((0, "conv_signal.weight"), (1, "conv_gate.weight")):
-                dw = v[key]
-                for i in range((D + 127) // 128):
-                    mv = min(128, D - 128 * i)
-                    base = dict(g_act=0, g_row=h * D + 128 * i, m_valid=mv, t_lo=lo4, t_hi=T0)
-                    for (c0, n) in chunks(R):
-                        items.append(dict(base, x_act=1, x_row=c0, n_valid=n, shift=sh0, out=dw,
-                                          out_off=(128 * i) * R * 2 + c0 * 2 + 0, out_rs=2 * R, out_cs=2))
-                        items.append(dict(base, x_act=2, x_row=c0, n_valid=n, shift=0, out=dw,
-                                          out_off=(128 * i) * R * 2 + c0 * 2 + 1, out_rs=2 * R, out_cs=2))
-                    for (c0, n) in chunks(Cc + 1):
-                        items.append(dict(base, x_act=3, x_row=c0, n_valid=n, shift=0, out=v["dpb"],
-                                          out_off=(h * D + 128 * i) * (Cc + 1) + c0, out_rs=Cc + 1, out_cs=1))
-            launches += build_wgrad(acts, items, B, self.err, tag=f"wgrad1.{l}")
+            mtiles = [(h, i) for h in (0, 1) for i in range((D + 127) // 128)]
+            keys = ("conv_signal.weight", "conv_gate.weight")
+
+            def g_item(h, i):
+                return dict(g_act=0, g_row=h * D + 128 * i, m_valid=min(128, D - 128 * i), t_lo=lo4, t_hi=T0)
+
+            groups = []
+            for (c0, n) in chunks(R):
+                for tap, (xa, sh) in enumerate(((1, sh0), (2, 0))):
+                    groups.append([dict(g_item(h, i), x_act=xa, x_row=c0, n_valid=n, shift=sh, out=v[keys[h]],
+                                        out_off=(128 * i) * R * 2 + c0 * 2 + tap, out_rs=2 * R, out_cs=2)
+                                   for (h, i) in mtiles])
+            for (c0, n) in chunks(Cc + 1):
+                groups.append([dict(g_item(h, i), x_act=3, x_row=c0, n_valid=n, shift=0, out=v["dpb"],
+                                    out_off=(h * D + 128 * i) * (Cc + 1) + c0, out_rs=Cc + 1, out_cs=1)
+                               for (h, i) in mtiles])
+            items = pair_items(groups)
+            launches += build_wgrad(acts, items, B, self.err, tag=f"wgrad1.{l}", pair=True)
             # (4) dWs = sum g_skp z^T (tau >= RF);  dWr = sum g_sig z^T (tau >= lead_l)
             acts = [act_of(g_skp, T0), act_of(self.z[l], T0)]
-            items = []
-            for i in range((S + 127) // 128):
-                for (c0, n) in chunks(D):
-                    items.append(dict(g_act=0, x_act=1, g_row=128 * i, x_row=c0, m_valid=min(128, S - 128 * i),
-                                      n_valid=n, t_lo=rf4, t_hi=T0, out=v["dil_skp.weight"], out_off=128 * i * D + c0,
-                                      out_rs=D, out_cs=1))
+            groups = []
+            for (c0, n) in chunks(D):
+                groups.append([dict(g_act=0, x_act=1, g_row=128 * i, x_row=c0, m_valid=min(128, S - 128 * i), n_valid=n,
+                                    t_lo=rf4, t_hi=T0, out=v["dil_skp.weight"], out_off=128 * i * D + c0, out_rs=D,
+                                    out_cs=1) for i in range((S + 127) // 128)])
             if not final and g_sig is not None:
                 acts.append(act_of(g_sig, T0))
-                for i in range((R + 127) // 128):
-                    for (c0, n) in chunks(D):
-                        items.append(dict(g_act=2, x_act=1, g_row=128 * i, x_row=c0, m_valid=min(128, R - 128 * i),
-                                          n_valid=n, t_lo=lo4, t_hi=T0, out=v["dil_res.weight"],
-                                          out_off=128 * i * D + c0, out_rs=D, out_cs=1))
-            launches += build_wgrad(acts, items, B, self.err, tag=f"wgrad2.{l}")
+                for (c0, n) in chunks(D):
+                    groups.append([dict(g_act=2, x_act=1, g_row=128 * i, x_row=c0, m_valid=min(128, R - 128 * i),
+                                        n_valid=n, t_lo=lo4, t_hi=T0, out=v["dil_res.weight"], out_off=128 * i * D + c0,
+                                        out_rs=D, out_cs=1) for i in range((R + 127) // 128)])
+            items = pair_items(groups)
+            launches += build_wgrad(acts, items, B, self.err, tag=f"wgrad2.{l}", pair=True)
             g_sig = gx
         bw["launches"] = launches
         bw["gx0"] = g_sig

@@ -201,6 +201,8 @@ static int test_layer(bool ints, double tol, int variant = 0) {
   if (variant == 1) { d.n_ntiles = 1; }                       // only the 256-wide tile
   if (variant == 2) { d.ntiles[0] = d.ntiles[1]; d.n_ntiles = 1; }  // only the 112-wide tile
   if (variant == 3) { d.n_segs = 1; d.ntiles[0].seg_mask = 1; d.ntiles[1].seg_mask = 1; }
+  const bool tma = variant == 4;   // TMA-store epilogue: rows of the first active tile below t_lo receive zeros
+  d.no_tma_store = tma ? 0 : 1;
   d.batch = B;
   d.t_begin = 32;
   d.t_end = T;
@@ -225,7 +227,7 @@ static int test_layer(bool ints, double tol, int variant = 0) {
         double ref;
         const float prev = out0[((size_t)b * N + n) * out.pitch + t];
         if (n < 256) {
-          if (t < t_lo) ref = prev;
+          if (t < t_lo) ref = (tma && t >= 32) ? 0.0 : prev;
           else {
             double acc = bias[n] + add.at(b, n, t);
             for (int k = 0; k < R; ++k)
@@ -249,7 +251,7 @@ static int test_layer(bool ints, double tol, int variant = 0) {
           ++bad;
         }
       }
-  printf("  layer ints=%d: max|err|=%g device_err=%d -> %s\n", (int)ints, maxerr, derr,
+  printf("  layer ints=%d variant=%d: max|err|=%g device_err=%d -> %s\n", (int)ints, variant, maxerr, derr,
          (maxerr <= tol && derr == 0) ? "PASS" : "FAIL");
   return (maxerr <= tol && derr == 0) ? 0 : 1;
 }
@@ -574,7 +576,7 @@ int main(int argc, char** argv) {
     CK(cudaMemset(g_err, 0, 4));
     const char* t = argv[1];
     if (!strcmp(t, "shift")) { g_shift = atoi(argv[2]); return test_basic(0, 0, true, 1e-3); }
-    if (!strcmp(t, "layer")) return test_layer(true, 1e-3);
+    if (!strcmp(t, "layer")) return test_layer(true, 1e-3) + test_layer(true, 1e-3, 4) + test_layer(false, 5e-2, 4);
     if (!strcmp(t, "layer1")) { test_layer(true, 1e9, 1); return 0; }
     if (!strcmp(t, "layer2")) { test_layer(true, 1e9, 2); return 0; }
     if (!strcmp(t, "layer3")) { test_layer(true, 1e9, 3); return 0; }

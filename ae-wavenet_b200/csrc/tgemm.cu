@@ -25,7 +25,8 @@ constexpr int TG_WBOX_BYTES = 128 * TG_BK * 4;  // 16 KB per 128-row W box
 constexpr int TG_STAGE_BYTES = TG_A_BYTES + 2 * TG_WBOX_BYTES;  // 48 KB
 constexpr int TG_THREADS = 384;
 constexpr int TG_EPI_WARPS = 8;
-constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+constexpr int TG_STG_BYTES = TG_EPI_WARPS * 4096;  // one 32 ch x 32 t fp32 staging tile per epilogue warp (TMA stores)
+constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + TG_STG_BYTES + 256 + 1024;  // + barriers + alignment slack
 
 struct TgSeg {
   int map;
@@ -48,6 +49,11 @@ struct TgParams {
   uint32_t a_lbo, a_sbo;
   int cluster;   // 1, 2 or 4: CTAs of a cluster work on adjacent time tiles of the same (batch, n-tile) and share W
   int n_tgroups; // ceil(n_ttiles / cluster)
+  // Output maps for the TMA-store epilogue: o_map[tile][0] covers `out` (for GATE_BWD: the whole g_f;g_g tensor),
+  // [1] `out2`, [2] `out3`.  o_tma[tile] != 0 when the tile's main outputs go through TMA (see tma_eligible()).
+  CUtensorMap o_map[AEWN_MAX_NTILES][3];
+  int o_tma[AEWN_MAX_NTILES];
+  int gg_ch_off[AEWN_MAX_NTILES];  // GATE_BWD: channel offset of g_gate inside the g_f;g_g tensor
 };
 
 struct TgItem {
@@ -74,241 +80,413 @@ __device__ __forceinline__ TgItem tg_decode(const TgParams& p, int item, int cra
 // ------------------------------------------------------------------------------------------------ epilogues
 // Common conventions: lane = time step tau; stores happen for tau in [t_lo, t_hi); values for tau < t_zero_lo are
 // forced to 0 so that the aligned-down margin of every tensor stays finite (TMA reads it, 0 * garbage must be 0).
-// Addend / accumulate source of a LINEAR tile, software-pipelined: the loads of column chunk i+1 are issued before
-// chunk i is processed, and those of the first chunk BEFORE the epilogue waits for the accumulator, so the global
-// load latency hides behind the MMAs instead of stalling each chunk (GEMM2 of a GRCC layer is epilogue-bound).
-struct LinSrc {
-  const float* p;   // element (b, first channel of tile, tau [+ toff])
-  long long cs;
-  bool ok;          // this lane may load
-  bool is_add;      // true: `add` operand (or mask);  false: previous value of `out` (accumulate)
+//
+// Instruction economy matters here (the LINEAR / GATE_BWD tiles have little MMA work to hide behind): every n-tile field
+// the inner loops need is copied into registers ONCE per item (the descriptor lives in the kernel parameter space and
+// is selected by a runtime index, so touching it per element costs a constant-bank load + 64-bit address rebuild
+// each time -- measured 35 instructions per stored element), row pointers advance by the channel stride, stores are
+// predicated rather than branched, and fully valid 32-column chunks take a path with no per-column bounds test.
+
+// ---- TMA-store staging ---------------------------------------------------------------------------------------------
+// Each epilogue warp owns one 4 KB tile [32 channels][32 time steps].  Lane = time step, so element (j, lane) sits at
+// j*128 + lane*4 bytes: bank-conflict free, and the offsets are compile-time immediates (one STS per element, no
+// address arithmetic).  After a proxy fence one lane issues a TMA store (or reduce-add) of the box; rows outside the
+// tensor extents (time >= t_hi, channel >= n_valid) are clipped by the hardware.  Rows of a partially active tile
+// that lie below t_lo are written as zeros (stores) / add zero (reduce) -- by construction those positions are
+// margins that hold zeros anyway.
+struct StgOut {
+  float* tile;       // this warp's staging tile
+  int t0;            // first time step of this warp's 32-row slab (tile origin + 32*q), output coordinates
+  int b;
+  int lane;
+  bool slab_on;      // slab intersects [t_lo, t_hi)
+};
+
+__device__ __forceinline__ void stg_acquire(const StgOut& so) {
+  if (so.lane == 0) tma_store_wait_read();   // the previous box of this warp has been read out of the tile
+  __syncwarp();
+}
+__device__ __forceinline__ void stg_flush(const StgOut& so, const CUtensorMap* map, int c0, bool reduce) {
+  fence_proxy_async_smem();                  // make this lane's generic-proxy writes visible to the async proxy
+  __syncwarp();
+  if (so.lane == 0) {
+    if (reduce) tma_reduce_add_3d(map, so.tile, so.t0, c0, so.b);
+    else tma_store_3d(map, so.tile, so.t0, c0, so.b);
+    tma_store_commit();
+  }
+}
+
+// ---- LINEAR -------------------------------------------------------------------------------------------------------
+struct LinRegs {
+  const CUtensorMap* omap;   // non-null: `out` goes through the TMA-store path
+  bool tma_reduce;
+  float* outp;         // (b, tile channel 0, tau + out_toff)
+  float* dupp;         // dup store row or nullptr
+  float* out3p;        // relu(pre) row or nullptr
+  const float* srcp;   // prefetch source row (addend, mask source, or previous output) or nullptr
+  const float* bias;
+  long long out_cs, src_cs;
+  int n, n_valid;
   float fill;
+  bool in_range, live, src_ok, src_is_add, accum, relu, relu_first, maskpos, count;
 };
 
-__device__ __forceinline__ LinSrc lin_src(const aewn_ntile& nt, int b, int tau) {
-  LinSrc s;
-  const bool in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
+__device__ __forceinline__ LinRegs lin_regs(const aewn_ntile& nt, int b, int tau, const CUtensorMap* omap) {
+  LinRegs c;
+  c.omap = omap;
+  c.tma_reduce = omap && (nt.flags & AEWN_F_ACCUM);
+  c.in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
+  c.live = tau >= nt.t_zero_lo;
+  c.out_cs = nt.out_cs;
+  c.outp = nt.out + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
+  const int dup_t = tau + nt.dup_toff;
+  const bool dup_ok = nt.out2 && c.in_range && dup_t >= 0 && dup_t < nt.dup_t_hi;
+  c.dupp = dup_ok ? nt.out2 + static_cast<long long>(b) * nt.out_bs + dup_t : nullptr;
+  c.relu_first = (nt.flags & AEWN_F_RELU_FIRST) != 0;
+  c.out3p = (c.relu_first && nt.out3) ? nt.out3 + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff) : nullptr;
+  c.accum = (nt.flags & AEWN_F_ACCUM) != 0;
+  c.relu = (nt.flags & AEWN_F_RELU) != 0;
+  c.maskpos = (nt.flags & AEWN_F_MASKPOS) != 0;
+  c.count = nt.zero_count != nullptr;
+  c.bias = nt.bias;
+  c.n = nt.n;
+  c.n_valid = nt.n_valid;
   if (nt.add) {
-    s.p = nt.add + static_cast<long long>(b) * nt.add_bs + (tau + nt.add_toff);
-    s.cs = nt.add_cs;
-    s.ok = in_range && tau >= nt.t_zero_lo && tau >= nt.add_t_lo;
-    s.is_add = true;
-    s.fill = (nt.flags & AEWN_F_MASKPOS) ? 1.0f : 0.0f;
-  } else if (nt.flags & AEWN_F_ACCUM) {
-    s.p = nt.out + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
-    s.cs = nt.out_cs;
-    s.ok = in_range;
-    s.is_add = false;
-    s.fill = 0.0f;
+    c.srcp = nt.add + static_cast<long long>(b) * nt.add_bs + (tau + nt.add_toff);
+    c.src_cs = nt.add_cs;
+    c.src_ok = c.in_range && c.live && tau >= nt.add_t_lo;
+    c.src_is_add = true;
+    c.fill = c.maskpos ? 1.0f : 0.0f;
+  } else if (c.accum && !c.tma_reduce) {
+    c.srcp = c.outp;
+    c.src_cs = nt.out_cs;
+    c.src_ok = c.in_range;
+    c.src_is_add = false;
+    c.fill = 0.0f;
   } else {
-    s.p = nullptr;
-    s.cs = 0;
-    s.ok = false;
-    s.is_add = false;
-    s.fill = 0.0f;
+    c.srcp = nullptr;
+    c.src_cs = 0;
+    c.src_ok = false;
+    c.src_is_add = false;
+    c.fill = 0.0f;
   }
-  return s;
+  return c;
 }
 
-__device__ __forceinline__ void lin_issue(const LinSrc& s, int n_valid, int c0, float (&a)[32]) {
+// Issue the 32 loads of one column chunk of the prefetch source (select, not branch: all 32 go out back to back).
+__device__ __forceinline__ void lin_issue(const LinRegs& c, int c0, float (&a)[32]) {
+  const float* q = c.srcp + static_cast<long long>(c0) * c.src_cs;
+  const int nrem = c.n_valid - c0;
+  if (nrem >= 32) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float* q = s.p + static_cast<long long>(c0 + j) * s.cs;
-    a[j] = (s.ok && c0 + j < n_valid) ? (s.is_add ? __ldg(q) : __ldcg(q)) : s.fill;
+    for (int j = 0; j < 32; ++j) {
+      a[j] = c.src_ok ? __ldcg(q) : c.fill;
+      q += c.src_cs;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      a[j] = (c.src_ok && j < nrem) ? __ldcg(q) : c.fill;
+      q += c.src_cs;
+    }
   }
 }
 
-struct LinCtx {
-  bool in_range, live, accum, relu, relu_first, maskpos, both, dup_ok;
-  float* outp;
-  float* dupp;
-};
-
-// One 32-column chunk of a LINEAR tile.  `buf` holds the prefetched addend / previous-output values of this chunk.
-__device__ __forceinline__ void lin_chunk(const aewn_ntile& nt, const LinCtx& cx, const LinSrc& src, uint32_t taddr, int c0,
-                                          int b, int tau, const float (&buf)[32], unsigned int& zeros) {
+template <bool FULL>
+__device__ __forceinline__ void lin_chunk(const LinRegs& c, const StgOut& so, uint32_t taddr, int c0,
+                                          const float (&buf)[32], unsigned int& zeros) {
   uint32_t v[32];
   tmem_ld32(taddr + c0, v);
   tmem_ld_wait();
-  if (c0 >= nt.n_valid) return;
+  const int nrem = c.n_valid - c0;
+  if (nrem <= 0) return;
   float r[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
-  if (nt.bias) {
+  if (c.bias) {
+    const float* bp = c.bias + c0;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (c0 + j < nt.n_valid) r[j] += __ldg(nt.bias + c0 + j);
+      if (FULL || j < nrem) r[j] += __ldg(bp + j);
   }
-  if (cx.relu_first) {
+  if (c.relu_first) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.0f);
-    if (nt.out3) {  // keep relu(pre) so the backward pass has the exact activation mask (wave_encoder.py:39)
-      float* o3 = nt.out3 + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
+    if (c.out3p) {  // keep relu(pre): exact activation mask for the backward pass (wave_encoder.py:39)
+      float* o3 = c.out3p + static_cast<long long>(c0) * c.out_cs;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (cx.in_range && c0 + j < nt.n_valid) o3[static_cast<long long>(c0 + j) * nt.out_cs] = cx.live ? r[j] : 0.0f;
+      for (int j = 0; j < 32; ++j) {
+        if (c.in_range && (FULL || j < nrem)) *o3 = c.live ? r[j] : 0.0f;
+        o3 += c.out_cs;
+      }
     }
   }
-  if (src.p && src.is_add) {
+  if (c.srcp && c.src_is_add) {
+    if (c.maskpos) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] = cx.maskpos ? (buf[j] > 0.0f ? r[j] : 0.0f) : r[j] + buf[j];
-  }
-  if (!cx.live) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] = 0.0f;
-  }
-  if (cx.accum) {
-    if (cx.both) {
-      float prev[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        prev[j] = (cx.in_range && c0 + j < nt.n_valid) ? __ldcg(cx.outp + static_cast<long long>(c0 + j) * nt.out_cs) : 0.0f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] += prev[j];
+      for (int j = 0; j < 32; ++j) r[j] = buf[j] > 0.0f ? r[j] : 0.0f;
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) r[j] += buf[j];
     }
   }
+  if (!c.live) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    if (cx.in_range && c0 + j < nt.n_valid) {
-      float x = r[j];
-      if (cx.relu) x = fmaxf(x, 0.0f);
-      cx.outp[static_cast<long long>(c0 + j) * nt.out_cs] = x;
-      if (cx.dup_ok) cx.dupp[static_cast<long long>(c0 + j) * nt.out_cs] = x;
-      zeros += (x == 0.0f) ? 1u : 0u;
+    for (int j = 0; j < 32; ++j) r[j] = 0.0f;
+  }
+  if (c.accum && !c.tma_reduce) {   // (an n-tile has either an addend or the accumulate flag, never both)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] += buf[j];
+  }
+  if (c.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.0f);
+  }
+  if (c.omap) {
+    if (so.slab_on) {
+      stg_acquire(so);
+      float* st = so.tile + so.lane;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) st[j * 32] = c.in_range ? r[j] : 0.0f;
+      stg_flush(so, c.omap, c0, c.tma_reduce);
+    }
+  } else {
+    float* o = c.outp + static_cast<long long>(c0) * c.out_cs;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (c.in_range && (FULL || j < nrem)) *o = r[j];
+      o += c.out_cs;
     }
   }
+  if (c.dupp) {
+    float* d = c.dupp + static_cast<long long>(c0) * c.out_cs;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (FULL || j < nrem) *d = r[j];
+      d += c.out_cs;
+    }
+  }
+  if (c.count && c.in_range) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) zeros += ((FULL || j < nrem) && r[j] == 0.0f) ? 1u : 0u;
+  }
+}
+
+__device__ __forceinline__ void lin_chunk_any(const LinRegs& c, const StgOut& so, uint32_t taddr, int c0,
+                                              const float (&buf)[32], unsigned int& zeros) {
+  if (c.n_valid - c0 >= 32) lin_chunk<true>(c, so, taddr, c0, buf, zeros);
+  else lin_chunk<false>(c, so, taddr, c0, buf, zeros);
 }
 
 // LINEAR epilogue of one tile.  Column chunks c0 = 32*half + 64*i; chunk i uses buffer A (i even) or B (i odd), and
 // as soon as a buffer is consumed the loads of chunk i+2 are issued into it: two chunks (2 x 32 x 128 B per warp) stay
-// in flight, the first two are issued by the caller BEFORE it waits for the accumulator.
-__device__ __forceinline__ void epi_linear(const aewn_ntile& nt, uint32_t taddr, int half, int b, int tau,
-                                           const LinSrc& src, float (&bufA)[32], float (&bufB)[32]) {
-  LinCtx cx;
-  cx.in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
-  cx.live = tau >= nt.t_zero_lo;
-  cx.outp = nt.out + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
-  const int dup_t = tau + nt.dup_toff;
-  cx.dup_ok = nt.out2 && cx.in_range && dup_t >= 0 && dup_t < nt.dup_t_hi;
-  cx.dupp = nt.out2 ? nt.out2 + static_cast<long long>(b) * nt.out_bs + dup_t : nullptr;
-  cx.accum = (nt.flags & AEWN_F_ACCUM) != 0;
-  cx.relu = (nt.flags & AEWN_F_RELU) != 0;
-  cx.relu_first = (nt.flags & AEWN_F_RELU_FIRST) != 0;
-  cx.maskpos = (nt.flags & AEWN_F_MASKPOS) != 0;
-  cx.both = nt.add && cx.accum;  // rare: addend prefetched, previous value loaded inline
+// in flight; the first two are issued by the caller BEFORE it waits for the accumulator.
+__device__ __forceinline__ void epi_linear(const LinRegs& c, const StgOut& so, uint32_t taddr, int half,
+                                           float (&bufA)[32], float (&bufB)[32], unsigned long long* zero_count) {
   unsigned int zeros = 0;
-  for (int c0 = half * 32; c0 < nt.n; c0 += 128) {
-    lin_chunk(nt, cx, src, taddr, c0, b, tau, bufA, zeros);
-    if (src.p && c0 + 128 < nt.n && c0 + 128 < nt.n_valid) lin_issue(src, nt.n_valid, c0 + 128, bufA);
-    if (c0 + 64 < nt.n) {
-      lin_chunk(nt, cx, src, taddr, c0 + 64, b, tau, bufB, zeros);
-      if (src.p && c0 + 192 < nt.n && c0 + 192 < nt.n_valid) lin_issue(src, nt.n_valid, c0 + 192, bufB);
+  for (int c0 = half * 32; c0 < c.n; c0 += 128) {
+    lin_chunk_any(c, so, taddr, c0, bufA, zeros);
+    if (c.srcp && c0 + 128 < c.n_valid) lin_issue(c, c0 + 128, bufA);
+    if (c0 + 64 < c.n) {
+      lin_chunk_any(c, so, taddr, c0 + 64, bufB, zeros);
+      if (c.srcp && c0 + 192 < c.n_valid) lin_issue(c, c0 + 192, bufB);
     }
   }
-  if (nt.zero_count) {
+  if (c.count) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
-    if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(nt.zero_count, static_cast<unsigned long long>(zeros));
+    if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(zero_count, static_cast<unsigned long long>(zeros));
   }
 }
 
+// ---- GATE_FWD -----------------------------------------------------------------------------------------------------
 // wavenet.py:102  z = tanh(filt) * sigmoid(gate); columns [0,128) = filt, [128,256) = gate of the same channels.
-__device__ __forceinline__ void epi_gate_fwd(const aewn_ntile& nt, uint32_t taddr, int half, int b, int tau) {
+__device__ __forceinline__ void epi_gate_fwd(const aewn_ntile& nt, const StgOut& so, const CUtensorMap* omaps,
+                                             uint32_t taddr, int half, int b, int tau) {
   const bool in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
   const bool live = tau >= nt.t_zero_lo;
+  const long long cs = nt.out_cs;
   const long long off = static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
+  float* const th_base = nt.out ? nt.out + off : nullptr;
+  float* const sg_base = nt.out2 ? nt.out2 + off : nullptr;
+  float* const z_base = nt.out3 + off;
+  const float* const bias = nt.bias;
+  const int n_valid = nt.n_valid;
   for (int c0 = half * 32; c0 < 128; c0 += 64) {
     uint32_t vf[32], vg[32];
     tmem_ld32(taddr + c0, vf);
     tmem_ld32(taddr + 128 + c0, vg);
     tmem_ld_wait();
+    const int nrem = n_valid - c0;
+    if (nrem <= 0) continue;
+    float th[32], sg[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float f = __uint_as_float(vf[j]);
       float g = __uint_as_float(vg[j]);
-      if (nt.bias) {
-        f += __ldg(nt.bias + c0 + j);
-        g += __ldg(nt.bias + 128 + c0 + j);
+      if (bias) {
+        f += __ldg(bias + c0 + j);
+        g += __ldg(bias + 128 + c0 + j);
       }
-      const float th = live ? fast_tanh(f) : 0.0f;
-      const float sg = live ? fast_sigmoid(g) : 0.0f;
-      if (in_range && c0 + j < nt.n_valid) {
-        const long long o = off + static_cast<long long>(c0 + j) * nt.out_cs;
-        if (nt.out) nt.out[o] = th;
-        if (nt.out2) nt.out2[o] = sg;
-        nt.out3[o] = th * sg;
+      th[j] = live ? fast_tanh(f) : 0.0f;
+      sg[j] = live ? fast_sigmoid(g) : 0.0f;
+    }
+    if (omaps) {   // TMA-store path: tanh, sigmoid, z through the warp's staging tile, one box each
+      if (so.slab_on) {
+        float* st = so.tile + so.lane;
+        if (th_base) {
+          stg_acquire(so);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st[j * 32] = in_range ? th[j] : 0.0f;
+          stg_flush(so, &omaps[0], c0, false);
+        }
+        if (sg_base) {
+          stg_acquire(so);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st[j * 32] = in_range ? sg[j] : 0.0f;
+          stg_flush(so, &omaps[1], c0, false);
+        }
+        stg_acquire(so);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[j * 32] = in_range ? th[j] * sg[j] : 0.0f;
+        stg_flush(so, &omaps[2], c0, false);
       }
+      continue;
+    }
+    const long long o0 = static_cast<long long>(c0) * cs;
+    if (th_base) {
+      float* o = th_base + o0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (in_range && j < nrem) *o = th[j];
+        o += cs;
+      }
+    }
+    if (sg_base) {
+      float* o = sg_base + o0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (in_range && j < nrem) *o = sg[j];
+        o += cs;
+      }
+    }
+    float* o = z_base + o0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (in_range && j < nrem) *o = th[j] * sg[j];
+      o += cs;
     }
   }
 }
 
+// ---- GATE_BWD -----------------------------------------------------------------------------------------------------
 // g_f = g_z * sg * (1 - th^2), g_g = g_z * th * sg * (1 - sg); acc columns = g_z of all D channels.
 struct GateBwdCtx {
-  bool in_range, live, dup_ok;
-  long long ooff, aoff, doff, g_delta;
+  const CUtensorMap* omap;   // non-null: g_f / g_g go through the TMA-store path (map over the whole g_f;g_g tensor)
+  int gg_ch_off;
+  const float* thp;   // (b, channel 0, tau + add_toff)
+  const float* sgp;
+  float* gfp;         // (b, channel 0, tau + out_toff)
+  float* dupp;        // dup row of g_f or nullptr
+  long long add_cs, out_cs, g_delta;
+  int n, n_valid;
+  bool in_range, live;
 };
 
-__device__ __forceinline__ void gbwd_issue(const aewn_ntile& nt, const GateBwdCtx& cx, int c0, float (&th)[32],
-                                           float (&sg)[32]) {
+__device__ __forceinline__ GateBwdCtx gbwd_ctx(const aewn_ntile& nt, int b, int tau, const CUtensorMap* omap,
+                                               int gg_ch_off) {
+  GateBwdCtx cx;
+  cx.omap = omap;
+  cx.gg_ch_off = gg_ch_off;
+  cx.in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
+  cx.live = tau >= nt.t_zero_lo;
+  const long long aoff = static_cast<long long>(b) * nt.add_bs + (tau + nt.add_toff);
+  cx.thp = nt.add + aoff;
+  cx.sgp = nt.add2 + aoff;
+  cx.gfp = nt.out + static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
+  const int dup_t = tau + nt.dup_toff;
+  const bool dup_ok = nt.out3 && cx.in_range && dup_t >= 0 && dup_t < nt.dup_t_hi;
+  cx.dupp = dup_ok ? nt.out3 + static_cast<long long>(b) * nt.out_bs + dup_t : nullptr;
+  cx.g_delta = nt.out2 - nt.out;  // g_gate rows follow g_filt rows in the same tensor
+  cx.add_cs = nt.add_cs;
+  cx.out_cs = nt.out_cs;
+  cx.n = nt.n;
+  cx.n_valid = nt.n_valid;
+  return cx;
+}
+
+__device__ __forceinline__ void gbwd_issue(const GateBwdCtx& cx, int c0, float (&th)[32], float (&sg)[32]) {
+  const float* pt = cx.thp + static_cast<long long>(c0) * cx.add_cs;
+  const float* ps = cx.sgp + static_cast<long long>(c0) * cx.add_cs;
+  const int nrem = cx.n_valid - c0;
+  const bool ok = cx.in_range && cx.live;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const bool ok = cx.in_range && cx.live && (c0 + j < nt.n_valid);
-    th[j] = ok ? __ldg(nt.add + cx.aoff + static_cast<long long>(c0 + j) * nt.add_cs) : 0.0f;
-    sg[j] = ok ? __ldg(nt.add2 + cx.aoff + static_cast<long long>(c0 + j) * nt.add_cs) : 0.0f;
+    th[j] = (ok && j < nrem) ? __ldcg(pt) : 0.0f;
+    sg[j] = (ok && j < nrem) ? __ldcg(ps) : 0.0f;
+    pt += cx.add_cs;
+    ps += cx.add_cs;
   }
 }
 
-__device__ __forceinline__ void gbwd_chunk(const aewn_ntile& nt, const GateBwdCtx& cx, uint32_t taddr, int c0,
+__device__ __forceinline__ void gbwd_chunk(const GateBwdCtx& cx, const StgOut& so, uint32_t taddr, int c0,
                                            const float (&th)[32], const float (&sg)[32]) {
   uint32_t v[32];
   tmem_ld32(taddr + c0, v);
   tmem_ld_wait();
+  const int nrem = cx.n_valid - c0;
+  if (nrem <= 0) return;
+  if (cx.omap) {   // TMA-store path (tile-uniform: the host disables it for tiles that need the shifted duplicate)
+    if (!so.slab_on) return;
+    float* st = so.tile + so.lane;
+    float gg[32];
+    stg_acquire(so);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float gz = cx.live ? __uint_as_float(v[j]) : 0.0f;   // th, sg are 0 when !live
+      const float gs = gz * sg[j];
+      st[j * 32] = cx.in_range ? gs * (1.0f - th[j] * th[j]) : 0.0f;
+      gg[j] = cx.in_range ? gs * th[j] * (1.0f - sg[j]) : 0.0f;
+    }
+    stg_flush(so, cx.omap, c0, false);
+    stg_acquire(so);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) st[j * 32] = gg[j];
+    stg_flush(so, cx.omap, cx.gg_ch_off + c0, false);
+    return;
+  }
+  float* o = cx.gfp + static_cast<long long>(c0) * cx.out_cs;
+  float* d = cx.dupp ? cx.dupp + static_cast<long long>(c0) * cx.out_cs : nullptr;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    if (cx.in_range && c0 + j < nt.n_valid) {
-      const float gz = cx.live ? __uint_as_float(v[j]) : 0.0f;
-      const float gs = gz * sg[j];
-      const float gf = cx.live ? gs * (1.0f - th[j] * th[j]) : 0.0f;
-      const float gg = cx.live ? gs * th[j] * (1.0f - sg[j]) : 0.0f;
-      const long long o = cx.ooff + static_cast<long long>(c0 + j) * nt.out_cs;
-      nt.out[o] = gf;
-      nt.out2[o] = gg;
-      if (cx.dup_ok) {
-        const long long od = cx.doff + static_cast<long long>(c0 + j) * nt.out_cs;
-        nt.out3[od] = gf;
-        nt.out3[od + cx.g_delta] = gg;
+    const float gz = cx.live ? __uint_as_float(v[j]) : 0.0f;   // th, sg are 0 when !live
+    const float gs = gz * sg[j];
+    const float gf = gs * (1.0f - th[j] * th[j]);
+    const float gg = gs * th[j] * (1.0f - sg[j]);
+    if (cx.in_range && j < nrem) {
+      o[0] = gf;
+      o[cx.g_delta] = gg;
+      if (d) {
+        d[0] = gf;
+        d[cx.g_delta] = gg;
       }
     }
+    o += cx.out_cs;
+    if (d) d += cx.out_cs;
   }
-}
-
-__device__ __forceinline__ GateBwdCtx gbwd_ctx(const aewn_ntile& nt, int b, int tau) {
-  GateBwdCtx cx;
-  cx.in_range = (tau >= nt.t_lo) && (tau < nt.t_hi);
-  cx.live = tau >= nt.t_zero_lo;
-  cx.ooff = static_cast<long long>(b) * nt.out_bs + (tau + nt.out_toff);
-  cx.aoff = static_cast<long long>(b) * nt.add_bs + (tau + nt.add_toff);
-  const int dup_t = tau + nt.dup_toff;
-  cx.dup_ok = nt.out3 && cx.in_range && dup_t >= 0 && dup_t < nt.dup_t_hi;
-  cx.doff = static_cast<long long>(b) * nt.out_bs + dup_t;
-  cx.g_delta = nt.out2 - nt.out;  // g_gate rows follow g_filt rows in the same tensor
-  return cx;
 }
 
 // tanh / sigmoid of the first chunk are loaded by the caller before it waits for the accumulator; those of chunk i+1
 // are issued before chunk i is processed.
-__device__ __forceinline__ void epi_gate_bwd(const aewn_ntile& nt, uint32_t taddr, int half, const GateBwdCtx& cx,
+__device__ __forceinline__ void epi_gate_bwd(const GateBwdCtx& cx, const StgOut& so, uint32_t taddr, int half,
                                              float (&thA)[32], float (&sgA)[32]) {
   float thB[32], sgB[32];
-  for (int c0 = half * 32; c0 < nt.n; c0 += 128) {
-    const bool hasB = c0 + 64 < nt.n;
-    if (hasB) gbwd_issue(nt, cx, c0 + 64, thB, sgB);
-    gbwd_chunk(nt, cx, taddr, c0, thA, sgA);
-    if (c0 + 128 < nt.n) gbwd_issue(nt, cx, c0 + 128, thA, sgA);
-    if (hasB) gbwd_chunk(nt, cx, taddr, c0 + 64, thB, sgB);
+  for (int c0 = half * 32; c0 < cx.n; c0 += 128) {
+    const bool hasB = c0 + 64 < cx.n;
+    if (hasB) gbwd_issue(cx, c0 + 64, thB, sgB);
+    gbwd_chunk(cx, so, taddr, c0, thA, sgA);
+    if (c0 + 128 < cx.n) gbwd_issue(cx, c0 + 128, thA, sgA);
+    if (hasB) gbwd_chunk(cx, so, taddr, c0 + 64, thB, sgB);
   }
 }
 
@@ -318,7 +496,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TG_STAGES * TG_STAGE_BYTES);
+  float* stg_base = reinterpret_cast<float*>(smem + TG_STAGES * TG_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TG_STAGES * TG_STAGE_BYTES + TG_STG_BYTES);
   uint64_t* empty_bar = full_bar + TG_STAGES;
   uint64_t* tfull_bar = empty_bar + TG_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -456,30 +635,52 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
       if (!it.active) continue;
       const aewn_ntile& nt = p.nt[it.ni];
       const int tau = it.tau0 + q * 32 + lane;
-      // issue the first chunk's addend / accumulate loads before waiting for the accumulator
-      LinSrc src;
-      src.p = nullptr;
-      float pre[32], pre2[32];
-      GateBwdCtx gcx;
-      if (nt.mode == AEWN_EPI_LINEAR) {
-        src = lin_src(nt, it.b, tau);
-        if (src.p && half * 32 < nt.n_valid) lin_issue(src, nt.n_valid, half * 32, pre);
-        if (src.p && half * 32 + 64 < nt.n_valid) lin_issue(src, nt.n_valid, half * 32 + 64, pre2);
-      } else if (nt.mode == AEWN_EPI_GATE_BWD) {
-        gcx = gbwd_ctx(nt, it.b, tau);
-        gbwd_issue(nt, gcx, half * 32, pre, pre2);
-      }
-      if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) break;
-      tc_fence_after();
+      // Each mode keeps its own register context (exclusive branches, so the contexts can share registers); the first
+      // chunks' loads (addend / previous output / tanh+sigmoid) are issued BEFORE waiting for the accumulator.
       const uint32_t taddr = tmem_base + acc * 256u + (static_cast<uint32_t>(q * 32) << 16);
-      if (nt.mode == AEWN_EPI_LINEAR) epi_linear(nt, taddr, half, it.b, tau, src, pre, pre2);
-      else if (nt.mode == AEWN_EPI_GATE_FWD) epi_gate_fwd(nt, taddr, half, it.b, tau);
-      else epi_gate_bwd(nt, taddr, half, gcx, pre, pre2);
+      const int mode = nt.mode;
+      const bool use_tma = p.o_tma[it.ni] != 0;
+      StgOut so;
+      so.tile = stg_base + (warp - 4) * 1024;
+      so.lane = lane;
+      so.b = it.b;
+      so.t0 = it.tau0 + q * 32 + nt.out_toff;
+      so.slab_on = (it.tau0 + q * 32 + 32 > nt.t_lo) && (it.tau0 + q * 32 < nt.t_hi);
+      bool ok;
+      if (mode == AEWN_EPI_LINEAR) {
+        const LinRegs lc = lin_regs(nt, it.b, tau, use_tma ? &p.o_map[it.ni][0] : nullptr);
+        float bufA[32], bufB[32];
+        if (lc.srcp && half * 32 < lc.n_valid) lin_issue(lc, half * 32, bufA);
+        if (lc.srcp && half * 32 + 64 < lc.n_valid) lin_issue(lc, half * 32 + 64, bufB);
+        ok = mbar_wait(&tfull_bar[acc], acc_phase, abort_flag);
+        if (ok) {
+          tc_fence_after();
+          epi_linear(lc, so, taddr, half, bufA, bufB, nt.zero_count);
+        }
+      } else if (mode == AEWN_EPI_GATE_BWD) {
+        const GateBwdCtx gcx = gbwd_ctx(nt, it.b, tau, use_tma ? &p.o_map[it.ni][0] : nullptr, p.gg_ch_off[it.ni]);
+        float thA[32], sgA[32];
+        gbwd_issue(gcx, half * 32, thA, sgA);
+        ok = mbar_wait(&tfull_bar[acc], acc_phase, abort_flag);
+        if (ok) {
+          tc_fence_after();
+          epi_gate_bwd(gcx, so, taddr, half, thA, sgA);
+        }
+      } else {
+        ok = mbar_wait(&tfull_bar[acc], acc_phase, abort_flag);
+        if (ok) {
+          tc_fence_after();
+          epi_gate_fwd(nt, so, use_tma ? &p.o_map[it.ni][0] : nullptr, taddr, half, it.b, tau);
+        }
+      }
+      if (!ok) break;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0) tma_store_wait_all();   // bulk stores must have completed before the CTA's smem goes away
+    __syncwarp();
   }
 
   __syncwarp();
@@ -550,6 +751,8 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
     if ((nt.seg_mask & all_mask) == 0) return set_err(AEWN_ERR_INVALID, "tgemm: n-tile %d uses no segment", i);
     if (nt.mode == AEWN_EPI_LINEAR) {
       if (!nt.out) return set_err(AEWN_ERR_INVALID, "tgemm: n-tile %d has no output", i);
+      if (nt.add && (nt.flags & AEWN_F_ACCUM))
+        return set_err(AEWN_ERR_INVALID, "tgemm: n-tile %d: an addend and AEWN_F_ACCUM are mutually exclusive", i);
     } else if (nt.mode == AEWN_EPI_GATE_FWD) {
       if (nt.n != 256 || !nt.out3 || nt.n_valid > 128)
         return set_err(AEWN_ERR_INVALID, "tgemm: GATE_FWD tile %d needs n=256, n_valid<=128 and out3", i);
@@ -563,6 +766,36 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
     if (nt.t_lo < d->t_begin) nt.t_lo = d->t_begin;
     if (nt.t_hi > d->t_end) nt.t_hi = d->t_end;
     p.nt[i] = nt;
+
+    // ---- TMA-store eligibility (otherwise the tile keeps the st.global epilogue)
+    auto aligned = [&](const float* q) { return q && (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const bool geo_ok = !d->no_tma_store && (nt.out_toff & 3) == 0 && (nt.out_cs & 3) == 0 && (nt.out_bs & 3) == 0 &&
+                        nt.t_hi + nt.out_toff > 0;
+    const int t_ext = nt.t_hi + nt.out_toff;
+    p.o_tma[i] = 0;
+    p.gg_ch_off[i] = 0;
+    if (geo_ok && nt.mode == AEWN_EPI_LINEAR && aligned(nt.out) &&
+        !((nt.flags & AEWN_F_ACCUM) && (nt.flags & AEWN_F_RELU))) {
+      int rc2 = encode_out_map(&p.o_map[i][0], nt.out, t_ext, nt.n_valid, d->batch, nt.out_cs, nt.out_bs);
+      if (rc2) return rc2;
+      p.o_tma[i] = 1;
+    } else if (geo_ok && nt.mode == AEWN_EPI_GATE_FWD && aligned(nt.out3) && (!nt.out || aligned(nt.out)) &&
+               (!nt.out2 || aligned(nt.out2))) {
+      float* ptrs[3] = {nt.out, nt.out2, nt.out3};
+      for (int k = 0; k < 3; ++k) {
+        if (!ptrs[k]) continue;
+        int rc2 = encode_out_map(&p.o_map[i][k], ptrs[k], t_ext, nt.n_valid, d->batch, nt.out_cs, nt.out_bs);
+        if (rc2) return rc2;
+      }
+      p.o_tma[i] = 1;
+    } else if (geo_ok && nt.mode == AEWN_EPI_GATE_BWD && aligned(nt.out) && !nt.out3 && (nt.n_valid & 31) == 0 &&
+               nt.out2 > nt.out && ((nt.out2 - nt.out) % nt.out_cs) == 0) {
+      const int off = static_cast<int>((nt.out2 - nt.out) / nt.out_cs);
+      int rc2 = encode_out_map(&p.o_map[i][0], nt.out, t_ext, off + nt.n_valid, d->batch, nt.out_cs, nt.out_bs);
+      if (rc2) return rc2;
+      p.o_tma[i] = 1;
+      p.gg_ch_off[i] = off;
+    }
   }
   p.n_ntiles = d->n_ntiles;
   p.batch = d->batch;

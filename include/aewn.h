@@ -123,6 +123,9 @@ typedef struct {
   int max_ctas;       /* 0 = one per SM */
   int dbg_lbo, dbg_sbo; /* 0 = defaults; descriptor probing only */
   int cluster;        /* CTAs per cluster sharing W by TMA multicast: 0 = default (2), or 1, 2, 4 */
+  int no_tma_store;   /* 1 = force the st.global epilogue (default: tiles whose outputs are 16-byte aligned are written
+                         through shared memory + TMA store / reduce-add; rows of a partially active tile below t_lo
+                         then receive zeros, i.e. the caller's margins must be don't-care or zero) */
 } aewn_tgemm_desc;
 
 int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream);
@@ -139,7 +142,7 @@ int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream);
 typedef struct {
   int g_act, x_act;   /* indices into acts[] */
   int g_row, x_row;   /* first channel row of each operand */
-  int m_valid;        /* rows stored (<= 128) */
+  int m_valid;        /* rows stored (<= 128; 0 = padding partner of a pair, stores nothing) */
   int n;              /* UMMA N: multiple of 16, 16..256 */
   int n_valid;        /* columns stored */
   int shift;          /* X time coordinate = u + shift; multiple of 4 */
@@ -160,6 +163,7 @@ typedef struct {
   int batch;
   int* err;
   int max_ctas;
+  int pair_x;  /* 1: items (2i, 2i+1) share their X tile; they run as a 2-CTA cluster and X is TMA-multicast */
 } aewn_wgrad_desc;
 
 int aewn_wgrad(const aewn_wgrad_desc* d, aewn_stream_t stream);
