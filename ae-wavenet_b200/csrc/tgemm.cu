@@ -436,57 +436,59 @@ __device__ __forceinline__ void gbwd_chunk(const GateBwdCtx& cx, const StgOut& s
   tmem_ld_wait();
   const int nrem = cx.n_valid - c0;
   if (nrem <= 0) return;
-  if (cx.omap) {   // TMA-store path (tile-uniform: the host disables it for tiles that need the shifted duplicate)
-    if (!so.slab_on) return;
-    float* st = so.tile + so.lane;
-    float gg[32];
-    stg_acquire(so);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float gz = cx.live ? __uint_as_float(v[j]) : 0.0f;   // th, sg are 0 when !live
-      const float gs = gz * sg[j];
-      st[j * 32] = cx.in_range ? gs * (1.0f - th[j] * th[j]) : 0.0f;
-      gg[j] = cx.in_range ? gs * th[j] * (1.0f - sg[j]) : 0.0f;
-    }
-    stg_flush(so, cx.omap, c0, false);
-    stg_acquire(so);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) st[j * 32] = gg[j];
-    stg_flush(so, cx.omap, cx.gg_ch_off + c0, false);
-    return;
-  }
-  float* o = cx.gfp + static_cast<long long>(c0) * cx.out_cs;
-  float* d = cx.dupp ? cx.dupp + static_cast<long long>(c0) * cx.out_cs : nullptr;
+  float gf[32], gg[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const float gz = cx.live ? __uint_as_float(v[j]) : 0.0f;   // th, sg are 0 when !live
     const float gs = gz * sg[j];
-    const float gf = gs * (1.0f - th[j] * th[j]);
-    const float gg = gs * th[j] * (1.0f - sg[j]);
-    if (cx.in_range && j < nrem) {
-      o[0] = gf;
-      o[cx.g_delta] = gg;
-      if (d) {
-        d[0] = gf;
-        d[cx.g_delta] = gg;
-      }
+    gf[j] = cx.in_range ? gs * (1.0f - th[j] * th[j]) : 0.0f;
+    gg[j] = cx.in_range ? gs * th[j] * (1.0f - sg[j]) : 0.0f;
+  }
+  if (cx.omap) {   // TMA-store path (tile-uniform decision): g_f box, then g_g box, through the warp's staging tile
+    if (so.slab_on) {
+      float* st = so.tile + so.lane;
+      stg_acquire(so);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) st[j * 32] = gf[j];
+      stg_flush(so, cx.omap, c0, false);
+      stg_acquire(so);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) st[j * 32] = gg[j];
+      stg_flush(so, cx.omap, cx.gg_ch_off + c0, false);
     }
-    o += cx.out_cs;
-    if (d) d += cx.out_cs;
+  } else {
+    float* o = cx.gfp + static_cast<long long>(c0) * cx.out_cs;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (cx.in_range && j < nrem) {
+        o[0] = gf[j];
+        o[cx.g_delta] = gg[j];
+      }
+      o += cx.out_cs;
+    }
+  }
+  if (cx.dupp) {   // shifted duplicate for a dilation-1/2 data-gradient tap: plain stores (unaligned time origin)
+    float* d = cx.dupp + static_cast<long long>(c0) * cx.out_cs;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < nrem) {
+        d[0] = gf[j];
+        d[cx.g_delta] = gg[j];
+      }
+      d += cx.out_cs;
+    }
   }
 }
 
-// tanh / sigmoid of the first chunk are loaded by the caller before it waits for the accumulator; those of chunk i+1
-// are issued before chunk i is processed.
+// tanh / sigmoid of the first chunk are loaded by the caller before it waits for the accumulator; later chunks load
+// theirs right after the TMEM read is issued (a deeper software pipeline costs 64 more registers and spilled).
 __device__ __forceinline__ void epi_gate_bwd(const GateBwdCtx& cx, const StgOut& so, uint32_t taddr, int half,
-                                             float (&thA)[32], float (&sgA)[32]) {
-  float thB[32], sgB[32];
-  for (int c0 = half * 32; c0 < cx.n; c0 += 128) {
-    const bool hasB = c0 + 64 < cx.n;
-    if (hasB) gbwd_issue(cx, c0 + 64, thB, sgB);
-    gbwd_chunk(cx, so, taddr, c0, thA, sgA);
-    if (c0 + 128 < cx.n) gbwd_issue(cx, c0 + 128, thA, sgA);
-    if (hasB) gbwd_chunk(cx, so, taddr, c0 + 64, thB, sgB);
+                                             float (&th)[32], float (&sg)[32]) {
+  bool first = true;
+  for (int c0 = half * 32; c0 < cx.n; c0 += 64) {
+    if (!first) gbwd_issue(cx, c0, th, sg);
+    first = false;
+    gbwd_chunk(cx, so, taddr, c0, th, sg);
   }
 }
 
@@ -788,7 +790,7 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
         if (rc2) return rc2;
       }
       p.o_tma[i] = 1;
-    } else if (geo_ok && nt.mode == AEWN_EPI_GATE_BWD && aligned(nt.out) && !nt.out3 && (nt.n_valid & 31) == 0 &&
+    } else if (geo_ok && nt.mode == AEWN_EPI_GATE_BWD && aligned(nt.out) && (nt.n_valid & 31) == 0 &&
                nt.out2 > nt.out && ((nt.out2 - nt.out) % nt.out_cs) == 0) {
       const int off = static_cast<int>((nt.out2 - nt.out) / nt.out_cs);
       int rc2 = encode_out_map(&p.o_map[i][0], nt.out, t_ext, off + nt.n_valid, d->batch, nt.out_cs, nt.out_bs);
