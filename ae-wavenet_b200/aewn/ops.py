@@ -154,9 +154,19 @@ def build_wgrad(acts, items, batch, err=None, tag=None, pair=False):
             d.acts[j] = a
         d.n_acts = len(acts)
         n_work = len(chunk) // 2 if pair else len(chunk)          # clusters (pairs) or CTAs per split
-        target_units = max(1, (5 * (sms // 2 if pair else sms) // 2) // max(1, n_work))
+        n_slots = sms // 2 if pair else sms                        # clusters / CTAs resident at once
         min_kb = min(batch * ((it["t_hi"] - it["t_lo"] + 31) // 32) for it in chunk)
-        n_split = max(1, min(target_units, min_kb // 48))         # uniform: split-major unit order (wgrad.cu)
+        # split-K factor: fill whole waves of the persistent grid (units = n_work * n_split), keep >= 48 K blocks per
+        # unit so the fp32 atomics of the epilogue stay a small fraction, prefer ~2 waves (epilogue/MMA overlap)
+        best, n_split = -1.0, 1
+        for cand in range(1, max(1, min_kb // 48) + 1):
+            units = n_work * cand
+            waves = -(-units // n_slots)
+            if waves > 3:
+                break
+            eff = units / (waves * n_slots) - (0.03 if waves == 1 else 0.0)
+            if eff > best + 1e-9:
+                best, n_split = eff, cand
         for j, it in enumerate(chunk):
             w = L.WGradItem()
             w.g_act, w.x_act, w.g_row, w.x_row = it["g_act"], it["x_act"], it["g_row"], it["x_row"]

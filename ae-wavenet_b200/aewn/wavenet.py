@@ -428,16 +428,53 @@ class _DecoderCoreFn(torch.autograd.Function):
         return (None, g_cond[:, :, :T0].clone(), None, None, d_base.reshape(ctx.base_shape), d_bias) + wgrads
 
 
+class _NLLFn(torch.autograd.Function):
+    """-mean log_softmax(pred)[target] with the log-softmax, gather, mean and their backward fused into two kernels."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        B, Q, N = pred.shape
+        p = pred.detach()
+        if p.stride(2) != 1:
+            p = p.contiguous()
+        tg = target.detach().float()
+        if tg.stride(1) != 1:
+            tg = tg.contiguous()
+        lse = torch.empty(B, N, device=p.device)
+        loss_sum = torch.empty(1, device=p.device)
+        err = ops.err_word(p.device)
+        L.check(L.lib().aewn_nll_fwd(
+            L.C.c_void_p(p.data_ptr()), L.C.c_longlong(p.stride(0)), L.C.c_longlong(p.stride(1)),
+            L.C.c_void_p(tg.data_ptr()), L.C.c_longlong(tg.stride(0)), L.C.c_void_p(lse.data_ptr()),
+            L.C.c_void_p(loss_sum.data_ptr()), L.C.c_int(B), L.C.c_int(Q), L.C.c_int(N), L.C.c_void_p(err.data_ptr()),
+            ops._stream()), "aewn_nll_fwd")
+        ctx.save_for_backward(p, tg, lse)
+        return (loss_sum / float(B * N)).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        p, tg, lse = ctx.saved_tensors
+        B, Q, N = p.shape
+        gx = torch.empty(B, Q, N, device=p.device)
+        gl = g.detach().float().reshape(1).contiguous()
+        L.check(L.lib().aewn_nll_bwd(
+            L.C.c_void_p(p.data_ptr()), L.C.c_longlong(p.stride(0)), L.C.c_longlong(p.stride(1)),
+            L.C.c_void_p(tg.data_ptr()), L.C.c_longlong(tg.stride(0)), L.C.c_void_p(lse.data_ptr()),
+            L.C.c_void_p(gl.data_ptr()), L.C.c_float(1.0 / float(B * N)), L.C.c_void_p(gx.data_ptr()),
+            L.C.c_longlong(gx.stride(0)), L.C.c_longlong(gx.stride(1)), L.C.c_int(B), L.C.c_int(Q), L.C.c_int(N),
+            ops._stream()), "aewn_nll_bwd")
+        return gx, None
+
+
 class RecLoss(nn.Module):
-    """wavenet.py:536-552."""
+    """wavenet.py:536-552.  On CUDA the log-softmax + gather + mean run as one fused kernel pair."""
 
     def __init__(self):
         super().__init__()
         self.logsoftmax = nn.LogSoftmax(1)
 
     def forward(self, quant_pred, target_wav):
-        log_pred = self.logsoftmax(quant_pred)
-        log_pred_target = torch.gather(log_pred, 1, target_wav.long().unsqueeze(1))
-        rec_loss = -log_pred_target.mean()
+        _require_cuda(quant_pred)
+        rec_loss = _NLLFn.apply(quant_pred, target_wav)
         self.metrics = {"rec": rec_loss}
         return rec_loss

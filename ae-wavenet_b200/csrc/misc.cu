@@ -195,3 +195,109 @@ int aewn_relu_mask_bwd(const float* g, long long g_bs, long long g_cs, const flo
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Reconstruction loss (RecLoss, wavenet.py:536-552): -mean_{b,t} log_softmax(logits[b, :, t])[target[b, t]].
+// Forward: one pass over the logits with an online max / sum-exp per (b, t) (lane = time step, so every channel row
+// read is a coalesced 128 B line), writes lse[b, t] and adds the per-CTA partial of -(x_target - lse) to `loss_sum`.
+// Backward: g_logits[b, q, t] = (exp(x - lse) - [q == target]) * scale.  Replaces log_softmax + gather + mean and their
+// three backward kernels (2 reads + 1 write of the logits instead of ~7 passes).
+// ---------------------------------------------------------------------------------------------------------------
+namespace aewn {
+
+__global__ void __launch_bounds__(256) nll_fwd_kernel(const float* __restrict__ x, long long x_bs, long long x_cs,
+                                                      const float* __restrict__ tgt, long long t_bs,
+                                                      float* __restrict__ lse, float* __restrict__ loss_sum, int Q,
+                                                      int N, int* err) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  float part = 0.0f;
+  if (t < N) {
+    const float* p = x + static_cast<long long>(b) * x_bs + t;
+    int code = static_cast<int>(tgt[static_cast<long long>(b) * t_bs + t]);
+    if (code < 0 || code >= Q) {
+      if (err) atomicExch(err, AEWN_ERR_INVALID);
+      code = code < 0 ? 0 : Q - 1;
+    }
+    float m = -INFINITY, s = 0.0f, xt = 0.0f;
+    for (int q = 0; q < Q; ++q) {
+      const float v = __ldg(p);
+      p += x_cs;
+      if (q == code) xt = v;
+      if (v > m) {
+        s = s * __expf(m - v) + 1.0f;
+        m = v;
+      } else {
+        s += __expf(v - m);
+      }
+    }
+    const float l = m + __logf(s);
+    lse[static_cast<long long>(b) * N + t] = l;
+    part = l - xt;
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.0f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) tot += red[w];
+    atomicAdd(loss_sum, tot);
+  }
+}
+
+__global__ void __launch_bounds__(256) nll_bwd_kernel(const float* __restrict__ x, long long x_bs, long long x_cs,
+                                                      const float* __restrict__ tgt, long long t_bs,
+                                                      const float* __restrict__ lse, const float* __restrict__ g_loss,
+                                                      float scale, float* __restrict__ gx, long long g_bs,
+                                                      long long g_cs, int Q, int N) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N) return;
+  const float* p = x + static_cast<long long>(b) * x_bs + t;
+  float* g = gx + static_cast<long long>(b) * g_bs + t;
+  int code = static_cast<int>(tgt[static_cast<long long>(b) * t_bs + t]);
+  code = code < 0 ? 0 : (code >= Q ? Q - 1 : code);
+  const float l = lse[static_cast<long long>(b) * N + t];
+  const float sc = scale * __ldg(g_loss);
+#pragma unroll 8
+  for (int q = 0; q < Q; ++q) {
+    const float v = __ldg(p);
+    *g = (__expf(v - l) - (q == code ? 1.0f : 0.0f)) * sc;
+    p += x_cs;
+    g += g_cs;
+  }
+}
+
+}  // namespace aewn
+
+extern "C" {
+
+int aewn_nll_fwd(const float* logits, long long x_bs, long long x_cs, const float* target, long long t_bs, float* lse,
+                 float* loss_sum, int batch, int Q, int N, int* err, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!logits || !target || !lse || !loss_sum || batch <= 0 || Q <= 0 || N <= 0)
+    return aewn::set_err(AEWN_ERR_INVALID, "nll_fwd: bad arguments");
+  cudaError_t e = cudaMemsetAsync(loss_sum, 0, sizeof(float), stream);
+  if (e != cudaSuccess) return aewn::cuda_err(e, "nll_fwd: memset");
+  dim3 grid((N + 255) / 256, batch);
+  aewn::nll_fwd_kernel<<<grid, 256, 0, stream>>>(logits, x_bs, x_cs, target, t_bs, lse, loss_sum, Q, N, err);
+  aewn::count_launch();
+  return aewn::cuda_err(cudaGetLastError(), "nll_fwd launch");
+}
+
+int aewn_nll_bwd(const float* logits, long long x_bs, long long x_cs, const float* target, long long t_bs,
+                 const float* lse, const float* g_loss, float scale, float* g_logits, long long g_bs, long long g_cs,
+                 int batch, int Q, int N, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!logits || !target || !lse || !g_loss || !g_logits || batch <= 0 || Q <= 0 || N <= 0)
+    return aewn::set_err(AEWN_ERR_INVALID, "nll_bwd: bad arguments");
+  dim3 grid((N + 255) / 256, batch);
+  aewn::nll_bwd_kernel<<<grid, 256, 0, stream>>>(logits, x_bs, x_cs, target, t_bs, lse, g_loss, scale, g_logits, g_bs,
+                                                 g_cs, Q, N);
+  aewn::count_launch();
+  return aewn::cuda_err(cudaGetLastError(), "nll_bwd launch");
+}
+
+}  // extern "C"

@@ -25,6 +25,8 @@ for p in (ROOT, os.path.join(ROOT, "ae-wavenet_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: stdout carries ONE JSON line
+
 import torch  # noqa: E402
 
 ARCH_BASIC = dict(filter_sz=2, n_lc_out=128, lc_upsample_strides=[5, 4, 4, 4], lc_upsample_filt_sizes=[25, 16, 16, 16],
@@ -232,7 +234,7 @@ def main():
     wn = wn.to(dev).train()
     loss_fn = aewn.RecLoss()
     sync = FlatGradSync(wn.parameters())
-    opt = torch.optim.Adam(wn.parameters(), lr=2e-5)          # checkpoint.py:49, par/train.basic.json:6
+    opt = torch.optim.Adam(wn.parameters(), lr=2e-5, fused=True)   # checkpoint.py:49, par/train.basic.json:6
     wav_h, lc_h, spk_h, jit_h = [t.pin_memory() for t in synth_batch(B, geo["wav_len"], geo["lc_len"], 64, 40, 1234 + rank)]
     t0w, t1w = geo["trim_dec_out"]
 

@@ -213,6 +213,17 @@ int aewn_vq_commit_bwd(const float* ze, long long ze_bs, long long ze_cs, const 
 int aewn_ema_update(float* ema_numer, float* ema_denom, const float* z_sum, const float* n_sum, float gamma, float* emb,
                     int K, int d, aewn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Reconstruction loss (RecLoss.forward, wavenet.py:541-552): loss_sum = sum_{b,t} ( lse[b,t] - logits[b, target, t] ),
+ * lse = log-sum-exp over the Q channels; the caller divides by batch*N.  aewn_nll_bwd writes
+ * g_logits[b,q,t] = (exp(logits - lse) - [q == target]) * scale * (*g_loss).  Targets are float mu-law codes.
+ * ------------------------------------------------------------------------------------------------------------ */
+int aewn_nll_fwd(const float* logits, long long x_bs, long long x_cs, const float* target, long long t_bs, float* lse,
+                 float* loss_sum, int batch, int Q, int N, int* err, aewn_stream_t stream);
+int aewn_nll_bwd(const float* logits, long long x_bs, long long x_cs, const float* target, long long t_bs,
+                 const float* lse, const float* g_loss, float scale, float* g_logits, long long g_bs, long long g_cs,
+                 int batch, int Q, int N, aewn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

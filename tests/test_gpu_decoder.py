@@ -105,3 +105,21 @@ def test_wavenet_small_train_step_matches_reference_golden(golden_dir):
         assert e < 0.15, (k, e, worst)
     for k, c in coss.items():
         assert c > 0.995, (k, c)
+
+
+def test_fused_rec_loss_matches_torch_log_softmax_gather():
+    """RecLoss (wavenet.py:541-552) as the fused kernel pair vs plain PyTorch fp32, on a non-contiguous slice like the
+    caller's quant[..., :-1] (mfcc_inverter.py:99)."""
+    import aewn
+    g = torch.Generator().manual_seed(0)
+    quant = (3.0 * torch.randn(3, 256, 301, generator=g)).cuda().requires_grad_(True)
+    wav = torch.randint(0, 256, (3, 301), generator=g).float().cuda()
+    pred, target = quant[..., :-1], wav[..., 1:]
+    loss = aewn.RecLoss()(pred, target)
+    (gq,) = torch.autograd.grad(loss * 2.0, quant)
+    q2 = quant.detach().clone().requires_grad_(True)
+    ref = -torch.gather(torch.log_softmax(q2[..., :-1], 1), 1, target.long().unsqueeze(1)).mean()
+    (gr,) = torch.autograd.grad(ref * 2.0, q2)
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert float((gq - gr).abs().max()) < 1e-6 + 1e-4 * float(gr.abs().max())
+    assert float(gq[..., -1].abs().max()) == 0.0
