@@ -14,7 +14,7 @@ namespace aewn {
 constexpr int WG_BK = 32;
 constexpr int WG_STAGES = 4;
 constexpr int WG_BOX_BYTES = 128 * WG_BK * 4;        // 16 KB
-constexpr int WG_STAGE_BYTES = 3 * WG_BOX_BYTES;     // G box + 2 X boxes
+constexpr int WG_STAGE_BYTES = 3 * WG_BOX_BYTES;     // G box + 2 X boxes (4 stages); "wide" launches: G + 3 X boxes, 3 stages
 constexpr int WG_THREADS = 384;
 constexpr int WG_EPI_WARPS = 8;
 constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 256 + 1024;
@@ -28,6 +28,7 @@ struct WgParams {
   int* err;
   int uniform_split;  // > 0: every item has this split count and units are ordered split-major (see wg_decode)
   int pair;           // 1: 2-CTA clusters; CTA r of cluster c takes item 2*pair_index + r; the pair shares its X tile
+  int wide;           // 1: some item has 256 < n <= 384: 3 stages of (G + 3 X boxes), one 512-column accumulator
 };
 
 struct WgUnit {
@@ -77,6 +78,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // Wide launches trade pipeline depth and the second accumulator for N up to 384 per unit: the G tile is then loaded
+  // once for a whole 368-row X tile instead of once for 256 + once for 112 rows (the 112-wide units were L2-bound).
+  const uint32_t n_stages = p.wide ? 3u : 4u;
+  const uint32_t stage_bytes = p.wide ? 4u * WG_BOX_BYTES : 3u * WG_BOX_BYTES;
+  const uint32_t acc_stages = p.wide ? 1u : 2u;
 
   if (threadIdx.x == 0) {
     *abort_flag = 0;
@@ -120,18 +126,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           const int b = kb / u.blocks_per_b;
           const int t = im.t_lo + (kb - b * u.blocks_per_b) * WG_BK;
           if (!mbar_wait(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
-          uint8_t* sg = smem + stage * WG_STAGE_BYTES;
+          uint8_t* sg = smem + stage * stage_bytes;
           uint8_t* sx = sg + WG_BOX_BYTES;
           mbar_expect_tx(&full_bar[stage], (1 + xboxes) * WG_BOX_BYTES);
           tma_load_3d(sg, &p.map[im.g_act], &full_bar[stage], t, im.g_row, b);
           if (!p.pair) {
             for (int j = 0; j < xboxes; ++j)
               tma_load_3d(sx + j * WG_BOX_BYTES, &p.map[im.x_act], &full_bar[stage], t + im.shift, im.x_row + j * 128, b);
-          } else if (crank < xboxes) {   // CTA r fetches X box r and multicasts it to both CTAs of the pair
-            tma_load_3d_mcast(sx + crank * WG_BOX_BYTES, &p.map[im.x_act], &full_bar[stage], t + im.shift,
-                              im.x_row + crank * 128, b, 0x3);
+          } else {   // CTA r fetches X boxes r, r+2 and multicasts them to both CTAs of the pair
+            for (int j = crank; j < xboxes; j += 2)
+              tma_load_3d_mcast(sx + j * WG_BOX_BYTES, &p.map[im.x_act], &full_bar[stage], t + im.shift,
+                                im.x_row + j * 128, b, 0x3);
           }
-          if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -146,25 +153,32 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256u;
-        const uint32_t idesc = make_idesc_tf32(128, im.n, 0, 0);
+        const int n0 = im.n > 256 ? 256 : im.n;
+        const int n1 = im.n - n0;                       // second MMA part (wide items): X rows 256.., TMEM columns 256..
+        const uint32_t idesc = make_idesc_tf32(128, n0, 0, 0);
+        const uint32_t idesc1 = n1 > 0 ? make_idesc_tf32(128, n1, 0, 0) : 0u;
         for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
           if (!mbar_wait(&full_bar[stage], phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t g_addr = smem_u32(smem + stage * WG_STAGE_BYTES);
+          const uint32_t g_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t x_addr = g_addr + WG_BOX_BYTES;
 #pragma unroll
           for (int ks = 0; ks < WG_BK / 8; ++ks) {
             const uint64_t adesc = make_smem_desc(g_addr + ks * 32, 16, 1024, kLayoutSW128);
             const uint64_t bdesc = make_smem_desc(x_addr + ks * 32, 16, 1024, kLayoutSW128);
             umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kb > u.kb_begin) || (ks > 0));
+            if (n1 > 0) {
+              const uint64_t bdesc1 = make_smem_desc(x_addr + 2 * WG_BOX_BYTES + ks * 32, 16, 1024, kLayoutSW128);
+              umma_tf32_ss(d_tmem + 256u, adesc, bdesc1, idesc1, (kb > u.kb_begin) || (ks > 0));
+            }
           }
           if (p.pair) umma_commit_mcast(&empty_bar[stage], 0x3);
           else umma_commit(&empty_bar[stage]);
-          if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
         if (!ok) break;
         umma_commit(&tfull_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == acc_stages) { acc = 0; acc_phase ^= 1u; }
       }
     }
   }
@@ -195,7 +209,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
@@ -238,7 +252,7 @@ extern "C" int aewn_wgrad(const aewn_wgrad_desc* d, aewn_stream_t stream_) {
     const aewn_wgrad_item& im = d->items[i];
     if (im.g_act < 0 || im.g_act >= d->n_acts || im.x_act < 0 || im.x_act >= d->n_acts)
       return set_err(AEWN_ERR_INVALID, "wgrad: item %d operand index out of range", i);
-    if (im.n < 16 || im.n > 256 || (im.n & 15) || im.n_valid < 1 || im.n_valid > im.n || im.m_valid < 0 ||
+    if (im.n < 16 || im.n > 384 || (im.n & 15) || im.n_valid < 1 || im.n_valid > im.n || im.m_valid < 0 ||
         im.m_valid > 128)
       return set_err(AEWN_ERR_INVALID, "wgrad: item %d tile shape invalid (m_valid=%d n=%d n_valid=%d)", i, im.m_valid,
                      im.n, im.n_valid);
@@ -253,6 +267,9 @@ extern "C" int aewn_wgrad(const aewn_wgrad_desc* d, aewn_stream_t stream_) {
   }
   p.unit_begin[d->n_items] = units;
   p.n_items = d->n_items;
+  p.wide = 0;
+  for (int i = 0; i < d->n_items; ++i)
+    if (d->items[i].n > 256) p.wide = 1;
   p.uniform_split = d->items[0].n_split;
   for (int i = 1; i < d->n_items; ++i)
     if (d->items[i].n_split != d->items[0].n_split) p.uniform_split = 0;

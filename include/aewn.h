@@ -143,7 +143,7 @@ typedef struct {
   int g_act, x_act;   /* indices into acts[] */
   int g_row, x_row;   /* first channel row of each operand */
   int m_valid;        /* rows stored (<= 128; 0 = padding partner of a pair, stores nothing) */
-  int n;              /* UMMA N: multiple of 16, 16..256 */
+  int n;              /* columns of the tile: multiple of 16, 16..384 (two MMAs when > 256) */
   int n_valid;        /* columns stored */
   int shift;          /* X time coordinate = u + shift; multiple of 4 */
   int t_lo, t_hi;     /* u range (G's time axis); t_lo multiple of 4 */
