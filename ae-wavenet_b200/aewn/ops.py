@@ -497,7 +497,9 @@ class StackPlan:
                 return dict(g_act=0, g_row=h * D + 128 * i, m_valid=min(128, D - 128 * i), t_lo=lo4, t_hi=T0)
 
             groups = []
-            for (c0, n) in chunks(R, 384):      # up to 384 X rows per unit: the G tile is loaded once for all of them
+            # (wide units of up to 384 X rows are supported by the kernel but measured no faster: they give up the second
+            #  accumulator and one pipeline stage)
+            for (c0, n) in chunks(R):
                 for tap, (xa, sh) in enumerate(((1, sh0), (2, 0))):
                     groups.append([dict(g_item(h, i), x_act=xa, x_row=c0, n_valid=n, shift=sh, out=v[keys[h]],
                                         out_off=(128 * i) * R * 2 + c0 * 2 + tap, out_rs=2 * R, out_cs=2)
