@@ -101,3 +101,53 @@ def test_full_size_backward_is_finite_and_weight_grads_scale_linearly():
     for a, b, (k, _) in zip(g1, g3, wn.named_parameters()):
         assert torch.isfinite(a).all(), k
         assert torch.allclose(4.0 * a, b, rtol=1e-3, atol=1e-4 * float(b.abs().max())), k
+
+
+def test_cfg5_deep_stack_window_matches_cpu_oracle():
+    """BASELINE cfg5: 30 dilation layers (3 x 10), 512 residual channels, window 65536 (decoder input 68605).  The last
+    32 output steps of the kernel path are compared with the CPU oracle evaluated on just their receptive field."""
+    import aewn
+    from aewn import geometry as vc, ops
+    from oracle import torch_oracle as orc
+    hp = dict(ARCH_BASIC, n_blocks=3, n_res=512)
+    W = 65536
+    torch.manual_seed(2507)
+    parent = vc.VirtualConv(filter_info=1, stride=320, parent=None, name="LC-grid")
+    wn = aewn.WaveNet(HP(hp), parent_vc=parent)
+    vc.compute_inputs(wn.vc["end_grcc"], vc.GridRange((0, 10 ** 7), (0, W), 1))
+    T0 = wn.vc["beg_grcc"].in_len()
+    wav_len, lc_len = parent.in_len(), parent.child.in_len()
+    wn.trim_ups_out = torch.tensor([0, T0], dtype=torch.long)
+    wn.post_init(W)
+    assert T0 == 68605 and wav_len == 70721 and lc_len == 222          # cfg5 behind a stride-320 conditioning grid
+    wn = wn.cuda().train()
+    g = torch.Generator().manual_seed(7)
+    wav = torch.randint(0, 256, (1, wav_len), generator=g).float()
+    lc = torch.randn(1, 64, lc_len, generator=g)
+    spk = torch.randint(0, 40, (1,), generator=g)
+    jit = torch.arange(lc_len).unsqueeze(0)
+    with torch.no_grad():
+        q = wn(wav.cuda(), lc.cuda(), spk.cuda(), jit.cuda())
+    ops.check_device_errors()
+    assert q.shape == (1, 256, W) and torch.isfinite(q).all()
+    sd = {k: v.cpu() for k, v in wn.state_dict().items()}
+    rf, n_out = 3069, 32
+    o0, o1 = wn.wav_cond_offset
+    leads = [l.leads.tolist() for l in wn.conv_layers]
+    cond = orc.conditioning(sd, hp, lc, spk, jit, [0, T0])
+    s = T0 - (rf + n_out)
+    onehot = torch.nn.functional.one_hot(wav[:, o0:o1].long(), 256).permute(0, 2, 1).float()[:, :, s:]
+    sig = torch.nn.functional.conv1d(onehot, sd["base_layer.weight"], sd["base_layer.bias"])
+    c = cond[:, :, s:]
+    skp_sum = 0
+    dils = orc.dilations(hp)
+    for li, d in enumerate(dils):
+        sig, skp = orc.grcc_layer(sig, c, orc.sub(sd, f"conv_layers.{li}"), d, leads[li], li == len(dils) - 1)
+        skp_sum = skp_sum + skp
+    post1 = torch.nn.functional.conv1d(torch.relu(skp_sum), sd["post1.weight"], sd["post1.bias"])
+    ref = torch.nn.functional.conv1d(torch.relu(post1), sd["post2.weight"], sd["post2.bias"])
+    got = q[:, :, -n_out:].cpu()
+    err = float((got - ref).abs().max()) / float(ref.abs().max())
+    assert err < 8e-3, err
+    ops._plans.clear()          # release the ~20 GB workspace before the next test
+    torch.cuda.empty_cache()
