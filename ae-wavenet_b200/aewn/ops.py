@@ -553,6 +553,126 @@ class StackPlan:
         return bw["gx0"], bw["g_cond"], grads
 
 
+class PostPlan:
+    """Post-net of the decoder on the kernel path (wavenet.py:359-360): logits = post2(relu(post1(relu(skp_sum)))).
+    relu(skp_sum) is already in plan.skp (fused into the last GRCC layer's epilogue); post1 fuses bias + ReLU, post2 the
+    bias.  The backward pass writes the gradient w.r.t. the pre-ReLU skip sum straight into the stack's g_skp buffer."""
+
+    def __init__(self, plan, pw):
+        self.plan = plan
+        g, B, S, dev = plan.geom, plan.B, plan.S, plan.device
+        w1, w2 = pw["post1.weight"], pw["post2.weight"]
+        self.P, self.Q = w1.shape[0], w2.shape[0]
+        P, Q = self.P, self.Q
+        self.pw = pw
+        self.ptrs = tuple(t.data_ptr() for t in pw.values() if t is not None)
+        KS, KP, KQ = ceil_to(S, 32), ceil_to(P, 32), ceil_to(Q, 32)
+        self.w1 = torch.zeros(P, KS, device=dev)
+        self.w2 = torch.zeros(Q, KP, device=dev)
+        self.w1t = torch.zeros(S, KP, device=dev)
+        self.w2t = torch.zeros(P, KQ, device=dev)
+        blocks = [(w1.data_ptr(), self.w1.data_ptr(), P, S, S, 1, KS), (w2.data_ptr(), self.w2.data_ptr(), Q, P, P, 1, KP),
+                  (w1.data_ptr(), self.w1t.data_ptr(), S, P, 1, S, KP), (w2.data_ptr(), self.w2t.data_ptr(), P, Q, 1, P, KQ)]
+        import numpy as np
+        dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("ni", "<i4"), ("nj", "<i4"), ("si", "<i8"), ("sj", "<i8"),
+                       ("di", "<i8")])
+        self.n_blocks = len(blocks)
+        self.block_table = torch.from_numpy(np.array(blocks, dtype=dt).view(np.uint8).reshape(-1).copy()).to(dev)
+        T0, Tp, RF = g.T0, g.Tp, g.RF
+        rf4 = RF & ~3
+        self.h1 = new_buf(B, P, Tp, dev)
+        b1, b2 = pw.get("post1.bias"), pw.get("post2.bias")
+        tiles = [ntile(c0, n, self.h1[:, c0:], flags=L.F_RELU, bias=b1[c0:] if b1 is not None else None, t_lo=rf4,
+                       t_hi=T0, t_zero_lo=RF) for (c0, n) in chunks(P)]
+        self.fwd1 = build_tgemm([act_of(plan.skp, T0)], [(0, 0, S, 0)], self.w1, tiles, B, rf4 & ~31, T0, plan.err,
+                                tag="post1")
+        self._b2 = b2
+        self._bwd = None
+
+    def matches(self, pw):
+        return tuple(t.data_ptr() for t in pw.values() if t is not None) == self.ptrs
+
+    def forward(self):
+        """Returns logits on the absolute time axis: a fresh (B, Q, Tp) tensor, valid on [RF, T0)."""
+        plan = self.plan
+        g, B = plan.geom, plan.B
+        L.check(L.lib().aewn_pack_blocks(C.c_void_p(self.block_table.data_ptr()), C.c_int(self.n_blocks), _stream()),
+                "aewn_pack_blocks")
+        run_launches(self.fwd1)
+        logits = torch.empty(B, self.Q, g.Tp, device=plan.device)
+        rf4 = g.RF & ~3
+        b2 = self._b2
+        tiles = [ntile(c0, n, logits[:, c0:], bias=b2[c0:] if b2 is not None else None, t_lo=rf4, t_hi=g.T0,
+                       t_zero_lo=g.RF) for (c0, n) in chunks(self.Q)]
+        run_launches(build_tgemm([act_of(self.h1, g.T0)], [(0, 0, self.P, 0)], self.w2, tiles, B, rf4 & ~31, g.T0,
+                                 plan.err, tag="post2"))
+        return logits
+
+    def bwd(self):
+        if self._bwd is not None:
+            return self._bwd
+        plan = self.plan
+        g, B, S, dev = plan.geom, plan.B, plan.S, plan.device
+        P, Q, T0, Tp, RF = self.P, self.Q, g.T0, g.Tp, g.RF
+        rf4 = RF & ~3
+        sb = plan.bwd()
+        bw = dict(g_logits=new_buf(B, Q, Tp, dev), g_h1=new_buf(B, P, Tp, dev))
+        has_b = self._b2 is not None
+        sizes = [("post1.weight", (P, S, 1)), ("post2.weight", (Q, P, 1))]
+        if has_b:
+            sizes += [("post1.bias", (P,)), ("post2.bias", (Q,))]
+        off, lay = 0, {}
+        for k, sh in sizes:
+            n = 1
+            for v in sh:
+                n *= v
+            lay[k] = (off, sh, n)
+            off += ceil_to(n, 4)
+        flat = torch.zeros(off, device=dev)
+        bw["flat"] = flat
+        bw["views"] = {k: flat[o:o + n].view(sh) for k, (o, sh, n) in lay.items()}
+        v = bw["views"]
+        launches = []
+        # g_h1 = (W2^T g_logits) * [h1 > 0]
+        tiles = [ntile(c0, n, bw["g_h1"][:, c0:], flags=L.F_MASKPOS, add=self.h1[:, c0:], t_lo=rf4, t_hi=T0, t_zero_lo=RF)
+                 for (c0, n) in chunks(P)]
+        launches += build_tgemm([act_of(bw["g_logits"], T0)], [(0, 0, Q, 0)], self.w2t, tiles, B, rf4 & ~31, T0, plan.err,
+                                tag="post2_dgrad")
+        # g_skp = (W1^T g_h1) * [relu(skp) > 0]  -> the stack's skip-gradient buffer (absolute axis, zero below RF)
+        tiles = [ntile(c0, n, sb["g_skp"][:, c0:], flags=L.F_MASKPOS, add=plan.skp[:, c0:], t_lo=rf4, t_hi=T0,
+                       t_zero_lo=RF) for (c0, n) in chunks(S)]
+        launches += build_tgemm([act_of(bw["g_h1"], T0)], [(0, 0, P, 0)], self.w1t, tiles, B, rf4 & ~31, T0, plan.err,
+                                tag="post1_dgrad")
+        # weight / bias gradients (bias via the all-ones row)
+        acts = [act_of(bw["g_logits"], T0), act_of(self.h1, T0), act_of(ones_row(B, Tp, dev), T0), act_of(bw["g_h1"], T0),
+                act_of(plan.skp, T0)]
+        groups = []
+        for (g_act, M, x_act, Nx, wkey, bkey) in ((0, Q, 1, P, "post2.weight", "post2.bias"),
+                                                 (3, P, 4, S, "post1.weight", "post1.bias")):
+            mt = range((M + 127) // 128)
+            for (c0, n) in chunks(Nx):
+                groups.append([dict(g_act=g_act, x_act=x_act, g_row=128 * i, x_row=c0, m_valid=min(128, M - 128 * i),
+                                    n_valid=n, t_lo=rf4, t_hi=T0, out=v[wkey], out_off=128 * i * Nx + c0, out_rs=Nx,
+                                    out_cs=1) for i in mt])
+            if has_b:
+                groups.append([dict(g_act=g_act, x_act=2, g_row=128 * i, x_row=0, m_valid=min(128, M - 128 * i), n_valid=1,
+                                    t_lo=rf4, t_hi=T0, out=v[bkey], out_off=128 * i, out_rs=1, out_cs=1) for i in mt])
+        launches += build_wgrad(acts, pair_items(groups), B, plan.err, tag="post_wgrad", pair=True)
+        bw["launches"] = launches
+        self._bwd = bw
+        return bw
+
+    def backward(self, g_quant):
+        """g_quant: gradient w.r.t. logits[:, :, RF:T0].  Fills the stack's g_skp buffer; returns the dict of gradient
+        views (aliasing plan-owned memory)."""
+        g = self.plan.geom
+        bw = self.bwd()
+        bw["g_logits"][:, :, g.RF:g.T0] = g_quant
+        bw["flat"].zero_()
+        run_launches(bw["launches"])
+        return bw["views"]
+
+
 _plans = {}
 
 

@@ -335,11 +335,12 @@ class WaveNet(nn.Module):
             for k, t in layer.param_dict().items():
                 keys.append((li, k))
                 weights.append(t)
-        bias = self.base_layer.bias
-        h = _DecoderCoreFn.apply(wav, cond, self, keys, self.base_layer.weight,
-                                 bias if bias is not None else wav.new_zeros(0), *weights)
-        post1 = self.post1(h)                               # h = relu(skp_sum), fused into the last layer's epilogue
-        return self.post2(self.relu(post1))
+        none = wav.new_zeros(0)
+        opt = lambda t: t if t is not None else none
+        # base layer + 20 GRCC layers + ReLU + post1 + ReLU + post2, all on the kernel path
+        return _DecoderCoreFn.apply(wav, cond, self, keys, self.base_layer.weight, opt(self.base_layer.bias),
+                                    self.post1.weight, opt(self.post1.bias), self.post2.weight, opt(self.post2.bias),
+                                    *weights)
 
     def forward_test(self, wav, lc_sparse, speaker_inds, jitter_index):
         raise NotImplementedError(
@@ -352,7 +353,7 @@ class _DecoderCoreFn(torch.autograd.Function):
     Inputs: wav (B, T_wav) float mu-law codes, cond (B, C, T0).  Output: relu(skp_sum) (B, S, W)."""
 
     @staticmethod
-    def forward(ctx, wav, cond, net, keys, base_w, base_b, *weights):
+    def forward(ctx, wav, cond, net, keys, base_w, base_b, p1w, p1b, p2w, p2b, *weights):
         o0, o1 = net.wav_cond_offset
         T0 = o1 - o0
         B, Cc = cond.shape[0], cond.shape[1]
@@ -385,7 +386,14 @@ class _DecoderCoreFn(torch.autograd.Function):
                 L.C.c_int(d0), L.C.c_int(T0), L.C.c_int(B), L.C.c_int(R), L.C.c_int(Q), L.C.c_int(T0),
                 L.C.c_void_p(plan.err.data_ptr()), ops._stream()), "aewn_base_embed_fwd")
             plan.forward(save=True)
-            out = plan.skp[:, :, geom.RF:T0].clone()
+            pw = {"post1.weight": p1w, "post1.bias": p1b if p1b.numel() else None, "post2.weight": p2w,
+                  "post2.bias": p2b if p2b.numel() else None}
+            post = getattr(plan, "post", None)
+            if post is None or not post.matches(pw):
+                post = plan.post = ops.PostPlan(plan, pw)
+            out = post.forward()[:, :, geom.RF:T0]       # (B, Q, W) view of a fresh (B, Q, Tp) buffer
+        ctx.post = post
+        ctx.post_has_bias = (p1b.numel() > 0, p2b.numel() > 0)
         ctx.plan, ctx.keys = plan, keys
         ctx.gen = plan.generation
         ctx.wav, ctx.o0 = wav_c, o0
@@ -403,17 +411,8 @@ class _DecoderCoreFn(torch.autograd.Function):
                                "(one in-flight forward per configuration)")
         B, R, D, S, Cc, Q, T0 = ctx.dims
         lib = L.lib()
-        bw = plan.bwd()
-        gs = bw["g_skp"]
-        g_out = g_out if g_out.stride(2) == 1 else g_out.contiguous()
-        mask = plan.skp[:, :, geom.RF:]
-        gsv = gs[:, :, geom.RF:]
-        # g wrt the pre-ReLU skip sum, written straight onto the absolute time axis (margin [RF&~3, RF) stays 0)
-        L.check(lib.aewn_relu_mask_bwd(
-            L.C.c_void_p(g_out.data_ptr()), L.C.c_longlong(g_out.stride(0)), L.C.c_longlong(g_out.stride(1)),
-            L.C.c_void_p(mask.data_ptr()), L.C.c_longlong(mask.stride(0)), L.C.c_longlong(mask.stride(1)),
-            L.C.c_void_p(gsv.data_ptr()), L.C.c_longlong(gsv.stride(0)), L.C.c_longlong(gsv.stride(1)),
-            L.C.c_int(B), L.C.c_int(S), L.C.c_int(geom.W), ops._stream()), "aewn_relu_mask_bwd")
+        # post-net backward: fills the stack's g_skp buffer (gradient w.r.t. the pre-ReLU skip sum, absolute time axis)
+        pviews = ctx.post.backward(g_out)
         gx0, g_cond, grads = plan.backward()
         d_base = torch.zeros(R, Q, device=g_out.device)
         d_bias = torch.zeros(R, device=g_out.device) if ctx.has_bias else None
@@ -425,7 +424,10 @@ class _DecoderCoreFn(torch.autograd.Function):
         # gradient views alias the plan's flat buffer (overwritten by the next backward): autograd accumulates them
         # into .grad right away; a caller that keeps them (torch.autograd.grad) gets private copies
         wgrads = tuple(grads[li][k].clone() for (li, k) in ctx.keys)
-        return (None, g_cond[:, :, :T0].clone(), None, None, d_base.reshape(ctx.base_shape), d_bias) + wgrads
+        b1, b2 = ctx.post_has_bias
+        pg = (pviews["post1.weight"].clone(), pviews["post1.bias"].clone() if b1 else None,
+              pviews["post2.weight"].clone(), pviews["post2.bias"].clone() if b2 else None)
+        return (None, g_cond[:, :, :T0].clone(), None, None, d_base.reshape(ctx.base_shape), d_bias) + pg + wgrads
 
 
 class _NLLFn(torch.autograd.Function):
