@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libaewn.so")
 
-MAX_ACTS, MAX_SEGS, MAX_NTILES = 4, 4, 4
+MAX_ACTS, MAX_SEGS, MAX_NTILES = 6, 6, 4
 WGRAD_MAX_ACTS, WGRAD_MAX_ITEMS = 6, 32
 
 EPI_LINEAR, EPI_GATE_FWD, EPI_GATE_BWD = 0, 1, 2

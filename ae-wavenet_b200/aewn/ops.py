@@ -42,7 +42,7 @@ def act_of(t, t_extent=None, channels=None):
     return a
 
 
-def ntile(w_row, n_valid, out, mode=L.EPI_LINEAR, flags=0, seg_mask=0xF, t_lo=0, t_hi=0, t_zero_lo=0, out2=None,
+def ntile(w_row, n_valid, out, mode=L.EPI_LINEAR, flags=0, seg_mask=0x3F, t_lo=0, t_hi=0, t_zero_lo=0, out2=None,
           out3=None, out_toff=0, dup_toff=0, dup_t_hi=0, add=None, add2=None, add_toff=0, add_t_lo=0, bias=None,
           zero_count=None, n=None):
     """Build an aewn_ntile.  `out`/`out2`/`out3`/`add`/`add2` are (B, C', Tp) views already sliced to the tile's first
@@ -271,6 +271,9 @@ class StackPlan:
 
     def __init__(self, B, R, D, S, Cc, geom, params, device, relu_last):
         g = self.geom = geom
+        if D > 256:
+            raise NotImplementedError(f"aewn: n_dil = {D} > 256: the gate-derivative kernel keeps all dilation channels "
+                                      "of a time tile in one 256-column accumulator (the reference presets use 256)")
         self.B, self.R, self.D, self.S, self.Cc = B, R, D, S, Cc
         self.device = device
         self.relu_last = relu_last
@@ -840,3 +843,129 @@ class _TapConvFn(torch.autograd.Function):
 
 def tap_conv(x, weight, bias=None, stride=1, mode=0, res_lw=0, zero_count=None):
     return _TapConvFn.apply(x, weight, bias, stride, mode, res_lw, zero_count)
+
+
+class _TapConvTransposeFn(torch.autograd.Function):
+    """ConvTranspose1d(C_in -> C_out, kernel f, stride s, padding p) on the tcgen05 engines (wavenet.py:154-155 uses
+    p = f - s).  Polyphase form: with o' = o + p, r = o' mod s, q = o' // s,
+
+        y[b, n, o] = bias[n] + sum_m sum_c W[c, n, r + s*m] * x[b, c, q - m]
+
+    i.e. one time-major GEMM per output phase r over the M = ceil(f/s) tap-shifted copies of x (no zero-stuffed input,
+    no wasted MACs).  Backward: g_x = strided correlation of g_y (again one GEMM per phase, accumulated), dW through the
+    weight-gradient engine, d(bias) = sum g_y."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding):
+        B, Ci, Lx = x.shape
+        _, Co, f = weight.shape
+        s, p = stride, padding
+        Lo = (Lx - 1) * s - 2 * p + f
+        dev = x.device
+        err = err_word(dev)
+        kc = ceil_to(Ci, 32)
+        xd, wd = x.detach(), weight.detach()
+        y = torch.empty(B, Co, Lo, device=dev)
+        phases = []
+        with torch.no_grad():
+            for r in range(s):
+                js = list(range(r, f, s))
+                # outputs of this phase: o = s*q + r - p, 0 <= o < Lo
+                q0 = max(0, -((r - p) // s))
+                q1 = (Lo - 1 - (r - p)) // s          # inclusive
+                if q1 < q0 or not js:
+                    continue
+                nq = q1 + 1
+                Tp = ceil_to(nq + 4, 32)
+                shifted = []
+                for m in range(len(js)):              # xm[q] = x[q - m]
+                    sb = new_buf(B, Ci, Tp, dev)
+                    hi = min(nq, Lx + m)
+                    if hi > m:
+                        sb[:, :, m:hi] = xd[:, :, :hi - m]
+                    shifted.append(sb)
+                wp = torch.cat([_pad_k(wd[:, :, j].t(), kc) for j in js], 1).contiguous()      # [Co][M*kc]
+                yr = new_buf(B, Co, Tp, dev)
+                for g0 in range(0, len(js), L.MAX_SEGS):        # at most MAX_SEGS taps per launch; later groups accumulate
+                    ms = list(range(g0, min(len(js), g0 + L.MAX_SEGS)))
+                    tiles = [ntile(c0, n, yr[:, c0:], flags=L.F_ACCUM if g0 else 0,
+                                   bias=bias.detach()[c0:] if (bias is not None and g0 == 0) else None, t_lo=0, t_hi=nq)
+                             for (c0, n) in chunks(Co)]
+                    tgemm([act_of(shifted[m], nq) for m in ms], [(i, 0, Ci, m * kc) for i, m in enumerate(ms)], wp, tiles,
+                          B, 0, nq, err, tag="tconv_fwd")
+                o0 = s * q0 + r - p
+                y[:, :, o0::s] = yr[:, :, q0:nq]
+                phases.append((r, js, q0, nq, shifted))
+        ctx.save_for_backward(weight)
+        ctx.cfg = (B, Ci, Lx, Co, f, s, p, Lo, bias is not None)
+        ctx.phases = phases
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (weight,) = ctx.saved_tensors
+        B, Ci, Lx, Co, f, s, p, Lo, has_bias = ctx.cfg
+        dev = g.device
+        err = err_word(dev)
+        wd = weight.detach()
+        kn = ceil_to(Co, 32)
+        dw = torch.zeros_like(weight)
+        Tx = ceil_to(Lx + 4, 32)
+        gx = new_buf(B, Ci, Tx, dev)
+        first = True
+        for (r, js, q0, nq, shifted) in ctx.phases:
+            Tp = shifted[0].shape[2]
+            # g_yr[q] = g_y[s*q + r - p]
+            gyr = new_buf(B, Co, Tp, dev)
+            gyr[:, :, q0:nq] = g[:, :, s * q0 + r - p::s]
+            # data gradient: g_x[i] += sum_m W[:, :, r + s*m] g_yr[i + m]
+            M = len(js)
+            adv = []
+            for m in range(M):                        # gm[i] = g_yr[i + m]
+                if m == 0:
+                    adv.append(gyr)
+                else:
+                    sb = new_buf(B, Co, Tp, dev)
+                    if nq > m:
+                        sb[:, :, :nq - m] = gyr[:, :, m:nq]
+                    adv.append(sb)
+            wt = torch.cat([_pad_k(wd[:, :, j], kn) for j in js], 1).contiguous()              # [Ci][M*kn]
+            for g0 in range(0, M, L.MAX_SEGS):
+                ms = list(range(g0, min(M, g0 + L.MAX_SEGS)))
+                tiles = [ntile(c0, n, gx[:, c0:], flags=0 if first else L.F_ACCUM, t_lo=0, t_hi=Lx)
+                         for (c0, n) in chunks(Ci)]
+                tgemm([act_of(adv[m], min(nq, adv[m].shape[2])) for m in ms], [(i, 0, Co, m * kn) for i, m in enumerate(ms)],
+                      wt, tiles, B, 0, Lx, err, tag="tconv_dgrad")
+                first = False
+            # weight gradient: dW[c, n, r + s*m] = sum_{b,q} x[c, q - m] * g_yr[n, q]
+            for g0 in range(0, M, L.WGRAD_MAX_ACTS - 1):      # the engine takes 6 operand tensors: g_yr + 5 taps
+                ms = list(range(g0, min(M, g0 + L.WGRAD_MAX_ACTS - 1)))
+                acts = [act_of(gyr, nq)] + [act_of(shifted[m], nq) for m in ms]
+                items = []
+                for i in range((Co + 127) // 128):
+                    for k, m in enumerate(ms):
+                        for (c0, n) in chunks(Ci):
+                            items.append(dict(g_act=0, x_act=1 + k, g_row=128 * i, x_row=c0,
+                                              m_valid=min(128, Co - 128 * i), n_valid=n, t_lo=0, t_hi=nq, out=dw,
+                                              out_off=c0 * Co * f + (128 * i) * f + js[m], out_rs=f, out_cs=Co * f))
+                wgrad(acts, items, B, err, tag="tconv_wgrad")
+        db = g.sum(dim=(0, 2)) if has_bias else None
+        return gx[:, :, :Lx].clone(), dw, db, None, None
+
+
+# Conditioning front-end (lc_conv + 4 transposed convs, ~0.5 % of the decoder FLOPs): "torch" = cuDNN through the
+# nn.Conv1d / nn.ConvTranspose1d parameter containers, "kernels" = the polyphase GEMMs above.  The kernel path is
+# parity-tested but its per-phase staging copies make the whole step ~10 % slower than cuDNN here (measured 39.5 vs
+# 35.7 ms on cfg2), so it is opt-in until the staging moves into the producing epilogues.
+FRONTEND = "torch"
+
+
+def set_frontend(mode):
+    global FRONTEND
+    if mode not in ("torch", "kernels"):
+        raise ValueError("frontend must be 'torch' or 'kernels'")
+    FRONTEND = mode
+
+
+def tap_conv_transpose(x, weight, bias=None, stride=1, padding=0):
+    return _TapConvTransposeFn.apply(x, weight, bias, stride, padding)

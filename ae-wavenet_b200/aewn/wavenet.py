@@ -185,8 +185,12 @@ class Upsampling(nn.Module):
                                     is_downsample=False, parent=parent_vc, name=name)
         self.tconv = nn.ConvTranspose1d(n_chan, n_chan, filter_sz, stride, padding=filter_sz - stride, bias=bias)
         self.apply(xavier_init)
+        self._stride, self._padding = stride, filter_sz - stride
 
     def forward(self, lc):
+        _require_cuda(lc)
+        if ops.FRONTEND == "kernels":   # polyphase transposed conv on the tcgen05 engine (opt-in, see ops.FRONTEND)
+            return ops.tap_conv_transpose(lc, self.tconv.weight, self.tconv.bias, self._stride, self._padding)
         return self.tconv(lc)
 
 
@@ -198,6 +202,12 @@ class Conv1dWrap(nn.Conv1d):
         self.apply(xavier_init)
         self.vc = vconv.VirtualConv(filter_info=kwargs["kernel_size"], stride=kwargs["stride"], name=name,
                                     parent=parent_vc)
+
+    def forward(self, x):
+        _require_cuda(x)
+        if ops.FRONTEND == "kernels" and self.dilation[0] == 1 and self.padding[0] == 0 and self.groups == 1:
+            return ops.tap_conv(x, self.weight, self.bias, stride=self.stride[0], mode=0)
+        return super().forward(x)
 
 
 _OLD_API_KEYS = ("filter_sz", "n_lc_out", "lc_upsample_strides", "lc_upsample_filt_sizes", "n_res", "n_dil", "n_skp",

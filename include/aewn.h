@@ -103,8 +103,8 @@ typedef struct {
   const float* bias; /* optional, pre-offset, indexed by column */
 } aewn_ntile;
 
-#define AEWN_MAX_ACTS 4
-#define AEWN_MAX_SEGS 4
+#define AEWN_MAX_ACTS 6
+#define AEWN_MAX_SEGS 6
 #define AEWN_MAX_NTILES 4
 
 typedef struct {

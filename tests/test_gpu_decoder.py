@@ -76,7 +76,19 @@ def build_wavenet(g):
     return wn.cuda().train()
 
 
-def test_wavenet_small_train_step_matches_reference_golden(golden_dir):
+@pytest.mark.parametrize("frontend", ["torch", "kernels"])
+def test_wavenet_small_train_step_matches_reference_golden(golden_dir, frontend):
+    """frontend: the conditioning convs through cuDNN (default) or through the polyphase tcgen05 path (opt-in)."""
+    import aewn
+    from aewn import ops
+    ops.set_frontend(frontend)
+    try:
+        _wavenet_small_body(golden_dir)
+    finally:
+        ops.set_frontend("torch")
+
+
+def _wavenet_small_body(golden_dir):
     import aewn
     from aewn import ops
     g = torch.load(os.path.join(golden_dir, "wavenet_small.pt"))
