@@ -62,12 +62,37 @@ class CopyBlock(C.Structure):
                 ("sj", C.c_longlong), ("di", C.c_longlong)]
 
 
+GEN_MAX_LAYERS = 64
+GEN_MAX_BLOCKS = 2 * GEN_MAX_LAYERS + 2
+GEN_MAX_REP = 4
+
+
+class GenBlock(C.Structure):
+    _fields_ = [("kind", C.c_int), ("rows", C.c_int), ("rowf", C.c_int), ("off", C.c_int)]
+
+
+class GenDesc(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("R", C.c_int), ("D", C.c_int), ("S", C.c_int), ("P", C.c_int), ("Q", C.c_int),
+                ("cluster", C.c_int), ("n_rep", C.c_int), ("n_groups", C.c_int),
+                ("t_begin", C.c_int), ("t_end", C.c_int), ("t_prime", C.c_int),
+                ("dil", C.c_int * GEN_MAX_LAYERS), ("hist_off", C.c_int * (GEN_MAX_LAYERS + 1)),
+                ("n_blocks", C.c_int), ("blocks", GenBlock * GEN_MAX_BLOCKS),
+                ("wstream", C.c_void_p), ("stream_stride", C.c_longlong),
+                ("cond", C.c_void_p), ("cond_pitch", C.c_int), ("cond_len", C.c_int),
+                ("base_t", C.c_void_p), ("base_pitch", C.c_int),
+                ("hist", C.c_void_p), ("wav", C.c_void_p), ("wav_pitch", C.c_int),
+                ("uniforms", C.c_void_p), ("logits_out", C.c_void_p),
+                ("stage_bytes", C.c_int), ("n_stages", C.c_int), ("err", C.c_void_p),
+                ("dbg_clock", C.c_void_p)]
+
+
 _lib = None
 
 # every symbol include/aewn.h declares (tests/test_capi.py checks the shared object exports all of them)
 SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_tgemm", "aewn_wgrad",
            "aewn_base_embed_fwd", "aewn_base_embed_bwd", "aewn_fill", "aewn_relu_mask_bwd",
-           "aewn_vq_fwd", "aewn_vq_commit_bwd", "aewn_ema_update", "aewn_pack_blocks", "aewn_nll_fwd", "aewn_nll_bwd"]
+           "aewn_vq_fwd", "aewn_vq_commit_bwd", "aewn_ema_update", "aewn_pack_blocks", "aewn_nll_fwd", "aewn_nll_bwd",
+           "aewn_gen_smem_bytes", "aewn_gen_max_clusters", "aewn_gen_run"]
 
 
 def lib():

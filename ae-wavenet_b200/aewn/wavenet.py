@@ -320,15 +320,18 @@ class WaveNet(nn.Module):
             return self.forward_train(wav, lc_sparse, speaker_inds, jitter_index)
         return self.forward_test(wav, lc_sparse, speaker_inds, jitter_index)
 
-    def conditioning(self, lc_sparse, speaker_inds, jitter_index):
+    def conditioning(self, lc_sparse, speaker_inds, jitter_index, trim=True):
         """wavenet.py:330-343.  The jitter gather reproduces the reference exactly, including its quirk (SURVEY.md
-        F8): torch.take on the flat tensor with an index that carries only the batch offset."""
+        F8): torch.take on the flat tensor with an index that carries only the batch offset.  ``trim=False`` is the
+        inference variant (wavenet.py:385-391), which conditions on the whole upsampled sequence."""
         B, D1, T = lc_sparse.shape
         flat_idx = jitter_index + (torch.arange(B, device=jitter_index.device) * jitter_index.shape[1]).unsqueeze(1)
         lc_jitter = lc_sparse.reshape(-1)[flat_idx].unsqueeze(1).expand(-1, D1, -1)
         lc_dense = self.lc_upsample(self.lc_conv(lc_jitter))
-        t0, t1 = int(self.trim_ups_out[0]), int(self.trim_ups_out[1])
-        return self.cond(lc_dense[:, :, t0:t1], speaker_inds)
+        if trim:
+            t0, t1 = int(self.trim_ups_out[0]), int(self.trim_ups_out[1])
+            lc_dense = lc_dense[:, :, t0:t1]
+        return self.cond(lc_dense, speaker_inds)
 
     def stack_geometry(self, T0):
         dils = [layer.dil for layer in self.conv_layers]
@@ -353,9 +356,30 @@ class WaveNet(nn.Module):
                                     *weights)
 
     def forward_test(self, wav, lc_sparse, speaker_inds, jitter_index):
-        raise NotImplementedError(
-            "aewn: incremental sampling (wavenet.py:367-531) is outside this round's hot-path scope (SURVEY.md 8f rank "
-            "3); run generation with the reference module, or call the model in training mode for teacher-forced logits")
+        """wavenet.py:367-531: draw ``n_replicas`` continuations of one utterance, sample by sample.
+
+        Returns (n_replicas + 1, T_wav - wav_cond_offset[0]) codes in ``wav``'s dtype: row 0 is the input, rows 1..
+        copy its first ``base_global_rf`` samples, are generated up to the end of the conditioning sequence and copy
+        the input after that -- exactly what the reference returns.  The whole loop is ONE persistent kernel per
+        ``generate.SLICE_STEPS`` samples (csrc/gen.cu); each draw is an inverse-CDF draw from the softmax, i.e. the same
+        distribution as the reference's ``torch.multinomial``.  ``self.gen_uniforms`` (n_replicas, T) may pin the
+        uniforms (tests); ``self.gen_logits`` receives the logits behind every draw when ``self.keep_gen_logits``."""
+        from . import generate
+        _require_cuda(wav, lc_sparse)
+        if wav.shape[0] != 1:
+            raise ValueError("aewn: forward_test generates for one utterance per call (the reference's buffers only "
+                             "line up for batch 1, wavenet.py:397,419,463)")
+        off0 = int(self.wav_cond_offset[0])
+        codes = wav[0, off0:].long()
+        with torch.no_grad():
+            cond = self.conditioning(lc_sparse, speaker_inds, jitter_index, trim=False)[0]
+            plan = generate.get_plan(self, int(self.n_replicas))
+            keep = bool(getattr(self, "keep_gen_logits", False))
+            res = plan.generate(codes, cond, int(self.base_global_rf), uniforms=getattr(self, "gen_uniforms", None),
+                                want_logits=keep)
+            if keep:
+                res, self.gen_logits = res
+        return torch.cat([codes.unsqueeze(0).to(wav.dtype), res.to(wav.dtype)], 0)
 
 
 class _DecoderCoreFn(torch.autograd.Function):

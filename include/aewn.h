@@ -224,6 +224,74 @@ int aewn_nll_bwd(const float* logits, long long x_bs, long long x_cs, const floa
                  const float* lse, const float* g_loss, float scale, float* g_logits, long long g_bs, long long g_cs,
                  int batch, int Q, int N, aewn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Incremental sampler (wavenet.py:367-531 WaveNet.forward_test): one PERSISTENT kernel generates many samples.
+ *
+ * The reference runs, per generated sample, 20 GatedResidualCondConv calls on (n_rep, R, d+1) slices plus the
+ * post-net, softmax and torch.multinomial -- hundreds of launches and several host syncs per sample
+ * (wavenet.py:455-509).  Here one thread-block cluster (`cluster` CTAs, distributed shared memory) owns `n_rep`
+ * replicas: every CTA owns 1/cluster of the output rows of every matrix, streams exactly those rows from L2 through
+ * a TMA bulk-copy ring (the row order is static, so the stream is a flat per-CTA array prepared once by the host),
+ * exchanges the small activation vectors (z, x, h) through remote shared-memory stores and synchronises with a
+ * cluster-scope mbarrier.  fp32 FMA arithmetic (no TF32).  State that outlives a launch -- the per-layer history
+ * rings x_l[tau-d .. tau] and the generated codes -- is in global memory, so a long utterance is a sequence of
+ * launches over [t_begin, t_end).
+ *
+ * Step tau: code = wav[rep][tau]; x_0 = base_t[code]; for every layer l (dilation d):
+ *   v = [x_l[tau-d] | x_l[tau] | cond[tau] | 1],  z = tanh(A_f v) * sigmoid(A_g v),
+ *   x_{l+1}[tau] = W_res z + b_res + x_l[tau],  skip += W_skp z + b_skp;
+ * if tau+1 >= t_prime: logits = post2(relu(post1(relu(skip)))); wav[rep][tau+1] = first k with
+ * cumsum(softmax(logits))[k] > uniforms[rep][tau+1]   (inverse-CDF draw, distributed like torch.multinomial).
+ *
+ * Per-CTA weight stream (floats), CTA rank c, in consumption order; every row is padded to a multiple of 4 floats:
+ *   kind 0 (gate)  : 2*D/cluster rows [filt_j, gate_j interleaved] x KA, KA = 2*Rp + cond_pitch
+ *   kind 1 (mix)   : R/cluster residual rows (absent in the final layer) then S/cluster skip rows, x (Dp + 4)
+ *   kind 2 (post1) : P/cluster rows x (Sp + 4);   kind 3 (post2): Q/cluster rows x (Pp + 4)
+ * where Xp = X rounded up to 4 and the column at index Xp holds the bias (the vector carries 1.0 there).
+ * ------------------------------------------------------------------------------------------------------------ */
+#define AEWN_GEN_MAX_LAYERS 64
+#define AEWN_GEN_MAX_BLOCKS (2 * AEWN_GEN_MAX_LAYERS + 2)
+#define AEWN_GEN_MAX_REP 4
+
+typedef struct {
+  int kind;  /* 0 gate, 1 mix, 2 post1, 3 post2 */
+  int rows;  /* rows of this CTA in the block */
+  int rowf;  /* floats per row (multiple of 4) */
+  int off;   /* float offset of the block inside the CTA's stream */
+} aewn_gen_block;
+
+typedef struct {
+  int n_layers, R, D, S, P, Q;
+  int cluster;      /* CTAs per cluster: 1, 2, 4, 8 or 16; must divide R, D, S, P and Q */
+  int n_rep;        /* replicas per cluster: 1, 2 or 4 (pad with dummies) */
+  int n_groups;     /* clusters; replica index = group * n_rep + rep */
+  int t_begin, t_end, t_prime;
+  int dil[AEWN_GEN_MAX_LAYERS];
+  int hist_off[AEWN_GEN_MAX_LAYERS + 1]; /* slot offset of layer l's ring (ring length d_l + 1); [n_layers] = total */
+  int n_blocks;
+  aewn_gen_block blocks[AEWN_GEN_MAX_BLOCKS];
+  const float* wstream;        /* [cluster][stream_stride] */
+  long long stream_stride;
+  const float* cond;           /* [cond_len][cond_pitch] time-major, = [cond(C) | 1 | 0..]; shared by all replicas */
+  int cond_pitch, cond_len;
+  const float* base_t;         /* [Q][base_pitch]: row q = base weight column q + bias (wavenet.py:253, 462-463) */
+  int base_pitch;              /* = Rp */
+  float* hist;                 /* [n_groups*n_rep][hist_off[n_layers]][Rp], zero before the first launch */
+  int* wav;                    /* [n_groups*n_rep][wav_pitch] int32 codes, read for tau < t_prime, written after */
+  int wav_pitch;
+  const float* uniforms;       /* [n_groups*n_rep][wav_pitch] U[0,1) */
+  float* logits_out;           /* optional [n_groups*n_rep][wav_pitch][Q] (row tau+1 = logits that drew wav[tau+1]) */
+  int stage_bytes, n_stages;   /* weight ring geometry (stage_bytes % 16 == 0, >= 16*KA) */
+  int* err;
+  long long* dbg_clock;        /* optional: cluster 0 / CTA 0 writes clock64() stamps of step t_begin+8 (profiling) */
+} aewn_gen_desc;
+
+/* dynamic shared memory the launch needs for this descriptor (bytes), or a negative error code */
+int aewn_gen_smem_bytes(const aewn_gen_desc* d);
+/* how many clusters of d->cluster CTAs can be co-resident on the current device (0 = not launchable) */
+int aewn_gen_max_clusters(const aewn_gen_desc* d, int* n_out);
+int aewn_gen_run(const aewn_gen_desc* d, aewn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import ref_harness as rh  # noqa: E402
+from oracle import torch_oracle  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 os.makedirs(OUT, exist_ok=True)
@@ -177,8 +178,44 @@ def golden_geometry_and_init():
     print("geometry:", {k: v.get("dec_in_len") for k, v in geo_out.items()})
 
 
+def golden_forward_test():
+    """The reference's own sampler (wavenet.py:367-531) on CPU, 2 replicas, with torch.multinomial swapped for an
+    inverse-CDF draw on recorded uniforms (generator seed 99) so that the run is reproducible by any implementation.
+    Pins the alignment of wav / cond / base_global_rf, the output layout and every per-step distribution."""
+    m = rh.load()
+    hp = rh.HP(SMALL)
+    torch.manual_seed(2507)
+    wn, geo = rh.standalone_wavenet(hp, 96)
+    wav, lc, spk, jit = synth_inputs(1, geo, hp.n_lc_in, hp.n_speakers, 1234, jitter=True)
+    wn.eval()
+    wn.set_n_replicas(2)
+    g = torch.Generator().manual_seed(99)
+    rec = []
+
+    def draw(probs, n, replacement):
+        u = torch.rand(probs.shape[0], generator=g)
+        idx = torch_oracle.inverse_cdf_draw(probs, u)
+        rec.append((probs.clone(), u))
+        return idx.unsqueeze(1)
+
+    real = torch.multinomial
+    torch.multinomial = draw
+    try:
+        with torch.no_grad(), rh.quiet():
+            out = wn(wav, lc, spk, jit)
+    finally:
+        torch.multinomial = real
+    probs = torch.stack([r[0] for r in rec])
+    u = torch.stack([r[1] for r in rec])
+    torch.save(dict(hp=dict(hp), W=96, geo=geo, state_dict={k: v.clone() for k, v in wn.state_dict().items()},
+                    wav=wav, lc=lc, spk=spk, jit=jit, n_rep=2, base_global_rf=int(wn.base_global_rf),
+                    uniforms=u, probs=probs.half(), out=out), os.path.join(OUT, "forward_test.pt"))
+    print("forward_test: out", tuple(out.shape), "steps", len(rec))
+
+
 if __name__ == "__main__":
     golden_wavenet_small()
+    golden_forward_test()
     golden_grcc_layer()
     golden_encoder()
     golden_vq()

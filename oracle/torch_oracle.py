@@ -54,8 +54,9 @@ def conditioning(sd, hp, lc_sparse, speaker_inds, jitter_index, trim_ups_out):
     for i, (f, s) in enumerate(zip(hp["lc_upsample_filt_sizes"], hp["lc_upsample_strides"])):
         lc = F.conv_transpose1d(lc, sd[f"lc_upsample.{i}.tconv.weight"], sd.get(f"lc_upsample.{i}.tconv.bias"),
                                 stride=s, padding=f - s)  # wavenet.py:154-155
-    lc = lc[:, :, int(trim_ups_out[0]):int(trim_ups_out[1])]
-    one_hot = F.one_hot(speaker_inds.long(), hp["n_speakers"]).float()  # wavenet.py:135
+    if trim_ups_out is not None:                                          # forward_test does not trim (:385-391)
+        lc = lc[:, :, int(trim_ups_out[0]):int(trim_ups_out[1])]
+    one_hot = F.one_hot(speaker_inds.long(), hp["n_speakers"]).to(lc.dtype)  # wavenet.py:135
     gc = F.linear(one_hot, sd["cond.speaker_embedding.weight"], sd.get("cond.speaker_embedding.bias"))
     return torch.cat((lc, gc.unsqueeze(2).expand(-1, -1, lc.shape[2])), dim=1)
 
@@ -83,6 +84,55 @@ def wavenet_forward_train(sd, hp, geo, wav, lc_sparse, speaker_inds, jitter_inde
     if return_intermediates:
         return quant, dict(cond=cond, sigs=inter, skp_sum=skp_sum)
     return quant
+
+
+def stack_window_logits(sd, hp, codes, cond):
+    """Logits of ONE output step from a full receptive-field window (wavenet.py:459-477 in 'full' mode):
+    codes (n, RF+1) long, cond (n, C, RF+1)  ->  (n, Q).  Leads follow init_leads (wavenet.py:53-75) for a one-step
+    output: cond_lead_l = sum_{j<=l} d_j, skip_lead_l = RF - cond_lead_l, lw = d_l."""
+    dils = dilations(hp)
+    rf = sum(dils)
+    assert codes.shape[1] == rf + 1 and cond.shape[2] == rf + 1
+    sig = F.conv1d(F.one_hot(codes, hp["n_quant"]).permute(0, 2, 1).to(cond.dtype), sd["base_layer.weight"],
+                   sd.get("base_layer.bias"))
+    skp_sum, lead = 0, 0
+    for li, d in enumerate(dils):
+        lead += d
+        sig, skp = grcc_layer(sig, cond, sub(sd, f"conv_layers.{li}"), d, (lead, rf - lead, d), li == len(dils) - 1)
+        skp_sum = skp_sum + skp
+    post1 = F.conv1d(F.relu(skp_sum), sd["post1.weight"], sd.get("post1.bias"))
+    return F.conv1d(F.relu(post1), sd["post2.weight"], sd.get("post2.bias")).squeeze(2)
+
+
+def inverse_cdf_draw(probs, u):
+    """Index of the first bin whose cumulative probability exceeds u * total; probs (n, Q), u (n,).  Distributed like
+    torch.multinomial(probs, 1) (wavenet.py:479), but reproducible from the uniforms."""
+    cdf = probs.double().cumsum(-1)
+    idx = (cdf <= (u.double() * cdf[:, -1]).unsqueeze(1)).sum(-1)
+    return idx.clamp(max=probs.shape[-1] - 1)
+
+
+def wavenet_forward_test(sd, hp, wav_cond_offset, wav, lc_sparse, speaker_inds, jitter_index, n_rep, uniforms,
+                         n_steps=None):
+    """WaveNet.forward_test, wavenet.py:367-531, restated without the ring-buffer bookkeeping: every step evaluates the
+    stack on the last RF+1 samples (what the reference's incremental buffers hold, :455-509).  wav (1, T_wav) codes;
+    uniforms (steps, n_rep) replace torch.multinomial's RNG.  Returns (wav_out (n_rep+1, T) float, probs (steps, n_rep, Q))
+    with row 0 = the input and rows 1.. = input up to base_global_rf, then drawn samples up to the end of cond."""
+    assert wav.shape[0] == 1
+    rf1 = sum(dilations(hp)) + 1                                           # base_global_rf (:298, vc.in_len())
+    cond = conditioning(sd, hp, lc_sparse, speaker_inds, jitter_index, None)   # (1, C, n_ts)
+    n_ts = cond.shape[2]
+    codes = wav[0, int(wav_cond_offset[0]):].long()
+    out = codes.unsqueeze(0).repeat(n_rep + 1, 1)
+    end = n_ts if n_steps is None else min(n_ts, rf1 + n_steps)
+    probs_all = []
+    for cur in range(rf1, end):                                            # :455; the draw lands at index cur (:480)
+        win = out[1:, cur - rf1:cur]
+        logits = stack_window_logits(sd, hp, win, cond[:, :, cur - rf1:cur].expand(n_rep, -1, -1))
+        probs = F.softmax(logits, dim=-1)                                  # :478
+        out[1:, cur] = inverse_cdf_draw(probs, uniforms[cur - rf1])
+        probs_all.append(probs)
+    return out.float(), torch.stack(probs_all)
 
 
 def rec_loss(quant_pred, target_wav):

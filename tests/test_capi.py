@@ -27,15 +27,17 @@ def test_struct_layouts_match_header_sizes():
     import subprocess
     import tempfile
     from aewn import _lib
-    src = '#include "aewn.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(aewn_act), ' \
-          'sizeof(aewn_seg), sizeof(aewn_ntile), sizeof(aewn_tgemm_desc), sizeof(aewn_wgrad_item), ' \
-          'sizeof(aewn_wgrad_desc)); return 0;}\n'
+    src = '#include "aewn.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", ' \
+          'sizeof(aewn_act), sizeof(aewn_seg), sizeof(aewn_ntile), sizeof(aewn_tgemm_desc), sizeof(aewn_wgrad_item), ' \
+          'sizeof(aewn_wgrad_desc), sizeof(aewn_copy_block), sizeof(aewn_gen_block), sizeof(aewn_gen_desc)); ' \
+          'return 0;}\n'
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(td, "p.c"), "w").write(src)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(td, "p"), os.path.join(td, "p.c")],
                        check=True)
         sizes = [int(v) for v in subprocess.run([os.path.join(td, "p")], capture_output=True, text=True).stdout.split()]
-    mine = [ctypes.sizeof(t) for t in (_lib.Act, _lib.Seg, _lib.NTile, _lib.TGemmDesc, _lib.WGradItem, _lib.WGradDesc)]
+    mine = [ctypes.sizeof(t) for t in (_lib.Act, _lib.Seg, _lib.NTile, _lib.TGemmDesc, _lib.WGradItem, _lib.WGradDesc,
+                                       _lib.CopyBlock, _lib.GenBlock, _lib.GenDesc)]
     assert mine == sizes
 
 
@@ -49,3 +51,10 @@ def test_invalid_arguments_are_rejected_with_message():
     d.n_acts, d.n_segs, d.n_ntiles, d.batch, d.t_begin, d.t_end = 1, 1, 1, 1, 0, 128
     rc = lib.aewn_tgemm(ctypes.byref(d), None)
     assert rc != 0      # null activation pointer or missing driver entry point -- never a crash
+    g = _lib.GenDesc()
+    g.cluster, g.n_rep, g.n_layers, g.n_blocks = 3, 1, 1, 4
+    assert lib.aewn_gen_run(ctypes.byref(g), None) == -1001
+    assert b"cluster must be" in lib.aewn_last_error_string()
+    g.cluster, g.n_rep = 4, 3
+    assert lib.aewn_gen_run(ctypes.byref(g), None) == -1001
+    assert b"n_rep must be" in lib.aewn_last_error_string()

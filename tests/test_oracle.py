@@ -97,3 +97,18 @@ def test_oracle_matches_live_reference_on_fresh_seed():
     geo = dict(geo, trim_ups_out=wn.trim_ups_out.tolist(), n_win_batch=64)
     mine = orc.wavenet_forward_train(dict(wn.state_dict()), dict(hp), geo, wav, lc, spk, jit)
     assert torch.allclose(mine, quant, atol=1e-5)
+
+
+def test_forward_test_oracle_equals_reference_golden(golden_dir):
+    """The sampler restatement reproduces the reference's own forward_test run (wavenet.py:367-531) draw for draw."""
+    g = torch.load(os.path.join(golden_dir, "forward_test.pt"))
+    out, probs = orc.wavenet_forward_test(g["state_dict"], g["hp"], g["geo"]["wav_cond_offset"], g["wav"], g["lc"],
+                                          g["spk"], g["jit"], g["n_rep"], g["uniforms"])
+    assert out.shape == g["out"].shape and out.dtype == g["out"].dtype
+    assert torch.equal(out, g["out"])
+    assert probs.shape == g["probs"].shape
+    assert float((probs - g["probs"].float()).abs().max()) < 1e-3      # golden probabilities are stored in fp16
+    rf1 = g["base_global_rf"]
+    assert torch.equal(out[1:, :rf1], out[:1, :rf1].expand(2, -1))      # primed with the input
+    n_ts = rf1 + probs.shape[0]
+    assert torch.equal(out[1:, n_ts:], out[:1, n_ts:].expand(2, -1))    # untouched past the conditioning sequence
