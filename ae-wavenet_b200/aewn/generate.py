@@ -13,16 +13,24 @@ from . import ops
 
 SLICE_STEPS = 4096          # steps per launch
 SMEM_BUDGET = 227 * 1024
-GATE_CHUNK_ROWS = 4
+GATE_CHUNK_ROWS = 8
 
 
 def _r4(x):
     return (x + 3) & ~3
 
 
-def _pad_cols(m, width):
+def _slice_map(n_total, cl, device):
+    """Slice-padded layout (include/aewn.h): element i of a vector owned 1/cl per CTA -> padded position."""
+    n = n_total // cl
+    i = torch.arange(n_total, device=device)
+    return (i // n) * _r4(n) + (i % n), cl * _r4(n)
+
+
+def _scatter_cols(m, pos, width):
+    """(rows, N) -> (rows, width) with column i moved to pos[i], zeros elsewhere."""
     out = m.new_zeros(m.shape[0], width)
-    out[:, :m.shape[1]] = m
+    out[:, pos] = m
     return out
 
 
@@ -41,9 +49,7 @@ class GenPlan:
         self.R, self.D, self.S = wn.n_res, wn.n_dil, wn.n_skp
         self.P, self.Q, self.Cc = wn.post1.out_channels, wn.n_quant, wn.n_cond
         self.dils = [int(layer.dil) for layer in layers]
-        self.Rp = _r4(self.R)
         self.cond_pitch = _r4(self.Cc + 1)
-        self.KA = 2 * self.Rp + self.cond_pitch
         self.n_rep_real = int(n_rep)
         per = 1 if n_rep == 1 else 2 if n_rep == 2 else 4
         self.n_rep = per
@@ -52,7 +58,7 @@ class GenPlan:
         d = L.GenDesc()
         d.n_layers, d.R, d.D, d.S, d.P, d.Q = self.n_layers, self.R, self.D, self.S, self.P, self.Q
         d.n_rep, d.n_groups = per, self.n_groups
-        d.cond_pitch, d.base_pitch = self.cond_pitch, self.Rp
+        d.cond_pitch = self.cond_pitch
         off = 0
         for l, dl in enumerate(self.dils):
             d.dil[l] = dl
@@ -71,6 +77,10 @@ class GenPlan:
     def _set_cluster(self, cl):
         d = self.desc
         d.cluster = cl
+        self.Rp = cl * _r4(self.R // cl)
+        self.Dp, self.Sp, self.Pp = cl * _r4(self.D // cl), cl * _r4(self.S // cl), cl * _r4(self.P // cl)
+        self.KA = 2 * self.Rp + self.cond_pitch
+        d.base_pitch = self.Rp
         stage = _r4(GATE_CHUNK_ROWS * self.KA) * 4
         stage = (stage + 127) & ~127
         d.stage_bytes = stage
@@ -87,12 +97,12 @@ class GenPlan:
             a, b = d.blocks[2 * l], d.blocks[2 * l + 1]
             a.kind, a.rows, a.rowf, a.off = 0, 2 * pairs, self.KA, off
             off += a.rows * a.rowf
-            b.kind, b.rows, b.rowf, b.off = 1, (0 if final else nres) + nskp, _r4(self.D) + 4, off
+            b.kind, b.rows, b.rowf, b.off = 1, (0 if final else nres) + nskp, self.Dp + 4, off
             off += b.rows * b.rowf
         p1, p2 = d.blocks[2 * self.n_layers], d.blocks[2 * self.n_layers + 1]
-        p1.kind, p1.rows, p1.rowf, p1.off = 2, self.P // cl, _r4(self.S) + 4, off
+        p1.kind, p1.rows, p1.rowf, p1.off = 2, self.P // cl, self.Sp + 4, off
         off += p1.rows * p1.rowf
-        p2.kind, p2.rows, p2.rowf, p2.off = 3, self.Q // cl, _r4(self.P) + 4, off
+        p2.kind, p2.rows, p2.rowf, p2.off = 3, self.Q // cl, self.Pp + 4, off
         off += p2.rows * p2.rowf
         self.stream_len = _r4(off)
         d.stream_stride = self.stream_len
@@ -131,37 +141,41 @@ class GenPlan:
         def bias_of(m, n):
             return m.bias.detach().float() if m.bias is not None else torch.zeros(n, **f32)
 
+        xpos, _ = _slice_map(R, cl, dev)
+        zpos, _ = _slice_map(D, cl, dev)
+        spos, _ = _slice_map(S, cl, dev)
+        ppos, _ = _slice_map(self.P, cl, dev)
         with torch.no_grad():
             for l, layer in enumerate(wn.conv_layers):
                 rows = []
                 for conv, proj in ((layer.conv_signal, layer.proj_signal), (layer.conv_gate, layer.proj_gate)):
                     w = conv.weight.detach().float()                      # (D, R, 2): tap 0 -> x[t-d], tap 1 -> x[t]
                     m = torch.zeros(D, self.KA, **f32)
-                    m[:, :R] = w[:, :, 0]
-                    m[:, Rp:Rp + R] = w[:, :, 1]
+                    m[:, xpos] = w[:, :, 0]
+                    m[:, Rp + xpos] = w[:, :, 1]
                     m[:, 2 * Rp:2 * Rp + Cc] = proj.weight.detach().float()[:, :, 0]
                     m[:, 2 * Rp + Cc] = bias_of(conv, D)
                     rows.append(m)
                 gate = torch.stack(rows, 1)                               # (D, 2, KA): [filt_j, gate_j]
                 parts.append(gate.reshape(cl, pairs * 2 * self.KA))
-                kb = _r4(D) + 4
+                kb = self.Dp + 4
                 mix = []
                 if not layer.final_layer:
-                    mix.append(_pad_cols(layer.dil_res.weight.detach().float()[:, :, 0], kb).reshape(cl, nres * kb))
-                mix.append(_pad_cols(layer.dil_skp.weight.detach().float()[:, :, 0], kb).reshape(cl, nskp * kb))
+                    mix.append(_scatter_cols(layer.dil_res.weight.detach().float()[:, :, 0], zpos, kb)
+                               .reshape(cl, nres * kb))
+                mix.append(_scatter_cols(layer.dil_skp.weight.detach().float()[:, :, 0], zpos, kb)
+                           .reshape(cl, nskp * kb))
                 parts.append(torch.cat(mix, 1))
-            for conv, k in ((wn.post1, S), (wn.post2, self.P)):
-                kb = _r4(k) + 4
-                m = _pad_cols(conv.weight.detach().float()[:, :, 0], kb)
-                m[:, _r4(k)] = bias_of(conv, m.shape[0])
+            for conv, pos, kp in ((wn.post1, spos, self.Sp), (wn.post2, ppos, self.Pp)):
+                m = _scatter_cols(conv.weight.detach().float()[:, :, 0], pos, kp + 4)
+                m[:, kp] = bias_of(conv, m.shape[0])
                 parts.append(m.reshape(cl, -1))
             stream = torch.cat(parts, 1)
             assert stream.shape[1] <= self.stream_len, (stream.shape, self.stream_len)
             self.wstream = torch.zeros(cl, self.stream_len, **f32)
             self.wstream[:, :stream.shape[1]] = stream
             base = wn.base_layer.weight.detach().float()[:, :, 0].t()     # (Q, R)
-            self.base_t = torch.zeros(self.Q, Rp, **f32)
-            self.base_t[:, :R] = base + bias_of(wn.base_layer, R)
+            self.base_t = _scatter_cols(base + bias_of(wn.base_layer, R), xpos, Rp)
         self.desc.wstream = self.wstream.data_ptr()
         self.desc.base_t = self.base_t.data_ptr()
 

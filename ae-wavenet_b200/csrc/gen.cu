@@ -2,12 +2,17 @@
 //
 // One thread-block cluster generates for n_rep replicas.  Every CTA owns 1/cluster of the rows of every matrix of the
 // decoder and streams them (fp32, consumption order, prepared once by the host) from L2 into a shared-memory ring with
-// 1-D TMA bulk copies issued by a dedicated producer warp, so the ~54 MB of weights an arch.basic step touches flow at
+// 1-D TMA bulk copies issued by a dedicated producer warp, so the ~50 MB of weights an arch.basic step touches flow at
 // the aggregate L2 bandwidth of the cluster while the eight compute warps do the mat-vec work out of shared memory.
-// The vectors that cross CTAs (z: D floats, x: R floats, h: S/P floats, logits: Q floats per replica) are pushed with
-// st.shared::cluster into every CTA and published by a cluster-scope mbarrier (one remote arrive per CTA pair), which
-// costs a few hundred cycles where a grid-wide barrier through L2 would cost microseconds.  Per generated sample the
-// kernel executes 2*L + 3 such barriers and no launch; the reference issues several hundred launches per sample.
+//
+// The vectors that cross CTAs (z: D floats, x: R floats, h: S/P floats, logits: Q floats per replica) are exchanged
+// all-to-all through distributed shared memory: every CTA writes its slice locally, then one thread per peer issues a
+// shared->remote-shared bulk copy (cp.async.bulk.shared::cluster.shared::cta) that completes transaction bytes on the
+// PEER's mbarrier -- data movement and synchronisation are one operation, there is no separate arrive and no scalar
+// remote store (measured on B200: a scalar st.shared::cluster costs ~50 issue cycles; the first version of this kernel
+// spent 7000 cycles per layer pushing 368 of them one by one).  Vector layouts are padded per CTA slice to 16 bytes
+// (the bulk-copy granule); the host permutes weight columns to match.  Two barriers alternate so that a fast peer's
+// next-phase bytes can never complete the current phase.  Per generated sample: 2*L + 3 exchanges, zero launches.
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -17,25 +22,33 @@ namespace {
 constexpr int kGenComputeWarps = 8;
 constexpr int kCT = kGenComputeWarps * 32;  // compute threads
 constexpr int kGenThreads = kCT + 32;       // + producer warp
-constexpr int kGateChunkRows = 4;           // rows per ring stage in a gate block (2 channel pairs)
+constexpr int kGateChunkRows = 8;           // rows per ring stage in a gate block (4 channel pairs)
 
 __host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
 
-// Shared-memory carve-up, identical on host (size query) and device.
+// Shared-memory carve-up and slice geometry, identical on host (size query, validation) and device.
 struct GenLayout {
   int stages, xbuf, zbuf, h0, h1, lg, sacc, part, codes, bars, total;
-  int Rp, Dz, Sz, Pz, Qp, n_gate_chunks;
+  int pairs, pairs_p, nres, nres_p, nskp, nskp_p, np1, np1_p, np2, np2_p;  // rows per CTA and their padded slices
+  int Rp, Dp, Sp, Pp, Qp;  // padded vector lengths (cluster * slice)
+  int Dz, Sz, Pz;          // vector strides incl. the bias slot
+  int KA, n_gate_chunks, n_gate_groups;
 };
 
 __host__ __device__ inline GenLayout gen_layout(const aewn_gen_desc& p) {
   GenLayout L;
   const int nrep = p.n_rep, cl = p.cluster;
-  L.Rp = round4(p.R);
-  L.Dz = round4(p.D) + 4;
-  L.Sz = round4(p.S) + 4;
-  L.Pz = round4(p.P) + 4;
-  L.Qp = round4(p.Q);
-  L.n_gate_chunks = (2 * (p.D / cl) + kGateChunkRows - 1) / kGateChunkRows;
+  L.pairs = p.D / cl, L.pairs_p = round4(L.pairs);
+  L.nres = p.R / cl, L.nres_p = round4(L.nres);
+  L.nskp = p.S / cl, L.nskp_p = round4(L.nskp);
+  L.np1 = p.P / cl, L.np1_p = round4(L.np1);
+  L.np2 = p.Q / cl, L.np2_p = round4(L.np2);
+  L.Rp = cl * L.nres_p, L.Dp = cl * L.pairs_p, L.Sp = cl * L.nskp_p, L.Pp = cl * L.np1_p, L.Qp = cl * L.np2_p;
+  L.Dz = L.Dp + 4, L.Sz = L.Sp + 4, L.Pz = L.Pp + 4;
+  L.KA = 2 * L.Rp + p.cond_pitch;
+  L.n_gate_chunks = (2 * L.pairs + kGateChunkRows - 1) / kGateChunkRows;
+  const int group = 32 / (kGateChunkRows * nrep);  // chunks reduced together (32 partial sums per lane)
+  L.n_gate_groups = (L.n_gate_chunks + group - 1) / group;
   int o = 0;
   auto take = [&](int bytes) {
     int r = o;
@@ -48,10 +61,10 @@ __host__ __device__ inline GenLayout gen_layout(const aewn_gen_desc& p) {
   L.h0 = take(nrep * L.Sz * 4);
   L.h1 = take(nrep * L.Pz * 4);
   L.lg = take(nrep * L.Qp * 4);
-  L.sacc = take(nrep * (p.S / cl) * 4);
-  L.part = take(kGenComputeWarps * L.n_gate_chunks * kGateChunkRows * nrep * 4);
-  L.codes = take(64);
-  L.bars = take((2 * p.n_stages + 2) * 8);
+  L.sacc = take(nrep * L.nskp * 4);
+  L.part = take(kGenComputeWarps * L.n_gate_groups * 32 * 4);
+  L.codes = take(64 + 4 * AEWN_GEN_MAX_LAYERS);  // codes[4], flags, per-layer ring slots
+  L.bars = take((2 * p.n_stages + 4) * 8);
   L.total = o + 128;  // slack for aligning the dynamic base to 128 B
   return L;
 }
@@ -61,9 +74,6 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
-}
-__device__ __forceinline__ void st_cluster_f32(uint32_t raddr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
@@ -83,6 +93,21 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// 16 bytes -> a peer CTA's shared memory, completing 16 transaction bytes on the PEER's mbarrier (SASS: STAS.128)
+__device__ __forceinline__ void st_async_v4(uint32_t dst_remote, const float4& v, uint32_t bar_remote) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   dst_remote),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(bar_remote)
+               : "memory");
+}
+// Explicit shared-space 128-bit load.  The ring / vector pointers travel through structs and selects, where the compiler
+// loses the address space and falls back to generic LD.E.128 issued one at a time (measured: 2400 cycles for a 5-row
+// mat-vec pass); volatile keeps the loads in program order after the mbarrier wait, but lets them be issued together.
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
 }
 __device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
@@ -126,78 +151,164 @@ __host__ __device__ constexpr int multi_shift() {
 __device__ __forceinline__ int chunk_cap(int kind, int rowf, int stage_bytes) {
   if (kind == 0) return kGateChunkRows;
   int c = stage_bytes / (rowf * 4);
-  return c < 64 ? c : 64;
+  return c < 32 ? c : 32;
 }
 
 struct GenCtx {
-  float* stages;
+  uint32_t stages_a;  // shared-space address of the weight ring
   uint64_t* full;
   uint64_t* empty;
-  uint64_t* clbar;
+  uint64_t* xbar;     // [2] exchange barriers (count 1 + transaction bytes)
+  uint64_t* stepbar;  // arrive-counted barrier (count = cluster), once per step
   volatile int* abort;
-  uint32_t st, ph;  // ring stage / phase of the next chunk to consume
-  uint32_t clph;    // cluster barrier phase
+  uint32_t st, ph;    // ring stage / phase of the next chunk to consume
+  uint32_t xcnt;      // exchanges done
+  uint32_t stepph;
   int stage_floats, n_stages;
-  int cl;
+  int cl, cl_log2, nrep;
+  uint32_t rank;
 };
 
-// All compute threads: publish this CTA's remote stores and wait for every CTA of the cluster to do the same.
-__device__ __forceinline__ void cluster_exchange(GenCtx& g, int tid) {
-  compute_bar();
-  if (tid < g.cl) {
-    asm volatile("fence.acq_rel.cluster;" ::: "memory");
-    mbar_arrive_remote(mapa_u32(smem_u32(g.clbar), static_cast<uint32_t>(tid)));
-  }
+__device__ __forceinline__ void bounded_wait_cluster(GenCtx& g, uint64_t* bar, uint32_t parity) {
   bool ok = false;
   for (uint32_t i = 0; i < kSpinLimit; ++i) {
-    if (mbar_try_wait_cluster(g.clbar, g.clph)) {
+    if (mbar_try_wait_cluster(bar, parity)) {
       ok = true;
       break;
     }
     if ((i & 255u) == 255u && *g.abort) break;
   }
   if (!ok) *g.abort = 1;
-  g.clph ^= 1u;
 }
 
-__device__ __forceinline__ const float* acquire_chunk(GenCtx& g) {
-  if (!mbar_wait(&g.full[g.st], g.ph, g.abort)) return nullptr;
-  return g.stages + static_cast<size_t>(g.st) * g.stage_floats;
+// All-to-all exchange of one vector.  Every compute thread has finished writing this CTA's slice (n_pad floats per
+// replica, replica stride rep_stride) into its own copy of the vector; on return every CTA's slice is in place.
+// Each 16-byte piece travels as one st.async: the store and its "16 bytes arrived" signal on the peer's mbarrier are
+// a single instruction, so a peer wakes up as soon as the last piece of the last slice has landed.
+__device__ __forceinline__ void exchange_begin(GenCtx& g, int tid, const float* slice0, int rep_stride, int n_pad,
+                                               long long* dbg = nullptr) {
+  if (dbg) dbg[0] = clock64();
+  compute_bar();
+  if (dbg) dbg[1] = clock64();
+  uint64_t* bar = &g.xbar[g.xcnt & 1u];
+  const int nq = n_pad >> 2;
+  const int per_dst = g.nrep * nq;
+  if (tid == 0) mbar_expect_tx(bar, static_cast<uint32_t>(g.cl - 1) * per_dst * 16u);
+  const uint32_t bar_a = smem_u32(bar);
+  // item i: destination CTA = i mod cluster (a power of two), piece j = i / cluster = (replica q, 16-byte piece k)
+  for (int i = tid; i < (per_dst << g.cl_log2); i += kCT) {
+    const uint32_t c = static_cast<uint32_t>(i) & static_cast<uint32_t>(g.cl - 1);
+    const int j = i >> g.cl_log2;
+    const int q = (j >= nq) + (j >= 2 * nq) + (j >= 3 * nq);  // n_rep <= 4
+    const int k = j - q * nq;
+    if (c != g.rank) {
+      const float* src = slice0 + q * rep_stride + 4 * k;
+      st_async_v4(mapa_u32(smem_u32(src), c), *reinterpret_cast<const float4*>(src), mapa_u32(bar_a, c));
+    }
+  }
+  if (dbg) dbg[2] = clock64();
 }
-__device__ __forceinline__ void release_chunk(GenCtx& g, int lane) {
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&g.empty[g.st]);
+__device__ __forceinline__ void exchange_wait(GenCtx& g) {
+  bounded_wait_cluster(g, &g.xbar[g.xcnt & 1u], (g.xcnt >> 1) & 1u);
+  ++g.xcnt;
+}
+
+// Release/acquire barrier over the cluster (remote arrives): orders the GLOBAL-memory history-ring stores of one step
+// before the ring loads of later steps.  Once per step; the per-phase exchanges above carry no release semantics for
+// generic-proxy global stores.
+__device__ __forceinline__ void step_barrier(GenCtx& g, int tid) {
+  compute_bar();
+  if (tid < g.cl) {
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    mbar_arrive_remote(mapa_u32(smem_u32(g.stepbar), static_cast<uint32_t>(tid)));
+  }
+  bounded_wait_cluster(g, g.stepbar, g.stepph);
+  g.stepph ^= 1u;
+}
+
+// Returns false once the CTA is aborting (the caller skips the math but keeps the control flow).
+__device__ __forceinline__ bool acquire_chunk(GenCtx& g, uint32_t& addr) {
+  addr = g.stages_a + g.st * static_cast<uint32_t>(g.stage_floats) * 4u;
+  return mbar_wait(&g.full[g.st], g.ph, g.abort);
+}
+__device__ __forceinline__ void advance_chunk(GenCtx& g) {
   if (++g.st == static_cast<uint32_t>(g.n_stages)) {
     g.st = 0;
     g.ph ^= 1u;
   }
 }
+__device__ __forceinline__ void release_chunk(GenCtx& g, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&g.empty[g.st]);
+  advance_chunk(g);
+}
 
-// A "mix"-type block: rows x rowf weights against vec[NREP][rowf]; warp w takes rows w, w+8, ...; lanes split the
-// columns.  epi(row, rep, value) runs on exactly one lane per (row, rep).
+// A "mix"-type block: rows x rowf weights against vec[NREP][rowf].  Two ring stages are taken per pass and their rows
+// dealt to the 8 warps in one round (up to 8 consecutive rows per warp, all partial sums in flight together, ONE
+// multi-value reduction); lanes split the columns.  epi(row, rep, value) runs on exactly one lane per (row, rep).
 template <int NREP, typename Epi>
-__device__ __forceinline__ void matvec_block(GenCtx& g, const aewn_gen_block& blk, const float* vec, int stage_bytes,
-                                             int warp, int lane, Epi epi) {
+__device__ __forceinline__ void matvec_block(GenCtx& g, const aewn_gen_block& blk, const float* vec, int cap, int warp,
+                                             int lane, Epi epi, long long* dbg = nullptr) {
+  constexpr int RB = 8;
+  constexpr int V = RB * NREP;
+  constexpr int sh = multi_shift<V>();
   const int rowq = blk.rowf >> 2;
-  const int cap = chunk_cap(blk.kind, blk.rowf, stage_bytes);
-  constexpr int sh = multi_shift<NREP>();
-  for (int r0 = 0; r0 < blk.rows; r0 += cap) {
-    const int m = min(cap, blk.rows - r0);
-    const float* sp = acquire_chunk(g);  // nullptr once the CTA is aborting: skip the math, keep the control flow
-    const float4* w4 = reinterpret_cast<const float4*>(sp);
-    for (int r = warp; sp && r < m; r += kGenComputeWarps) {
-      float acc[NREP];
-#pragma unroll
-      for (int q = 0; q < NREP; ++q) acc[q] = 0.f;
-      for (int c = lane; c < rowq; c += 32) {
-        const float4 w = w4[r * rowq + c];
-#pragma unroll
-        for (int q = 0; q < NREP; ++q) acc[q] = dot4(w, reinterpret_cast<const float4*>(vec + q * blk.rowf)[c], acc[q]);
-      }
-      MultiReduce<NREP, 16>::run(acc, lane);
-      if ((lane & ((1 << sh) - 1)) == 0) epi(r0 + r, lane >> sh, acc[0]);
+  const uint32_t rowb = static_cast<uint32_t>(blk.rowf) * 4u;
+  const uint32_t vec_a = smem_u32(vec);
+  for (int r0 = 0; r0 < blk.rows; r0 += 2 * cap) {
+    const int m = min(2 * cap, blk.rows - r0);  // rows of this pass: [0, cap) in stage A, [cap, m) in stage B
+    if (dbg) *dbg++ = clock64();
+    uint32_t spA, spB;
+    bool ok = acquire_chunk(g, spA);
+    const uint32_t stA = g.st;
+    advance_chunk(g);
+    uint32_t stB = stA;
+    spB = spA;
+    if (m > cap) {
+      ok = acquire_chunk(g, spB) && ok;
+      stB = g.st;
+      advance_chunk(g);
     }
-    release_chunk(g, lane);
+    if (dbg) *dbg++ = clock64();
+    const int rbw = (m + kGenComputeWarps - 1) / kGenComputeWarps;  // rows per warp, <= RB by construction of cap
+    const int rb = warp * rbw;
+    const int nr = min(rbw, m - rb);  // rows of this warp (may be <= 0)
+    if (ok && nr > 0) {
+      float acc[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = 0.f;
+      uint32_t wrow[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int row = min(rb + r, m - 1);  // clamp: surplus slots re-read the last row, their sums are discarded
+        wrow[r] = (row < cap ? spA + row * rowb : spB + (row - cap) * rowb) + lane * 16u;
+      }
+      for (int c = lane; c < rowq; c += 32) {
+        float4 w[RB], zv[NREP];
+#pragma unroll
+        for (int q = 0; q < NREP; ++q) zv[q] = lds128(vec_a + q * rowb + c * 16u);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          w[r] = lds128(wrow[r]);
+          wrow[r] += 512u;
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r)
+#pragma unroll
+          for (int q = 0; q < NREP; ++q) acc[r * NREP + q] = dot4(w[r], zv[q], acc[r * NREP + q]);
+      }
+      MultiReduce<V, 16>::run(acc, lane);
+      const int vi = lane >> sh;  // value index r * NREP + q held by this lane
+      const int r = vi / NREP;
+      if ((lane & ((1 << sh) - 1)) == 0 && r < nr) epi(r0 + rb + r, vi % NREP, acc[0]);
+    }
+    if (dbg) *dbg++ = clock64();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&g.empty[stA]);
+      if (m > cap) mbar_arrive(&g.empty[stB]);
+    }
+    if (dbg) *dbg++ = clock64();
   }
 }
 
@@ -221,30 +332,36 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_kernel(const __grid_consta
   float* part = reinterpret_cast<float*>(smem + L.part);
   int* codes = reinterpret_cast<int*>(smem + L.codes);
   volatile int* abort_flag = codes + 8;
+  volatile int* stop_flag = codes + 9;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty = full + p.n_stages;
-  uint64_t* clbar = empty + p.n_stages;
+  uint64_t* xbar = empty + p.n_stages;  // [2]
+  uint64_t* stepbar = xbar + 2;
 
   const int Rp = L.Rp, RQ = Rp >> 2;
-  const int KA = 2 * Rp + p.cond_pitch, KAQ = KA >> 2;
-  const int pairs = p.D / CL, nres = p.R / CL, nskp = p.S / CL, np1 = p.P / CL, np2 = p.Q / CL;
+  const int KAQ = L.KA >> 2;
+  const int pairs = L.pairs, nres = L.nres, nskp = L.nskp, np1 = L.np1, np2 = L.np2;
 
   if (tid == 0) {
     for (int i = 0; i < p.n_stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], kGenComputeWarps);
     }
-    mbar_init(clbar, CL);
+    mbar_init(&xbar[0], 1);
+    mbar_init(&xbar[1], 1);
+    mbar_init(stepbar, CL);
     fence_barrier_init();
     *abort_flag = 0;
+    *stop_flag = 0;
   }
-  // constant parts of the exchanged vectors: bias column = 1, padding = 0
-  for (int i = tid; i < NREP * L.Dz; i += kGenThreads) zbuf[i] = (i % L.Dz == round4(p.D)) ? 1.f : 0.f;
-  for (int i = tid; i < NREP * L.Sz; i += kGenThreads) h0[i] = (i % L.Sz == round4(p.S)) ? 1.f : 0.f;
-  for (int i = tid; i < NREP * L.Pz; i += kGenThreads) h1[i] = (i % L.Pz == round4(p.P)) ? 1.f : 0.f;
+  // constant parts of the exchanged vectors: bias slot = 1, slice padding = 0 (finite, its weight columns are zero)
+  for (int i = tid; i < NREP * L.Dz; i += kGenThreads) zbuf[i] = (i % L.Dz == L.Dp) ? 1.f : 0.f;
+  for (int i = tid; i < NREP * L.Sz; i += kGenThreads) h0[i] = (i % L.Sz == L.Sp) ? 1.f : 0.f;
+  for (int i = tid; i < NREP * L.Pz; i += kGenThreads) h1[i] = (i % L.Pz == L.Pp) ? 1.f : 0.f;
+  for (int i = tid; i < NREP * L.Qp; i += kGenThreads) lg[i] = 0.f;
   for (int i = tid; i < 2 * NREP * Rp; i += kGenThreads) xbuf[i] = 0.f;
   __syncthreads();
-  cluster_sync_all();  // barriers initialised cluster-wide before any remote arrive / store
+  cluster_sync_all();  // barriers initialised cluster-wide before any remote copy / arrive
 
   const float* ws = p.wstream + static_cast<size_t>(rank) * p.stream_stride;
 
@@ -280,17 +397,22 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_kernel(const __grid_consta
   } else {
     // ================================================================ compute warps
     GenCtx g;
-    g.stages = stages;
+    g.stages_a = smem_u32(stages);
     g.full = full;
     g.empty = empty;
-    g.clbar = clbar;
+    g.xbar = xbar;
+    g.stepbar = stepbar;
     g.abort = abort_flag;
     g.st = 0;
     g.ph = 0;
-    g.clph = 0;
+    g.xcnt = 0;
+    g.stepph = 0;
     g.stage_floats = p.stage_bytes >> 2;
     g.n_stages = p.n_stages;
     g.cl = CL;
+    g.cl_log2 = 31 - __clz(CL);
+    g.nrep = NREP;
+    g.rank = rank;
 
     const size_t hist_slots = static_cast<size_t>(p.hist_off[p.n_layers]);
     float* hist_g = p.hist + static_cast<size_t>(group) * NREP * hist_slots * Rp;
@@ -303,9 +425,18 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_kernel(const __grid_consta
 #pragma unroll
       for (int q = 0; q < NREP; ++q) xv[c][q] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    // rows per ring stage of the mat-vec blocks; 2 stages are dealt to 8 warps x <= 8 rows in one round
+    const int cap_mix = chunk_cap(1, L.Dz, p.stage_bytes);
+    const int cap_p1 = chunk_cap(2, L.Sz, p.stage_bytes);
+    const int cap_p2 = chunk_cap(3, L.Pz, p.stage_bytes);
+
+    // history-ring slot of step t per layer (t mod (d+1)), kept incrementally: no divisions inside the step loop
+    int* hslot = codes + 16;  // [n_layers] ints in the codes/flags area
+    for (int l = tid; l < p.n_layers; l += kCT) hslot[l] = p.t_begin % (p.dil[l] + 1);
+    compute_bar();
+
     int cur = 0;
-    constexpr int shA = multi_shift<kGateChunkRows * NREP>();
-    volatile int* stop_flag = codes + 9;
+    constexpr int kGroup = 32 / (kGateChunkRows * NREP);  // gate chunks whose partial sums are reduced together
 
     // Abort protocol: a failed (bounded) wait raises *abort_flag and the math of the affected chunk is skipped, but the
     // control flow of the step -- every CTA barrier, every ring release -- still runs, so no thread is left behind at a
@@ -328,15 +459,14 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_kernel(const __grid_consta
         }
         codes[tid] = c;
       }
-      compute_bar();
+      step_barrier(g, tid);  // also publishes codes / stop_flag CTA-wide
       if (*stop_flag) break;
       for (int i = tid; i < NREP * RQ; i += kCT) {
         const int q = i / RQ, c = i - q * RQ;
         const float4 v = __ldg(reinterpret_cast<const float4*>(p.base_t + static_cast<size_t>(codes[q]) * p.base_pitch) + c);
         reinterpret_cast<float4*>(xbuf + (cur * NREP + q) * Rp)[c] = v;
         if (rank == 0) {
-          const int d0 = p.dil[0];
-          float* dst = hist_g + (static_cast<size_t>(q) * hist_slots + p.hist_off[0] + (t % (d0 + 1))) * Rp;
+          float* dst = hist_g + (static_cast<size_t>(q) * hist_slots + p.hist_off[0] + hslot[0]) * Rp;
           __stcg(reinterpret_cast<float4*>(dst) + c, v);
         }
       }
@@ -353,7 +483,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_kernel(const __grid_consta
       }
       auto prefetch_hist = [&](int l) {
         const int d = p.dil[l];
-        const int slot = (t + 1) % (d + 1);  // == (t - d) mod (d + 1)
+        const int slot = (hslot[l] == d) ? 0 : hslot[l] + 1;  // (t + 1) mod (d + 1) == (t - d) mod (d + 1)
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int col = tid + c * kCT;
@@ -384,34 +514,47 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_kernel(const __grid_consta
               xv[c][q] = reinterpret_cast<const float4*>(xbuf + (cur * NREP + q) * Rp)[col - RQ];
           }
         }
-        int chunk = 0;
-        for (int r0 = 0; r0 < blkA.rows; r0 += kGateChunkRows, ++chunk) {
-          const int m = min(kGateChunkRows, blkA.rows - r0);
-          const float* sp = acquire_chunk(g);
-          const float4* w4 = reinterpret_cast<const float4*>(sp);
-          float acc[kGateChunkRows * NREP];
+        for (int g0 = 0, grp = 0; g0 < L.n_gate_chunks; g0 += kGroup, ++grp) {
+          float acc[32];
 #pragma unroll
-          for (int i = 0; i < kGateChunkRows * NREP; ++i) acc[i] = 0.f;
-          if (sp) {
+          for (int i = 0; i < 32; ++i) acc[i] = 0.f;
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-              const int col = tid + c * kCT;
-              if (col < KAQ) {
+          for (int ci = 0; ci < kGroup; ++ci) {
+            const int chunk = g0 + ci;
+            if (chunk < L.n_gate_chunks) {
+              const int m = min(kGateChunkRows, blkA.rows - chunk * kGateChunkRows);
+              if (stamp && l == 3) p.dbg_clock[256 + 3 * chunk] = clock64();
+              uint32_t sp;
+              const bool ok = acquire_chunk(g, sp);
+              if (stamp && l == 3) p.dbg_clock[256 + 3 * chunk + 1] = clock64();
+              if (ok) {
 #pragma unroll
-                for (int r = 0; r < kGateChunkRows; ++r) {
-                  if (r < m) {
-                    const float4 w = w4[r * KAQ + col];
+                for (int c = 0; c < NC; ++c) {
+                  const int col = tid + c * kCT;
+                  if (col < KAQ) {
+                    float4 w[kGateChunkRows];
 #pragma unroll
-                    for (int q = 0; q < NREP; ++q) acc[r * NREP + q] = dot4(w, xv[c][q], acc[r * NREP + q]);
+                    for (int r = 0; r < kGateChunkRows; ++r)   // rows >= m of a ragged last chunk re-read row m-1
+                      w[r] = lds128(sp + (static_cast<uint32_t>(min(r, m - 1)) * KAQ + col) * 16u);
+#pragma unroll
+                    for (int r = 0; r < kGateChunkRows; ++r) {
+                      if (r < m) {
+#pragma unroll
+                        for (int q = 0; q < NREP; ++q) {
+                          const int ai = (ci * kGateChunkRows + r) * NREP + q;
+                          acc[ai] = dot4(w[r], xv[c][q], acc[ai]);
+                        }
+                      }
+                    }
                   }
                 }
               }
+              release_chunk(g, lane);
+              if (stamp && l == 3) p.dbg_clock[256 + 3 * chunk + 2] = clock64();
             }
           }
-          release_chunk(g, lane);
-          MultiReduce<kGateChunkRows * NREP, 16>::run(acc, lane);
-          if ((lane & ((1 << shA) - 1)) == 0)
-            part[(warp * L.n_gate_chunks + chunk) * (kGateChunkRows * NREP) + (lane >> shA)] = acc[0];
+          MultiReduce<32, 16>::run(acc, lane);
+          part[(warp * L.n_gate_groups + grp) * 32 + lane] = acc[0];
         }
         mark();
         compute_bar();
@@ -419,77 +562,99 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_kernel(const __grid_consta
         for (int v = tid; v < pairs * NREP; v += kCT) {
           const int j = v / NREP, q = v - j * NREP;
           const int ch = (2 * j) / kGateChunkRows, r = (2 * j) % kGateChunkRows;
+          const int grp = ch / kGroup, ci = ch - grp * kGroup;
+          const int vi = (ci * kGateChunkRows + r) * NREP + q;
           float f = 0.f, gt = 0.f;
 #pragma unroll
           for (int w = 0; w < kGenComputeWarps; ++w) {
-            const float* pp = part + (w * L.n_gate_chunks + ch) * (kGateChunkRows * NREP);
-            f += pp[r * NREP + q];
-            gt += pp[(r + 1) * NREP + q];
+            const float* pp = part + (w * L.n_gate_groups + grp) * 32;
+            f += pp[vi];
+            gt += pp[vi + NREP];
           }
-          const float z = tanhf(f) * (1.0f / (1.0f + expf(-gt)));
-          const uint32_t la = smem_u32(zbuf + q * L.Dz + rank * pairs + j);
-          for (int c = 0; c < CL; ++c) st_cluster_f32(mapa_u32(la, c), z);
+          zbuf[q * L.Dz + rank * L.pairs_p + j] = tanhf(f) * (1.0f / (1.0f + expf(-gt)));
         }
         mark();
-        cluster_exchange(g, tid);
+        exchange_begin(g, tid, zbuf + rank * L.pairs_p, L.Dz, L.pairs_p, (stamp && l == 3) ? p.dbg_clock + 320 : nullptr);
+        if (l + 1 < p.n_layers) prefetch_hist(l + 1);
+        if (stamp && l == 3) p.dbg_clock[323] = clock64();
+        exchange_wait(g);
+        if (stamp && l == 3) p.dbg_clock[324] = clock64();
         mark();
         // ------------------------------------------------------------ mix block: residual rows, then skip rows
-        if (l + 1 < p.n_layers) prefetch_hist(l + 1);
         const int nres_l = final_layer ? 0 : nres;
-        const int dn = (l + 1 < p.n_layers) ? p.dil[l + 1] : 0;
-        const size_t ring_next = (l + 1 < p.n_layers) ? static_cast<size_t>(p.hist_off[l + 1] + (t % (dn + 1))) : 0;
-        const bool push_h0 = samp && (l + 1 == p.n_layers);
-        matvec_block<NREP>(g, blkB, zbuf, p.stage_bytes, warp, lane, [&](int row, int q, float val) {
+        matvec_block<NREP>(g, blkB, zbuf, cap_mix, warp, lane, [&](int row, int q, float val) {
           if (row < nres_l) {
-            const int grow = rank * nres + row;
-            const float xn = val + xbuf[(cur * NREP + q) * Rp + grow];
-            const uint32_t la = smem_u32(xbuf + ((cur ^ 1) * NREP + q) * Rp + grow);
-            for (int c = 0; c < CL; ++c) st_cluster_f32(mapa_u32(la, c), xn);
-            __stcg(hist_g + (static_cast<size_t>(q) * hist_slots + ring_next) * Rp + grow, xn);
+            const int grow = rank * L.nres_p + row;
+            xbuf[((cur ^ 1) * NREP + q) * Rp + grow] = val + xbuf[(cur * NREP + q) * Rp + grow];
           } else {
             const int srow = row - nres_l;
             const float sv = sacc[q * nskp + srow] + val;
             sacc[q * nskp + srow] = sv;
-            if (push_h0) {
-              const uint32_t la = smem_u32(h0 + q * L.Sz + rank * nskp + srow);
-              const float h = fmaxf(sv, 0.f);
-              for (int c = 0; c < CL; ++c) st_cluster_f32(mapa_u32(la, c), h);
-            }
+            h0[q * L.Sz + rank * L.nskp_p + srow] = fmaxf(sv, 0.f);  // only the last layer's value is exchanged
           }
-        });
+        }, (stamp && l == 3) ? p.dbg_clock + 300 : nullptr);
         mark();
-        cluster_exchange(g, tid);
+        if (!final_layer) {
+          exchange_begin(g, tid, xbuf + (cur ^ 1) * NREP * Rp + rank * L.nres_p, Rp, L.nres_p);
+          // this CTA's slice of x_{l+1}[t] -> history ring (after the bar.sync inside exchange_begin)
+          const size_t slot = static_cast<size_t>(p.hist_off[l + 1] + hslot[l + 1]);
+          const int nq = L.nres_p >> 2;
+          for (int i = tid; i < NREP * nq; i += kCT) {
+            const int q = i / nq, c = i - q * nq;
+            const float4 v = reinterpret_cast<const float4*>(xbuf + ((cur ^ 1) * NREP + q) * Rp + rank * L.nres_p)[c];
+            __stcg(reinterpret_cast<float4*>(hist_g + (static_cast<size_t>(q) * hist_slots + slot) * Rp +
+                                             rank * L.nres_p) + c, v);
+          }
+          exchange_wait(g);
+          cur ^= 1;
+        } else {
+          exchange_begin(g, tid, h0 + rank * L.nskp_p, L.Sz, L.nskp_p);
+          exchange_wait(g);
+        }
         mark();
-        if (!final_layer) cur ^= 1;
       }
+
+      if (tid < p.n_layers) hslot[tid] = (hslot[tid] == p.dil[tid]) ? 0 : hslot[tid] + 1;  // read again after a bar.sync
 
       if (samp) {
         // ---------------------------------------------------------------- post-net, softmax, inverse-CDF draw
         const aewn_gen_block blk1 = p.blocks[2 * p.n_layers];
         const aewn_gen_block blk2 = p.blocks[2 * p.n_layers + 1];
-        matvec_block<NREP>(g, blk1, h0, p.stage_bytes, warp, lane, [&](int row, int q, float val) {
-          const uint32_t la = smem_u32(h1 + q * L.Pz + rank * np1 + row);
-          const float h = fmaxf(val, 0.f);
-          for (int c = 0; c < CL; ++c) st_cluster_f32(mapa_u32(la, c), h);
+        matvec_block<NREP>(g, blk1, h0, cap_p1, warp, lane, [&](int row, int q, float val) {
+          h1[q * L.Pz + rank * L.np1_p + row] = fmaxf(val, 0.f);
         });
-        cluster_exchange(g, tid);
-        matvec_block<NREP>(g, blk2, h1, p.stage_bytes, warp, lane, [&](int row, int q, float val) {
-          const uint32_t la = smem_u32(lg + q * L.Qp + rank * np2 + row);
-          for (int c = 0; c < CL; ++c) st_cluster_f32(mapa_u32(la, c), val);
-        });
-        cluster_exchange(g, tid);
+        exchange_begin(g, tid, h1 + rank * L.np1_p, L.Pz, L.np1_p);
+        exchange_wait(g);
+        matvec_block<NREP>(g, blk2, h1, cap_p2, warp, lane,
+                           [&](int row, int q, float val) { lg[q * L.Qp + rank * L.np2_p + row] = val; });
+        exchange_begin(g, tid, lg + rank * L.np2_p, L.Qp, L.np2_p);
+        exchange_wait(g);
         if (warp < NREP && !*abort_flag) {
           // every CTA draws redundantly from identical logits, so the new code needs no further exchange
           const int q = warp;
           const float* lq = lg + q * L.Qp;
           const int per = (p.Q + 31) / 32;
           const int k0 = lane * per, k1 = min(p.Q, k0 + per);
+          const int pad = L.np2_p - np2;
+          const int base = (k0 / np2) * L.np2_p + (k0 % np2), left0 = np2 - (k0 % np2);
+          // logit(k) for k = k0, k0+1, ...: walk the slice-padded layout without a division per element
+          auto walk = [&](auto&& body) {
+            int pos = base, left = left0;
+            for (int k = k0; k < k1; ++k) {
+              body(lq[pos]);
+              ++pos;
+              if (--left == 0) {
+                pos += pad;
+                left = np2;
+              }
+            }
+          };
           float m = -INFINITY;
-          for (int k = k0; k < k1; ++k) m = fmaxf(m, lq[k]);
+          walk([&](float v) { m = fmaxf(m, v); });
 #pragma unroll
           for (int s = 16; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
           float mine = 0.f;
-          for (int k = k0; k < k1; ++k) mine += expf(lq[k] - m);
+          walk([&](float v) { mine += expf(v - m); });
           float incl = mine;
 #pragma unroll
           for (int s = 1; s < 32; s <<= 1) {
@@ -501,10 +666,10 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_kernel(const __grid_consta
           const float target = u * total;
           float run = incl - mine;
           int cnt = 0;
-          for (int k = k0; k < k1; ++k) {
-            run += expf(lq[k] - m);
+          walk([&](float v) {
+            run += expf(v - m);
             cnt += (run <= target) ? 1 : 0;
-          }
+          });
 #pragma unroll
           for (int s = 16; s >= 1; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
           const int idx = min(cnt, p.Q - 1);
@@ -514,7 +679,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_kernel(const __grid_consta
           }
           if (rank == 0 && p.logits_out) {
             float* dst = p.logits_out + ((static_cast<size_t>(group) * NREP + q) * p.wav_pitch + t + 1) * p.Q;
-            for (int k = lane; k < p.Q; k += 32) dst[k] = lq[k];
+            for (int k = lane; k < p.Q; k += 32) dst[k] = lq[(k / np2) * L.np2_p + (k % np2)];
           }
         }
       }
@@ -522,7 +687,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_kernel(const __grid_consta
     if (tid == 0 && *abort_flag) atomicCAS(p.err, 0, AEWN_ERR_TIMEOUT);
   }
   __syncthreads();
-  cluster_sync_all();  // no CTA leaves while a peer may still store into or arrive on its shared memory
+  cluster_sync_all();  // no CTA leaves while a peer may still copy into or arrive on its shared memory
 }
 
 typedef void (*GenKernel)(const aewn_gen_desc);
@@ -555,12 +720,16 @@ int validate(const aewn_gen_desc* d, int* nc_out) {
                    d->P, d->Q);
   if (d->Q > 1024) return set_err(AEWN_ERR_INVALID, "gen: Q=%d > 1024", d->Q);
   if (d->n_groups < 1) return set_err(AEWN_ERR_INVALID, "gen: n_groups must be positive");
-  if ((d->cond_pitch & 3) || d->base_pitch != round4(d->R))
-    return set_err(AEWN_ERR_INVALID, "gen: cond_pitch %% 4 and base_pitch == round4(R) required");
+  aewn_gen_desc probe = *d;
+  probe.n_stages = probe.n_stages > 0 ? probe.n_stages : 2;
+  const GenLayout L = gen_layout(probe);
+  if ((d->cond_pitch & 3) || d->base_pitch != L.Rp)
+    return set_err(AEWN_ERR_INVALID, "gen: cond_pitch %% 4 and base_pitch == cluster*round4(R/cluster) = %d required",
+                   L.Rp);
   if (d->t_begin < 0 || d->t_end < d->t_begin || d->t_end >= d->wav_pitch || d->t_end > d->cond_len)
     return set_err(AEWN_ERR_INVALID, "gen: step range [%d, %d) outside wav_pitch %d / cond_len %d", d->t_begin,
                    d->t_end, d->wav_pitch, d->cond_len);
-  const int ka = 2 * round4(d->R) + d->cond_pitch;
+  const int ka = L.KA;
   const int nc = (ka / 4 + kCT - 1) / kCT;
   if (nc > 2) return set_err(AEWN_ERR_INVALID, "gen: gate row of %d floats exceeds %d", ka, 8 * kCT);
   if ((d->stage_bytes & 15) || d->stage_bytes < kGateChunkRows * ka * 4 || d->n_stages < 2 || d->n_stages > 32)
@@ -574,14 +743,14 @@ int validate(const aewn_gen_desc* d, int* nc_out) {
     if (a.kind != 0 || a.rows != 2 * (d->D / cl) || a.rowf != ka)
       return set_err(AEWN_ERR_INVALID, "gen: layer %d gate block malformed", l);
     const bool fin = (b.rows == d->S / cl);
-    if (b.kind != 1 || b.rowf != round4(d->D) + 4 || !(fin || b.rows == d->R / cl + d->S / cl))
+    if (b.kind != 1 || b.rowf != L.Dz || !(fin || b.rows == d->R / cl + d->S / cl))
       return set_err(AEWN_ERR_INVALID, "gen: layer %d mix block malformed", l);
     if (b.rowf * 4 > d->stage_bytes) return set_err(AEWN_ERR_INVALID, "gen: mix row larger than a stage");
   }
   const aewn_gen_block& p1 = d->blocks[2 * d->n_layers];
   const aewn_gen_block& p2 = d->blocks[2 * d->n_layers + 1];
-  if (p1.kind != 2 || p1.rows != d->P / cl || p1.rowf != round4(d->S) + 4 || p2.kind != 3 || p2.rows != d->Q / cl ||
-      p2.rowf != round4(d->P) + 4 || p1.rowf * 4 > d->stage_bytes || p2.rowf * 4 > d->stage_bytes)
+  if (p1.kind != 2 || p1.rows != d->P / cl || p1.rowf != L.Sz || p2.kind != 3 || p2.rows != d->Q / cl ||
+      p2.rowf != L.Pz || p1.rowf * 4 > d->stage_bytes || p2.rowf * 4 > d->stage_bytes)
     return set_err(AEWN_ERR_INVALID, "gen: post-net blocks malformed");
   if (!d->wstream || !d->cond || !d->base_t || !d->hist || !d->wav || !d->uniforms || !d->err)
     return set_err(AEWN_ERR_INVALID, "gen: null device pointer");

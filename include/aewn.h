@@ -243,11 +243,17 @@ int aewn_nll_bwd(const float* logits, long long x_bs, long long x_cs, const floa
  * if tau+1 >= t_prime: logits = post2(relu(post1(relu(skip)))); wav[rep][tau+1] = first k with
  * cumsum(softmax(logits))[k] > uniforms[rep][tau+1]   (inverse-CDF draw, distributed like torch.multinomial).
  *
- * Per-CTA weight stream (floats), CTA rank c, in consumption order; every row is padded to a multiple of 4 floats:
- *   kind 0 (gate)  : 2*D/cluster rows [filt_j, gate_j interleaved] x KA, KA = 2*Rp + cond_pitch
+ * Slice-padded vector layout.  A vector of N elements owned 1/cluster per CTA (n = N/cluster each) is stored with
+ * every CTA's slice padded to n_p = round4(n) floats -- element i lives at (i / n) * n_p + (i % n), total length
+ * Np = cluster * n_p -- because slices travel between CTAs as 16-byte-granular bulk copies.  x (R), z (D), h0 (S),
+ * h1 (P) and the logits (Q) use it; matrix columns that multiply such a vector are permuted / zero-padded to match.
+ *
+ * Per-CTA weight stream (floats), CTA rank c, in consumption order:
+ *   kind 0 (gate)  : 2*D/cluster rows [filt_j, gate_j interleaved] x KA, KA = 2*Rp + cond_pitch, columns
+ *                    [tap x[t-d] (Rp) | tap x[t] (Rp) | cond (C) | bias | 0..]
  *   kind 1 (mix)   : R/cluster residual rows (absent in the final layer) then S/cluster skip rows, x (Dp + 4)
  *   kind 2 (post1) : P/cluster rows x (Sp + 4);   kind 3 (post2): Q/cluster rows x (Pp + 4)
- * where Xp = X rounded up to 4 and the column at index Xp holds the bias (the vector carries 1.0 there).
+ * where the column at index Xp holds the bias (the vector carries 1.0 there).
  * ------------------------------------------------------------------------------------------------------------ */
 #define AEWN_GEN_MAX_LAYERS 64
 #define AEWN_GEN_MAX_BLOCKS (2 * AEWN_GEN_MAX_LAYERS + 2)
@@ -274,9 +280,10 @@ typedef struct {
   long long stream_stride;
   const float* cond;           /* [cond_len][cond_pitch] time-major, = [cond(C) | 1 | 0..]; shared by all replicas */
   int cond_pitch, cond_len;
-  const float* base_t;         /* [Q][base_pitch]: row q = base weight column q + bias (wavenet.py:253, 462-463) */
+  const float* base_t;         /* [Q][base_pitch]: row q = base weight column q + bias (wavenet.py:253, 462-463),
+                                  slice-padded x layout */
   int base_pitch;              /* = Rp */
-  float* hist;                 /* [n_groups*n_rep][hist_off[n_layers]][Rp], zero before the first launch */
+  float* hist;                 /* [n_groups*n_rep][hist_off[n_layers]][Rp] (x layout), zero before the first launch */
   int* wav;                    /* [n_groups*n_rep][wav_pitch] int32 codes, read for tau < t_prime, written after */
   int wav_pitch;
   const float* uniforms;       /* [n_groups*n_rep][wav_pitch] U[0,1) */

@@ -1,7 +1,7 @@
 """GPU parity of the persistent incremental sampler (csrc/gen.cu) behind WaveNet.forward_test (wavenet.py:367-531).
 
-The kernel computes in fp32 FMA (no TF32); against the fp32 CPU oracle the logits agree to ~1e-5 relative, the tests
-assert 2e-4.  Draws are inverse-CDF draws on supplied uniforms, so a whole generated sequence is reproducible and
+The kernel computes in fp32 FMA (no TF32); against a float64 oracle fed the same conditioning the logits agree to
+~1e-6 of the logit scale, the tests assert 2e-5.  Draws are inverse-CDF draws on supplied uniforms, so a whole generated sequence is reproducible and
 is compared sample for sample with the reference's own run (golden) and with the oracle."""
 import os
 
@@ -130,13 +130,16 @@ def test_arch_basic_generation_is_teacher_forced_consistent(n_rep, n_res):
     # float64 oracle: separates the kernel's fp32 rounding from the fp32 CPU oracle's own (both ~1e-4 of the logit
     # scale after 20 layers of 875-term dot products)
     sd = {k: (v.detach().cpu().double() if v.is_floating_point() else v.detach().cpu()) for k, v in wn.state_dict().items()}
-    cond = orc.conditioning(sd, hp, lc.double(), spk, jit, None)
+    # conditioning comes from the module's own front-end (cuDNN, TF32 by default -- like the reference on a GPU), so
+    # that the comparison isolates the sampler kernel
+    with torch.no_grad():
+        cond = wn.conditioning(lc.cuda(), spk.cuda(), jit.cuda(), trim=False).cpu().double()
     logits = wn.gen_logits.cpu()
     for cur in (rf1, rf1 + 1, rf1 + 2, rf1 + 77, n_ts - 1):
         ref = orc.stack_window_logits(sd, hp, out[1:, cur - rf1:cur], cond[:, :, cur - rf1:cur].expand(n_rep, -1, -1))
         got = logits[:, cur]
         err = float((got.double() - ref).abs().max()) / float(ref.abs().max())
-        assert err < 2e-4, (cur, err)
+        assert err < 2e-5, (cur, err)
         draw = orc.inverse_cdf_draw(F.softmax(got, -1), u[:, cur])
         cdf = F.softmax(got.double(), -1).cumsum(-1)
         for r in range(n_rep):
@@ -150,8 +153,8 @@ def test_invalid_code_is_reported():
     from aewn import ops
     g_hp = dict(ARCH_BASIC, n_res=64, n_dil=32, n_skp=32, n_post=32, n_lc_out=16, n_blocks=1, n_block_layers=3)
     wn = build(g_hp, 64, seed=3)
-    lc = torch.randn(1, g_hp["n_lc_in"], 4)
+    lc = torch.randn(1, g_hp["n_lc_in"], 8)
     off0 = int(wn.wav_cond_offset[0])
     wav = torch.full((1, off0 + 2000), 300.0)        # 300 is not a mu-law code; the reference raises in F.one_hot
     with pytest.raises(RuntimeError, match="invalid input"):
-        wn(wav.cuda(), lc.cuda(), torch.zeros(1, dtype=torch.long).cuda(), torch.arange(4).unsqueeze(0).cuda())
+        wn(wav.cuda(), lc.cuda(), torch.zeros(1, dtype=torch.long).cuda(), torch.arange(8).unsqueeze(0).cuda())
