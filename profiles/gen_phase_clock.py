@@ -1,5 +1,12 @@
-import sys, torch, ctypes as C
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/ae-wavenet_b200')
+"""Phase breakdown of one generated sample inside the persistent sampler kernel (csrc/gen.cu).
+
+The kernel's optional `dbg_clock` hook makes CTA 0 / thread 0 write clock64() stamps for the 9th step of a launch:
+step prologue, then per layer: gate chunks, CTA barrier, z finalize, z exchange, mix block, x exchange.
+    python profiles/gen_phase_clock.py > profiles/r1g_gen_phase_clock.txt      (on the GPU box)
+"""
+import os, sys, torch, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'ae-wavenet_b200'))
 import bench_generate as bg
 from aewn import generate
 wn = bg.build()
