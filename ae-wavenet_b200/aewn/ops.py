@@ -7,10 +7,25 @@ on ONE time axis tau in [0, T0); layer l (dilation d_l) produces valid values fo
 reads x[tau - d_l] and x[tau] (wavenet.py:100: Conv1d is a cross-correlation, tap 0 <-> x[t], tap 1 <-> x[t+d]).
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib as L
+
+
+# Engine mode of the plans built from here on (tests and bench.py A/B the two; prebuilt plans keep theirs):
+#   "pair"  2-CTA clusters issuing ONE cta_group::2 MMA stream (M = 256), operands split between the two CTAs
+#   "mcast" 2-CTA clusters sharing W / X by TMA multicast, every CTA issuing its own cta_group::1 MMAs (M = 128)
+ENGINE_MODE = os.environ.get("AEWN_ENGINE_MODE", "mcast")
+
+
+def set_engine_mode(mode):
+    global ENGINE_MODE
+    if mode not in ("pair", "mcast"):
+        raise ValueError("engine mode must be 'pair' or 'mcast'")
+    ENGINE_MODE = mode
+    _plans.clear()
 
 
 # ------------------------------------------------------------------------------------------------- small helpers
@@ -125,6 +140,7 @@ def build_tgemm(acts, segs, w, ntiles, batch, t_begin, t_end, err=None, tag=None
         d.n_ntiles = len(chunk)
         d.batch, d.t_begin, d.t_end = int(batch), int(t_begin), int(t_end)
         d.err = err.data_ptr() if err is not None else None
+        d.cluster = L.CLUSTER_PAIR_MMA if ENGINE_MODE == "pair" else 2
         out.append(("tgemm", d, tag))
     return out
 
@@ -180,7 +196,7 @@ def build_wgrad(acts, items, batch, err=None, tag=None, pair=False):
         d.n_items = len(chunk)
         d.batch = int(batch)
         d.err = err.data_ptr() if err is not None else None
-        d.pair_x = 1 if pair else 0
+        d.pair_x = (2 if (ENGINE_MODE == "pair" and all(it.n <= 256 for it in d.items[:len(chunk)])) else 1) if pair else 0
         out.append(("wgrad", d, tag))
     return out
 

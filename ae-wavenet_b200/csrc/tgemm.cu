@@ -26,7 +26,12 @@ constexpr int TG_STAGE_BYTES = TG_A_BYTES + 2 * TG_WBOX_BYTES;  // 48 KB
 constexpr int TG_THREADS = 384;
 constexpr int TG_EPI_WARPS = 8;
 constexpr int TG_STG_BYTES = TG_EPI_WARPS * 4096;  // one 32 ch x 32 t fp32 staging tile per epilogue warp (TMA stores)
-constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + TG_STG_BYTES + 256 + 1024;  // + barriers + alignment slack
+constexpr int TG_RING_BYTES = TG_STAGES * TG_STAGE_BYTES;      // 192 KB: 4 x 48 KB, or 6 x 32 KB in pair-MMA mode
+constexpr int TG_PAIR_STAGES = 6;
+constexpr int TG_PAIR_STAGE_BYTES = TG_A_BYTES + TG_WBOX_BYTES;  // 32 KB: own 128 time steps of A + own half of W
+constexpr int TG_MAX_STAGES = 6;
+static_assert(TG_PAIR_STAGES * TG_PAIR_STAGE_BYTES == TG_RING_BYTES, "both modes use the same ring");
+constexpr int TG_SMEM_BYTES = TG_RING_BYTES + TG_STG_BYTES + 256 + 1024;  // + barriers + alignment slack
 
 struct TgSeg {
   int map;
@@ -48,6 +53,8 @@ struct TgParams {
   int* err;
   uint32_t a_lbo, a_sbo;
   int cluster;   // 1, 2 or 4: CTAs of a cluster work on adjacent time tiles of the same (batch, n-tile) and share W
+  int pair;      // 1 (cluster == 2 only): the pair issues cta_group::2 MMAs (M = 256), each CTA stages its own 128 time
+                 // steps of A and HALF of the W rows in its own shared memory: no multicast, 2/3 of the smem traffic
   int n_tgroups; // ceil(n_ttiles / cluster)
   // Output maps for the TMA-store epilogue: o_map[tile][0] covers `out` (for GATE_BWD: the whole g_f;g_g tensor),
   // [1] `out2`, [2] `out3`.  o_tma[tile] != 0 when the tile's main outputs go through TMA (see tma_eligible()).
@@ -493,37 +500,50 @@ __device__ __forceinline__ void epi_gate_bwd(const GateBwdCtx& cx, const StgOut&
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
+template <bool PAIR>
 __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_constant__ TgParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  float* stg_base = reinterpret_cast<float*>(smem + TG_STAGES * TG_STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TG_STAGES * TG_STAGE_BYTES + TG_STG_BYTES);
-  uint64_t* empty_bar = full_bar + TG_STAGES;
-  uint64_t* tfull_bar = empty_bar + TG_STAGES;
+  float* stg_base = reinterpret_cast<float*>(smem + TG_RING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TG_RING_BYTES + TG_STG_BYTES);
+  uint64_t* empty_bar = full_bar + TG_MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + TG_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr bool pair = PAIR;   // compile-time: the two modes are separate instantiations (no spills at 40 registers)
+  const uint32_t n_stages = pair ? TG_PAIR_STAGES : TG_STAGES;
+  const uint32_t stage_bytes = pair ? TG_PAIR_STAGE_BYTES : TG_STAGE_BYTES;
 
   if (threadIdx.x == 0) {
     *abort_flag = 0;
-    for (int i = 0; i < TG_STAGES; ++i) {
+    for (int i = 0; i < TG_MAX_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], p.cluster);   // one tcgen05.commit arrival from every CTA that reads the stage's W
+      // multicast mode: one tcgen05.commit arrival from every CTA that reads the stage's W; pair mode: the leader's
+      // cta_group::2 commit alone releases the stage in both CTAs
+      mbar_init(&empty_bar[i], pair ? 1 : p.cluster);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], TG_EPI_WARPS);
+      // pair mode: the leader's MMA warp may only overwrite an accumulator stage once the epilogue warps of BOTH CTAs
+      // have drained it (the peer's warps arrive remotely on the leader's barrier)
+      mbar_init(&tempty_bar[i], pair ? 2 * TG_EPI_WARPS : TG_EPI_WARPS);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (pair) {
+      tmem_alloc_pair(tmem_slot, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < AEWN_MAX_ACTS; ++i) tma_prefetch_desc(&p.a_map[i]);
@@ -545,12 +565,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   // epilogue warps grow to 208, so 32-wide column chunks + prefetch buffers stay in registers
   // (128*88 + 256*208 = 64512 <= 65536).  Each setmaxnreg dominates its role code (no merge of limits).
   if (warp < 4) {
-  reg_dealloc<40>();
+  reg_dealloc<40>();   // 128*40 + 256*232 = 64512 = 384*168: the CTA pool is what the launch allocated, NOT the SM file
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       bool ok = true;
+      const uint32_t lead_full = pair ? mapa_u32(&full_bar[0], 0) : 0u;
       for (int item = cid; item < total && ok; item += n_clusters) {
         const TgItem it = tg_decode(p, item, crank);
         if (!it.active) continue;
@@ -563,8 +584,20 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
           const TgSeg sg = p.seg[s];
           for (int kb = 0; kb < sg.kblocks; ++kb) {
             if (!mbar_wait(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
-            uint8_t* sa = smem + stage * TG_STAGE_BYTES;
+            uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sw = sa + TG_A_BYTES;
+            if (pair) {
+              // Both CTAs signal the LEADER's full barrier (cta_group::2 loads); the leader expects the bytes of both.
+              // CTA r stages W rows [r * n/2, (r+1) * n/2) of the tile (a 128-row box; the MMA reads n/2 of them).
+              if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * TG_PAIR_STAGE_BYTES);
+              const uint32_t fb = lead_full + stage * 8u;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                tma_load_3d_pair(sa + i * 4096, &p.a_map[sg.map], fb, it.tau0 + sg.shift + 32 * i, kb * TG_BK, it.b);
+              tma_load_2d_pair(sw, &p.w_map, fb, sg.w_koff + kb * TG_BK, nt.w_row + crank * (nt.n >> 1));
+              if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+              continue;
+            }
             const int wboxes = (nt.n + 127) >> 7;
             mbar_expect_tx(&full_bar[stage], TG_A_BYTES + (p.cluster == 1 ? wboxes * TG_WBOX_BYTES : wslices * wrows * 128));
 #pragma unroll
@@ -579,14 +612,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
               tma_load_2d_mcast(sw + crank * wrows * 128, &p.w_map, &full_bar[stage], sg.w_koff + kb * TG_BK,
                                 nt.w_row + crank * wrows, cmask);
             }
-            if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================== MMA issuer (pair mode: the leader CTA issues for both)
+    if (lane == 0 && (!pair || crank == 0)) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       bool ok = true;
       for (int item = cid; item < total && ok; item += n_clusters) {
@@ -596,7 +629,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
         if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256u;
-        const uint32_t idesc = make_idesc_tf32(TG_BM, nt.n, /*a_mn=*/1, /*b_mn=*/0);
+        const uint32_t idesc = make_idesc_tf32(pair ? 2 * TG_BM : TG_BM, nt.n, /*a_mn=*/1, /*b_mn=*/0);
         uint32_t kiter = 0;
         for (int s = 0; s < p.n_segs && ok; ++s) {
           if (!((nt.seg_mask >> s) & 1)) continue;
@@ -604,7 +637,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
           for (int kb = 0; kb < kblocks; ++kb) {
             if (!mbar_wait(&full_bar[stage], phase, abort_flag)) { ok = false; break; }
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + stage * TG_STAGE_BYTES);
+            const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
             const uint32_t w_addr = a_addr + TG_A_BYTES;
 #pragma unroll
             for (int ks = 0; ks < TG_BK / 8; ++ks) {
@@ -612,16 +645,19 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
               const uint64_t adesc = make_smem_desc(a_addr + ks * 1024, p.a_lbo, p.a_sbo, kLayoutSW128Base32);
               // W: K-major, 128B swizzle: 8-row groups 1 KB apart (SBO); K advances 32 B inside the swizzle row
               const uint64_t bdesc = make_smem_desc(w_addr + ks * 32, 16, 1024, kLayoutSW128);
-              umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kiter | ks) != 0u);
+              if (pair) umma_tf32_ss_pair(d_tmem, adesc, bdesc, idesc, (kiter | ks) != 0u);
+              else umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kiter | ks) != 0u);
             }
-            if (p.cluster == 1) umma_commit(&empty_bar[stage]);
+            if (pair) umma_commit_pair(&empty_bar[stage], 0x3);
+            else if (p.cluster == 1) umma_commit(&empty_bar[stage]);
             else umma_commit_mcast(&empty_bar[stage], cmask);
             ++kiter;
-            if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
           }
         }
         if (!ok) break;
-        umma_commit(&tfull_bar[acc]);
+        if (pair) umma_commit_pair(&tfull_bar[acc], 0x3);   // accumulator ready: wake the epilogues of both CTAs
+        else umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -678,7 +714,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
       if (!ok) break;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (pair && crank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));   // the leader's barrier
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_all();   // bulk stores must have completed before the CTA's smem goes away
@@ -692,7 +731,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   if (threadIdx.x == 0 && *abort_flag && p.err) atomicExch(p.err, AEWN_ERR_TIMEOUT);
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (pair) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -712,7 +752,9 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
                    d->t_begin, d->t_end);
 
   {
-    cudaError_t e = cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
     if (e != cudaSuccess) return cuda_err(e, "tgemm: cudaFuncSetAttribute");
   }
 
@@ -724,8 +766,13 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
     if (d->acts[i].batch < d->batch) return set_err(AEWN_ERR_INVALID, "tgemm: act %d batch smaller than problem batch", i);
   }
   for (int i = d->n_acts; i < AEWN_MAX_ACTS; ++i) p.a_map[i] = p.a_map[0];
-  int cluster = d->cluster > 0 ? d->cluster : 2;
-  if (cluster != 1 && cluster != 2 && cluster != 4) return set_err(AEWN_ERR_INVALID, "tgemm: cluster must be 1, 2 or 4");
+  int cluster = d->cluster > 0 ? d->cluster : AEWN_TG_DEFAULT_CLUSTER;
+  if (cluster == AEWN_CLUSTER_PAIR_MMA) {
+    p.pair = 1;
+    cluster = 2;
+  }
+  if (cluster != 1 && cluster != 2 && cluster != 4)
+    return set_err(AEWN_ERR_INVALID, "tgemm: cluster must be 1, 2, 4 or AEWN_CLUSTER_PAIR_MMA");
   int rc = encode_w_map(&p.w_map, d->w, d->w_rows, d->w_kpad, cluster == 1 ? 128 : 256 / cluster);
   if (rc) return rc;
 
@@ -826,7 +873,7 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, tgemm_kernel, p);
+  cudaError_t le = p.pair ? cudaLaunchKernelEx(&cfg, tgemm_kernel<true>, p) : cudaLaunchKernelEx(&cfg, tgemm_kernel<false>, p);
   count_launch();
   if (le != cudaSuccess) return cuda_err(le, "tgemm launch");
   return cuda_err(cudaGetLastError(), "tgemm launch");

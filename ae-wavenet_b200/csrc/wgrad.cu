@@ -17,7 +17,9 @@ constexpr int WG_BOX_BYTES = 128 * WG_BK * 4;        // 16 KB
 constexpr int WG_STAGE_BYTES = 3 * WG_BOX_BYTES;     // G box + 2 X boxes (4 stages); "wide" launches: G + 3 X boxes, 3 stages
 constexpr int WG_THREADS = 384;
 constexpr int WG_EPI_WARPS = 8;
+constexpr int WG_MAX_STAGES = 6;                     // pair-MMA mode: 6 stages of (G box + own half of the X rows)
 constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 256 + 1024;
+static_assert(WG_MAX_STAGES * 2 * WG_BOX_BYTES == WG_STAGES * WG_STAGE_BYTES, "same ring in every mode");
 
 struct WgParams {
   CUtensorMap map[AEWN_WGRAD_MAX_ACTS];
@@ -28,6 +30,8 @@ struct WgParams {
   int* err;
   int uniform_split;  // > 0: every item has this split count and units are ordered split-major (see wg_decode)
   int pair;           // 1: 2-CTA clusters; CTA r of cluster c takes item 2*pair_index + r; the pair shares its X tile
+  int pair_mma;       // 1 (with pair): ONE cta_group::2 MMA stream per pair (M = 256 = the G rows of both items); each
+                      // CTA stages its own G box and HALF of the X rows in its own shared memory (no multicast)
   int wide;           // 1: some item has 256 < n <= 384: 3 stages of (G + 3 X boxes), one 512-column accumulator
 };
 
@@ -64,14 +68,15 @@ __device__ __forceinline__ WgUnit wg_decode(const WgParams& p, int unit, int cra
   return u;
 }
 
+template <bool PMMA>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + WG_STAGES;
-  uint64_t* tfull_bar = empty_bar + WG_STAGES;
+  uint64_t* empty_bar = full_bar + WG_MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + WG_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
@@ -80,25 +85,30 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   const int lane = threadIdx.x & 31;
   // Wide launches trade pipeline depth and the second accumulator for N up to 384 per unit: the G tile is then loaded
   // once for a whole 368-row X tile instead of once for 256 + once for 112 rows (the 112-wide units were L2-bound).
-  const uint32_t n_stages = p.wide ? 3u : 4u;
-  const uint32_t stage_bytes = p.wide ? 4u * WG_BOX_BYTES : 3u * WG_BOX_BYTES;
-  const uint32_t acc_stages = p.wide ? 1u : 2u;
+  const uint32_t n_stages = PMMA ? WG_MAX_STAGES : (p.wide ? 3u : 4u);
+  const uint32_t stage_bytes = PMMA ? 2u * WG_BOX_BYTES : (p.wide ? 4u * WG_BOX_BYTES : 3u * WG_BOX_BYTES);
+  const uint32_t acc_stages = (!PMMA && p.wide) ? 1u : 2u;
 
   if (threadIdx.x == 0) {
     *abort_flag = 0;
-    for (int i = 0; i < WG_STAGES; ++i) {
+    for (int i = 0; i < WG_MAX_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], p.pair ? 2 : 1);
+      mbar_init(&empty_bar[i], (p.pair && !PMMA) ? 2 : 1);   // pair-MMA: the leader's commit releases both CTAs' stages
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], WG_EPI_WARPS);
+      mbar_init(&tempty_bar[i], PMMA ? 2 * WG_EPI_WARPS : WG_EPI_WARPS);   // pair-MMA: both CTAs' epilogues, on the leader
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (PMMA) {
+      tmem_alloc_pair(tmem_slot, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -117,6 +127,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       bool ok = true;
+      const uint32_t lead_full = PMMA ? mapa_u32(&full_bar[0], 0) : 0u;
       for (int unit = cid; unit < total_units && ok; unit += n_cl) {
         const WgUnit u = wg_decode(p, unit, crank);
         if (u.kb_end <= u.kb_begin) continue;
@@ -128,6 +139,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           if (!mbar_wait(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
           uint8_t* sg = smem + stage * stage_bytes;
           uint8_t* sx = sg + WG_BOX_BYTES;
+          if (PMMA) {
+            // both CTAs complete their bytes on the LEADER's full barrier; CTA r stages X rows [r * n/2, +n/2) (one
+            // 128-row box, of which the MMA reads n/2)
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 4 * WG_BOX_BYTES);
+            const uint32_t fb = lead_full + stage * 8u;
+            tma_load_3d_pair(sg, &p.map[im.g_act], fb, t, im.g_row, b);
+            tma_load_3d_pair(sx, &p.map[im.x_act], fb, t + im.shift, im.x_row + crank * (im.n >> 1), b);
+            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], (1 + xboxes) * WG_BOX_BYTES);
           tma_load_3d(sg, &p.map[im.g_act], &full_bar[stage], t, im.g_row, b);
           if (!p.pair) {
@@ -143,7 +164,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && (!PMMA || crank == 0)) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       bool ok = true;
       for (int unit = cid; unit < total_units && ok; unit += n_cl) {
@@ -155,7 +176,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         const uint32_t d_tmem = tmem_base + acc * 256u;
         const int n0 = im.n > 256 ? 256 : im.n;
         const int n1 = im.n - n0;                       // second MMA part (wide items): X rows 256.., TMEM columns 256..
-        const uint32_t idesc = make_idesc_tf32(128, n0, 0, 0);
+        const uint32_t idesc = make_idesc_tf32(PMMA ? 256 : 128, n0, 0, 0);
         const uint32_t idesc1 = n1 > 0 ? make_idesc_tf32(128, n1, 0, 0) : 0u;
         for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
           if (!mbar_wait(&full_bar[stage], phase, abort_flag)) { ok = false; break; }
@@ -166,18 +187,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           for (int ks = 0; ks < WG_BK / 8; ++ks) {
             const uint64_t adesc = make_smem_desc(g_addr + ks * 32, 16, 1024, kLayoutSW128);
             const uint64_t bdesc = make_smem_desc(x_addr + ks * 32, 16, 1024, kLayoutSW128);
+            if (PMMA) {
+              umma_tf32_ss_pair(d_tmem, adesc, bdesc, idesc, (kb > u.kb_begin) || (ks > 0));
+              continue;
+            }
             umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kb > u.kb_begin) || (ks > 0));
             if (n1 > 0) {
               const uint64_t bdesc1 = make_smem_desc(x_addr + 2 * WG_BOX_BYTES + ks * 32, 16, 1024, kLayoutSW128);
               umma_tf32_ss(d_tmem + 256u, adesc, bdesc1, idesc1, (kb > u.kb_begin) || (ks > 0));
             }
           }
-          if (p.pair) umma_commit_mcast(&empty_bar[stage], 0x3);
+          if (PMMA) umma_commit_pair(&empty_bar[stage], 0x3);
+          else if (p.pair) umma_commit_mcast(&empty_bar[stage], 0x3);
           else umma_commit(&empty_bar[stage]);
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
         if (!ok) break;
-        umma_commit(&tfull_bar[acc]);
+        if (PMMA) umma_commit_pair(&tfull_bar[acc], 0x3);
+        else umma_commit(&tfull_bar[acc]);
         if (++acc == acc_stages) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -208,7 +235,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PMMA && crank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));   // the leader's barrier
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -220,7 +250,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   if (threadIdx.x == 0 && *abort_flag && p.err) atomicExch(p.err, AEWN_ERR_TIMEOUT);
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PMMA) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -235,7 +266,9 @@ extern "C" int aewn_wgrad(const aewn_wgrad_desc* d, aewn_stream_t stream_) {
       d->batch <= 0)
     return set_err(AEWN_ERR_INVALID, "wgrad: n_acts/n_items/batch out of range (%d/%d/%d)", d->n_acts, d->n_items,
                    d->batch);
-  cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
   if (e != cudaSuccess) return cuda_err(e, "wgrad: cudaFuncSetAttribute");
 
   // kernel parameters are limited to 4 KB: the item table rides in the parameter block
@@ -288,6 +321,10 @@ extern "C" int aewn_wgrad(const aewn_wgrad_desc* d, aewn_stream_t stream_) {
         return set_err(AEWN_ERR_INVALID, "wgrad: pair_x items %d/%d do not share their X tile", i, i + 1);
     }
     p.pair = 1;
+    if (d->pair_x == 2) {
+      if (p.wide) return set_err(AEWN_ERR_INVALID, "wgrad: pair_x = 2 (cta_group::2 MMAs) needs n <= 256 for every item");
+      p.pair_mma = 1;
+    }
   }
   int ctas = d->max_ctas > 0 ? d->max_ctas : sm_count();
   const int work = p.pair ? 2 * p.uniform_split * (d->n_items / 2) : units;
@@ -306,7 +343,7 @@ extern "C" int aewn_wgrad(const aewn_wgrad_desc* d, aewn_stream_t stream_) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, wgrad_kernel, p);
+  cudaError_t le = p.pair_mma ? cudaLaunchKernelEx(&cfg, wgrad_kernel<true>, p) : cudaLaunchKernelEx(&cfg, wgrad_kernel<false>, p);
   count_launch();
   if (le != cudaSuccess) return cuda_err(le, "wgrad launch");
   return cuda_err(cudaGetLastError(), "wgrad launch");

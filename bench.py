@@ -204,7 +204,11 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (cfg2: 8)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"],
+                    help="cfg2 (default, the headline): WaveNet decoder train step; cfg3: full VQ-VAE-EMA autoencoder "
+                         "train step (Encoder -> VQEMA -> WaveNet, par/arch.vqvae-ema.json), batch 16/GPU; with "
+                         "--gpus N this is cfg4 (grads + EMA statistics in ONE all-reduce)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: cfg2 8, cfg3 16)")
     ap.add_argument("--window", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -228,24 +232,49 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B, W = args.batch, args.window
+    cfg3 = args.workload == "cfg3"
+    B, W = (args.batch or (16 if cfg3 else 8)), args.window
     torch.manual_seed(2507)                      # identical replicas
-    wn, geo = build_decoder(W, aewn.WaveNet, vc)
-    wn = wn.to(dev).train()
-    loss_fn = aewn.RecLoss()
-    sync = FlatGradSync(wn.parameters())
-    opt = torch.optim.Adam(wn.parameters(), lr=2e-5, fused=True)   # checkpoint.py:49, par/train.basic.json:6
-    wav_h, lc_h, spk_h, jit_h = [t.pin_memory() for t in synth_batch(B, geo["wav_len"], geo["lc_len"], 64, 40, 1234 + rank)]
-    t0w, t1w = geo["trim_dec_out"]
+    if cfg3:
+        from aewn.autoencoder import AutoEncoder
+        ae = AutoEncoder(HP(dict(ARCH_BASIC, n_lc_in=32)), 39, 768, "vqvae-ema", 32, 0.25, 0.99, 4096, True)
+        ae.init_geometry(W)
+        ae = ae.to(dev).train()
+        wn = ae.decoder
+        geo = dict(wav_len=ae.dec_in_len, lc_len=ae.embed_len, dec_in_len=ae.dec_in_len)
+        model = ae
+        sync = FlatGradSync(ae.parameters(), vqema=ae.bottleneck)
+        wav_h, _, spk_h, jit_h = synth_batch(B, ae.dec_in_len, ae.embed_len, 32, 40, 1234 + rank)
+        lc_h = torch.randn(B, 39, ae.enc_in_mel_len, generator=torch.Generator().manual_seed(99 + rank))   # mel input
+        wav_h, lc_h, spk_h, jit_h = [t.pin_memory() for t in (wav_h, lc_h, spk_h, jit_h)]
 
-    def step(wav, lc, spk, jit):
-        sync.zero_grad()
-        quant = wn(wav, lc, spk, jit)
-        loss = loss_fn(quant[..., :-1], wav[:, t0w:t1w][..., 1:])
-        loss.backward()
-        sync.sync()
-        opt.step()
-        return loss
+        def step(wav, mels, spk, jit):
+            sync.zero_grad()
+            pred, target, com, rec = ae.run(mels, wav, spk, jit)
+            loss = com + rec
+            loss.backward()
+            sync.sync()                          # ONE all-reduce: grads | z_sum | n_sum | metrics, then the EMA update
+            opt.step()
+            return loss
+    else:
+        wn, geo = build_decoder(W, aewn.WaveNet, vc)
+        wn = wn.to(dev).train()
+        model = wn
+        loss_fn = aewn.RecLoss()
+        sync = FlatGradSync(wn.parameters())
+        wav_h, lc_h, spk_h, jit_h = [t.pin_memory() for t in
+                                     synth_batch(B, geo["wav_len"], geo["lc_len"], 64, 40, 1234 + rank)]
+        t0w, t1w = geo["trim_dec_out"]
+
+        def step(wav, lc, spk, jit):
+            sync.zero_grad()
+            quant = wn(wav, lc, spk, jit)
+            loss = loss_fn(quant[..., :-1], wav[:, t0w:t1w][..., 1:])
+            loss.backward()
+            sync.sync()
+            opt.step()
+            return loss
+    opt = torch.optim.Adam(model.parameters(), lr=2e-5, fused=True)   # checkpoint.py:49, par/train.basic.json:6
 
     def barrier():
         torch.cuda.synchronize()
@@ -324,8 +353,12 @@ def main():
             metric=METRIC, value=world * B * W / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="tf32", data="synthetic",
-            config=dict(workload="cfg2: WaveNet decoder par/arch.basic.json train step, batch 8/GPU, window 16384",
-                        step="H2D(e2e only)+fwd+RecLoss+bwd+allreduce+Adam", global_batch=world * B, window=W,
+            config=dict(workload=("cfg3/cfg4: full VQ-VAE-EMA autoencoder par/arch.vqvae-ema.json train step (Encoder -> "
+                                  f"VQEMA -> WaveNet), batch {B}/GPU, window {W}" if cfg3 else
+                                  f"cfg2: WaveNet decoder par/arch.basic.json train step, batch {B}/GPU, window {W}"),
+                        step=("H2D(e2e only)+fwd+VQEMALoss+RecLoss+bwd+allreduce(grads|z_sum|n_sum)+EMA+Adam" if cfg3 else
+                              "H2D(e2e only)+fwd+RecLoss+bwd+allreduce+Adam"), global_batch=world * B, window=W,
+                        engine_mode=ops.ENGINE_MODE,
                         dec_in_len=geo["dec_in_len"], parallelism=f"dp{world}",
                         l2="activations per step ~13 GB >> 126 MB L2 (no flush needed)", seed=2507,
                         final_loss=final_loss),
@@ -345,7 +378,7 @@ def main():
                      d2h_bytes_per_step=4),
             gpu_launches=launches,
         )
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and not cfg3:
             pick_cpu_threads()
             sps, ctimes = cpu_port_step(2, 2048, 2, 1)
             out["cpu_baseline"] = dict(value=sps, unit=UNIT, cores=torch.get_num_threads(), kind="port",

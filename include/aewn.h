@@ -103,6 +103,8 @@ typedef struct {
   const float* bias; /* optional, pre-offset, indexed by column */
 } aewn_ntile;
 
+#define AEWN_CLUSTER_PAIR_MMA 102
+#define AEWN_TG_DEFAULT_CLUSTER 2
 #define AEWN_MAX_ACTS 6
 #define AEWN_MAX_SEGS 6
 #define AEWN_MAX_NTILES 4
@@ -122,7 +124,10 @@ typedef struct {
   int* err;           /* device error word (may be NULL) */
   int max_ctas;       /* 0 = one per SM */
   int dbg_lbo, dbg_sbo; /* 0 = defaults; descriptor probing only */
-  int cluster;        /* CTAs per cluster sharing W by TMA multicast: 0 = default (2), or 1, 2, 4 */
+  int cluster;        /* 0 = library default (AEWN_TG_DEFAULT_CLUSTER); 1, 2, 4 = CTAs per cluster sharing W by TMA
+                         multicast, each CTA issuing cta_group::1 MMAs (M = 128); AEWN_CLUSTER_PAIR_MMA = 2-CTA clusters
+                         issuing ONE cta_group::2 MMA stream (M = 256): each CTA stages its own 128 time steps and half
+                         of the W rows, which cuts the shared-memory traffic per MMA by a third */
   int no_tma_store;   /* 1 = force the st.global epilogue (default: tiles whose outputs are 16-byte aligned are written
                          through shared memory + TMA store / reduce-add; rows of a partially active tile below t_lo
                          then receive zeros, i.e. the caller's margins must be don't-care or zero) */
@@ -163,7 +168,9 @@ typedef struct {
   int batch;
   int* err;
   int max_ctas;
-  int pair_x;  /* 1: items (2i, 2i+1) share their X tile; they run as a 2-CTA cluster and X is TMA-multicast */
+  int pair_x;  /* 1: items (2i, 2i+1) share their X tile; they run as a 2-CTA cluster and X is TMA-multicast;
+                  2: same pairing, but the cluster issues cta_group::2 MMAs (M = 256 = both items' G rows) and each CTA
+                     stages only half of the X rows (items must have n <= 256) */
 } aewn_wgrad_desc;
 
 int aewn_wgrad(const aewn_wgrad_desc* d, aewn_stream_t stream);

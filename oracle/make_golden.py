@@ -213,11 +213,53 @@ def golden_forward_test():
     print("forward_test: out", tuple(out.shape), "steps", len(rec))
 
 
+def golden_autoencoder():
+    """cfg3 in miniature: Encoder -> VQEMA -> WaveNet wired by oracle/ae_harness.py from the unmodified reference
+    modules; one forward + backward of (commitment + reconstruction) loss.  Also records the cfg3 geometry at the
+    BASELINE size (W = 16384) for the product-side wiring (aewn/autoencoder.py) to be checked against."""
+    from oracle import ae_harness as ah
+    hp = rh.HP(dict(SMALL))
+    W, B, n_mel, enc_out, K = 96, 3, 13, 64, 256
+    torch.manual_seed(2507)
+    enc, bn, dec, geo = ah.build(hp, n_mel, enc_out, hp.n_lc_in, 0.25, 0.99, K, W)
+    for mod in (enc, bn, dec):
+        mod.train()
+    g = torch.Generator().manual_seed(4321)
+    fake_geo = dict(wav_len=geo["dec_in_len"], lc_len=geo["embed_len"])
+    wav_dec, _, spk, jit = synth_inputs(B, fake_geo, hp.n_lc_in, hp.n_speakers, 4321, jitter=True)
+    mels = torch.randn(B, n_mel, geo["enc_in_mel_len"], generator=g, requires_grad=True)
+    sd = {name: {k: v.clone() for k, v in mod.state_dict().items()}
+          for name, mod in (("encoder", enc), ("bottleneck", bn), ("decoder", dec))}
+    quant, com, rec = ah.train_forward(enc, bn, dec, geo, mels, wav_dec, spk, jit)
+    (com + rec).backward()
+    grads = {name: {k: p.grad.clone() for k, p in mod.named_parameters()}
+             for name, mod in (("encoder", enc), ("bottleneck", bn), ("decoder", dec))}
+    torch.save(dict(hp=dict(hp), W=W, n_mel=n_mel, enc_n_out=enc_out, K=K, geo=geo, state_dict=sd, mels=mels.detach(),
+                    wav_dec=wav_dec, spk=spk, jit=jit, quant=quant.detach(), com=com.detach(), rec=rec.detach(),
+                    min_ind=bn.min_ind.clone(), min_dist=bn.min_dist.detach(), ze=bn.ze.detach(),
+                    z_sum=bn.z_sum.clone(), n_sum=bn.n_sum.clone(), ema_numer=bn.ema_numer.clone(),
+                    ema_denom=bn.ema_denom.clone(), grads=grads, mel_grad=mels.grad.clone(),
+                    frac_zero=[float(m_.frac_zero_act) for m_ in enc.net]), os.path.join(OUT, "autoencoder_small.pt"))
+    print("autoencoder_small: com", float(com), "rec", float(rec), "uniq", int(bn.min_ind.unique().numel()),
+          {k: v for k, v in geo.items() if k != "leads"})
+    # cfg3 geometry at full size (par/arch.vqvae-ema.json: 39 mel channels, 768 encoder channels, d = 32, K = 4096)
+    torch.manual_seed(2507)
+    _, _, _, geo3 = ah.build(rh.HP(dict(rh.ARCH_BASIC, n_lc_in=32)), 39, 768, 32, 0.25, 0.99, 4096, 16384)
+    path = os.path.join(OUT, "geometry.json")
+    allgeo = json.load(open(path)) if os.path.exists(path) else {}
+    allgeo["cfg3_vqvae_ema_W16384"] = geo3
+    json.dump(allgeo, open(path, "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "autoencoder":
+        golden_autoencoder()
+        sys.exit(0)
     golden_wavenet_small()
     golden_forward_test()
     golden_grcc_layer()
     golden_encoder()
     golden_vq()
     golden_geometry_and_init()
+    golden_autoencoder()
     print("goldens written to", OUT)

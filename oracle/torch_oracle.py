@@ -227,3 +227,24 @@ def vq_forward(lin_w, emb, z):
     min_dist, min_ind, zq = vq_assign(ze, emb.detach(), "sq_l2")
     out = zq.detach() + (ze - ze.detach())  # value == zq exactly, d(out)/d(ze) = I
     return dict(ze=ze, min_dist=min_dist, min_ind=min_ind, zq=zq, out=out)
+
+
+# ------------------------------------------------------------------------------------------------ autoencoder (cfg3)
+def autoencoder_step(sd, hp, geo, mels, wav_dec, speaker_inds, jitter_index, vq_gamma, ema_gamma):
+    """The VQ-VAE-EMA train step as oracle/ae_harness.py wires it from the reference modules
+    (autoencoder_model.py:206-259): Encoder -> VQEMA -> WaveNet on the pre-trimmed wav_dec, losses
+    com = vq_gamma * sum(min_dist) (VQEMALoss total, vqema_bn.py:237,246) and rec = RecLoss (wavenet.py:541-552).
+    sd: dict(encoder=..., bottleneck=..., decoder=...) of state dicts (tensors that need gradients must require them).
+    geo: ae_harness geometry (trim_ups_out, dec_in_len, trim_dec_out, leads).  Returns a dict."""
+    encoding, fracs = encoder_forward(sd["encoder"], mels)
+    bsd = sd["bottleneck"]
+    vq = vqema_forward(bsd["linear.weight"], bsd["emb"], encoding, bsd["ema_numer"], bsd["ema_denom"], ema_gamma)
+    dgeo = dict(trim_ups_out=geo["trim_ups_out"], wav_cond_offset=[0, geo["dec_in_len"]], leads=geo["leads"],
+                n_win_batch=geo["trim_dec_out"][1] - geo["trim_dec_out"][0])
+    quant = wavenet_forward_train(sd["decoder"], hp, dgeo, wav_dec, vq["out"], speaker_inds, jitter_index)
+    t0, t1 = geo["trim_dec_out"]
+    pred, target = quant[..., :-1], wav_dec[:, t0:t1][..., 1:]
+    com = (vq["min_dist"] * vq_gamma).sum()
+    rec = rec_loss(pred, target)
+    return dict(quant=quant, com=com, rec=rec, frac_zero=fracs, **{k: vq[k] for k in
+                ("ze", "min_ind", "min_dist", "z_sum", "n_sum", "ema_numer", "ema_denom")})

@@ -1,6 +1,6 @@
 """Unit parity of the two tcgen05 engines through the C ABI (ops.tgemm / ops.wgrad) against plain PyTorch fp32
 (TF32 tolerance), covering: shifted segments, ragged channel counts (K not a multiple of 32, N not a multiple of 16),
-all three cluster sizes, both epilogue store paths (TMA store / st.global), accumulate via TMA reduce-add, the
+all three multicast cluster sizes and the CTA-pair (cta_group::2) mode, both epilogue store paths (TMA store / st.global), accumulate via TMA reduce-add, the
 16-byte origin rule (rejected host-side instead of faulting on the device)."""
 import ctypes as C
 
@@ -21,7 +21,7 @@ def make_desc_run(acts, segs, w, tiles, B, t0, t1, cluster, no_tma):
     assert int(err.item()) == 0
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("cluster", [1, 2, 4, 102])      # 102 = AEWN_CLUSTER_PAIR_MMA (cta_group::2 MMAs)
 @pytest.mark.parametrize("no_tma", [0, 1])
 def test_tgemm_shifted_segments_match_torch(cluster, no_tma):
     from aewn import ops
@@ -61,9 +61,12 @@ def test_unaligned_shift_is_rejected_on_the_host():
         ops.tgemm([ops.act_of(x, 256)], [(0, -1, 32, 0)], w, [ops.ntile(0, 16, out, t_lo=0, t_hi=256)], 1, 0, 256)
 
 
-@pytest.mark.parametrize("pair,N,chunk", [(False, 150, 128), (True, 150, 128), (True, 368, 384), (False, 300, 384)])
-def test_wgrad_matches_torch(pair, N, chunk):
+@pytest.mark.parametrize("engine", ["mcast", "pair"])
+@pytest.mark.parametrize("pair,N,chunk", [(False, 150, 128), (True, 150, 128), (True, 368, 384), (False, 300, 384),
+                                          (True, 368, 256)])
+def test_wgrad_matches_torch(pair, N, chunk, engine, monkeypatch):
     from aewn import ops, _lib as L
+    monkeypatch.setattr(ops, "ENGINE_MODE", engine)   # "pair": X-sharing item pairs run cta_group::2 MMAs (pair_x = 2)
     g = torch.Generator().manual_seed(3)
     B, M, T, shift, t_lo = 2, 200, 1500, -8, 12
     G = torch.randn(B, M, T, generator=g)

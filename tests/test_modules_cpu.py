@@ -81,3 +81,36 @@ def test_encoder_and_vq_state_dicts(golden_dir):
     assert torch.equal(vq.emb.detach(), gv["vq"]["emb"])
     with pytest.raises(RuntimeError):
         vqema_bn.VQEMA(96, 32, 0.25, 1.0, 64, True)
+
+
+def test_autoencoder_wiring_geometry_and_state_dicts_match_reference(golden_dir):
+    """aewn/autoencoder.py (the product-side stand-in for autoencoder_model.AutoEncoder, which cannot be constructed at
+    the reference's HEAD) must derive the same geometry and expose the same state_dict as the reference modules wired
+    by oracle/ae_harness.py -- small fixture and the BASELINE cfg3 size."""
+    from aewn.autoencoder import AutoEncoder
+    g = torch.load(os.path.join(golden_dir, "autoencoder_small.pt"))
+    torch.manual_seed(2507)
+    ae = AutoEncoder(HP(g["hp"]), g["n_mel"], g["enc_n_out"], "vqvae-ema", g["hp"]["n_lc_in"], 0.25, 0.99, g["K"], True)
+    ae.init_geometry(g["W"])
+    geo = g["geo"]
+    assert (ae.enc_in_len, ae.enc_in_mel_len, ae.embed_len, ae.dec_in_len) == (
+        geo["enc_in_len"], geo["enc_in_mel_len"], geo["embed_len"], geo["dec_in_len"])
+    assert ae.trim_dec_in.tolist() == geo["trim_dec_in"] and ae.trim_dec_out.tolist() == geo["trim_dec_out"]
+    assert ae.decoder.trim_ups_out.tolist() == geo["trim_ups_out"]
+    assert [l.leads.tolist() for l in ae.decoder.conv_layers] == geo["leads"]
+    for part, mod in (("encoder", ae.encoder), ("bottleneck", ae.bottleneck), ("decoder", ae.decoder)):
+        sd, ref = mod.state_dict(), g["state_dict"][part]
+        assert list(sd) == list(ref), part
+        for k in sd:
+            assert sd[k].shape == ref[k].shape, (part, k)
+            # same seed, same construction order => bit-identical initial parameters (same RNG stream)
+            if k not in ("z_sum", "n_sum"):                      # torch.empty buffers (vqema_bn.py:113-114)
+                assert torch.equal(sd[k], ref[k]), (part, k)
+    geo3 = json.load(open(os.path.join(golden_dir, "geometry.json")))["cfg3_vqvae_ema_W16384"]
+    arch = dict(ARCH_BASIC, n_lc_in=32)
+    with torch.device("meta"):
+        ae3 = AutoEncoder(HP(arch), 39, 768, "vqvae-ema", 32, 0.25, 0.99, 4096, True)
+    ae3.init_geometry(16384)
+    assert (ae3.enc_in_len, ae3.enc_in_mel_len, ae3.embed_len, ae3.dec_in_len) == (23280, 144, 65, 18430)
+    assert ae3.trim_dec_in.tolist() == geo3["trim_dec_in"] and ae3.trim_dec_out.tolist() == geo3["trim_dec_out"]
+    assert ae3.decoder.trim_ups_out.tolist() == geo3["trim_ups_out"]

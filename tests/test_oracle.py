@@ -112,3 +112,26 @@ def test_forward_test_oracle_equals_reference_golden(golden_dir):
     assert torch.equal(out[1:, :rf1], out[:1, :rf1].expand(2, -1))      # primed with the input
     n_ts = rf1 + probs.shape[0]
     assert torch.equal(out[1:, n_ts:], out[:1, n_ts:].expand(2, -1))    # untouched past the conditioning sequence
+
+
+def test_autoencoder_step_oracle_equals_reference_golden(golden_dir):
+    """cfg3 in miniature: the travelling oracle's Encoder -> VQEMA -> WaveNet step against the golden written by
+    oracle/ae_harness.py from the unmodified reference modules (values, VQ indices, EMA statistics, every gradient)."""
+    from oracle import torch_oracle as O
+    g = torch.load(os.path.join(golden_dir, "autoencoder_small.pt"))
+    sd = {part: {k: (v.clone().requires_grad_(True) if v.dtype == torch.float32 and k in g["grads"][part] else v)
+                 for k, v in d.items()} for part, d in g["state_dict"].items()}
+    mels = g["mels"].clone().requires_grad_(True)
+    r = O.autoencoder_step(sd, g["hp"], g["geo"], mels, g["wav_dec"], g["spk"], g["jit"], 0.25, 0.99)
+    assert torch.equal(r["min_ind"], g["min_ind"])
+    assert float((r["quant"] - g["quant"]).abs().max()) < 1e-5
+    assert abs(float(r["com"]) - float(g["com"])) < 1e-5 and abs(float(r["rec"]) - float(g["rec"])) < 1e-6
+    for k in ("z_sum", "n_sum", "ema_numer", "ema_denom"):
+        assert float((r[k] - g[k]).abs().max()) < 1e-5, k
+    (r["com"] + r["rec"]).backward()
+    assert float((mels.grad - g["mel_grad"]).abs().max()) <= 1e-3 * float(g["mel_grad"].abs().max())
+    for part, grads in g["grads"].items():
+        for k, ref in grads.items():
+            got = sd[part][k].grad
+            assert got is not None, (part, k)
+            assert float((got - ref).abs().max()) <= 1e-3 * max(float(ref.abs().max()), 1e-12), (part, k)
