@@ -14,18 +14,27 @@ import torch
 from . import _lib as L
 
 
-# Engine mode of the plans built from here on (tests and bench.py A/B the two; prebuilt plans keep theirs):
+# Engine mode of the plans built from here on (tests and bench.py A/B them; prebuilt plans keep theirs):
 #   "pair"  2-CTA clusters issuing ONE cta_group::2 MMA stream (M = 256), operands split between the two CTAs
 #   "mcast" 2-CTA clusters sharing W / X by TMA multicast, every CTA issuing its own cta_group::1 MMAs (M = 128)
-ENGINE_MODE = os.environ.get("AEWN_ENGINE_MODE", "mcast")
+#   "auto"  per launch class, whichever measured faster on B200 at the cfg2 shapes (profiles/r2_engine_ab.json): the
+#           tensor-bound launches (conv+gate, data gradient, wgrad1) take "pair", the HBM-bound ones "mcast"
+ENGINE_MODE = os.environ.get("AEWN_ENGINE_MODE", "auto")
+PAIR_CLASSES = ("fwd_gemm1", "bwd_dgrad", "wgrad1")
 
 
 def set_engine_mode(mode):
     global ENGINE_MODE
-    if mode not in ("pair", "mcast"):
-        raise ValueError("engine mode must be 'pair' or 'mcast'")
+    if mode not in ("pair", "mcast", "auto"):
+        raise ValueError("engine mode must be 'pair', 'mcast' or 'auto'")
     ENGINE_MODE = mode
     _plans.clear()
+
+
+def _use_pair(tag):
+    if ENGINE_MODE == "auto":
+        return tag is not None and tag.split(".")[0] in PAIR_CLASSES
+    return ENGINE_MODE == "pair"
 
 
 # ------------------------------------------------------------------------------------------------- small helpers
@@ -140,7 +149,7 @@ def build_tgemm(acts, segs, w, ntiles, batch, t_begin, t_end, err=None, tag=None
         d.n_ntiles = len(chunk)
         d.batch, d.t_begin, d.t_end = int(batch), int(t_begin), int(t_end)
         d.err = err.data_ptr() if err is not None else None
-        d.cluster = L.CLUSTER_PAIR_MMA if ENGINE_MODE == "pair" else 2
+        d.cluster = L.CLUSTER_PAIR_MMA if _use_pair(tag) else 2
         out.append(("tgemm", d, tag))
     return out
 
@@ -196,7 +205,7 @@ def build_wgrad(acts, items, batch, err=None, tag=None, pair=False):
         d.n_items = len(chunk)
         d.batch = int(batch)
         d.err = err.data_ptr() if err is not None else None
-        d.pair_x = (2 if (ENGINE_MODE == "pair" and all(it.n <= 256 for it in d.items[:len(chunk)])) else 1) if pair else 0
+        d.pair_x = (2 if (_use_pair(tag) and all(it.n <= 256 for it in d.items[:len(chunk)])) else 1) if pair else 0
         out.append(("wgrad", d, tag))
     return out
 

@@ -58,6 +58,12 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
   return false;
 }
 
+// Warp-collective form: ALL 32 lanes of a converged warp poll; the result is made warp-uniform (a lane that timed out
+// takes the whole warp down the failure path, so no lane is left behind at a later __syncwarp / elect.sync).
+__device__ __forceinline__ bool mbar_wait_warp(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+  return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag));
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
@@ -160,7 +166,9 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 }
 // arrive on an mbarrier of any CTA of the cluster (address from mapa_u32)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  // default semantics (.release at CTA scope), the form CUTLASS's ClusterBarrier::arrive(cta_id) uses; the
+  // .release.cluster form costs a MEMBAR.ALL.CTA + ERRBAR per arrival (6 % of the peer's epilogue time in ncu)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
@@ -276,10 +284,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- math
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// ex2.approx.ftz / rcp.approx.ftz directly: __expf / __fdividef expand to the same MUFU ops PLUS a denormal-range
+// fix-up (compare, scale by 0.5, square) and a division range fix-up per call -- ~3x the instructions of the epilogue's
+// inner loop, for results that only differ when exp(-x) is denormal, i.e. where sigmoid / tanh have saturated anyway.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(x) = 1 / (1 + 2^(-x log2 e)); x -> -inf: 2^(+big) = inf, 1/inf = 0; x -> +inf: 1/(1+0) = 1.
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+// tanh(x) = 2*sigmoid(2x) - 1; absolute error ~1e-7, saturates cleanly for |x| large.
 __device__ __forceinline__ float fast_tanh(float x) {
-  // tanh(x) = 2*sigmoid(2x) - 1; absolute error ~1e-7, saturates cleanly for |x| large.
-  return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f;
+  return fmaf(2.0f, rcp_ftz(1.0f + ex2_ftz(-2.8853900817779268f * x)), -1.0f);
 }
 
 }  // namespace aewn

@@ -110,13 +110,14 @@ struct StgOut {
 };
 
 __device__ __forceinline__ void stg_acquire(const StgOut& so) {
-  if (so.lane == 0) tma_store_wait_read();   // the previous box of this warp has been read out of the tile
+  if (elect_one()) tma_store_wait_read();   // the previous box of this warp has been read out of the tile (elect.sync
+                                             // names the same lane every time, i.e. the one that committed the group)
   __syncwarp();
 }
 __device__ __forceinline__ void stg_flush(const StgOut& so, const CUtensorMap* map, int c0, bool reduce) {
   fence_proxy_async_smem();                  // make this lane's generic-proxy writes visible to the async proxy
   __syncwarp();
-  if (so.lane == 0) {
+  if (elect_one()) {
     if (reduce) tma_reduce_add_3d(map, so.tile, so.t0, c0, so.b);
     else tma_store_3d(map, so.tile, so.t0, c0, so.b);
     tma_store_commit();
@@ -319,11 +320,41 @@ __device__ __forceinline__ void epi_gate_fwd(const aewn_ntile& nt, const StgOut&
   float* const z_base = nt.out3 + off;
   const float* const bias = nt.bias;
   const int n_valid = nt.n_valid;
+  // Fast path (warp-uniform decision): every row of this warp's slab is live and in range, full 128-channel block, no
+  // separate bias, TMA stores.  It is the common case (all but the first tile of a sequence) and carries no per-element
+  // selects: ~14 instructions per (filt, gate) pair instead of ~59 -- the gated epilogue was the kernel's critical path
+  // once the MMA issue loop had been fixed (profiles/r2_*).
+  const bool fast = omaps && !bias && n_valid == 128 && so.slab_on && __all_sync(0xffffffffu, in_range && live);
   for (int c0 = half * 32; c0 < 128; c0 += 64) {
     uint32_t vf[32], vg[32];
     tmem_ld32(taddr + c0, vf);
     tmem_ld32(taddr + 128 + c0, vg);
     tmem_ld_wait();
+    if (fast) {
+      float* st = so.tile + so.lane;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        vf[j] = __float_as_uint(fast_tanh(__uint_as_float(vf[j])));
+        vg[j] = __float_as_uint(fast_sigmoid(__uint_as_float(vg[j])));
+      }
+      if (th_base) {
+        stg_acquire(so);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[j * 32] = __uint_as_float(vf[j]);
+        stg_flush(so, &omaps[0], c0, false);
+      }
+      if (sg_base) {
+        stg_acquire(so);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[j * 32] = __uint_as_float(vg[j]);
+        stg_flush(so, &omaps[1], c0, false);
+      }
+      stg_acquire(so);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) st[j * 32] = __uint_as_float(vf[j]) * __uint_as_float(vg[j]);
+      stg_flush(so, &omaps[2], c0, false);
+      continue;
+    }
     const int nrem = n_valid - c0;
     if (nrem <= 0) continue;
     float th[32], sg[32];
@@ -566,9 +597,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   // (128*88 + 256*208 = 64512 <= 65536).  Each setmaxnreg dominates its role code (no merge of limits).
   if (warp < 4) {
   reg_dealloc<40>();   // 128*40 + 256*232 = 64512 = 384*168: the CTA pool is what the launch allocated, NOT the SM file
+  // Both single-issuer roles run WARP-CONVERGENT: all 32 lanes walk the loops (so the pipeline state, tile coordinates
+  // and descriptors are warp-uniform and live in uniform registers) and one elected lane issues the TMA / MMA /
+  // commit instructions.  A loop walked by `if (lane == 0)` alone compiles to vector-register state and a
+  // waterfall (ELECT + 7 x R2UR + BRA.U.ANY) around EVERY tcgen05 / TMA instruction: ncu showed the MMA thread spending
+  // ~1000 cycles per K block on issue overhead against 512 cycles of tensor work (profiles/r2_*).
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0;
       bool ok = true;
       const uint32_t lead_full = pair ? mapa_u32(&full_bar[0], 0) : 0u;
@@ -583,35 +619,42 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
           if (!((nt.seg_mask >> s) & 1)) continue;
           const TgSeg sg = p.seg[s];
           for (int kb = 0; kb < sg.kblocks; ++kb) {
-            if (!mbar_wait(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
+            if (!mbar_wait_warp(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
             uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sw = sa + TG_A_BYTES;
             if (pair) {
               // Both CTAs signal the LEADER's full barrier (cta_group::2 loads); the leader expects the bytes of both.
               // CTA r stages W rows [r * n/2, (r+1) * n/2) of the tile (a 128-row box; the MMA reads n/2 of them).
-              if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * TG_PAIR_STAGE_BYTES);
-              const uint32_t fb = lead_full + stage * 8u;
+              if (elect_one()) {
+                if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * TG_PAIR_STAGE_BYTES);
+                const uint32_t fb = lead_full + stage * 8u;
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                tma_load_3d_pair(sa + i * 4096, &p.a_map[sg.map], fb, it.tau0 + sg.shift + 32 * i, kb * TG_BK, it.b);
-              tma_load_2d_pair(sw, &p.w_map, fb, sg.w_koff + kb * TG_BK, nt.w_row + crank * (nt.n >> 1));
+                for (int i = 0; i < 4; ++i)
+                  tma_load_3d_pair(sa + i * 4096, &p.a_map[sg.map], fb, it.tau0 + sg.shift + 32 * i, kb * TG_BK, it.b);
+                tma_load_2d_pair(sw, &p.w_map, fb, sg.w_koff + kb * TG_BK, nt.w_row + crank * (nt.n >> 1));
+              }
+              __syncwarp();
               if (++stage == n_stages) { stage = 0; phase ^= 1u; }
               continue;
             }
             const int wboxes = (nt.n + 127) >> 7;
-            mbar_expect_tx(&full_bar[stage], TG_A_BYTES + (p.cluster == 1 ? wboxes * TG_WBOX_BYTES : wslices * wrows * 128));
+            if (elect_one()) {
+              mbar_expect_tx(&full_bar[stage],
+                             TG_A_BYTES + (p.cluster == 1 ? wboxes * TG_WBOX_BYTES : wslices * wrows * 128));
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              tma_load_3d(sa + i * 4096, &p.a_map[sg.map], &full_bar[stage], it.tau0 + sg.shift + 32 * i, kb * TG_BK,
-                          it.b);
-            if (p.cluster == 1) {
-              for (int j = 0; j < wboxes; ++j)
-                tma_load_2d(sw + j * TG_WBOX_BYTES, &p.w_map, &full_bar[stage], sg.w_koff + kb * TG_BK,
-                            nt.w_row + j * 128);
-            } else if (crank < wslices) {
-              tma_load_2d_mcast(sw + crank * wrows * 128, &p.w_map, &full_bar[stage], sg.w_koff + kb * TG_BK,
-                                nt.w_row + crank * wrows, cmask);
+              for (int i = 0; i < 4; ++i)
+                tma_load_3d(sa + i * 4096, &p.a_map[sg.map], &full_bar[stage], it.tau0 + sg.shift + 32 * i, kb * TG_BK,
+                            it.b);
+              if (p.cluster == 1) {
+                for (int j = 0; j < wboxes; ++j)
+                  tma_load_2d(sw + j * TG_WBOX_BYTES, &p.w_map, &full_bar[stage], sg.w_koff + kb * TG_BK,
+                              nt.w_row + j * 128);
+              } else if (crank < wslices) {
+                tma_load_2d_mcast(sw + crank * wrows * 128, &p.w_map, &full_bar[stage], sg.w_koff + kb * TG_BK,
+                                  nt.w_row + crank * wrows, cmask);
+              }
             }
+            __syncwarp();
             if (++stage == n_stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -619,14 +662,20 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (pair mode: the leader CTA issues for both)
-    if (lane == 0 && (!pair || crank == 0)) {
+    if (!pair || crank == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       bool ok = true;
+      // A: MN-major, 128B swizzle with 32B atoms: 4-row groups 512 B apart (SBO), 32-step chunks 4 KB apart (LBO);
+      // W: K-major, 128B swizzle: 8-row groups 1 KB apart (SBO).  The descriptors of a stage differ from these only in
+      // the 14-bit start-address field (bytes >> 4), so they are built once and the address is ADDED per MMA.
+      const uint64_t adesc0 = make_smem_desc(0, p.a_lbo, p.a_sbo, kLayoutSW128Base32);
+      const uint64_t bdesc0 = make_smem_desc(0, 16, 1024, kLayoutSW128);
+      const uint32_t ring = smem_u32(smem);
       for (int item = cid; item < total && ok; item += n_clusters) {
         const TgItem it = tg_decode(p, item, crank);
         if (!it.active) continue;
         const aewn_ntile& nt = p.nt[it.ni];
-        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) break;
+        if (!mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256u;
         const uint32_t idesc = make_idesc_tf32(pair ? 2 * TG_BM : TG_BM, nt.n, /*a_mn=*/1, /*b_mn=*/0);
@@ -635,29 +684,36 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
           if (!((nt.seg_mask >> s) & 1)) continue;
           const int kblocks = p.seg[s].kblocks;
           for (int kb = 0; kb < kblocks; ++kb) {
-            if (!mbar_wait(&full_bar[stage], phase, abort_flag)) { ok = false; break; }
+            if (!mbar_wait_warp(&full_bar[stage], phase, abort_flag)) { ok = false; break; }
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-            const uint32_t w_addr = a_addr + TG_A_BYTES;
+            if (elect_one()) {
+              // start-address fields (16-byte units).  The mask matters: in CTA rank 1 of a cluster the shared::cta
+              // window address carries the rank in bit 24, which would otherwise spill into the LBO field.
+              const uint32_t a16 = ((ring + stage * stage_bytes) >> 4) & 0x3FFFu;
+              const uint32_t w16 = a16 + (TG_A_BYTES >> 4);
 #pragma unroll
-            for (int ks = 0; ks < TG_BK / 8; ++ks) {
-              // A: MN-major, 128B swizzle with 32B atoms: 4-row groups 512 B apart (SBO), 32-step chunks 4 KB apart (LBO)
-              const uint64_t adesc = make_smem_desc(a_addr + ks * 1024, p.a_lbo, p.a_sbo, kLayoutSW128Base32);
-              // W: K-major, 128B swizzle: 8-row groups 1 KB apart (SBO); K advances 32 B inside the swizzle row
-              const uint64_t bdesc = make_smem_desc(w_addr + ks * 32, 16, 1024, kLayoutSW128);
-              if (pair) umma_tf32_ss_pair(d_tmem, adesc, bdesc, idesc, (kiter | ks) != 0u);
-              else umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kiter | ks) != 0u);
+              for (int ks = 0; ks < TG_BK / 8; ++ks) {
+                // A advances 8 K rows = 1 KB per MMA; W advances 8 K columns = 32 B inside the swizzle row
+                const uint64_t adesc = adesc0 + (a16 + ks * 64);
+                const uint64_t bdesc = bdesc0 + (w16 + ks * 2);
+                if (pair) umma_tf32_ss_pair(d_tmem, adesc, bdesc, idesc, (kiter | ks) != 0u);
+                else umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kiter | ks) != 0u);
+              }
+              if (pair) umma_commit_pair(&empty_bar[stage], 0x3);
+              else if (p.cluster == 1) umma_commit(&empty_bar[stage]);
+              else umma_commit_mcast(&empty_bar[stage], cmask);
             }
-            if (pair) umma_commit_pair(&empty_bar[stage], 0x3);
-            else if (p.cluster == 1) umma_commit(&empty_bar[stage]);
-            else umma_commit_mcast(&empty_bar[stage], cmask);
+            __syncwarp();
             ++kiter;
             if (++stage == n_stages) { stage = 0; phase ^= 1u; }
           }
         }
         if (!ok) break;
-        if (pair) umma_commit_pair(&tfull_bar[acc], 0x3);   // accumulator ready: wake the epilogues of both CTAs
-        else umma_commit(&tfull_bar[acc]);
+        if (elect_one()) {
+          if (pair) umma_commit_pair(&tfull_bar[acc], 0x3);   // accumulator ready: wake the epilogues of both CTAs
+          else umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -720,7 +776,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (lane == 0) tma_store_wait_all();   // bulk stores must have completed before the CTA's smem goes away
+    if (elect_one()) tma_store_wait_all();   // bulk stores must have completed before the CTA's smem goes away
     __syncwarp();
   }
 

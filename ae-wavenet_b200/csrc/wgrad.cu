@@ -123,8 +123,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
 
   if (warp < 4) {
   reg_dealloc<88>();
+  // Single-issuer roles run warp-convergent with one elected issuing lane (see tgemm.cu: keeps the loop state in
+  // uniform registers and removes the per-instruction waterfall loops).
   if (warp == 0) {
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0;
       bool ok = true;
       const uint32_t lead_full = PMMA ? mapa_u32(&full_bar[0], 0) : 0u;
@@ -133,45 +135,58 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         if (u.kb_end <= u.kb_begin) continue;
         const aewn_wgrad_item& im = p.items[u.item];
         const int xboxes = (im.n + 127) >> 7;
+        int b_next = u.kb_begin / u.blocks_per_b;                  // (batch, time block) of the unit's first K block;
+        int tb = u.kb_begin - b_next * u.blocks_per_b;             // advanced incrementally (no division per block)
         for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
-          const int b = kb / u.blocks_per_b;
-          const int t = im.t_lo + (kb - b * u.blocks_per_b) * WG_BK;
-          if (!mbar_wait(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
+          const int b = b_next;
+          const int t = im.t_lo + tb * WG_BK;
+          if (++tb == u.blocks_per_b) { tb = 0; ++b_next; }
+          if (!mbar_wait_warp(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
           uint8_t* sg = smem + stage * stage_bytes;
           uint8_t* sx = sg + WG_BOX_BYTES;
           if (PMMA) {
             // both CTAs complete their bytes on the LEADER's full barrier; CTA r stages X rows [r * n/2, +n/2) (one
             // 128-row box, of which the MMA reads n/2)
-            if (crank == 0) mbar_expect_tx(&full_bar[stage], 4 * WG_BOX_BYTES);
-            const uint32_t fb = lead_full + stage * 8u;
-            tma_load_3d_pair(sg, &p.map[im.g_act], fb, t, im.g_row, b);
-            tma_load_3d_pair(sx, &p.map[im.x_act], fb, t + im.shift, im.x_row + crank * (im.n >> 1), b);
+            if (elect_one()) {
+              if (crank == 0) mbar_expect_tx(&full_bar[stage], 4 * WG_BOX_BYTES);
+              const uint32_t fb = lead_full + stage * 8u;
+              tma_load_3d_pair(sg, &p.map[im.g_act], fb, t, im.g_row, b);
+              tma_load_3d_pair(sx, &p.map[im.x_act], fb, t + im.shift, im.x_row + crank * (im.n >> 1), b);
+            }
+            __syncwarp();
             if (++stage == n_stages) { stage = 0; phase ^= 1u; }
             continue;
           }
-          mbar_expect_tx(&full_bar[stage], (1 + xboxes) * WG_BOX_BYTES);
-          tma_load_3d(sg, &p.map[im.g_act], &full_bar[stage], t, im.g_row, b);
-          if (!p.pair) {
-            for (int j = 0; j < xboxes; ++j)
-              tma_load_3d(sx + j * WG_BOX_BYTES, &p.map[im.x_act], &full_bar[stage], t + im.shift, im.x_row + j * 128, b);
-          } else {   // CTA r fetches X boxes r, r+2 and multicasts them to both CTAs of the pair
-            for (int j = crank; j < xboxes; j += 2)
-              tma_load_3d_mcast(sx + j * WG_BOX_BYTES, &p.map[im.x_act], &full_bar[stage], t + im.shift,
-                                im.x_row + j * 128, b, 0x3);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], (1 + xboxes) * WG_BOX_BYTES);
+            tma_load_3d(sg, &p.map[im.g_act], &full_bar[stage], t, im.g_row, b);
+            if (!p.pair) {
+              for (int j = 0; j < xboxes; ++j)
+                tma_load_3d(sx + j * WG_BOX_BYTES, &p.map[im.x_act], &full_bar[stage], t + im.shift, im.x_row + j * 128,
+                            b);
+            } else {   // CTA r fetches X boxes r, r+2 and multicasts them to both CTAs of the pair
+              for (int j = crank; j < xboxes; j += 2)
+                tma_load_3d_mcast(sx + j * WG_BOX_BYTES, &p.map[im.x_act], &full_bar[stage], t + im.shift,
+                                  im.x_row + j * 128, b, 0x3);
+            }
           }
+          __syncwarp();
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && (!PMMA || crank == 0)) {
+    if (!PMMA || crank == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       bool ok = true;
+      // both operands K-major, 128B swizzle, 8-row groups 1 KB apart; per stage only the start-address field changes
+      const uint64_t desc0 = make_smem_desc(0, 16, 1024, kLayoutSW128);
+      const uint32_t ring = smem_u32(smem);
       for (int unit = cid; unit < total_units && ok; unit += n_cl) {
         const WgUnit u = wg_decode(p, unit, crank);
         if (u.kb_end <= u.kb_begin) continue;
         const aewn_wgrad_item& im = p.items[u.item];
-        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) break;
+        if (!mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256u;
         const int n0 = im.n > 256 ? 256 : im.n;
@@ -179,32 +194,40 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         const uint32_t idesc = make_idesc_tf32(PMMA ? 256 : 128, n0, 0, 0);
         const uint32_t idesc1 = n1 > 0 ? make_idesc_tf32(128, n1, 0, 0) : 0u;
         for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
-          if (!mbar_wait(&full_bar[stage], phase, abort_flag)) { ok = false; break; }
+          if (!mbar_wait_warp(&full_bar[stage], phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t g_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t x_addr = g_addr + WG_BOX_BYTES;
+          if (elect_one()) {
+            // start-address fields (16-byte units), masked: the window address of CTA rank 1 carries the rank above
+            const uint32_t g16 = ((ring + stage * stage_bytes) >> 4) & 0x3FFFu;
+            const uint32_t x16 = g16 + (WG_BOX_BYTES >> 4);
+            const uint32_t accum = kb > u.kb_begin;
 #pragma unroll
-          for (int ks = 0; ks < WG_BK / 8; ++ks) {
-            const uint64_t adesc = make_smem_desc(g_addr + ks * 32, 16, 1024, kLayoutSW128);
-            const uint64_t bdesc = make_smem_desc(x_addr + ks * 32, 16, 1024, kLayoutSW128);
-            if (PMMA) {
-              umma_tf32_ss_pair(d_tmem, adesc, bdesc, idesc, (kb > u.kb_begin) || (ks > 0));
-              continue;
+            for (int ks = 0; ks < WG_BK / 8; ++ks) {
+              const uint64_t adesc = desc0 + (g16 + ks * 2);            // K advances 32 B inside the swizzle row
+              const uint64_t bdesc = desc0 + (x16 + ks * 2);
+              if (PMMA) {
+                umma_tf32_ss_pair(d_tmem, adesc, bdesc, idesc, accum | (ks > 0));
+                continue;
+              }
+              umma_tf32_ss(d_tmem, adesc, bdesc, idesc, accum | (ks > 0));
+              if (n1 > 0) {
+                const uint64_t bdesc1 = bdesc + ((2 * WG_BOX_BYTES) >> 4);
+                umma_tf32_ss(d_tmem + 256u, adesc, bdesc1, idesc1, accum | (ks > 0));
+              }
             }
-            umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kb > u.kb_begin) || (ks > 0));
-            if (n1 > 0) {
-              const uint64_t bdesc1 = make_smem_desc(x_addr + 2 * WG_BOX_BYTES + ks * 32, 16, 1024, kLayoutSW128);
-              umma_tf32_ss(d_tmem + 256u, adesc, bdesc1, idesc1, (kb > u.kb_begin) || (ks > 0));
-            }
+            if (PMMA) umma_commit_pair(&empty_bar[stage], 0x3);
+            else if (p.pair) umma_commit_mcast(&empty_bar[stage], 0x3);
+            else umma_commit(&empty_bar[stage]);
           }
-          if (PMMA) umma_commit_pair(&empty_bar[stage], 0x3);
-          else if (p.pair) umma_commit_mcast(&empty_bar[stage], 0x3);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
         if (!ok) break;
-        if (PMMA) umma_commit_pair(&tfull_bar[acc], 0x3);
-        else umma_commit(&tfull_bar[acc]);
+        if (elect_one()) {
+          if (PMMA) umma_commit_pair(&tfull_bar[acc], 0x3);
+          else umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
         if (++acc == acc_stages) { acc = 0; acc_phase ^= 1u; }
       }
     }

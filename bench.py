@@ -296,8 +296,12 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    # a START/END range (process-wide, unlike push/pop which is per thread: backward runs on autograd's thread) lets ncu
+    # restrict a capture to the timed steps:  ncu --nvtx --nvtx-include "aewn_timed" ...
+    nvtx_id = torch.cuda.nvtx.range_start("aewn_timed")
     for _ in range(args.steps):
         loss = step(dwav, dlc, dspk, djit)
+    torch.cuda.nvtx.range_end(nvtx_id)           # (ncu filters on the LAUNCH being inside the range: no sync needed)
     e1.record()
     barrier()
     clocks = sampler.stop()
