@@ -58,6 +58,24 @@ class WGradDesc(C.Structure):
                 ("pair_x", C.c_int)]
 
 
+WGW_MAX_CHUNKS, WGW_MAX_UNITS = 3, 8
+
+
+class WGWChunk(C.Structure):
+    _fields_ = [("x_act", C.c_int), ("x_row", C.c_int), ("n", C.c_int), ("n_valid", C.c_int), ("shift", C.c_int),
+                ("reserved", C.c_int), ("out", C.c_void_p), ("out_rs", C.c_longlong), ("out_cs", C.c_longlong)]
+
+
+class WGWUnit(C.Structure):
+    _fields_ = [("g_act", C.c_int), ("g_row", C.c_int), ("m_valid", C.c_int), ("t_lo", C.c_int), ("t_hi", C.c_int),
+                ("n_chunks", C.c_int), ("n_split", C.c_int), ("reserved", C.c_int), ("chunk", WGWChunk * WGW_MAX_CHUNKS)]
+
+
+class WGradWDesc(C.Structure):
+    _fields_ = [("acts", Act * WGRAD_MAX_ACTS), ("n_acts", C.c_int), ("units", WGWUnit * WGW_MAX_UNITS),
+                ("n_units", C.c_int), ("batch", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int)]
+
+
 class CopyBlock(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("ni", C.c_int), ("nj", C.c_int), ("si", C.c_longlong),
                 ("sj", C.c_longlong), ("di", C.c_longlong)]
@@ -90,7 +108,7 @@ class GenDesc(C.Structure):
 _lib = None
 
 # every symbol include/aewn.h declares (tests/test_capi.py checks the shared object exports all of them)
-SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_tgemm", "aewn_wgrad",
+SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_tgemm", "aewn_wgrad", "aewn_wgradw",
            "aewn_base_embed_fwd", "aewn_base_embed_bwd", "aewn_fill", "aewn_relu_mask_bwd",
            "aewn_vq_fwd", "aewn_vq_commit_bwd", "aewn_ema_update", "aewn_pack_blocks", "aewn_nll_fwd", "aewn_nll_bwd",
            "aewn_gen_smem_bytes", "aewn_gen_max_clusters", "aewn_gen_run"]

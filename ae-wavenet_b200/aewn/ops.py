@@ -21,6 +21,7 @@ from . import _lib as L
 #           tensor-bound launches (conv+gate, data gradient, wgrad1) take "pair", the HBM-bound ones "mcast"
 ENGINE_MODE = os.environ.get("AEWN_ENGINE_MODE", "auto")
 PAIR_CLASSES = ("fwd_gemm1", "bwd_dgrad", "wgrad1")
+WIDE_WGRAD = os.environ.get("AEWN_WIDE_WGRAD", "1") == "1"     # "auto" only: stack weight gradients through aewn_wgradw
 
 
 def set_engine_mode(mode):
@@ -210,6 +211,73 @@ def build_wgrad(acts, items, batch, err=None, tag=None, pair=False):
     return out
 
 
+def pack_wide_units(g_act, g_row, m_valid, t_lo, t_hi, chunks):
+    """Group column chunks (dicts: x_act, x_row, n_valid, shift, out, out_off, out_rs, out_cs) that share one G tile
+    into wgradw units: <= 3 chunks, <= 512 accumulator columns (each chunk rounded up to 32), <= 256 staged rows per
+    CTA (64 for a chunk of <= 128 columns, else 128).  First-fit on the chunks sorted widest first."""
+    units = []
+    for ch in sorted(chunks, key=lambda c: -c["n_valid"]):
+        n = max(16, ceil_to(ch["n_valid"], 16))
+        assert n <= 256
+        cols, rows = ceil_to(n, 32), (128 if n > 128 else 64)
+        for u in units:
+            if len(u["chunks"]) < L.WGW_MAX_CHUNKS and u["cols"] + cols <= 512 and u["rows"] + rows <= 256:
+                break
+        else:
+            u = dict(g_act=g_act, g_row=g_row, m_valid=m_valid, t_lo=t_lo, t_hi=t_hi, chunks=[], cols=0, rows=0)
+            units.append(u)
+        u["chunks"].append(dict(ch, n=n))
+        u["cols"] += cols
+        u["rows"] += rows
+    return units
+
+
+def build_wgradw(acts, units, batch, err=None, tag=None, waves=1):
+    """Descriptors of one logical wide-unit weight gradient.  Split-K factors are chosen per unit, proportional to the
+    unit's estimated cost per K block (operand bytes per CTA vs MMA cycles, whichever is larger), so that all CTA pairs
+    of a wave finish together."""
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    slots = (sms // 2) * waves
+    out = []
+    for i in range(0, len(units), L.WGW_MAX_UNITS):
+        grp = units[i:i + L.WGW_MAX_UNITS]
+        cost = []
+        for u in grp:
+            mma = sum(2.0 * c["n"] for c in u["chunks"])                      # cycles per K block: 4 x (n / 2)
+            bytes_ = 16384 + 128 * u["rows"]
+            kbs = batch * ((u["t_hi"] - u["t_lo"] + 31) // 32)
+            cost.append(max(mma, bytes_ / 45.0) * kbs)
+        tot = sum(cost)
+        share = max(1, slots // max(1, -(-len(units) // L.WGW_MAX_UNITS)))    # pairs available to this launch
+        splits = [max(1, int(round(share * c / tot))) for c in cost]
+        while sum(splits) > share and max(splits) > 1:
+            splits[splits.index(max(splits))] -= 1
+        d = L.WGradWDesc()
+        for j, a in enumerate(acts):
+            d.acts[j] = a
+        d.n_acts = len(acts)
+        for j, u in enumerate(grp):
+            w = L.WGWUnit()
+            w.g_act, w.g_row, w.m_valid = int(u["g_act"]), int(u["g_row"]), int(u["m_valid"])
+            w.t_lo, w.t_hi = int(u["t_lo"]), int(u["t_hi"])
+            kbs = batch * ((u["t_hi"] - u["t_lo"] + 31) // 32)
+            w.n_split = max(1, min(splits[j], kbs // 16))
+            w.n_chunks = len(u["chunks"])
+            for k, c in enumerate(u["chunks"]):
+                cc = L.WGWChunk()
+                cc.x_act, cc.x_row, cc.n, cc.n_valid = int(c["x_act"]), int(c["x_row"]), int(c["n"]), int(c["n_valid"])
+                cc.shift = int(c.get("shift", 0))
+                cc.out = c["out"].data_ptr() + 4 * int(c.get("out_off", 0))
+                cc.out_rs, cc.out_cs = int(c["out_rs"]), int(c["out_cs"])
+                w.chunk[k] = cc
+            d.units[j] = w
+        d.n_units = len(grp)
+        d.batch = int(batch)
+        d.err = err.data_ptr() if err is not None else None
+        out.append(("wgradw", d, tag))
+    return out
+
+
 def run_launches(launches):
     """Enqueue prebuilt descriptors on the current stream (ctypes call only: ~2 us of host time per launch)."""
     lib = L.lib()
@@ -218,6 +286,8 @@ def run_launches(launches):
         e0 = _prof_begin(tag)
         if kind == "tgemm":
             L.check(lib.aewn_tgemm(C.byref(d), st), "aewn_tgemm")
+        elif kind == "wgradw":
+            L.check(lib.aewn_wgradw(C.byref(d), st), "aewn_wgradw")
         else:
             L.check(lib.aewn_wgrad(C.byref(d), st), "aewn_wgrad")
         _prof_end(tag, e0)
@@ -520,6 +590,35 @@ class StackPlan:
             sh0 = 0 if needs_dup(d) else -d
             mtiles = [(h, i) for h in (0, 1) for i in range((D + 127) // 128)]
             keys = ("conv_signal.weight", "conv_gate.weight")
+            wide = ENGINE_MODE == "auto" and WIDE_WGRAD
+            if wide:
+                # wide units (aewn_wgradw): M = the D filt (h = 0) or gate (h = 1) rows of gfg as ONE CTA pair, against
+                # [x(tau-d) | x(tau) | cond, 1] in <= 512-column units: 256 + 256, then the tails 112 + 112 + 144
+                units = []
+                for h in (0, 1):
+                    cks = []
+                    for (c0, n) in chunks(R):
+                        for tap, (xa, sh) in enumerate(((1, sh0), (2, 0))):
+                            cks.append(dict(x_act=xa, x_row=c0, n_valid=n, shift=sh, out=v[keys[h]], out_off=c0 * 2 + tap,
+                                            out_rs=2 * R, out_cs=2))
+                    for (c0, n) in chunks(Cc + 1):
+                        cks.append(dict(x_act=3, x_row=c0, n_valid=n, shift=0, out=v["dpb"],
+                                        out_off=h * D * (Cc + 1) + c0, out_rs=Cc + 1, out_cs=1))
+                    units += pack_wide_units(0, h * D, D, lo4, T0, cks)
+                launches += build_wgradw(acts, units, B, self.err, tag=f"wgrad1.{l}")
+                # dWs, dWr with the roles swapped: M = the D rows of z (one CTA pair), columns = [g_skp | g_sig], so z
+                # is staged once per 512 gradient rows; outputs are written transposed (out_rs = 1, out_cs = D).
+                # g_skp is zero below RF (PostPlan / caller contract), so both share the K range [lead_l, T0).
+                acts2 = [act_of(self.z[l], T0), act_of(g_skp, T0)]
+                cks = [dict(x_act=1, x_row=c0, n_valid=n, shift=0, out=v["dil_skp.weight"], out_off=c0 * D, out_rs=1,
+                            out_cs=D) for (c0, n) in chunks(S)]
+                if not final and g_sig is not None:
+                    acts2.append(act_of(g_sig, T0))
+                    cks += [dict(x_act=2, x_row=c0, n_valid=n, shift=0, out=v["dil_res.weight"], out_off=c0 * D, out_rs=1,
+                                 out_cs=D) for (c0, n) in chunks(R)]
+                launches += build_wgradw(acts2, pack_wide_units(0, 0, D, lo4, T0, cks), B, self.err, tag=f"wgrad2.{l}")
+                g_sig = gx
+                continue
 
             def g_item(h, i):
                 return dict(g_act=0, g_row=h * D + 128 * i, m_valid=min(128, D - 128 * i), t_lo=lo4, t_hi=T0)

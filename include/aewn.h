@@ -176,6 +176,52 @@ typedef struct {
 int aewn_wgrad(const aewn_wgrad_desc* d, aewn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Weight-gradient GEMM with wide units on CTA pairs ("wgradw"): same contraction as aewn_wgrad, tiled for operand
+ * reuse.  A unit is 256 rows of G (m = 0..255) against up to AEWN_WGW_MAX_CHUNKS column chunks of X, each chunk with
+ * its own operand, time shift and output matrix:
+ *
+ *   chunk.out[m * out_rs + n * out_cs] += sum_b sum_{u in [t_lo,t_hi)} G[b, g_row + m, u] * X[b, x_row + n, u + shift]
+ *
+ * The chunks of a unit need <= 512 accumulator columns (each chunk rounded up to 32) and <= 256 staged rows per CTA
+ * (a chunk of n <= 128 columns stages 64, a wider one 128).  Every unit has its own split-K factor so that units of
+ * different cost can be balanced over one wave of CTA pairs.  Callers zero the outputs first.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int x_act, x_row;   /* X operand: acts[] index and first channel row */
+  int n;              /* columns of the chunk: multiple of 16, 16..256 */
+  int n_valid;        /* columns stored */
+  int shift;          /* X time coordinate = u + shift; multiple of 4 */
+  int reserved;
+  float* out;
+  long long out_rs, out_cs;
+} aewn_wgw_chunk;
+
+#define AEWN_WGW_MAX_CHUNKS 3
+#define AEWN_WGW_MAX_UNITS 8
+
+typedef struct {
+  int g_act, g_row;   /* G operand: rows [g_row, g_row + 256); rows beyond the tensor read as zero */
+  int m_valid;        /* rows stored (1..256) */
+  int t_lo, t_hi;     /* u range; t_lo multiple of 4 */
+  int n_chunks;
+  int n_split;        /* split-K factor of this unit (>= 1) */
+  int reserved;
+  aewn_wgw_chunk chunk[AEWN_WGW_MAX_CHUNKS];
+} aewn_wgw_unit;
+
+typedef struct {
+  aewn_act acts[AEWN_WGRAD_MAX_ACTS];
+  int n_acts;
+  aewn_wgw_unit units[AEWN_WGW_MAX_UNITS];
+  int n_units;
+  int batch;
+  int* err;
+  int max_ctas;
+} aewn_wgradw_desc;
+
+int aewn_wgradw(const aewn_wgradw_desc* d, aewn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Decoder base layer (wavenet.py:348-351): one_hot(wav.long())[..., off0:off0+T] -> Conv1d(Q->R, k=1) evaluated as
  * a column gather  out[b, r, tau] = w[r, code(b, off0 + tau)] + bias[r]  (no one-hot tensor is materialised).
  * `dup` (optional) receives the same values at time index tau + dup_toff (pre-shifted copy for a dilation-1/2 tap).

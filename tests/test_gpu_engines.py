@@ -110,3 +110,37 @@ def test_polyphase_conv_transpose_matches_torch(f, s, L):
     ops.check_device_errors()
     for a, r, name in ((xc.grad, xr.grad, "x"), (wc.grad, wr.grad, "w"), (bc.grad, br.grad, "b")):
         assert float((a.cpu() - r).abs().max()) / float(r.abs().max()) < 5e-3, name
+
+
+@pytest.mark.parametrize("M,widths", [(256, (256, 256)), (200, (112, 112, 139)), (40, (48,)), (256, (256, 100, 16))])
+def test_wgradw_wide_units_match_torch(M, widths):
+    """aewn_wgradw: one CTA pair per unit (M <= 256 rows of G) against up to three column chunks with their own operand
+    rows, time shifts and (strided / transposed) outputs; per-unit split-K."""
+    from aewn import ops, _lib as L
+    g = torch.Generator().manual_seed(11)
+    B, T, t_lo = 2, 1700, 8
+    G = torch.randn(B, M, T, generator=g)
+    Gb = ops.to_buf(G.cuda())
+    acts, keep = [ops.act_of(Gb, T)], []
+    cks, refs = [], []
+    for i, n in enumerate(widths):
+        X = torch.randn(B, n + 5, T, generator=g)            # operand with extra rows: the chunk starts at row 3
+        shift = (0, -8, 4)[i % 3]
+        transposed = i % 2 == 1
+        out = torch.zeros((n, M) if transposed else (M, n), device="cuda")
+        keep.append(ops.to_buf(X.cuda()))                # descriptors hold raw pointers: keep the buffers alive
+        acts.append(ops.act_of(keep[-1], T))
+        cks.append(dict(x_act=len(acts) - 1, x_row=3, n_valid=n, shift=shift, out=out, out_off=0,
+                        out_rs=1 if transposed else n, out_cs=M if transposed else 1))
+        Xs = torch.nn.functional.pad(X, (max(0, -shift), max(0, shift)))
+        Xs = Xs[:, :, :T] if shift <= 0 else Xs[:, :, shift:shift + T]          # X[u + shift], zero outside [0, T)
+        ref = torch.einsum("bmt,bnt->mn", G[:, :, t_lo:], Xs[:, 3:3 + n, t_lo:])
+        refs.append((out, ref.t() if transposed else ref))
+    units = ops.pack_wide_units(0, 0, M, t_lo, T, cks)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for kind, d, tag in ops.build_wgradw(acts, units, B, err):
+        L.check(L.lib().aewn_wgradw(C.byref(d), ops._stream()), "aewn_wgradw")
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    for out, ref in refs:
+        assert float((out.cpu() - ref).abs().max()) / float(ref.abs().max()) < 3e-3

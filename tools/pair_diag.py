@@ -63,10 +63,48 @@ def run_wgrad(engine, N=256, M=256, T=2048, B=2):
                 print(f"   m-tile {mh} col-half {nh}: max {float(blk.max()):.1f} frac_wrong {float((blk > 0).float().mean()):.3f}")
 
 
+def run_wgradw(widths=(256, 256), M=256, T=2048, B=2):
+    g = torch.Generator().manual_seed(3)
+    G = torch.randint(-2, 3, (B, M, T), generator=g).float()
+    keep = [ops.to_buf(G.cuda())]                      # the descriptors hold raw pointers: keep the buffers alive
+    acts = [ops.act_of(keep[0], T)]
+    cks, refs = [], []
+    for n in widths:
+        X = torch.randint(-2, 3, (B, n, T), generator=g).float()
+        out = torch.zeros(M, n).cuda()
+        keep.append(ops.to_buf(X.cuda()))
+        acts.append(ops.act_of(keep[-1], T))
+        cks.append(dict(x_act=len(acts) - 1, x_row=0, n_valid=n, shift=0, out=out, out_off=0, out_rs=n, out_cs=1))
+        refs.append((out, torch.einsum("bmt,bnt->mn", G, X)))
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rc = 0
+    for kind, d, tag in ops.build_wgradw(acts, ops.pack_wide_units(0, 0, M, 0, T, cks), B, err):
+        rc = L.lib().aewn_wgradw(C.byref(d), ops._stream())
+    torch.cuda.synchronize()
+    worst = max(float((o.cpu() - r).abs().max()) for o, r in refs)
+    print(f"wgradw widths={widths}: rc={rc} err_word={int(err.item())} max_err={worst}")
+    if worst > 0:
+        for ci, (o, r) in enumerate(refs):
+            diff = (o.cpu() - r).abs()
+            n = diff.shape[1]
+            for mh in (0, 1):
+                for nh in (0, 1):
+                    blk = diff[mh * 128:(mh + 1) * 128, nh * (n // 2):(nh + 1) * (n // 2)]
+                    if blk.numel():
+                        print(f"   chunk {ci} m-half {mh} col-half {nh}: max {float(blk.max()):.1f} frac_wrong {float((blk > 0).float().mean()):.3f}")
+
+
 if __name__ == "__main__":
-    for cl in (2, L.CLUSTER_PAIR_MMA):
-        for N in (256, 48, 368):
-            run_tgemm(cl, N=N)
-    for eng in ("mcast", "pair"):
-        for N in (256, 112):
-            run_wgrad(eng, N=N)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "tgemm"):
+        for cl in (2, L.CLUSTER_PAIR_MMA):
+            for N in (256, 48, 368):
+                run_tgemm(cl, N=N)
+    if which in ("all", "wgrad"):
+        for eng in ("mcast", "pair"):
+            for N in (256, 112):
+                run_wgrad(eng, N=N)
+    if which in ("all", "wgradw"):
+        for widths in ((256, 256), (112, 112, 144), (256,), (48,)):
+            print("launching wgradw", widths, flush=True)
+            run_wgradw(widths)
