@@ -110,7 +110,7 @@ _lib = None
 # every symbol include/aewn.h declares (tests/test_capi.py checks the shared object exports all of them)
 SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_tgemm", "aewn_wgrad", "aewn_wgradw",
            "aewn_base_embed_fwd", "aewn_base_embed_bwd", "aewn_fill", "aewn_relu_mask_bwd",
-           "aewn_vq_fwd", "aewn_vq_commit_bwd", "aewn_ema_update", "aewn_pack_blocks", "aewn_nll_fwd", "aewn_nll_bwd",
+           "aewn_vq_fwd", "aewn_vq_commit_bwd", "aewn_ema_update", "aewn_pack_blocks", "aewn_add_blocks", "aewn_nll_fwd", "aewn_nll_bwd",
            "aewn_gen_smem_bytes", "aewn_gen_max_clusters", "aewn_gen_run"]
 
 

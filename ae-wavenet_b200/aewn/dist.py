@@ -29,6 +29,13 @@ class FlatGradSync:
             off += p.numel()
         if vqema is not None:
             vqema.defer_ema = True
+        # this engine owns persistent .grad buffers and only ever runs loss.backward(): let the decoder's backward add
+        # its weight gradients into them with one launch instead of one clone + one add per parameter (ops.py)
+        try:
+            from . import ops
+            ops.ACCUMULATE_INTO_GRAD = True
+        except Exception:          # CPU-only unit tests of the reduction logic import this module without the kernels
+            pass
 
     def zero_grad(self):
         self.flat[:self.n_grad].zero_()

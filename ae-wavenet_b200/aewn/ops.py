@@ -17,10 +17,9 @@ from . import _lib as L
 # Engine mode of the plans built from here on (tests and bench.py A/B them; prebuilt plans keep theirs):
 #   "pair"  2-CTA clusters issuing ONE cta_group::2 MMA stream (M = 256), operands split between the two CTAs
 #   "mcast" 2-CTA clusters sharing W / X by TMA multicast, every CTA issuing its own cta_group::1 MMAs (M = 128)
-#   "auto"  per launch class, whichever measured faster on B200 at the cfg2 shapes (profiles/r2_engine_ab.json): the
-#           tensor-bound launches (conv+gate, data gradient, wgrad1) take "pair", the HBM-bound ones "mcast"
+#   "auto"  what measured fastest on B200 at the cfg2 shapes (profiles/r2_engine_ab.json): "pair" for every tgemm / wgrad
+#           launch, and the stack's weight gradients through the wide-unit kernel aewn_wgradw (WIDE_WGRAD)
 ENGINE_MODE = os.environ.get("AEWN_ENGINE_MODE", "auto")
-PAIR_CLASSES = ("fwd_gemm1", "bwd_dgrad", "wgrad1")
 WIDE_WGRAD = os.environ.get("AEWN_WIDE_WGRAD", "1") == "1"     # "auto" only: stack weight gradients through aewn_wgradw
 
 
@@ -33,9 +32,7 @@ def set_engine_mode(mode):
 
 
 def _use_pair(tag):
-    if ENGINE_MODE == "auto":
-        return tag is not None and tag.split(".")[0] in PAIR_CLASSES
-    return ENGINE_MODE == "pair"
+    return ENGINE_MODE in ("auto", "pair")
 
 
 # ------------------------------------------------------------------------------------------------- small helpers
@@ -276,6 +273,46 @@ def build_wgradw(acts, units, batch, err=None, tag=None, waves=1):
         d.err = err.data_ptr() if err is not None else None
         out.append(("wgradw", d, tag))
     return out
+
+
+# ------------------------------------------------------------------------------------------------- fused grad accumulation
+# When True (set by dist.FlatGradSync, i.e. by a training engine that owns persistent .grad buffers and only ever calls
+# loss.backward()), the decoder's backward adds ALL its weight gradients into the parameters' existing .grad tensors with
+# one aewn_add_blocks launch and returns None for them -- autograd would otherwise run one clone + one add kernel per
+# parameter (~240 launches per step).  Must stay False for torch.autograd.grad(...) style callers, which expect the
+# gradients as return values and .grad untouched (mfcc_inverter.py:103 does that for lc_sparse only, never for weights).
+ACCUMULATE_INTO_GRAD = False
+_grad_tables = {}
+
+
+def add_into_grads(pairs):
+    """pairs: [(src_view, dst)], dst contiguous, src of the same shape with contiguous inner dimensions.  Returns False
+    (and does nothing) if any destination is missing or incompatible."""
+    for src, dst in pairs:
+        if dst is None or not dst.is_contiguous() or dst.shape != src.shape or dst.dtype != torch.float32:
+            return False
+    key = tuple((src.data_ptr(), dst.data_ptr()) for src, dst in pairs)
+    ent = _grad_tables.get(key)
+    if ent is None:
+        import numpy as np
+        blocks = []
+        for src, dst in pairs:
+            rows = int(src.shape[0]) if src.dim() > 0 else 1
+            cols = int(src.numel() // max(rows, 1))
+            inner_ok = src.dim() <= 1 or src[0].is_contiguous()
+            if not inner_ok:
+                return False
+            si = int(src.stride(0)) if src.dim() > 0 else 1
+            blocks.append((src.data_ptr(), dst.data_ptr(), rows, cols, si, 1, cols))
+        dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("ni", "<i4"), ("nj", "<i4"), ("si", "<i8"), ("sj", "<i8"),
+                       ("di", "<i8")])
+        arr = np.array(blocks, dtype=dt)
+        if len(_grad_tables) >= 4:
+            _grad_tables.clear()
+        ent = _grad_tables[key] = (torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(pairs[0][1].device),
+                                   len(blocks))
+    L.check(L.lib().aewn_add_blocks(C.c_void_p(ent[0].data_ptr()), C.c_int(ent[1]), _stream()), "aewn_add_blocks")
+    return True
 
 
 def run_launches(launches):

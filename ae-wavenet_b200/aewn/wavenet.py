@@ -434,6 +434,7 @@ class _DecoderCoreFn(torch.autograd.Function):
         ctx.dims = (B, R, D, S, Cc, Q, T0)
         ctx.has_bias = base_b.numel() > 0
         ctx.base_shape = base_w.shape
+        ctx.leaves = (p1w, p1b, p2w, p2b) + tuple(weights)      # the parameters themselves (for .grad, see backward)
         return out
 
     @staticmethod
@@ -457,11 +458,17 @@ class _DecoderCoreFn(torch.autograd.Function):
             L.C.c_int(B), L.C.c_int(R), L.C.c_int(Q), L.C.c_int(T0), ops._stream()), "aewn_base_embed_bwd")
         # gradient views alias the plan's flat buffer (overwritten by the next backward): autograd accumulates them
         # into .grad right away; a caller that keeps them (torch.autograd.grad) gets private copies
-        wgrads = tuple(grads[li][k].clone() for (li, k) in ctx.keys)
         b1, b2 = ctx.post_has_bias
-        pg = (pviews["post1.weight"].clone(), pviews["post1.bias"].clone() if b1 else None,
-              pviews["post2.weight"].clone(), pviews["post2.bias"].clone() if b2 else None)
-        return (None, g_cond[:, :, :T0].clone(), None, None, d_base.reshape(ctx.base_shape), d_bias) + pg + wgrads
+        views = [pviews["post1.weight"], pviews["post1.bias"] if b1 else None, pviews["post2.weight"],
+                 pviews["post2.bias"] if b2 else None] + [grads[li][k] for (li, k) in ctx.keys]
+        if ops.ACCUMULATE_INTO_GRAD:
+            # training-engine mode: ONE launch adds every weight gradient into the existing .grad buffers
+            pairs = [(v, leaf.grad) for v, leaf in zip(views, ctx.leaves) if v is not None]
+            if ops.add_into_grads(pairs):
+                return (None, g_cond[:, :, :T0].clone(), None, None, d_base.reshape(ctx.base_shape), d_bias) + \
+                       (None,) * len(views)
+        out = tuple(v.clone() if v is not None else None for v in views)
+        return (None, g_cond[:, :, :T0].clone(), None, None, d_base.reshape(ctx.base_shape), d_bias) + out
 
 
 class _NLLFn(torch.autograd.Function):

@@ -1,6 +1,7 @@
 #include "host_util.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace aewn {
@@ -50,6 +51,19 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// L2 promotion of activation boxes.  Every box row is one 128-byte piece of a channel row (rows are ~74 KB apart), and
+// the next K block / time tile reads the adjacent 128 bytes.  Promoting misses to 256 bytes was measured equal within
+// noise (gpurun ab1: 31.6 vs 31.7 ms/step), so 128 stays; AEWN_ACT_L2_PROMOTION=64|256 overrides for A/B runs.
+static CUtensorMapL2promotion act_l2_promotion() {
+  static const CUtensorMapL2promotion v = []() {
+    const char* e = getenv("AEWN_ACT_L2_PROMOTION");
+    if (e && atoi(e) == 256) return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (e && atoi(e) == 64) return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+    return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;   // 256 measured equal within noise (wgrad2 -10 %, wgrad1 +4 %)
+  }();
+  return v;
+}
+
 int encode_act_map(CUtensorMap* map, const aewn_act& a, int box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_err(AEWN_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
@@ -68,7 +82,7 @@ int encode_act_map(CUtensorMap* map, const aewn_act& a, int box_rows, CUtensorMa
   cuuint32_t box[3] = {32u, static_cast<cuuint32_t>(box_rows), 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<float*>(a.ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, act_l2_promotion(),
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(AEWN_ERR_DRIVER, "cuTensorMapEncodeTiled(act) failed: CUresult %d", (int)r);
   return AEWN_OK;

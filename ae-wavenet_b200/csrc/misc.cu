@@ -127,6 +127,19 @@ __global__ void pack_blocks_kernel(const aewn_copy_block* __restrict__ blocks, i
   }
 }
 
+// Same table, accumulating:  dst[i*di + j] += src[i*si + j*sj].  One launch adds every weight gradient of a backward
+// pass into the caller's .grad buffers (instead of one clone + one add launch per parameter).
+__global__ void add_blocks_kernel(const aewn_copy_block* __restrict__ blocks, int n_blocks) {
+  for (int bi = blockIdx.x; bi < n_blocks; bi += gridDim.x) {
+    const aewn_copy_block b = blocks[bi];
+    const long long total = static_cast<long long>(b.ni) * b.nj;
+    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+      const long long i = e / b.nj, j = e - i * b.nj;
+      b.dst[i * b.di + j] += b.src[i * b.si + j * b.sj];
+    }
+  }
+}
+
 }  // namespace aewn
 
 using namespace aewn;
@@ -180,6 +193,15 @@ int aewn_pack_blocks(const aewn_copy_block* blocks_dev, int n_blocks, aewn_strea
   pack_blocks_kernel<<<grid, 256, 0, stream>>>(blocks_dev, n_blocks);
   count_launch();
   return cuda_err(cudaGetLastError(), "pack_blocks launch");
+}
+
+int aewn_add_blocks(const aewn_copy_block* blocks_dev, int n_blocks, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!blocks_dev || n_blocks <= 0) return set_err(AEWN_ERR_INVALID, "add_blocks: bad arguments");
+  int grid = n_blocks < 148 * 8 ? n_blocks : 148 * 8;
+  add_blocks_kernel<<<grid, 256, 0, stream>>>(blocks_dev, n_blocks);
+  count_launch();
+  return cuda_err(cudaGetLastError(), "add_blocks launch");
 }
 
 int aewn_relu_mask_bwd(const float* g, long long g_bs, long long g_cs, const float* mask, long long m_bs, long long m_cs,

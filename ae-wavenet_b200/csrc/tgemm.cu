@@ -531,7 +531,10 @@ __device__ __forceinline__ void epi_gate_bwd(const GateBwdCtx& cx, const StgOut&
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <bool PAIR>
+// MODE: epilogue mode shared by every n-tile of the launch (AEWN_EPI_*), or -1 = per-tile dispatch.  The three epilogues
+// are fully unrolled; compiled into one kernel they make 230 KB of SASS and the epilogue warps spent 16 % of their
+// samples on instruction fetch (stall_no_inst, profiles/r2b_*), so each mode gets its own instantiation.
+template <bool PAIR, int MODE>
 __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_constant__ TgParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -732,7 +735,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
       // Each mode keeps its own register context (exclusive branches, so the contexts can share registers); the first
       // chunks' loads (addend / previous output / tanh+sigmoid) are issued BEFORE waiting for the accumulator.
       const uint32_t taddr = tmem_base + acc * 256u + (static_cast<uint32_t>(q * 32) << 16);
-      const int mode = nt.mode;
+      const int mode = MODE >= 0 ? MODE : nt.mode;
       const bool use_tma = p.o_tma[it.ni] != 0;
       StgOut so;
       so.tile = stg_base + (warp - 4) * 1024;
@@ -808,10 +811,7 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
                    d->t_begin, d->t_end);
 
   {
-    cudaError_t e = cudaFuncSetAttribute(tgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
-    if (e != cudaSuccess) return cuda_err(e, "tgemm: cudaFuncSetAttribute");
+    // (the attribute is set on the selected instantiation right before the launch)
   }
 
   TgParams p;
@@ -929,7 +929,23 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = p.pair ? cudaLaunchKernelEx(&cfg, tgemm_kernel<true>, p) : cudaLaunchKernelEx(&cfg, tgemm_kernel<false>, p);
+  int mode = d->ntiles[0].mode;
+  for (int i = 1; i < d->n_ntiles; ++i)
+    if (d->ntiles[i].mode != mode) mode = -1;
+  using KernelFn = void (*)(TgParams);
+  KernelFn fn;
+  if (p.pair) {
+    fn = mode == AEWN_EPI_LINEAR ? tgemm_kernel<true, AEWN_EPI_LINEAR>
+         : mode == AEWN_EPI_GATE_FWD ? tgemm_kernel<true, AEWN_EPI_GATE_FWD>
+         : mode == AEWN_EPI_GATE_BWD ? tgemm_kernel<true, AEWN_EPI_GATE_BWD> : tgemm_kernel<true, -1>;
+  } else {
+    fn = mode == AEWN_EPI_LINEAR ? tgemm_kernel<false, AEWN_EPI_LINEAR>
+         : mode == AEWN_EPI_GATE_FWD ? tgemm_kernel<false, AEWN_EPI_GATE_FWD>
+         : mode == AEWN_EPI_GATE_BWD ? tgemm_kernel<false, AEWN_EPI_GATE_BWD> : tgemm_kernel<false, -1>;
+  }
+  cudaError_t ae = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
+  if (ae != cudaSuccess) return cuda_err(ae, "tgemm: cudaFuncSetAttribute");
+  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
   count_launch();
   if (le != cudaSuccess) return cuda_err(le, "tgemm launch");
   return cuda_err(cudaGetLastError(), "tgemm launch");

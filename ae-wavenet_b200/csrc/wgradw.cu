@@ -23,7 +23,8 @@ constexpr int WW_BOX_BYTES = 128 * WW_BK * 4;         // 16 KB: 128 rows x 32 ti
 constexpr int WW_STAGE_BYTES = 3 * WW_BOX_BYTES;      // G box + 32 KB of X half-boxes (<= 256 rows per CTA)
 constexpr int WW_THREADS = 384;
 constexpr int WW_EPI_WARPS = 8;
-constexpr int WW_SMEM_BYTES = WW_STAGES * WW_STAGE_BYTES + 256 + 1024;
+constexpr int WW_XPOSE_BYTES = WW_EPI_WARPS * 4096;   // one 32 x 32 fp32 transpose tile per epilogue warp
+constexpr int WW_SMEM_BYTES = WW_STAGES * WW_STAGE_BYTES + WW_XPOSE_BYTES + 256 + 1024;
 
 struct WwParams {
   CUtensorMap map128[AEWN_WGRAD_MAX_ACTS];   // box {32 t, 128 rows}
@@ -63,7 +64,8 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgradw_kernel(const __grid_cons
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WW_STAGES * WW_STAGE_BYTES);
+  float* xpose = reinterpret_cast<float*>(smem + WW_STAGES * WW_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WW_STAGES * WW_STAGE_BYTES + WW_XPOSE_BYTES);
   uint64_t* empty_bar = full_bar + WW_STAGES;
   uint64_t* tfull_bar = empty_bar + WW_STAGES;
   uint64_t* tempty_bar = tfull_bar + 1;
@@ -185,19 +187,40 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgradw_kernel(const __grid_cons
       const aewn_wgw_unit& un = p.units[w.unit];
       if (!mbar_wait(tfull_bar, acc_phase, abort_flag)) break;
       tc_fence_after();
-      const int m = crank * 128 + q * 32 + lane;
+      const int m0 = crank * 128 + q * 32;          // first output row of this warp's 32 TMEM lanes
+      const int m = m0 + lane;
+      float* tile = xpose + (warp - 4) * 1024;
       for (int c = 0; c < un.n_chunks; ++c) {
         const aewn_wgw_chunk& ch = un.chunk[c];
         const uint32_t taddr = tmem_base + static_cast<uint32_t>(p.tm_col[w.unit][c]) + (static_cast<uint32_t>(q * 32) << 16);
+        // Lane = output row m.  When the rows are contiguous in memory (out_rs == 1: the transposed outputs) a warp-wide
+        // red already hits one 128-byte line.  Otherwise (conv weights: rows 2R floats apart) every lane would touch
+        // its own line -- 8 M single-lane reds per launch were a third of all L2 tag requests in ncu -- so the 32 x 32
+        // block goes through a swizzled shared-memory tile and is reduced with lane = column instead.
+        const bool direct = ch.out_rs == 1;
         float* orow = ch.out + static_cast<long long>(m) * ch.out_rs;
         for (int c0 = half * 32; c0 < ch.n; c0 += 64) {
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
-          if (m < un.m_valid) {
+          if (direct) {
+            if (m < un.m_valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < ch.n_valid) atomicAdd(orow + static_cast<long long>(c0 + j) * ch.out_cs, __uint_as_float(v[j]));
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < ch.n_valid) atomicAdd(orow + static_cast<long long>(c0 + j) * ch.out_cs, __uint_as_float(v[j]));
+            }
+          } else {
+            __syncwarp();                            // the previous block has been read out of the tile
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tile[lane * 32 + (j ^ lane)] = __uint_as_float(v[j]);   // (row lane, col j)
+            __syncwarp();
+            if (c0 + lane < ch.n_valid) {
+              float* ocol = ch.out + static_cast<long long>(m0) * ch.out_rs + static_cast<long long>(c0 + lane) * ch.out_cs;
+              const int rows = un.m_valid - m0 < 32 ? un.m_valid - m0 : 32;
+#pragma unroll 8
+              for (int r = 0; r < rows; ++r)         // (row r, col lane) sits at physical column lane ^ r
+                atomicAdd(ocol + static_cast<long long>(r) * ch.out_rs, tile[r * 32 + (lane ^ r)]);
+            }
           }
         }
       }

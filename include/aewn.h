@@ -243,6 +243,9 @@ typedef struct {
   long long si, sj, di;
 } aewn_copy_block;
 int aewn_pack_blocks(const aewn_copy_block* blocks_dev, int n_blocks, aewn_stream_t stream);
+/* Same table, accumulating: dst[i*di + j] += src[i*si + j*sj].  Adds all weight gradients of one backward pass into the
+ * caller's gradient buffers with one launch (what autograd does with one add per parameter, chassis.py:157). */
+int aewn_add_blocks(const aewn_copy_block* blocks_dev, int n_blocks, aewn_stream_t stream);
 /* out = mask > 0 ? g : 0   (ReLU backward) */
 int aewn_relu_mask_bwd(const float* g, long long g_bs, long long g_cs, const float* mask, long long m_bs, long long m_cs,
                        float* out, long long o_bs, long long o_cs, int batch, int C, int T, aewn_stream_t stream);

@@ -135,3 +135,31 @@ def test_fused_rec_loss_matches_torch_log_softmax_gather():
     assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
     assert float((gq - gr).abs().max()) < 1e-6 + 1e-4 * float(gr.abs().max())
     assert float(gq[..., -1].abs().max()) == 0.0
+
+
+def test_fused_grad_accumulation_equals_autograd_accumulation(golden_dir, monkeypatch):
+    """ops.ACCUMULATE_INTO_GRAD (the training-engine mode FlatGradSync switches on): one aewn_add_blocks launch adds every
+    weight gradient into the existing .grad buffers; must equal what autograd's per-parameter accumulation produces,
+    including accumulation over two backward passes."""
+    import aewn
+    from aewn import ops
+    g = torch.load(os.path.join(golden_dir, "wavenet_small.pt"))
+    wn = build_wavenet(g)
+    wav, lc = g["wav"].cuda(), g["lc"].cuda()
+    t0, t1 = g["geo"]["trim_dec_out"]
+
+    def run(flag):
+        monkeypatch.setattr(ops, "ACCUMULATE_INTO_GRAD", flag)
+        for p in wn.parameters():
+            p.grad = torch.zeros_like(p)
+        for _ in range(2):
+            quant = wn(wav, lc, g["spk"].cuda(), g["jit"].cuda())
+            aewn.RecLoss()(quant[..., :-1], wav[:, t0:t1][..., 1:]).backward()
+        ops.check_device_errors()
+        return {k: p.grad.clone() for k, p in wn.named_parameters()}
+
+    ref, got = run(False), run(True)
+    for k in ref:
+        scale = max(float(ref[k].abs().max()), 1e-12)
+        assert float((got[k] - ref[k]).abs().max()) <= 1e-4 * scale, k      # fp32 atomics: order differs run to run
+    assert rel_err(got["conv_layers.0.conv_signal.weight"], 2 * g["grads"]["conv_layers.0.conv_signal.weight"]) < 0.15

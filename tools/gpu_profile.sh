@@ -10,10 +10,10 @@ timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --n
 # layer-0 forward (conv+gate, res+skip) = the first two tgemm launches of the timed step
 timeout 420 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "aewn_timed" -k regex:tgemm -c 2 \
    -f -o $O/${TAG}_fwd $B > $O/${TAG}_fwd.log 2>&1
-# backward of the last layer: first gate-derivative + data-gradient (tgemm launches after 40 stack + 2 post forward
-# + 2 post backward) and the first two wgrad launches after the post-net's
+# backward of the last layer: gate-derivative + data-gradient = the tgemm launches after 40 stack + 2 post forward + 2
+# post backward ones; wide-unit weight gradients of the last layer = the first two wgradw launches
 timeout 420 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "aewn_timed" -k regex:tgemm -s 44 -c 2 \
    -f -o $O/${TAG}_bwd $B > $O/${TAG}_bwd.log 2>&1
-timeout 420 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "aewn_timed" -k regex:wgrad -s 2 -c 2 \
+timeout 420 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "aewn_timed" -k regex:wgradw -c 2 \
    -f -o $O/${TAG}_wgrad $B > $O/${TAG}_wgrad.log 2>&1
 ls -la $O | grep $TAG
