@@ -116,6 +116,8 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const 
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the bulk groups of this thread have finished READING shared memory (the buffer may be rewritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// same, but the most recent group may still be reading (double-buffered staging tiles)
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // wait until they have completed entirely (global writes performed)
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 

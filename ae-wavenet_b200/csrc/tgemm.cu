@@ -26,11 +26,14 @@ constexpr int TG_STAGE_BYTES = TG_A_BYTES + 2 * TG_WBOX_BYTES;  // 48 KB
 constexpr int TG_THREADS = 384;
 constexpr int TG_EPI_WARPS = 8;
 constexpr int TG_STG_BYTES = TG_EPI_WARPS * 4096;  // one 32 ch x 32 t fp32 staging tile per epilogue warp (TMA stores)
+constexpr int TG_PAIR_STG_BYTES = 2 * TG_STG_BYTES;  // pair mode: TWO tiles per warp (the next box is written while the
+                                                    // TMA engine still reads the previous one), paid for with one ring stage
 constexpr int TG_RING_BYTES = TG_STAGES * TG_STAGE_BYTES;      // 192 KB: 4 x 48 KB, or 6 x 32 KB in pair-MMA mode
-constexpr int TG_PAIR_STAGES = 6;
+constexpr int TG_PAIR_STAGES = 5;
 constexpr int TG_PAIR_STAGE_BYTES = TG_A_BYTES + TG_WBOX_BYTES;  // 32 KB: own 128 time steps of A + own half of W
 constexpr int TG_MAX_STAGES = 6;
-static_assert(TG_PAIR_STAGES * TG_PAIR_STAGE_BYTES == TG_RING_BYTES, "both modes use the same ring");
+static_assert(TG_PAIR_STAGES * TG_PAIR_STAGE_BYTES + TG_PAIR_STG_BYTES == TG_RING_BYTES + TG_STG_BYTES,
+              "both modes use the same amount of shared memory");
 constexpr int TG_SMEM_BYTES = TG_RING_BYTES + TG_STG_BYTES + 256 + 1024;  // + barriers + alignment slack
 
 struct TgSeg {
@@ -102,24 +105,31 @@ __device__ __forceinline__ TgItem tg_decode(const TgParams& p, int item, int cra
 // that lie below t_lo are written as zeros (stores) / add zero (reduce) -- by construction those positions are
 // margins that hold zeros anyway.
 struct StgOut {
-  float* tile;       // this warp's staging tile
+  float* tile;       // this warp's staging tile(s)
+  int ntiles;        // 1, or 2 (alternating: the box of store k is written while store k-1 is still being read)
+  mutable int cur;   // tile of the most recent stg_acquire
   int t0;            // first time step of this warp's 32-row slab (tile origin + 32*q), output coordinates
   int b;
   int lane;
   bool slab_on;      // slab intersects [t_lo, t_hi)
 };
 
-__device__ __forceinline__ void stg_acquire(const StgOut& so) {
-  if (elect_one()) tma_store_wait_read();   // the previous box of this warp has been read out of the tile (elect.sync
-                                             // names the same lane every time, i.e. the one that committed the group)
+// Returns this lane's column of the tile to fill next (element (j, lane) at [j * 32]).
+__device__ __forceinline__ float* stg_acquire(const StgOut& so) {
+  so.cur ^= so.ntiles - 1;
+  if (elect_one()) {   // elect.sync names the same lane every time, i.e. the one that committed the bulk groups
+    if (so.ntiles == 2) tma_store_wait_read1();   // all but the latest box have been read out: the older tile is free
+    else tma_store_wait_read();
+  }
   __syncwarp();
+  return so.tile + so.cur * 1024 + so.lane;
 }
 __device__ __forceinline__ void stg_flush(const StgOut& so, const CUtensorMap* map, int c0, bool reduce) {
   fence_proxy_async_smem();                  // make this lane's generic-proxy writes visible to the async proxy
   __syncwarp();
   if (elect_one()) {
-    if (reduce) tma_reduce_add_3d(map, so.tile, so.t0, c0, so.b);
-    else tma_store_3d(map, so.tile, so.t0, c0, so.b);
+    if (reduce) tma_reduce_add_3d(map, so.tile + so.cur * 1024, so.t0, c0, so.b);
+    else tma_store_3d(map, so.tile + so.cur * 1024, so.t0, c0, so.b);
     tma_store_commit();
   }
 }
@@ -252,8 +262,7 @@ __device__ __forceinline__ void lin_chunk(const LinRegs& c, const StgOut& so, ui
   }
   if (c.omap) {
     if (so.slab_on) {
-      stg_acquire(so);
-      float* st = so.tile + so.lane;
+      float* st = stg_acquire(so);
 #pragma unroll
       for (int j = 0; j < 32; ++j) st[j * 32] = c.in_range ? r[j] : 0.0f;
       stg_flush(so, c.omap, c0, c.tma_reduce);
@@ -331,25 +340,25 @@ __device__ __forceinline__ void epi_gate_fwd(const aewn_ntile& nt, const StgOut&
     tmem_ld32(taddr + 128 + c0, vg);
     tmem_ld_wait();
     if (fast) {
-      float* st = so.tile + so.lane;
+      float* st;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         vf[j] = __float_as_uint(fast_tanh(__uint_as_float(vf[j])));
         vg[j] = __float_as_uint(fast_sigmoid(__uint_as_float(vg[j])));
       }
       if (th_base) {
-        stg_acquire(so);
+        st = stg_acquire(so);
 #pragma unroll
         for (int j = 0; j < 32; ++j) st[j * 32] = __uint_as_float(vf[j]);
         stg_flush(so, &omaps[0], c0, false);
       }
       if (sg_base) {
-        stg_acquire(so);
+        st = stg_acquire(so);
 #pragma unroll
         for (int j = 0; j < 32; ++j) st[j * 32] = __uint_as_float(vg[j]);
         stg_flush(so, &omaps[1], c0, false);
       }
-      stg_acquire(so);
+      st = stg_acquire(so);
 #pragma unroll
       for (int j = 0; j < 32; ++j) st[j * 32] = __uint_as_float(vf[j]) * __uint_as_float(vg[j]);
       stg_flush(so, &omaps[2], c0, false);
@@ -371,20 +380,20 @@ __device__ __forceinline__ void epi_gate_fwd(const aewn_ntile& nt, const StgOut&
     }
     if (omaps) {   // TMA-store path: tanh, sigmoid, z through the warp's staging tile, one box each
       if (so.slab_on) {
-        float* st = so.tile + so.lane;
+        float* st;
         if (th_base) {
-          stg_acquire(so);
+          st = stg_acquire(so);
 #pragma unroll
           for (int j = 0; j < 32; ++j) st[j * 32] = in_range ? th[j] : 0.0f;
           stg_flush(so, &omaps[0], c0, false);
         }
         if (sg_base) {
-          stg_acquire(so);
+          st = stg_acquire(so);
 #pragma unroll
           for (int j = 0; j < 32; ++j) st[j * 32] = in_range ? sg[j] : 0.0f;
           stg_flush(so, &omaps[1], c0, false);
         }
-        stg_acquire(so);
+        st = stg_acquire(so);
 #pragma unroll
         for (int j = 0; j < 32; ++j) st[j * 32] = in_range ? th[j] * sg[j] : 0.0f;
         stg_flush(so, &omaps[2], c0, false);
@@ -484,12 +493,11 @@ __device__ __forceinline__ void gbwd_chunk(const GateBwdCtx& cx, const StgOut& s
   }
   if (cx.omap) {   // TMA-store path (tile-uniform decision): g_f box, then g_g box, through the warp's staging tile
     if (so.slab_on) {
-      float* st = so.tile + so.lane;
-      stg_acquire(so);
+      float* st = stg_acquire(so);
 #pragma unroll
       for (int j = 0; j < 32; ++j) st[j * 32] = gf[j];
       stg_flush(so, cx.omap, c0, false);
-      stg_acquire(so);
+      st = stg_acquire(so);
 #pragma unroll
       for (int j = 0; j < 32; ++j) st[j * 32] = gg[j];
       stg_flush(so, cx.omap, cx.gg_ch_off + c0, false);
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  float* stg_base = reinterpret_cast<float*>(smem + TG_RING_BYTES);
+  float* stg_base = reinterpret_cast<float*>(smem + (PAIR ? TG_PAIR_STAGES * TG_PAIR_STAGE_BYTES : TG_RING_BYTES));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TG_RING_BYTES + TG_STG_BYTES);
   uint64_t* empty_bar = full_bar + TG_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + TG_MAX_STAGES;
@@ -727,6 +735,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     uint32_t acc = 0, acc_phase = 0;
+    int stg_cur = 0;
     for (int item = cid; item < total; item += n_clusters) {
       const TgItem it = tg_decode(p, item, crank);
       if (!it.active) continue;
@@ -738,7 +747,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
       const int mode = MODE >= 0 ? MODE : nt.mode;
       const bool use_tma = p.o_tma[it.ni] != 0;
       StgOut so;
-      so.tile = stg_base + (warp - 4) * 1024;
+      so.ntiles = PAIR ? 2 : 1;
+      so.cur = stg_cur;     // the alternation continues across items: the last box of the previous item may still be read
+      so.tile = stg_base + (warp - 4) * 1024 * so.ntiles;
       so.lane = lane;
       so.b = it.b;
       so.t0 = it.tau0 + q * 32 + nt.out_toff;
@@ -771,6 +782,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
         }
       }
       if (!ok) break;
+      stg_cur = so.cur;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
