@@ -519,5 +519,7 @@ class RecLoss(nn.Module):
     def forward(self, quant_pred, target_wav):
         _require_cuda(quant_pred)
         rec_loss = _NLLFn.apply(quant_pred, target_wav)
-        self.metrics = {"rec": rec_loss}
+        # detached: a metrics entry that keeps the autograd graph alive also keeps every AccumulateGrad node (and the
+        # stream it was created on) alive across steps, which breaks CUDA-graph capture of the step (aewn/train.py)
+        self.metrics = {"rec": rec_loss.detach()}
         return rec_loss

@@ -29,11 +29,12 @@ constexpr int TG_STG_BYTES = TG_EPI_WARPS * 4096;  // one 32 ch x 32 t fp32 stag
 constexpr int TG_PAIR_STG_BYTES = 2 * TG_STG_BYTES;  // pair mode: TWO tiles per warp (the next box is written while the
                                                     // TMA engine still reads the previous one), paid for with one ring stage
 constexpr int TG_RING_BYTES = TG_STAGES * TG_STAGE_BYTES;      // 192 KB: 4 x 48 KB, or 6 x 32 KB in pair-MMA mode
-constexpr int TG_PAIR_STAGES = 5;
+constexpr int TG_PAIR_STAGES = 6;      // pair mode, one staging tile per warp (long K loops: ring depth hides HBM latency)
+constexpr int TG_PAIR_STAGES_STG2 = 5; // pair mode, two staging tiles per warp (short K loops: the epilogue is the critical path)
 constexpr int TG_PAIR_STAGE_BYTES = TG_A_BYTES + TG_WBOX_BYTES;  // 32 KB: own 128 time steps of A + own half of W
 constexpr int TG_MAX_STAGES = 6;
-static_assert(TG_PAIR_STAGES * TG_PAIR_STAGE_BYTES + TG_PAIR_STG_BYTES == TG_RING_BYTES + TG_STG_BYTES,
-              "both modes use the same amount of shared memory");
+static_assert(TG_PAIR_STAGES_STG2 * TG_PAIR_STAGE_BYTES + TG_PAIR_STG_BYTES == TG_RING_BYTES + TG_STG_BYTES &&
+              TG_PAIR_STAGES * TG_PAIR_STAGE_BYTES == TG_RING_BYTES, "every mode uses the same amount of shared memory");
 constexpr int TG_SMEM_BYTES = TG_RING_BYTES + TG_STG_BYTES + 256 + 1024;  // + barriers + alignment slack
 
 struct TgSeg {
@@ -56,6 +57,7 @@ struct TgParams {
   int* err;
   uint32_t a_lbo, a_sbo;
   int cluster;   // 1, 2 or 4: CTAs of a cluster work on adjacent time tiles of the same (batch, n-tile) and share W
+  int stg2;      // 1 (pair only): 5 ring stages + two epilogue staging tiles per warp instead of 6 + one
   int pair;      // 1 (cluster == 2 only): the pair issues cta_group::2 MMAs (M = 256), each CTA stages its own 128 time
                  // steps of A and HALF of the W rows in its own shared memory: no multicast, 2/3 of the smem traffic
   int n_tgroups; // ceil(n_ttiles / cluster)
@@ -548,7 +550,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  float* stg_base = reinterpret_cast<float*>(smem + (PAIR ? TG_PAIR_STAGES * TG_PAIR_STAGE_BYTES : TG_RING_BYTES));
+  float* stg_base = reinterpret_cast<float*>(
+      smem + ((PAIR && p.stg2) ? TG_PAIR_STAGES_STG2 * TG_PAIR_STAGE_BYTES : TG_RING_BYTES));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TG_RING_BYTES + TG_STG_BYTES);
   uint64_t* empty_bar = full_bar + TG_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + TG_MAX_STAGES;
@@ -559,7 +562,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr bool pair = PAIR;   // compile-time: the two modes are separate instantiations (no spills at 40 registers)
-  const uint32_t n_stages = pair ? TG_PAIR_STAGES : TG_STAGES;
+  const bool stg2 = pair && p.stg2 != 0;
+  const uint32_t n_stages = pair ? (stg2 ? TG_PAIR_STAGES_STG2 : TG_PAIR_STAGES) : TG_STAGES;
   const uint32_t stage_bytes = pair ? TG_PAIR_STAGE_BYTES : TG_STAGE_BYTES;
 
   if (threadIdx.x == 0) {
@@ -747,7 +751,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
       const int mode = MODE >= 0 ? MODE : nt.mode;
       const bool use_tma = p.o_tma[it.ni] != 0;
       StgOut so;
-      so.ntiles = PAIR ? 2 : 1;
+      so.ntiles = stg2 ? 2 : 1;
       so.cur = stg_cur;     // the alternation continues across items: the last box of the previous item may still be read
       so.tile = stg_base + (warp - 4) * 1024 * so.ntiles;
       so.lane = lane;
@@ -838,6 +842,15 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
   if (cluster == AEWN_CLUSTER_PAIR_MMA) {
     p.pair = 1;
     cluster = 2;
+  }
+  {
+    // Short K loops (res+skip: 8 K blocks, gate derivative: 20) are bound by the epilogue's store chain: give them the
+    // second staging tile.  Long ones (conv+gate: 29, data gradient: 32) need the sixth ring stage to cover HBM
+    // latency (measured: 4.36 vs 4.72 ms / 20 layers for conv+gate, 3.96 vs 3.79 for res+skip).  AEWN_TG_STG2=0|1 forces.
+    int kb_total = 0;
+    for (int s2 = 0; s2 < d->n_segs; ++s2) kb_total += (d->segs[s2].channels + TG_BK - 1) / TG_BK;
+    static const int forced = []() { const char* e = getenv("AEWN_TG_STG2"); return e ? atoi(e) : -1; }();
+    p.stg2 = p.pair && (forced >= 0 ? forced : (kb_total <= 24));
   }
   if (cluster != 1 && cluster != 2 && cluster != 4)
     return set_err(AEWN_ERR_INVALID, "tgemm: cluster must be 1, 2, 4 or AEWN_CLUSTER_PAIR_MMA");

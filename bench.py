@@ -211,6 +211,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: cfg2 8, cfg3 16)")
     ap.add_argument("--window", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -274,7 +275,8 @@ def main():
             sync.sync()
             opt.step()
             return loss
-    opt = torch.optim.Adam(model.parameters(), lr=2e-5, fused=True)   # checkpoint.py:49, par/train.basic.json:6
+    # checkpoint.py:49, par/train.basic.json:6; capturable: the step counter lives on the device (CUDA-graph replay)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-5, fused=True, capturable=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -286,6 +288,27 @@ def main():
     for _ in range(args.warmup):
         loss = step(dwav, dlc, dspk, djit)
     ops.check_device_errors()
+
+    # The public training-step API (aewn.train.GraphedStep): the whole step replayed as ONE CUDA graph.  Not used for the
+    # VQ-VAE step (VQEMA's unique() diagnostic has a data-dependent shape) nor across ranks (the NCCL all-reduce stays
+    # outside graph capture here); falls back to eager steps if capture fails, and says so in `config`.
+    eager_step, graph_note = step, "eager"
+    launches_per_step = None
+    if not args.no_graph and not cfg3 and world == 1:
+        try:
+            from aewn.train import GraphedStep
+            loss = None                    # drop the eager warm-up's autograd graph: its AccumulateGrad nodes are bound
+            torch.cuda.synchronize()       # to the default stream and would invalidate the capture
+            l0 = _lib.launch_count()
+            gstep = GraphedStep(step, [dwav, dlc, dspk, djit], warmup=1)
+            launches_per_step = (_lib.launch_count() - l0) // 2      # 1 warm-up step + 1 captured step
+            step = gstep
+            dwav, dlc, dspk, djit = gstep.static_in
+            graph_note = "cuda_graph"
+        except Exception as e:   # noqa: BLE001 -- report and measure eagerly
+            graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            step = eager_step
+            torch.cuda.synchronize()
 
     # ---- timed region 1: device-resident inputs, CUDA events around the K steps (no per-launch instrumentation)
     sampler = ClockSampler(local_rank)
@@ -304,6 +327,8 @@ def main():
     barrier()
     clocks = sampler.stop()
     launches = _lib.launch_count() - launches0
+    if launches_per_step is not None and graph_note == "cuda_graph":
+        launches = launches_per_step * args.steps          # replayed from the graph: no host-side launch calls to count
     ms = e0.elapsed_time(e1) / args.steps
     final_loss = float(loss.detach())
     ops.check_device_errors()
@@ -317,7 +342,7 @@ def main():
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
     for _ in range(args.steps):
-        loss = step(dwav, dlc, dspk, djit)
+        loss = eager_step(dwav, dlc, dspk, djit)           # eager: a graph replay cannot carry per-launch events
     p1.record()
     barrier()
     ops.set_profiler(None)
@@ -327,8 +352,10 @@ def main():
     barrier()
     t_start = time.perf_counter()
     for _ in range(args.steps):
-        ins = [t.to(dev, non_blocking=True) for t in (wav_h, lc_h, spk_h, jit_h)]
-        loss = step(*ins)
+        if graph_note == "cuda_graph":
+            loss = step(wav_h, lc_h, spk_h, jit_h)    # H2D copies from pinned memory straight into the graph's inputs
+        else:
+            loss = step(*[t.to(dev, non_blocking=True) for t in (wav_h, lc_h, spk_h, jit_h)])
         _ = loss.item()                           # D2H read of the step's result
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t_start) / args.steps
@@ -374,7 +401,7 @@ def main():
                                   f"cfg2: WaveNet decoder par/arch.basic.json train step, batch {B}/GPU, window {W}"),
                         step=("H2D(e2e only)+fwd+VQEMALoss+RecLoss+bwd+allreduce(grads|z_sum|n_sum)+EMA+Adam" if cfg3 else
                               "H2D(e2e only)+fwd+RecLoss+bwd+allreduce+Adam"), global_batch=world * B, window=W,
-                        engine_mode=ops.ENGINE_MODE,
+                        engine_mode=ops.ENGINE_MODE, step_execution=graph_note,
                         dec_in_len=geo["dec_in_len"], parallelism=f"dp{world}",
                         l2="activations per step ~13 GB >> 126 MB L2 (no flush needed)", seed=2507,
                         final_loss=final_loss),
