@@ -20,6 +20,7 @@ from . import _lib as L
 #   "auto"  what measured fastest on B200 at the cfg2 shapes (profiles/r2_engine_ab.json): "pair" for every tgemm / wgrad
 #           launch, and the stack's weight gradients through the wide-unit kernel aewn_wgradw (WIDE_WGRAD)
 ENGINE_MODE = os.environ.get("AEWN_ENGINE_MODE", "auto")
+MERGE_DGRAD_TILES = os.environ.get("AEWN_MERGE_DGRAD", "1") == "1"
 WIDE_WGRAD = os.environ.get("AEWN_WIDE_WGRAD", "1") == "1"     # "auto" only: stack weight gradients through aewn_wgradw
 
 
@@ -142,6 +143,8 @@ def build_tgemm(acts, segs, w, ntiles, batch, t_begin, t_end, err=None, tag=None
             d.segs[j] = L.Seg(int(ai), int(sh), int(ch), int(ko))
         d.n_segs = len(segs)
         d.w, d.w_rows, d.w_kpad = w.data_ptr(), int(w.shape[0]), int(w.shape[1])
+        if chunk[-1].flags & L.F_MERGE_NEXT:             # a merged pair never straddles two launches
+            chunk[-1].flags &= ~L.F_MERGE_NEXT
         for j, nt in enumerate(chunk):
             d.ntiles[j] = nt
         d.n_ntiles = len(chunk)
@@ -618,8 +621,16 @@ class StackPlan:
             for (c0, n) in chunks(R):
                 tiles.append(ntile(c0, n, gx[:, c0:], add=g_sig[:, c0:] if g_sig is not None else None, add_t_lo=lo,
                                    t_lo=lop4, t_hi=T0, t_zero_lo=lo_prev))
-            for (c0, n) in chunks(Cc):
-                tiles.append(ntile(R + c0, n, g_cond[:, c0:], flags=L.F_ACCUM, seg_mask=2, t_lo=lo, t_hi=T0))
+            cond_tiles = [ntile(R + c0, n, g_cond[:, c0:], flags=L.F_ACCUM, seg_mask=2, t_lo=lo, t_hi=T0)
+                          for (c0, n) in chunks(Cc)]
+            # The tail tile of g_x (R - 256 = 112 columns) and the g_cond tile (138 -> 144) fit ONE 256-column accumulator and
+            # their rows are adjacent in w1t: one pass over [g_f; g_g] instead of two (the cond rows hold zeros under the
+            # shifted tap block, so running them over both segments adds exact zeros).  AEWN_F_MERGE_NEXT, pair mode only.
+            tail, first = tiles[-1], cond_tiles[0]
+            if (MERGE_DGRAD_TILES and _use_pair("bwd_dgrad") and tail.n == tail.n_valid and first.n >= 32 and
+                    tail.n + first.n <= 256 and tail.w_row + tail.n == first.w_row):
+                tail.flags |= L.F_MERGE_NEXT
+            tiles += cond_tiles
             launches += build_tgemm(acts, segs, self.w1t[l], tiles, B, lop4 & ~31, T0, self.err, tag=f"bwd_dgrad.{l}")
             # (3) weight gradients of conv_signal/conv_gate/proj_signal/proj_gate (+ biases via the ones channel)
             x0_act = act_of(self.xs[l], T0) if needs_dup(d) else act_of(x, T0)

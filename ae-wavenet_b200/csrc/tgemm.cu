@@ -51,6 +51,11 @@ struct TgParams {
   int n_segs;
   aewn_ntile nt[AEWN_MAX_NTILES];
   int n_ntiles;
+  // AEWN_F_MERGE_NEXT: tile i and tile i+1 share ONE accumulator (one MMA of n_i + n_{i+1} columns over contiguous W rows,
+  // one pass over the A operand); work items walk the head tiles only
+  int n_heads;
+  int head[AEWN_MAX_NTILES];
+  int merged[AEWN_MAX_NTILES];
   int batch;
   int t_begin;
   int n_ttiles;
@@ -78,8 +83,8 @@ struct TgItem {
 // exchange multicast data and barrier arrivals); a CTA whose own tile lies outside the store range just stores nothing.
 __device__ __forceinline__ TgItem tg_decode(const TgParams& p, int item, int crank) {
   TgItem it;
-  it.ni = item % p.n_ntiles;
-  int r = item / p.n_ntiles;
+  it.ni = p.head[item % p.n_heads];
+  int r = item / p.n_heads;
   int tg = r % p.n_tgroups;
   it.b = r / p.n_tgroups;
   const int g0 = p.t_begin + tg * p.cluster * TG_BM;
@@ -315,6 +320,32 @@ __device__ __forceinline__ void epi_linear(const LinRegs& c, const StgOut& so, u
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
     if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(zero_count, static_cast<unsigned long long>(zeros));
+  }
+}
+
+// Second tile of a merged pair (AEWN_F_MERGE_NEXT): plain "accumulator -> TMA store / reduce-add", no addend, bias or
+// ReLU (validated host-side).  Its columns start at an arbitrary offset inside the 256-column accumulator stage, so the
+// last 32-column group is aligned to the tile's END (it must not read past the stage); the columns that group shares with
+// the previous one are re-stored unchanged (plain store) or contribute zero (reduce-add).
+__device__ __forceinline__ void epi_linear_tail(const aewn_ntile& nt, const StgOut& so, uint32_t taddr, int half, int tau,
+                                                const CUtensorMap* omap) {
+  const bool keep = (tau >= nt.t_lo) && (tau < nt.t_hi) && (tau >= nt.t_zero_lo);
+  const bool reduce = (nt.flags & AEWN_F_ACCUM) != 0;
+  for (int c0 = half * 32; c0 < nt.n; c0 += 64) {
+    int c0e = c0, skip = 0;
+    if (c0 + 32 > nt.n) {
+      c0e = nt.n - 32;
+      skip = c0 - c0e;
+    }
+    uint32_t v[32];
+    tmem_ld32(taddr + c0e, v);
+    tmem_ld_wait();
+    if (so.slab_on) {
+      float* st = stg_acquire(so);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) st[j * 32] = (keep && (j >= skip || !reduce)) ? __uint_as_float(v[j]) : 0.0f;
+      stg_flush(so, omap, c0e, reduce);
+    }
   }
 }
 
@@ -605,7 +636,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   const int cid = blockIdx.x / p.cluster;            // cluster index; all CTAs of a cluster walk the same items
   const int n_clusters = gridDim.x / p.cluster;
   const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1u);
-  const int total = p.batch * p.n_tgroups * p.n_ntiles;
+  const int total = p.batch * p.n_tgroups * p.n_heads;
 
   // Register reallocation: warps 0-3 (TMA / MMA / TMEM-alloc roles, one warpgroup) shrink to 88 registers and the 8
   // epilogue warps grow to 208, so 32-wide column chunks + prefetch buffers stay in registers
@@ -627,6 +658,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
         const TgItem it = tg_decode(p, item, crank);
         if (!it.active) continue;
         const aewn_ntile& nt = p.nt[it.ni];
+        const int n_mma = nt.n + (p.merged[it.ni] ? p.nt[it.ni + 1].n : 0);   // columns of the (merged) accumulator
         // W rows are split into `cluster` slices of wrows each; CTA r loads slice r and multicasts it to all peers
         const int wrows = 256 / p.cluster;
         const int wslices = (nt.n + wrows - 1) / wrows;
@@ -646,7 +678,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                   tma_load_3d_pair(sa + i * 4096, &p.a_map[sg.map], fb, it.tau0 + sg.shift + 32 * i, kb * TG_BK, it.b);
-                tma_load_2d_pair(sw, &p.w_map, fb, sg.w_koff + kb * TG_BK, nt.w_row + crank * (nt.n >> 1));
+                tma_load_2d_pair(sw, &p.w_map, fb, sg.w_koff + kb * TG_BK, nt.w_row + crank * (n_mma >> 1));
               }
               __syncwarp();
               if (++stage == n_stages) { stage = 0; phase ^= 1u; }
@@ -693,7 +725,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
         if (!mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256u;
-        const uint32_t idesc = make_idesc_tf32(pair ? 2 * TG_BM : TG_BM, nt.n, /*a_mn=*/1, /*b_mn=*/0);
+        const int n_mma = nt.n + (p.merged[it.ni] ? p.nt[it.ni + 1].n : 0);
+        const uint32_t idesc = make_idesc_tf32(pair ? 2 * TG_BM : TG_BM, n_mma, /*a_mn=*/1, /*b_mn=*/0);
         uint32_t kiter = 0;
         for (int s = 0; s < p.n_segs && ok; ++s) {
           if (!((nt.seg_mask >> s) & 1)) continue;
@@ -768,6 +801,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
         if (ok) {
           tc_fence_after();
           epi_linear(lc, so, taddr, half, bufA, bufB, nt.zero_count);
+          if (p.merged[it.ni]) {   // the partner tile sits in the columns after this tile's n
+            const aewn_ntile& nt2 = p.nt[it.ni + 1];
+            StgOut so2 = so;
+            so2.t0 = it.tau0 + q * 32 + nt2.out_toff;
+            so2.slab_on = (it.tau0 + q * 32 + 32 > nt2.t_lo) && (it.tau0 + q * 32 < nt2.t_hi);
+            epi_linear_tail(nt2, so2, taddr + static_cast<uint32_t>(nt.n), half, tau, &p.o_map[it.ni + 1][0]);
+            so.cur = so2.cur;
+          }
         }
       } else if (mode == AEWN_EPI_GATE_BWD) {
         const GateBwdCtx gcx = gbwd_ctx(nt, it.b, tau, use_tma ? &p.o_map[it.ni][0] : nullptr, p.gg_ch_off[it.ni]);
@@ -928,6 +969,23 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
     }
   }
   p.n_ntiles = d->n_ntiles;
+  p.n_heads = 0;
+  for (int i = 0; i < d->n_ntiles; ++i) {
+    p.head[p.n_heads++] = i;
+    if (!(p.nt[i].flags & AEWN_F_MERGE_NEXT)) continue;
+    if (i + 1 >= d->n_ntiles) return set_err(AEWN_ERR_INVALID, "tgemm: AEWN_F_MERGE_NEXT on the last n-tile");
+    const aewn_ntile &a = p.nt[i], &b = p.nt[i + 1];
+    const bool ok = p.pair && a.mode == AEWN_EPI_LINEAR && b.mode == AEWN_EPI_LINEAR && a.n == a.n_valid &&
+                    b.w_row == a.w_row + a.n && a.n + b.n <= 256 && b.n >= 32 && !b.add && !b.bias && !b.out2 && !b.out3 &&
+                    !b.zero_count && (b.flags & ~AEWN_F_ACCUM) == 0 && p.o_tma[i + 1] &&
+                    ((b.seg_mask ^ a.seg_mask) & all_mask & b.seg_mask) == 0;
+    if (!ok)
+      return set_err(AEWN_ERR_INVALID,
+                     "tgemm: n-tiles %d/%d cannot share an accumulator (need pair mode, LINEAR, contiguous W rows, "
+                     "n <= 256 in total, a plain TMA-stored partner whose segments are a subset of the head's)", i, i + 1);
+    p.merged[i] = 1;
+    ++i;   // the partner is not a work item of its own
+  }
   p.batch = d->batch;
   p.t_begin = d->t_begin;
   p.n_ttiles = (d->t_end - d->t_begin + TG_BM - 1) / TG_BM;
@@ -937,7 +995,7 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
 
   p.cluster = cluster;
   p.n_tgroups = (p.n_ttiles + cluster - 1) / cluster;
-  const long long total = static_cast<long long>(p.batch) * p.n_tgroups * p.n_ntiles;   // items per cluster walk
+  const long long total = static_cast<long long>(p.batch) * p.n_tgroups * p.n_heads;   // items per cluster walk
   int clusters = (d->max_ctas > 0 ? d->max_ctas : sm_count()) / cluster;
   if (clusters > total) clusters = static_cast<int>(total);
   if (clusters < 1) clusters = 1;

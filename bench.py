@@ -267,11 +267,15 @@ def main():
                                      synth_batch(B, geo["wav_len"], geo["lc_len"], 64, 40, 1234 + rank)]
         t0w, t1w = geo["trim_dec_out"]
 
-        def step(wav, lc, spk, jit):
+        def fwd_bwd(wav, lc, spk, jit):
             sync.zero_grad()
             quant = wn(wav, lc, spk, jit)
             loss = loss_fn(quant[..., :-1], wav[:, t0w:t1w][..., 1:])
             loss.backward()
+            return loss
+
+        def step(wav, lc, spk, jit):
+            loss = fwd_bwd(wav, lc, spk, jit)
             sync.sync()
             opt.step()
             return loss
@@ -289,22 +293,30 @@ def main():
         loss = step(dwav, dlc, dspk, djit)
     ops.check_device_errors()
 
-    # The public training-step API (aewn.train.GraphedStep): the whole step replayed as ONE CUDA graph.  Not used for the
-    # VQ-VAE step (VQEMA's unique() diagnostic has a data-dependent shape) nor across ranks (the NCCL all-reduce stays
-    # outside graph capture here); falls back to eager steps if capture fails, and says so in `config`.
+    # The public training-step API (aewn.train.GraphedStep): the step replayed as ONE CUDA graph (one GPU), or zero-grad +
+    # forward + loss + backward as a graph followed by the eager NCCL all-reduce and Adam (N GPUs: collectives stay out
+    # of the capture).  Not used for the VQ-VAE step (VQEMA's unique() diagnostic has a data-dependent shape).  Falls
+    # back to eager steps if capture fails, and says so in `config`.
     eager_step, graph_note = step, "eager"
     launches_per_step = None
-    if not args.no_graph and not cfg3 and world == 1:
+    if not args.no_graph and not cfg3:
         try:
             from aewn.train import GraphedStep
             loss = None                    # drop the eager warm-up's autograd graph: its AccumulateGrad nodes are bound
             torch.cuda.synchronize()       # to the default stream and would invalidate the capture
             l0 = _lib.launch_count()
-            gstep = GraphedStep(step, [dwav, dlc, dspk, djit], warmup=1)
+            gstep = GraphedStep(step if world == 1 else fwd_bwd, [dwav, dlc, dspk, djit], warmup=1)
             launches_per_step = (_lib.launch_count() - l0) // 2      # 1 warm-up step + 1 captured step
-            step = gstep
+            if world == 1:
+                step = gstep
+            else:
+                def step(wav, lc, spk, jit):
+                    loss = gstep(wav, lc, spk, jit)
+                    sync.sync()
+                    opt.step()
+                    return loss
             dwav, dlc, dspk, djit = gstep.static_in
-            graph_note = "cuda_graph"
+            graph_note = "cuda_graph" if world == 1 else "cuda_graph(fwd+bwd) + eager all-reduce + Adam"
         except Exception as e:   # noqa: BLE001 -- report and measure eagerly
             graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
             step = eager_step
@@ -327,7 +339,7 @@ def main():
     barrier()
     clocks = sampler.stop()
     launches = _lib.launch_count() - launches0
-    if launches_per_step is not None and graph_note == "cuda_graph":
+    if launches_per_step is not None and graph_note.startswith("cuda_graph"):
         launches = launches_per_step * args.steps          # replayed from the graph: no host-side launch calls to count
     ms = e0.elapsed_time(e1) / args.steps
     final_loss = float(loss.detach())
@@ -352,7 +364,7 @@ def main():
     barrier()
     t_start = time.perf_counter()
     for _ in range(args.steps):
-        if graph_note == "cuda_graph":
+        if graph_note.startswith("cuda_graph"):
             loss = step(wav_h, lc_h, spk_h, jit_h)    # H2D copies from pinned memory straight into the graph's inputs
         else:
             loss = step(*[t.to(dev, non_blocking=True) for t in (wav_h, lc_h, spk_h, jit_h)])

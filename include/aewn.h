@@ -77,6 +77,10 @@ typedef struct {
 #define AEWN_F_MASKPOS 4    /* `add` is a mask source, not an addend: value = add[b,n,t] > 0 ? value : 0 */
 #define AEWN_F_RELU_FIRST 8 /* value = max(acc + bias, 0) + add  (wave_encoder.py:39-43 order); out3 (optional)
                                receives max(acc + bias, 0), the activation mask source for the backward pass */
+#define AEWN_F_MERGE_NEXT 16 /* this tile and the NEXT one in ntiles[] share one accumulator: one MMA of n + n_next (<= 256)
+                                columns over their contiguous W rows, one pass over the activations.  Pair mode, LINEAR
+                                tiles; the partner must be a plain store / AEWN_F_ACCUM tile on the TMA path and its
+                                segments a subset of this tile's (W holds zeros where it has none) */
 
 typedef struct {
   int w_row;      /* first W row of this n-tile */
