@@ -306,7 +306,10 @@ def add_into_grads(pairs):
             if not inner_ok:
                 return False
             si = int(src.stride(0)) if src.dim() > 0 else 1
-            blocks.append((src.data_ptr(), dst.data_ptr(), rows, cols, si, 1, cols))
+            step = max(1, 8192 // max(cols, 1))            # one CTA per table entry: keep entries <= 8 K elements
+            for r0 in range(0, rows, step):
+                nr = min(step, rows - r0)
+                blocks.append((src.data_ptr() + 4 * r0 * si, dst.data_ptr() + 4 * r0 * cols, nr, cols, si, 1, cols))
         dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("ni", "<i4"), ("nj", "<i4"), ("si", "<i8"), ("sj", "<i8"),
                        ("di", "<i8")])
         arr = np.array(blocks, dtype=dt)
@@ -450,8 +453,11 @@ class StackPlan:
         blocks = []
 
         def blk(src, s_off, dst, d_row, d_col, ni, nj, si, sj):
-            blocks.append((src.data_ptr() + 4 * s_off, dst.data_ptr() + 4 * (d_row * dst.shape[1] + d_col), ni, nj, si,
-                           sj, dst.shape[1]))
+            step = max(1, 8192 // max(nj, 1))              # one CTA per table entry: keep entries <= 8 K elements
+            for r0 in range(0, ni, step):
+                blocks.append((src.data_ptr() + 4 * (s_off + r0 * si),
+                               dst.data_ptr() + 4 * ((d_row + r0) * dst.shape[1] + d_col), min(step, ni - r0), nj, si, sj,
+                               dst.shape[1]))
 
         for l in range(g.L):
             p = params[l]
@@ -746,8 +752,12 @@ class PostPlan:
         self.w2 = torch.zeros(Q, KP, device=dev)
         self.w1t = torch.zeros(S, KP, device=dev)
         self.w2t = torch.zeros(P, KQ, device=dev)
-        blocks = [(w1.data_ptr(), self.w1.data_ptr(), P, S, S, 1, KS), (w2.data_ptr(), self.w2.data_ptr(), Q, P, P, 1, KP),
-                  (w1.data_ptr(), self.w1t.data_ptr(), S, P, 1, S, KP), (w2.data_ptr(), self.w2t.data_ptr(), P, Q, 1, P, KQ)]
+        whole = [(w1.data_ptr(), self.w1.data_ptr(), P, S, S, 1, KS), (w2.data_ptr(), self.w2.data_ptr(), Q, P, P, 1, KP),
+                 (w1.data_ptr(), self.w1t.data_ptr(), S, P, 1, S, KP), (w2.data_ptr(), self.w2t.data_ptr(), P, Q, 1, P, KQ)]
+        blocks = []
+        for (src, dst, ni, nj, si, sj, di) in whole:       # one CTA per table entry: 32-row slices
+            for r0 in range(0, ni, 32):
+                blocks.append((src + 4 * r0 * si, dst + 4 * r0 * di, min(32, ni - r0), nj, si, sj, di))
         import numpy as np
         dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("ni", "<i4"), ("nj", "<i4"), ("si", "<i8"), ("sj", "<i8"),
                        ("di", "<i8")])
