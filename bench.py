@@ -65,9 +65,9 @@ def synth_batch(B, wav_len, lc_len, n_lc_in, n_speakers, seed):
     return wav, lc, spk, jit
 
 
-def build_decoder(W, WaveNet, vc):
+def build_decoder(W, WaveNet, vc, arch=None):
     """Stand-alone decoder built exactly like MfccInverter._init_geometry (mfcc_inverter.py:38-65)."""
-    hp = HP(ARCH_BASIC)
+    hp = HP(arch or ARCH_BASIC)
     parent = vc.VirtualConv(filter_info=1, stride=320, parent=None, name="LC-grid")
     wn = WaveNet(hp, parent_vc=parent)
     end_gr = vc.GridRange((0, 10 ** 7), (0, W), 1)
@@ -126,7 +126,8 @@ class ClockSampler:
 def grcc_layer_fwd_bytes(B, R, D, S, C, T_in, d, W, train):
     """read x, read cond slice, write sig, RMW skip-sum, weights once (+ saved tanh/sigmoid/z if training)."""
     T_out = T_in - d
-    b = 4 * B * (R * T_in + C * T_out + R * T_out + 2 * S * W) + 4 * 607744
+    n_weights = 2 * (D * R * 2) + 2 * D + 2 * D * C + S * D + R * D          # 607 744 for arch.basic (SURVEY.md 8a)
+    b = 4 * B * (R * T_in + C * T_out + R * T_out + 2 * S * W) + 4 * n_weights
     if train:
         b += 4 * B * 3 * D * T_out
     return b
@@ -204,10 +205,11 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
                     help="cfg2 (default, the headline): WaveNet decoder train step; cfg3: full VQ-VAE-EMA autoencoder "
                          "train step (Encoder -> VQEMA -> WaveNet, par/arch.vqvae-ema.json), batch 16/GPU; with "
-                         "--gpus N this is cfg4 (grads + EMA statistics in ONE all-reduce)")
+                         "--gpus N this is cfg4 (grads + EMA statistics in ONE all-reduce); cfg5: deep decoder stress "
+                         "(30 dilation layers, 512 residual channels, window 65536, batch 2/GPU)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: cfg2 8, cfg3 16)")
     ap.add_argument("--window", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -233,8 +235,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg3 = args.workload == "cfg3"
-    B, W = (args.batch or (16 if cfg3 else 8)), args.window
+    cfg3, cfg5 = args.workload == "cfg3", args.workload == "cfg5"
+    if cfg5 and args.window == 16384:
+        args.window = 65536
+    B, W = (args.batch or (16 if cfg3 else 2 if cfg5 else 8)), args.window
+    arch = dict(ARCH_BASIC, n_blocks=3, n_res=512) if cfg5 else ARCH_BASIC
     torch.manual_seed(2507)                      # identical replicas
     if cfg3:
         from aewn.autoencoder import AutoEncoder
@@ -258,7 +263,7 @@ def main():
             opt.step()
             return loss
     else:
-        wn, geo = build_decoder(W, aewn.WaveNet, vc)
+        wn, geo = build_decoder(W, aewn.WaveNet, vc, arch)
         wn = wn.to(dev).train()
         model = wn
         loss_fn = aewn.RecLoss()
@@ -382,7 +387,7 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        R, D, S, C = 368, 256, 256, 138
+        R, D, S, C = arch["n_res"], 256, 256, 138
         times = prof.times_ms()
         geomS = wn.stack_geometry(geo["dec_in_len"])
         fwd_bytes = fwd_flops = fwd_ms = 0.0
@@ -410,6 +415,8 @@ def main():
             dtype="tf32", data="synthetic",
             config=dict(workload=("cfg3/cfg4: full VQ-VAE-EMA autoencoder par/arch.vqvae-ema.json train step (Encoder -> "
                                   f"VQEMA -> WaveNet), batch {B}/GPU, window {W}" if cfg3 else
+                                  f"cfg5: deep decoder stress (30 dilation layers, 512 residual channels) train step, batch "
+                                  f"{B}/GPU, window {W}" if cfg5 else
                                   f"cfg2: WaveNet decoder par/arch.basic.json train step, batch {B}/GPU, window {W}"),
                         step=("H2D(e2e only)+fwd+VQEMALoss+RecLoss+bwd+allreduce(grads|z_sum|n_sum)+EMA+Adam" if cfg3 else
                               "H2D(e2e only)+fwd+RecLoss+bwd+allreduce+Adam"), global_batch=world * B, window=W,
@@ -434,7 +441,7 @@ def main():
                      d2h_bytes_per_step=4),
             gpu_launches=launches,
         )
-        if not args.no_cpu_baseline and world == 1 and not cfg3:
+        if not args.no_cpu_baseline and world == 1 and not cfg3 and not cfg5:
             pick_cpu_threads()
             sps, ctimes = cpu_port_step(2, 2048, 2, 1)
             out["cpu_baseline"] = dict(value=sps, unit=UNIT, cores=torch.get_num_threads(), kind="port",
