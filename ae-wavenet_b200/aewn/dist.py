@@ -11,7 +11,7 @@ import torch.distributed as dist
 
 
 class FlatGradSync:
-    def __init__(self, params, vqema=None, n_metrics=2, process_group=None):
+    def __init__(self, params, vqema=None, n_metrics=2, process_group=None, fused_accumulate=False):
         self.params = [p for p in params if p.requires_grad]
         self.vqema = vqema
         self.group = process_group
@@ -29,13 +29,14 @@ class FlatGradSync:
             off += p.numel()
         if vqema is not None:
             vqema.defer_ema = True
-        # this engine owns persistent .grad buffers and only ever runs loss.backward(): let the decoder's backward add
-        # its weight gradients into them with one launch instead of one clone + one add per parameter (ops.py)
-        try:
+        # fused_accumulate=True: the decoder's backward adds its weight gradients into these persistent .grad buffers
+        # with ONE launch instead of one clone + one add per parameter (ops.ACCUMULATE_INTO_GRAD).  Only for steps that
+        # run exactly one loss.backward() per forward: a caller that ALSO takes torch.autograd.grad(...) through the
+        # decoder (mfcc_inverter.py:103 before chassis.py:157) would have the weight gradients added twice, because a
+        # custom Function cannot tell which of its input gradients a particular backward call asks for.
+        if fused_accumulate:
             from . import ops
             ops.ACCUMULATE_INTO_GRAD = True
-        except Exception:          # CPU-only unit tests of the reduction logic import this module without the kernels
-            pass
 
     def zero_grad(self):
         self.flat[:self.n_grad].zero_()

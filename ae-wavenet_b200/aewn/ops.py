@@ -279,11 +279,12 @@ def build_wgradw(acts, units, batch, err=None, tag=None, waves=1):
 
 
 # ------------------------------------------------------------------------------------------------- fused grad accumulation
-# When True (set by dist.FlatGradSync, i.e. by a training engine that owns persistent .grad buffers and only ever calls
-# loss.backward()), the decoder's backward adds ALL its weight gradients into the parameters' existing .grad tensors with
-# one aewn_add_blocks launch and returns None for them -- autograd would otherwise run one clone + one add kernel per
-# parameter (~240 launches per step).  Must stay False for torch.autograd.grad(...) style callers, which expect the
-# gradients as return values and .grad untouched (mfcc_inverter.py:103 does that for lc_sparse only, never for weights).
+# When True (dist.FlatGradSync(..., fused_accumulate=True): a training engine that owns persistent .grad buffers and runs
+# exactly ONE loss.backward() per forward), the decoder's backward adds ALL its weight gradients into the parameters'
+# existing .grad tensors with one aewn_add_blocks launch and returns None for them -- autograd would otherwise run one
+# clone + one add kernel per parameter (~240 launches per step).  Must stay False for callers that also take
+# torch.autograd.grad(...) through the decoder (mfcc_inverter.py:103 before chassis.py:157): a custom Function cannot
+# tell which input gradients a particular backward call asks for, so the weight gradients would be added twice.
 ACCUMULATE_INTO_GRAD = False
 _grad_tables = {}
 

@@ -249,7 +249,7 @@ def main():
         wn = ae.decoder
         geo = dict(wav_len=ae.dec_in_len, lc_len=ae.embed_len, dec_in_len=ae.dec_in_len)
         model = ae
-        sync = FlatGradSync(ae.parameters(), vqema=ae.bottleneck)
+        sync = FlatGradSync(ae.parameters(), vqema=ae.bottleneck, fused_accumulate=True)
         wav_h, _, spk_h, jit_h = synth_batch(B, ae.dec_in_len, ae.embed_len, 32, 40, 1234 + rank)
         lc_h = torch.randn(B, 39, ae.enc_in_mel_len, generator=torch.Generator().manual_seed(99 + rank))   # mel input
         wav_h, lc_h, spk_h, jit_h = [t.pin_memory() for t in (wav_h, lc_h, spk_h, jit_h)]
@@ -267,7 +267,7 @@ def main():
         wn = wn.to(dev).train()
         model = wn
         loss_fn = aewn.RecLoss()
-        sync = FlatGradSync(wn.parameters())
+        sync = FlatGradSync(wn.parameters(), fused_accumulate=True)   # one loss.backward() per step
         wav_h, lc_h, spk_h, jit_h = [t.pin_memory() for t in
                                      synth_batch(B, geo["wav_len"], geo["lc_len"], 64, 40, 1234 + rank)]
         t0w, t1w = geo["trim_dec_out"]
