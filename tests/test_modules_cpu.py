@@ -114,3 +114,27 @@ def test_autoencoder_wiring_geometry_and_state_dicts_match_reference(golden_dir)
     assert (ae3.enc_in_len, ae3.enc_in_mel_len, ae3.embed_len, ae3.dec_in_len) == (23280, 144, 65, 18430)
     assert ae3.trim_dec_in.tolist() == geo3["trim_dec_in"] and ae3.trim_dec_out.tolist() == geo3["trim_dec_out"]
     assert ae3.decoder.trim_ups_out.tolist() == geo3["trim_ups_out"]
+
+
+def test_wide_unit_packing_respects_tmem_and_staging_limits():
+    """ops.pack_wide_units (host logic of aewn_wgradw): <= 3 chunks per unit, <= 512 accumulator columns with every chunk
+    rounded up to 32, <= 256 staged rows per CTA (64 for a chunk of <= 128 columns, else 128); nothing lost or duplicated."""
+    from aewn import ops
+    out = torch.zeros(1)
+
+    def ck(n, tag):
+        return dict(x_act=1, x_row=0, n_valid=n, shift=0, out=out, out_off=0, out_rs=1, out_cs=1, tag=tag)
+
+    # arch.basic wgrad1: x[t-d] and x[t] in chunks (256, 112) each, plus [cond, 1] = 139
+    chunks = [ck(256, "xd0"), ck(112, "xd1"), ck(256, "x0"), ck(112, "x1"), ck(139, "c")]
+    units = ops.pack_wide_units(0, 0, 256, 4, 1000, chunks)
+    assert [sorted(c["tag"] for c in u["chunks"]) for u in units] == [["x0", "xd0"], ["c", "x1", "xd1"]]
+    for widths in ([256, 256, 256, 256, 144], [48], [16] * 7, [130, 130, 130, 130], [256, 100, 16]):
+        units = ops.pack_wide_units(0, 0, 200, 0, 640, [ck(n, i) for i, n in enumerate(widths)])
+        seen = sorted(c["tag"] for u in units for c in u["chunks"])
+        assert seen == list(range(len(widths)))
+        for u in units:
+            assert 1 <= len(u["chunks"]) <= 3
+            assert sum((c["n"] + 31) // 32 * 32 for c in u["chunks"]) <= 512
+            assert sum(128 if c["n"] > 128 else 64 for c in u["chunks"]) <= 256
+            assert all(c["n"] % 16 == 0 and c["n"] >= c["n_valid"] for c in u["chunks"])
