@@ -14,7 +14,7 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, step_fn, example_inputs, warmup=3):
+    def __init__(self, step_fn, example_inputs, warmup=3, capture_on_warmup_stream=False):
         """step_fn(*tensors) -> loss tensor (0-dim).  example_inputs: device tensors fixing shapes / dtypes.
         The caller must not hold results of earlier eager calls of step_fn (a live autograd graph keeps AccumulateGrad
         nodes bound to the stream they were created on, which invalidates the capture)."""
@@ -28,7 +28,10 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture_on_warmup_stream: capture on the SAME side stream as the warm-up, so that autograd's AccumulateGrad nodes
+        # created during the warm-up and kept alive by module attributes that hold graph tensors (VQEMA.ze, .min_dist,
+        # AutoEncoder.encoding_bn) match the capturing stream; by default torch.cuda.graph picks a stream of its own
+        with (torch.cuda.graph(self.graph, stream=side) if capture_on_warmup_stream else torch.cuda.graph(self.graph)):
             self.static_loss = step_fn(*self.static_in)
         torch.cuda.synchronize()
 

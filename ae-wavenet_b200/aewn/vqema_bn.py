@@ -130,6 +130,9 @@ class VQEMA(nn.Module):
             self.ema_denom = self.n_sum_ones * self.ema_gamma_comp
         xavier_init(self.linear)
         self.defer_ema = False
+        # True: diagnostics with data-dependent shapes (`uniq = min_ind.unique()`, vqema_bn.py:157) are replaced by
+        # static-shape device tensors (`n_unique`), so that the step can be captured into a CUDA graph (aewn/train.py)
+        self.static_diagnostics = False
 
     def forward(self, z):
         _require_cuda(z)
@@ -142,7 +145,11 @@ class VQEMA(nn.Module):
         self.min_dist = min_dist
         self.min_ind = min_ind
         if train:
-            self.uniq = min_ind.unique(sorted=False)
+            if self.static_diagnostics:
+                self.uniq = None
+                self.n_unique = (self.n_sum > 0).sum()       # number of codes used by this batch, as a device scalar
+            else:
+                self.uniq = min_ind.unique(sorted=False)
             self.ze_norm = ze_norm
             self.emb_norm = (self.emb ** 2).sum(dim=1).sqrt()
             if not self.defer_ema:
@@ -187,12 +194,18 @@ class VQEMALoss(nn.Module):
         n = h / h.sum()
         ent = -(n * torch.where(n == 0, torch.zeros_like(n), torch.log2(n))).sum()      # util.entropy, util.py:98-105
         peak, peak_idx = log_pred.max(dim=1)
+        if self.bn.uniq is None:       # static-shape diagnostics (bn.static_diagnostics): device scalars instead of ints
+            nunq = self.bn.n_unique
+            pk_nuq = torch.zeros(log_pred.shape[1], device=log_pred.device).index_fill_(0, peak_idx.flatten(), 1.0).sum()
+        else:
+            nunq, pk_nuq = self.bn.uniq.nelement(), peak_idx.unique().nelement()
+        # detached: metrics that keep the autograd graph alive pin its AccumulateGrad nodes across steps (aewn/train.py)
         self.metrics = {
-            "rec": rec_loss_ts.mean(), "com": com_loss_embeds.mean(),
+            "rec": rec_loss_ts.mean().detach(), "com": com_loss_embeds.mean().detach(),
             "min_ze": self.bn.ze_norm.min(), "max_ze": self.bn.ze_norm.max(),
             "min_emb": self.bn.emb_norm.min(), "max_emb": self.bn.emb_norm.max(),
-            "hst_ent": ent, "nunq": self.bn.uniq.nelement(),
-            "pk_m": peak.to(torch.float).mean(), "pk_nuq": peak_idx.unique().nelement(),
-            "pk_sd": peak.to(torch.float).std(),
+            "hst_ent": ent, "nunq": nunq,
+            "pk_m": peak.to(torch.float).mean().detach(), "pk_nuq": pk_nuq,
+            "pk_sd": peak.to(torch.float).std().detach(),
         }
         return total_loss

@@ -214,6 +214,9 @@ def main():
     ap.add_argument("--window", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graph-cfg3", action="store_true",
+                    help="cfg3 only: capture the VQ-VAE-EMA step too (VQEMA.static_diagnostics: unique() replaced by a "
+                         "static-shape count); default is the eager step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -254,14 +257,20 @@ def main():
         lc_h = torch.randn(B, 39, ae.enc_in_mel_len, generator=torch.Generator().manual_seed(99 + rank))   # mel input
         wav_h, lc_h, spk_h, jit_h = [t.pin_memory() for t in (wav_h, lc_h, spk_h, jit_h)]
 
-        def step(wav, mels, spk, jit):
+        def fwd_bwd(wav, mels, spk, jit):
             sync.zero_grad()
             pred, target, com, rec = ae.run(mels, wav, spk, jit)
             loss = com + rec
             loss.backward()
+            return loss
+
+        def step(wav, mels, spk, jit):
+            loss = fwd_bwd(wav, mels, spk, jit)
             sync.sync()                          # ONE all-reduce: grads | z_sum | n_sum | metrics, then the EMA update
             opt.step()
             return loss
+        if args.graph_cfg3:
+            ae.bottleneck.static_diagnostics = True
     else:
         wn, geo = build_decoder(W, aewn.WaveNet, vc, arch)
         wn = wn.to(dev).train()
@@ -304,13 +313,18 @@ def main():
     # back to eager steps if capture fails, and says so in `config`.
     eager_step, graph_note = step, "eager"
     launches_per_step = None
-    if not args.no_graph and not cfg3:
+    if not args.no_graph and (not cfg3 or args.graph_cfg3):
         try:
             from aewn.train import GraphedStep
             loss = None                    # drop the eager warm-up's autograd graph: its AccumulateGrad nodes are bound
-            torch.cuda.synchronize()       # to the default stream and would invalidate the capture
+            if cfg3:                       # to the default stream and would invalidate the capture; same for the module
+                ae.encoding_bn = None      # attributes that hold graph tensors
+                ae.bottleneck.ze = ae.bottleneck.min_dist = None
+                ae.objective.metrics = {}
+            torch.cuda.synchronize()
             l0 = _lib.launch_count()
-            gstep = GraphedStep(step if world == 1 else fwd_bwd, [dwav, dlc, dspk, djit], warmup=1)
+            gstep = GraphedStep(step if world == 1 else fwd_bwd, [dwav, dlc, dspk, djit], warmup=1,
+                                capture_on_warmup_stream=cfg3)
             launches_per_step = (_lib.launch_count() - l0) // 2      # 1 warm-up step + 1 captured step
             if world == 1:
                 step = gstep
