@@ -138,3 +138,49 @@ def test_wide_unit_packing_respects_tmem_and_staging_limits():
             assert sum((c["n"] + 31) // 32 * 32 for c in u["chunks"]) <= 512
             assert sum(128 if c["n"] > 128 else 64 for c in u["chunks"]) <= 256
             assert all(c["n"] % 16 == 0 and c["n"] >= c["n_valid"] for c in u["chunks"])
+
+
+_CFG1_SCRIPT = r"""
+import hashlib, json, sys, torch
+import wavenet, hparams, mfcc_inverter
+hps = hparams.setup_hparams("mfcc_inverter,mfcc,train", dict(n_win_batch=4096, n_batch=2))
+torch.manual_seed(2507)
+mi = mfcc_inverter.MfccInverter(hps)
+sd = mi.wavenet.state_dict()
+print(json.dumps(dict(
+    module=type(mi.wavenet).__module__, enc_in_len=mi.enc_in_len, embed_len=mi.embed_len, dec_in_len=mi.dec_in_len,
+    trim_dec_in=mi.trim_dec_in.tolist(), trim_dec_out=mi.trim_dec_out.tolist(),
+    wav_cond_offset=list(mi.wavenet.wav_cond_offset), leads=[l.leads.tolist() for l in mi.wavenet.conv_layers],
+    n_params=sum(p.numel() for p in mi.wavenet.parameters()),
+    digest={k: hashlib.sha256(v.numpy().tobytes()).hexdigest() for k, v in sd.items() if v.dtype == torch.float32},
+    keys=list(sd))))
+"""
+
+
+@pytest.mark.needs_reference
+def test_cfg1_unchanged_mfcc_inverter_constructs_on_the_dropins(golden_dir):
+    """BASELINE cfg1 (plumbing, CPU): the reference's UNMODIFIED mfcc_inverter.MfccInverter (arch.mi, window 4096), with
+    ae-wavenet_b200/dropin in front of the reference tree, builds on the kernel-backed WaveNet with the reference's own
+    geometry, state_dict keys and bit-identical initial weights (same RNG stream).  Both variants run in subprocesses so
+    that the flat module names (`wavenet`, ...) cannot leak into this test session."""
+    import subprocess
+    import sys
+    root = os.path.dirname(golden_dir.rstrip("/")).rsplit("/tests", 1)[0]
+    pkg = os.path.join(root, "ae-wavenet_b200")
+
+    def run(paths):
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join(paths), PYTHONWARNINGS="ignore")
+        out = subprocess.run([sys.executable, "-c", _CFG1_SCRIPT], env=env, capture_output=True, text=True, cwd="/tmp",
+                             timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return json.loads(out.stdout.strip().splitlines()[-1])
+
+    ours = run([os.path.join(pkg, "dropin"), pkg, "/root/reference"])
+    ref = run(["/root/reference"])
+    assert ours["module"] == "aewn.wavenet" and ref["module"] == "wavenet"
+    geo = json.load(open(os.path.join(golden_dir, "geometry.json")))["cfg1_mi_W4096"]
+    for k in ("enc_in_len", "embed_len", "dec_in_len", "trim_dec_in", "trim_dec_out", "wav_cond_offset", "leads"):
+        assert ours[k] == ref[k] == geo[k], k
+    assert ours["n_params"] == ref["n_params"] == 13498890            # arch.mi decoder, SURVEY.md 8a
+    assert ours["keys"] == ref["keys"]
+    assert ours["digest"] == ref["digest"]                             # bit-identical initial parameters
