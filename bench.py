@@ -405,13 +405,17 @@ def main():
         times = prof.times_ms()
         geomS = wn.stack_geometry(geo["dec_in_len"])
         fwd_bytes = fwd_flops = fwd_ms = 0.0
+        per_layer_gbs = []                       # BASELINE metric, second half: achieved HBM GB/s of every layer's forward
         T_in = geomS.T0
         for l, d in enumerate(geomS.dils):
             g1, g2 = times.get(f"fwd_gemm1.{l}", []), times.get(f"fwd_gemm2.{l}", [])
             if g1 and g2:
-                fwd_ms += sum(g1) / len(g1) + sum(g2) / len(g2)
-                fwd_bytes += grcc_layer_fwd_bytes(B, R, D, S, C, T_in, d, W, train=True)
+                l_ms = sum(g1) / len(g1) + sum(g2) / len(g2)
+                l_bytes = grcc_layer_fwd_bytes(B, R, D, S, C, T_in, d, W, train=True)
+                fwd_ms += l_ms
+                fwd_bytes += l_bytes
                 fwd_flops += grcc_layer_fwd_flops(B, R, D, S, C, T_in, d, W)
+                per_layer_gbs.append(round(l_bytes / (l_ms * 1e-3) / 1e9, 1))
             T_in -= d
         gemm_ms = sum(sum(v) for v in times.values()) / args.steps
         per_class = {}
@@ -442,7 +446,7 @@ def main():
                           frac=(hbm_ach / pk["hbm_gbs"]) if hbm_ach else None, traffic=traffic,
                           kernel="tgemm_kernel: GRCC layer forward (2 launches/layer: conv+gate, res+skip), "
                                  "algorithmic bytes per SURVEY.md 8d incl. saved activations, summed over 20 layers",
-                          ms_per_layer_fwd=fwd_ms / max(1, geomS.L), peak_source=pk["source"]),
+                          ms_per_layer_fwd=fwd_ms / max(1, geomS.L), per_layer_gbs=per_layer_gbs, peak_source=pk["source"]),
             roofline_tensor=dict(bound="tensor", achieved=tf_ach, peak=pk["bf16_tflops"], unit="TFLOP/s",
                                  frac=(tf_ach / pk["bf16_tflops"]) if tf_ach else None,
                                  note="TF32 operands (nominal peak = half of bf16); denominator is the measured bf16 "
