@@ -15,6 +15,7 @@ WGRAD_MAX_ACTS, WGRAD_MAX_ITEMS = 6, 32
 EPI_LINEAR, EPI_GATE_FWD, EPI_GATE_BWD = 0, 1, 2
 F_ACCUM, F_RELU, F_MASKPOS, F_RELU_FIRST, F_MERGE_NEXT = 1, 2, 4, 8, 16
 ERR_TIMEOUT = -1003
+ERR_RANGE = -1004     # an activation left the fp16 operand range of the fused layer kernel
 CLUSTER_PAIR_MMA = 102   # aewn.h AEWN_CLUSTER_PAIR_MMA: 2-CTA clusters issuing cta_group::2 MMAs
 
 
@@ -81,6 +82,22 @@ class CopyBlock(C.Structure):
                 ("sj", C.c_longlong), ("di", C.c_longlong)]
 
 
+class GrccFwdDesc(C.Structure):
+    """aewn_grcc_fwd_desc: one fused dilation layer (include/aewn.h)."""
+    _fields_ = [("x16", C.c_void_p), ("x16_bs", C.c_longlong), ("x16_cp", C.c_int),
+                ("c16", C.c_void_p), ("c16_bs", C.c_longlong), ("c16_cp", C.c_int), ("t_rows", C.c_int),
+                ("w1h", C.c_void_p), ("w1_k", C.c_int), ("w2h", C.c_void_p),
+                ("x32", C.c_void_p), ("xo32", C.c_void_p), ("x_bs", C.c_longlong), ("x_cs", C.c_longlong),
+                ("xo16", C.c_void_p), ("dup", C.c_void_p), ("dup_toff", C.c_int), ("dup_t_hi", C.c_int),
+                ("th", C.c_void_p), ("sg", C.c_void_p), ("z", C.c_void_p), ("a_bs", C.c_longlong),
+                ("a_cs", C.c_longlong), ("save", C.c_int),
+                ("skp", C.c_void_p), ("s_bs", C.c_longlong), ("s_cs", C.c_longlong), ("skp_mode", C.c_int),
+                ("batch", C.c_int), ("R", C.c_int), ("D", C.c_int), ("S", C.c_int), ("n_cond1", C.c_int),
+                ("dil", C.c_int), ("final_layer", C.c_int), ("t_lo", C.c_int), ("t_zero_lo", C.c_int),
+                ("t_hi", C.c_int), ("skp_t_lo", C.c_int), ("skp_zero_lo", C.c_int), ("err", C.c_void_p),
+                ("max_ctas", C.c_int)]
+
+
 GEN_MAX_LAYERS = 64
 GEN_MAX_BLOCKS = 2 * GEN_MAX_LAYERS + 2
 GEN_MAX_REP = 4
@@ -111,7 +128,8 @@ _lib = None
 SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_tgemm", "aewn_wgrad", "aewn_wgradw",
            "aewn_base_embed_fwd", "aewn_base_embed_bwd", "aewn_fill", "aewn_relu_mask_bwd",
            "aewn_vq_fwd", "aewn_vq_commit_bwd", "aewn_ema_update", "aewn_pack_blocks", "aewn_add_blocks", "aewn_nll_fwd", "aewn_nll_bwd",
-           "aewn_gen_smem_bytes", "aewn_gen_max_clusters", "aewn_gen_run"]
+           "aewn_gen_smem_bytes", "aewn_gen_max_clusters", "aewn_gen_run",
+           "aewn_grcc_fwd", "aewn_cvt_f16_cl", "aewn_pack_blocks_f16"]
 
 
 def lib():

@@ -22,6 +22,20 @@ from . import _lib as L
 ENGINE_MODE = os.environ.get("AEWN_ENGINE_MODE", "auto")
 MERGE_DGRAD_TILES = os.environ.get("AEWN_MERGE_DGRAD", "1") == "1"
 WIDE_WGRAD = os.environ.get("AEWN_WIDE_WGRAD", "1") == "1"     # "auto" only: stack weight gradients through aewn_wgradw
+# Forward of a dilation layer as ONE fused launch (aewn_grcc_fwd: fp16 tensor-core operands, fp32 accumulation and
+# residual stream) where the widths allow it; "0" keeps the two-launch TF32 path (aewn_tgemm) everywhere.
+FUSED_FWD = os.environ.get("AEWN_FUSED_FWD", "1") == "1"
+
+
+def set_fused_forward(on):
+    global FUSED_FWD
+    FUSED_FWD = bool(on)
+    _plans.clear()
+
+
+def fused_ok(R, D, S, Cc):
+    """Shapes aewn_grcc_fwd accepts (include/aewn.h); everything else runs through aewn_tgemm."""
+    return D in (128, 256) and R % 8 == 0 and 8 <= R <= 1024 and S % 32 == 0 and 32 <= S <= 1024 and 1 <= Cc < 1024
 
 
 def set_engine_mode(mode):
@@ -330,6 +344,8 @@ def run_launches(launches):
         e0 = _prof_begin(tag)
         if kind == "tgemm":
             L.check(lib.aewn_tgemm(C.byref(d), st), "aewn_tgemm")
+        elif kind == "grcc":
+            L.check(lib.aewn_grcc_fwd(C.byref(d), st), "aewn_grcc_fwd")
         elif kind == "wgradw":
             L.check(lib.aewn_wgradw(C.byref(d), st), "aewn_wgradw")
         else:
@@ -433,6 +449,13 @@ class StackPlan:
         self.KR, self.KC, self.KD = ceil_to(R, 32), ceil_to(Cc + 1, 32), ceil_to(D, 32)
         self.KS, self.K2 = ceil_to(S, 32), ceil_to(2 * D, 32)
         self.J = (D + 127) // 128
+        self.fused = FUSED_FWD and fused_ok(R, D, S, Cc)
+        if self.fused:
+            # fp16 channels-last operand copies: the layer input ping-pongs between two buffers (the
+            # backward pass reads the fp32 tensors), the conditioning copy is shared by all layers
+            self.KR16, self.KC16 = ceil_to(R, 64), ceil_to(Cc + 1, 64)
+            self.x16 = [torch.zeros(B, Tp, self.KR16, device=device, dtype=torch.float16) for _ in range(2)]
+            self.c16 = torch.zeros(B, Tp, self.KC16, device=device, dtype=torch.float16)
         self._build_packs(params)
         self.fwd_train = self._build_forward(save=True)
         self.fwd_infer = None
@@ -451,7 +474,16 @@ class StackPlan:
         KR, KC, KD, KS, K2, J = self.KR, self.KC, self.KD, self.KS, self.K2, self.J
         KP = 2 * KR + KC
         self.w1, self.w2, self.w2t, self.w1t = [], [], [], []
-        blocks = []
+        self.w1h, self.w2h = [], []
+        blocks, hblocks = [], []
+        fused = self.fused
+
+        def blkh(src, s_off, dst, d_row, d_col, ni, nj, si, sj):       # same table entry, fp16 destination
+            step = max(1, 8192 // max(nj, 1))
+            for r0 in range(0, ni, step):
+                hblocks.append((src.data_ptr() + 4 * (s_off + r0 * si),
+                                dst.data_ptr() + 2 * ((d_row + r0) * dst.shape[1] + d_col), min(step, ni - r0), nj, si, sj,
+                                dst.shape[1]))
 
         def blk(src, s_off, dst, d_row, d_col, ni, nj, si, sj):
             step = max(1, 8192 // max(nj, 1))              # one CTA per table entry: keep entries <= 8 K elements
@@ -463,8 +495,16 @@ class StackPlan:
         for l in range(g.L):
             p = params[l]
             final = g.is_final(l)
-            w1 = torch.zeros(256 * J, KP, device=dev)
-            w2 = torch.zeros((0 if final else R) + S, KD, device=dev)
+            # forward operand matrices: fp16 for the fused layer kernel, else fp32 (TF32) for aewn_tgemm
+            if fused:
+                KR16, KC16 = self.KR16, self.KC16
+                w1 = torch.zeros(256 * J, 2 * KR16 + KC16, device=dev, dtype=torch.float16)
+                w2 = torch.zeros((0 if final else R) + S, D, device=dev, dtype=torch.float16)
+                fblk, c_tap1, c_cond = blkh, KR16, 2 * KR16
+            else:
+                w1 = torch.zeros(256 * J, KP, device=dev)
+                w2 = torch.zeros((0 if final else R) + S, KD, device=dev)
+                fblk, c_tap1, c_cond = blk, KR, 2 * KR
             w2t = torch.zeros(D, KR + KS, device=dev)
             w1t = torch.zeros(R + Cc, 2 * K2, device=dev)
             wf, wg = p["conv_signal.weight"], p["conv_gate.weight"]          # (D, R, 2)
@@ -473,27 +513,27 @@ class StackPlan:
                 nj_ = min(128, D - 128 * j)
                 for h, (wc, pj, bk) in enumerate(((wf, pf, "conv_signal.bias"), (wg, pg, "conv_gate.bias"))):
                     row = 256 * j + 128 * h
-                    blk(wc, 128 * j * R * 2 + 0, w1, row, 0, nj_, R, 2 * R, 2)          # tap 0
-                    blk(wc, 128 * j * R * 2 + 1, w1, row, KR, nj_, R, 2 * R, 2)         # tap 1
-                    blk(pj, 128 * j * Cc, w1, row, 2 * KR, nj_, Cc, Cc, 1)              # cond projection
+                    fblk(wc, 128 * j * R * 2 + 0, w1, row, 0, nj_, R, 2 * R, 2)         # tap 0
+                    fblk(wc, 128 * j * R * 2 + 1, w1, row, c_tap1, nj_, R, 2 * R, 2)    # tap 1
+                    fblk(pj, 128 * j * Cc, w1, row, c_cond, nj_, Cc, Cc, 1)             # cond projection
                     if bk in p:
-                        blk(p[bk], 128 * j, w1, row, 2 * KR + Cc, nj_, 1, 1, 1)         # bias on the ones channel
+                        fblk(p[bk], 128 * j, w1, row, c_cond + Cc, nj_, 1, 1, 1)        # bias on the ones channel
             ws = p["dil_skp.weight"]                                                   # (S, D, 1)
             if not final:
                 wr = p["dil_res.weight"]                                               # (R, D, 1)
-                blk(wr, 0, w2, 0, 0, R, D, D, 1)
-                blk(ws, 0, w2, R, 0, S, D, D, 1)
+                fblk(wr, 0, w2, 0, 0, R, D, D, 1)
+                fblk(ws, 0, w2, R, 0, S, D, D, 1)
                 blk(wr, 0, w2t, 0, 0, D, R, 1, D)                                      # Wr^T
             else:
-                blk(ws, 0, w2, 0, 0, S, D, D, 1)
+                fblk(ws, 0, w2, 0, 0, S, D, D, 1)
             blk(ws, 0, w2t, 0, KR, D, S, 1, D)                                         # Ws^T
             for h, wc in enumerate((wf, wg)):
                 for k in (0, 1):                                                       # tap k transposed
                     blk(wc, k, w1t, 0, k * K2 + h * D, R, D, 2, 2 * R)
             for h, pj in enumerate((pf, pg)):
                 blk(pj, 0, w1t, R, K2 + h * D, Cc, D, 1, Cc)                           # P^T under the unshifted block
-            self.w1.append(w1)
-            self.w2.append(w2)
+            (self.w1h if fused else self.w1).append(w1)
+            (self.w2h if fused else self.w2).append(w2)
             self.w2t.append(w2t)
             self.w1t.append(w1t)
         import numpy as np
@@ -503,13 +543,63 @@ class StackPlan:
         assert dt.itemsize == C.sizeof(L.CopyBlock)
         self.n_blocks = len(blocks)
         self.block_table = torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(dev)
+        self.n_hblocks = len(hblocks)
+        if hblocks:
+            self.hblock_table = torch.from_numpy(np.array(hblocks, dtype=dt).view(np.uint8).reshape(-1).copy()).to(dev)
 
     def repack(self):
         L.check(L.lib().aewn_pack_blocks(C.c_void_p(self.block_table.data_ptr()), C.c_int(self.n_blocks), _stream()),
                 "aewn_pack_blocks")
+        if self.n_hblocks:
+            L.check(L.lib().aewn_pack_blocks_f16(C.c_void_p(self.hblock_table.data_ptr()), C.c_int(self.n_hblocks),
+                                                 _stream()), "aewn_pack_blocks_f16")
+
+    def _to_f16_cl(self, src, dst, channels):
+        """(B, C, Tp) fp32 workspace -> (B, Tp, Cp) fp16 channels-last operand copy (one launch)."""
+        L.check(L.lib().aewn_cvt_f16_cl(
+            C.c_void_p(src.data_ptr()), C.c_longlong(src.stride(0)), C.c_longlong(src.stride(1)),
+            C.c_void_p(dst.data_ptr()), C.c_longlong(dst.stride(0)), C.c_int(dst.shape[2]), C.c_int(channels),
+            C.c_int(self.geom.T0), C.c_int(self.B), C.c_int(-1), C.c_void_p(self.err.data_ptr()), _stream()),
+            "aewn_cvt_f16_cl")
+
+    def _build_forward_fused(self, save):
+        """One aewn_grcc_fwd launch per layer (wavenet.py:91-111 in one kernel)."""
+        g, B, R, D, S, Cc = self.geom, self.B, self.R, self.D, self.S, self.Cc
+        T0, Tp = g.T0, g.Tp
+        rf4 = g.RF & ~3
+        out = []
+        for l, dil in enumerate(g.dils):
+            final = g.is_final(l)
+            lo = g.lead[l]
+            x, xin, xout = self.sig[l], self.x16[l % 2], self.x16[(l + 1) % 2]
+            d = L.GrccFwdDesc()
+            d.x16, d.x16_bs, d.x16_cp = xin.data_ptr(), int(xin.stride(0)), self.KR16
+            d.c16, d.c16_bs, d.c16_cp = self.c16.data_ptr(), int(self.c16.stride(0)), self.KC16
+            d.t_rows = Tp
+            d.w1h, d.w1_k, d.w2h = self.w1h[l].data_ptr(), int(self.w1h[l].shape[1]), self.w2h[l].data_ptr()
+            d.x32, d.x_bs, d.x_cs = x.data_ptr(), int(x.stride(0)), int(x.stride(1))
+            if not final:
+                d.xo32, d.xo16 = self.sig[l + 1].data_ptr(), xout.data_ptr()
+                d_next = g.dils[l + 1] if l + 1 < g.L else 4
+                if save and l + 1 < g.L and needs_dup(d_next):      # the backward pass's TF32 weight-gradient tap
+                    d.dup, d.dup_toff, d.dup_t_hi = self.xs[l + 1].data_ptr(), d_next, T0
+            if save:
+                d.th, d.sg, d.z, d.save = self.th[l].data_ptr(), self.sg[l].data_ptr(), self.z[l].data_ptr(), 1
+                d.a_bs, d.a_cs = int(self.th[l].stride(0)), int(self.th[l].stride(1))
+            d.skp, d.s_bs, d.s_cs = self.skp.data_ptr(), int(self.skp.stride(0)), int(self.skp.stride(1))
+            last_relu = l == g.L - 1 and self.relu_last
+            d.skp_mode = (3 if last_relu else 0) if l == 0 else (2 if last_relu else 1)
+            d.batch, d.R, d.D, d.S, d.n_cond1, d.dil, d.final_layer = B, R, D, S, Cc + 1, dil, int(final)
+            d.t_lo, d.t_zero_lo, d.t_hi = lo & ~3, lo, T0
+            d.skp_t_lo, d.skp_zero_lo = rf4, g.RF
+            d.err = self.err.data_ptr()
+            out.append(("grcc", d, f"fwd_layer.{l}"))
+        return out
 
     # ---------------------------------------------------------------------------------------------- forward
     def _build_forward(self, save):
+        if self.fused:
+            return self._build_forward_fused(save)
         g, B, R, D, S, Cc = self.geom, self.B, self.R, self.D, self.S, self.Cc
         T0 = g.T0
         out = []
@@ -554,6 +644,9 @@ class StackPlan:
         """Inputs already staged: sig[0] (and xs[0]) = base-layer output, cond.  Result: skp (B, S, Tp) valid on
         [RF, T0), ReLU applied when relu_last (wavenet.py:359)."""
         self.repack()
+        if self.fused:
+            self._to_f16_cl(self.sig[0], self.x16[0], self.R)
+            self._to_f16_cl(self.cond, self.c16, self.Cc + 1)
         if save:
             run_launches(self.fwd_train)
         else:

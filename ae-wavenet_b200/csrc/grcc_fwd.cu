@@ -1,0 +1,722 @@
+// grcc_fwd: ONE launch per dilation layer (wavenet.py:91-111): filter conv + gate conv + conditioning projections + bias,
+// tanh * sigmoid, 1x1 residual (+ x) and 1x1 skip (+= skip sum), on tcgen05 CTA pairs.
+//
+// Why a second engine next to tgemm.cu: ncu / bench arithmetic of the two-launch TF32 path showed the conv+gate launch
+// bound by operand DELIVERY -- every CTA needs 64 B/clk of operands from L2 (32 KB per 512-cycle K block) against ~42
+// B/clk/SM the chip delivers with all SMs pulling -- and the res+skip launch bound by HBM while the tensor pipe idles.
+// This kernel (a) feeds the tensor cores FP16 operands (10-bit mantissa = TF32's, round-to-nearest instead of TF32's
+// truncation; FP32 accumulation in TMEM; the residual stream itself stays FP32): half the bytes per MAC, twice the MMA
+// rate; (b) reads the activations from CHANNELS-LAST fp16 copies (B, T, C): both operands are plain K-major
+// SWIZZLE_128B tiles, one contiguous 16 KB box per K block, and a dilated tap is a shift of the box's ROW coordinate, so
+// the 16-byte TMA origin rule no longer forces pre-shifted duplicates; (c) keeps z = tanh*sigmoid in shared memory as
+// the A operand of the residual/skip GEMM (it never travels to HBM unless the caller asks for it), so the HBM-bound
+// epilogues of one tile overlap the MMAs of the next job.
+//
+// Per CTA pair and 256 time steps (128 per CTA), jobs run in a fixed order through two 256-column TMEM regions:
+//   G1.j (j < D/128): acc[t, 0:128 | 128:256] = filt | gate pre-activations of channels [128j, 128j+128)
+//                     K = [x16(t-d) | x16(t) | cond16(t), 1], 64 channels per ring stage
+//   epilogue G1.j   : tanh, sigmoid (-> th, sg for the backward pass), z -> fp16 -> zbuf (K-major, manual 128B swizzle)
+//   RES.c           : acc = Wr[c] . z   -> x32_next = acc + x32 ; x16_next = fp16(x32_next)   (A operand = zbuf)
+//   SKP.c           : acc = Ws[c] . z   -> skip sum (TMA store / reduce-add / relu(old + acc))
+// Warp roles as in tgemm.cu: warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator, warps 4-11
+// epilogue.  All waits are bounded.
+#include <cuda_fp16.h>
+
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace aewn {
+
+constexpr int GF_BM = 128;
+constexpr int GF_KB = 64;                         // K elements per ring stage: 64 fp16 = one 128-byte swizzle row
+constexpr int GF_STAGES = 4;
+constexpr int GF_A_BYTES = GF_BM * 128;           // 16 KB: 128 time rows x 128 B
+constexpr int GF_W_BYTES = 128 * 128;             // 16 KB: 128 weight rows x 128 B (this CTA's half of the N rows)
+constexpr int GF_STAGE_BYTES = GF_A_BYTES + GF_W_BYTES;
+constexpr int GF_MAX_D = 256;
+constexpr int GF_ZBUF_BYTES = (GF_MAX_D / GF_KB) * GF_A_BYTES;   // 64 KB: z of this CTA's 128 time rows, all D channels
+constexpr int GF_THREADS = 384;
+constexpr int GF_EPI_WARPS = 8;
+constexpr int GF_STG_BYTES = GF_EPI_WARPS * 4096;
+constexpr int GF_RING_BYTES = GF_STAGES * GF_STAGE_BYTES;
+constexpr int GF_SMEM_BYTES = GF_RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES + 256 + 1024;
+constexpr int GF_MAX_JOBS = 8;
+
+enum { GF_GATE = 0, GF_RES = 1, GF_SKP = 2 };
+
+struct GfJob {
+  int kind;
+  int w_row;     // first weight row (w1 for GATE, w2 otherwise)
+  int n;         // accumulator columns (MMA N)
+  int n_valid;   // output channels of this job
+  int ch0;       // first output channel (GATE: first z channel)
+};
+
+struct GfParams {
+  CUtensorMap xa, ca, w1, w2;             // operand loads (fp16)
+  CUtensorMap th_m, sg_m, z_m, xo_m, skp_m;   // fp32 (t, ch, b) outputs, box {32, 32, 1}
+  GfJob job[GF_MAX_JOBS];
+  int n_jobs, n_gate;
+  int kb_x, kb_c, kb_z;                   // ring stages per x tap, for cond, for z
+  int dil;
+  const float* x32;                        // residual source (B, R, Tp)
+  long long x_bs, x_cs;
+  float* dup;                              // optional pre-shifted fp32 duplicate of x_next (backward wgrad tap, d_next % 4 != 0)
+  int dup_toff, dup_t_hi;
+  __half* xo16;                            // (B, Tp, x16_cp) channels-last fp16 copy of x_next
+  long long x16_bs;
+  int x16_cp;
+  float* skp;
+  long long s_bs, s_cs;
+  int save, z_out, skp_mode;               // skp_mode: 0 store, 1 reduce-add, 2 relu(old + acc), 3 relu(acc)
+  int batch, t_begin, n_tgroups;
+  int t_lo, t_zero_lo, t_hi, skp_t_lo, skp_zero_lo;
+  int* err;
+};
+
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// kind::f16, A and B = F16 (format 0), both K-major, FP32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+struct GfItem {
+  int b, g0, tau0;
+  bool do_skp;
+};
+
+__device__ __forceinline__ GfItem gf_decode(const GfParams& p, int item, int crank) {
+  GfItem it;
+  const int tg = item % p.n_tgroups;
+  it.b = item / p.n_tgroups;
+  it.g0 = p.t_begin + tg * 2 * GF_BM;
+  it.tau0 = it.g0 + crank * GF_BM;
+  it.do_skp = it.g0 + 2 * GF_BM > p.skp_t_lo;   // decided per GROUP: both CTAs walk the same job sequence
+  return it;
+}
+
+// one 4 KB staging tile per epilogue warp: [32 channels][32 time steps] fp32, element (j, lane) at j*32 + lane
+__device__ __forceinline__ void gf_stg_wait() {
+  if (elect_one()) tma_store_wait_read();
+  __syncwarp();
+}
+__device__ __forceinline__ void gf_stg_flush(const CUtensorMap* map, const float* tile, int t0, int c0, int b, bool reduce) {
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (elect_one()) {
+    if (reduce) tma_reduce_add_3d(map, tile, t0, c0, b);
+    else tma_store_3d(map, tile, t0, c0, b);
+    tma_store_commit();
+  }
+}
+
+__global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_constant__ GfParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* zbuf = smem + GF_RING_BYTES;
+  float* stg_base = reinterpret_cast<float*>(smem + GF_RING_BYTES + GF_ZBUF_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GF_RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES);
+  uint64_t* empty_bar = full_bar + GF_STAGES;
+  uint64_t* tfull_bar = empty_bar + GF_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* zready_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zready_bar + 1);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    *abort_flag = 0;
+    for (int i = 0; i < GF_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);    // leader: its own arrive.expect_tx; the bytes of BOTH CTAs complete on it
+      mbar_init(&empty_bar[i], 1);   // the leader's cta_group::2 commit releases the stage in both CTAs
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * GF_EPI_WARPS);   // on the leader: the epilogue warps of both CTAs
+    }
+    mbar_init(zready_bar, 2 * GF_EPI_WARPS * p.n_gate);   // every epilogue warp of the pair, once per gate job
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.xa);
+    tma_prefetch_desc(&p.ca);
+    tma_prefetch_desc(&p.w1);
+    tma_prefetch_desc(&p.w2);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int crank = static_cast<int>(cluster_ctarank());
+  const int cid = blockIdx.x >> 1;
+  const int n_cl = gridDim.x >> 1;
+  const int total = p.batch * p.n_tgroups;
+  const int g1_stages = 2 * p.kb_x + p.kb_c;
+
+  if (warp < 4) {
+    reg_dealloc<40>();
+    if (warp == 0) {
+      // ===================================================== TMA producer (both CTAs)
+      uint32_t stage = 0, phase = 0;
+      bool ok = true;
+      const uint32_t lead_full = mapa_u32(&full_bar[0], 0);
+      for (int item = cid; item < total && ok; item += n_cl) {
+        const GfItem it = gf_decode(p, item, crank);
+        for (int jb = 0; jb < p.n_jobs && ok; ++jb) {
+          const GfJob jd = p.job[jb];
+          if (jd.kind == GF_SKP && !it.do_skp) continue;
+          const int nst = jd.kind == GF_GATE ? g1_stages : p.kb_z;
+          for (int s = 0; s < nst; ++s) {
+            if (!mbar_wait_warp(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
+            if (elect_one()) {
+              uint8_t* sa = smem + stage * GF_STAGE_BYTES;
+              uint8_t* sw = sa + GF_A_BYTES;
+              const uint32_t fb = lead_full + stage * 8u;
+              if (jd.kind == GF_GATE) {
+                if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * GF_STAGE_BYTES);
+                if (s < p.kb_x) tma_load_3d_pair(sa, &p.xa, fb, s * GF_KB, it.tau0 - p.dil, it.b);
+                else if (s < 2 * p.kb_x) tma_load_3d_pair(sa, &p.xa, fb, (s - p.kb_x) * GF_KB, it.tau0, it.b);
+                else tma_load_3d_pair(sa, &p.ca, fb, (s - 2 * p.kb_x) * GF_KB, it.tau0, it.b);
+                tma_load_2d_pair(sw, &p.w1, fb, s * GF_KB, jd.w_row + crank * 128);
+              } else {
+                // CTA r stages W2 rows [r * n/2, (r+1) * n/2) of the job (a 128-row box; the MMA reads n/2 of them)
+                if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * GF_W_BYTES);
+                tma_load_2d_pair(sw, &p.w2, fb, s * GF_KB, jd.w_row + crank * (jd.n >> 1));
+              }
+            }
+            __syncwarp();
+            if (++stage == GF_STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================================================== MMA issuer (the pair's leader CTA)
+      if (crank == 0) {
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, zphase = 0;
+        bool ok = true;
+        const uint64_t desc0 = make_smem_desc(0, 16, 1024, kLayoutSW128);   // K-major, 128B swizzle, 8-row groups 1 KB apart
+        const uint32_t ring = smem_u32(smem);
+        const uint32_t z16_0 = (smem_u32(zbuf) >> 4) & 0x3FFFu;
+        for (int item = cid; item < total && ok; item += n_cl) {
+          const GfItem it = gf_decode(p, item, crank);
+          bool z_waited = false;
+          for (int jb = 0; jb < p.n_jobs && ok; ++jb) {
+            const GfJob jd = p.job[jb];
+            if (jd.kind == GF_SKP && !it.do_skp) continue;
+            if (!mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) { ok = false; break; }
+            if (jd.kind != GF_GATE && !z_waited) {
+              // every epilogue warp of the pair has written its z columns of this tile (generic proxy -> fence -> arrive)
+              if (!mbar_wait_warp(zready_bar, zphase, abort_flag)) { ok = false; break; }
+              zphase ^= 1u;
+              z_waited = true;
+            }
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256u;
+            const uint32_t idesc = make_idesc_f16(2 * GF_BM, jd.n);
+            const int nst = jd.kind == GF_GATE ? g1_stages : p.kb_z;
+            for (int s = 0; s < nst; ++s) {
+              if (!mbar_wait_warp(&full_bar[stage], phase, abort_flag)) { ok = false; break; }
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t s16 = ((ring + stage * GF_STAGE_BYTES) >> 4) & 0x3FFFu;
+                const uint32_t w16 = s16 + (GF_A_BYTES >> 4);
+                const uint32_t a16 = jd.kind == GF_GATE ? s16 : z16_0 + static_cast<uint32_t>(s) * (GF_A_BYTES >> 4);
+#pragma unroll
+                for (int ks = 0; ks < GF_KB / 16; ++ks)   // K advances 16 fp16 = 32 B inside the swizzle row
+                  umma_f16_ss_pair(d_tmem, desc0 + (a16 + ks * 2), desc0 + (w16 + ks * 2), idesc,
+                                   static_cast<uint32_t>((s | ks) != 0));
+                umma_commit_pair(&empty_bar[stage], 0x3);
+              }
+              __syncwarp();
+              if (++stage == GF_STAGES) { stage = 0; phase ^= 1u; }
+            }
+            if (!ok) break;
+            if (elect_one()) umma_commit_pair(&tfull_bar[acc], 0x3);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          }
+          // a tile whose skip job was skipped still has to consume the z phase (the epilogues always arrive)
+          if (ok && !z_waited) {
+            if (!mbar_wait_warp(zready_bar, zphase, abort_flag)) { ok = false; break; }
+            zphase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    reg_alloc<232>();
+    // ===================================================== epilogue (both CTAs)
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    float* tile = stg_base + (warp - 4) * 1024;
+    const uint32_t lead_tempty = mapa_u32(&tempty_bar[0], 0);
+    const uint32_t lead_zready = mapa_u32(zready_bar, 0);
+    uint32_t acc = 0, acc_phase = 0;
+    float xmax = 0.0f;
+    bool ok = true;
+    for (int item = cid; item < total && ok; item += n_cl) {
+      const GfItem it = gf_decode(p, item, crank);
+      const int tau = it.tau0 + row;
+      const int slab0 = it.tau0 + q * 32;
+      const bool in_range = tau >= p.t_lo && tau < p.t_hi;
+      const bool keep = in_range && tau >= p.t_zero_lo;
+      const bool slab_on = (slab0 + 32 > p.t_lo) && (slab0 < p.t_hi);
+      for (int jb = 0; jb < p.n_jobs && ok; ++jb) {
+        const GfJob jd = p.job[jb];
+        if (jd.kind == GF_SKP && !it.do_skp) continue;
+        const uint32_t taddr = tmem_base + acc * 256u + (static_cast<uint32_t>(q * 32) << 16);
+        if (jd.kind == GF_GATE) {
+          if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
+          tc_fence_after();
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c0 = half * 32 + cc * 64;
+            uint32_t vf[32], vg[32];
+            tmem_ld32(taddr + c0, vf);
+            tmem_ld32(taddr + 128 + c0, vg);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float th = keep ? fast_tanh(__uint_as_float(vf[j])) : 0.0f;
+              const float sg = keep ? fast_sigmoid(__uint_as_float(vg[j])) : 0.0f;
+              vf[j] = __float_as_uint(th);
+              vg[j] = __float_as_uint(sg);
+            }
+            // z -> fp16 -> zbuf: K-major rows of 128 B (64 channels), 16-byte chunk index XOR (row & 7) = SWIZZLE_128B
+            const int ch = jd.ch0 + c0;
+            {
+              uint8_t* zrow = zbuf + (ch >> 6) * GF_A_BYTES + row * 128;
+              const int lc0 = (ch & 63) >> 3;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 v;
+                v.x = pack_f16x2(__uint_as_float(vf[8 * i + 0]) * __uint_as_float(vg[8 * i + 0]),
+                                 __uint_as_float(vf[8 * i + 1]) * __uint_as_float(vg[8 * i + 1]));
+                v.y = pack_f16x2(__uint_as_float(vf[8 * i + 2]) * __uint_as_float(vg[8 * i + 2]),
+                                 __uint_as_float(vf[8 * i + 3]) * __uint_as_float(vg[8 * i + 3]));
+                v.z = pack_f16x2(__uint_as_float(vf[8 * i + 4]) * __uint_as_float(vg[8 * i + 4]),
+                                 __uint_as_float(vf[8 * i + 5]) * __uint_as_float(vg[8 * i + 5]));
+                v.w = pack_f16x2(__uint_as_float(vf[8 * i + 6]) * __uint_as_float(vg[8 * i + 6]),
+                                 __uint_as_float(vf[8 * i + 7]) * __uint_as_float(vg[8 * i + 7]));
+                *reinterpret_cast<uint4*>(zrow + (((lc0 + i) ^ (row & 7)) << 4)) = v;
+              }
+            }
+            if (slab_on) {
+              if (p.save) {
+                gf_stg_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tile[j * 32 + lane] = __uint_as_float(vf[j]);
+                gf_stg_flush(&p.th_m, tile, slab0, ch, it.b, false);
+                gf_stg_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tile[j * 32 + lane] = __uint_as_float(vg[j]);
+                gf_stg_flush(&p.sg_m, tile, slab0, ch, it.b, false);
+              }
+              if (p.z_out) {
+                gf_stg_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tile[j * 32 + lane] = __uint_as_float(vf[j]) * __uint_as_float(vg[j]);
+                gf_stg_flush(&p.z_m, tile, slab0, ch, it.b, false);
+              }
+            }
+          }
+          fence_proxy_async_smem();   // the z rows written above are read by tcgen05.mma (async proxy)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (crank != 0) {
+              mbar_arrive_cluster_release(lead_zready);
+              mbar_arrive_cluster(lead_tempty + acc * 8u);
+            } else {
+              mbar_arrive_cluster_release(lead_zready);
+              mbar_arrive(&tempty_bar[acc]);
+            }
+          }
+        } else if (jd.kind == GF_RES) {
+          // x_next = acc + x (wavenet.py:108); fp32 through the staging tile + TMA store, fp16 channels-last copy with
+          // 16-byte stores (lane = time row: 64 contiguous bytes per 32 channels), optional shifted fp32 duplicate
+          const float* xsrc = p.x32 + static_cast<long long>(it.b) * p.x_bs + static_cast<long long>(jd.ch0) * p.x_cs + tau;
+          __half* x16row = p.xo16 + static_cast<long long>(it.b) * p.x16_bs + static_cast<long long>(tau) * p.x16_cp + jd.ch0;
+          const int dup_t = tau + p.dup_toff;
+          float* dupp = (p.dup && in_range && dup_t >= 0 && dup_t < p.dup_t_hi)
+                            ? p.dup + static_cast<long long>(it.b) * p.x_bs + static_cast<long long>(jd.ch0) * p.x_cs + dup_t
+                            : nullptr;
+          const int nv = jd.n_valid;
+          // sub-chunk i of this warp: columns c0(i) = 64 * (half + 2 * (i / 2)) + 32 * (i % 2)
+          float bufA[32], bufB[32];
+          auto issue = [&](int c0, float (&buf)[32]) {
+            const float* s = xsrc + static_cast<long long>(c0) * p.x_cs;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              buf[j] = (keep && c0 + j < nv) ? __ldcg(s) : 0.0f;
+              s += p.x_cs;
+            }
+          };
+          auto col_of = [&](int i) { return 64 * (half + 2 * (i >> 1)) + 32 * (i & 1); };
+          if (col_of(0) < nv) issue(col_of(0), bufA);
+          if (col_of(1) < nv) issue(col_of(1), bufB);
+          if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
+          tc_fence_after();
+          auto chunk = [&](int c0, float (&buf)[32]) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);
+            tmem_ld_wait();
+            float r[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              r[j] = (keep && c0 + j < nv) ? __uint_as_float(v[j]) + buf[j] : 0.0f;
+              xmax = fmaxf(xmax, fabsf(r[j]));
+            }
+            if (slab_on) {
+              gf_stg_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) tile[j * 32 + lane] = r[j];
+              gf_stg_flush(&p.xo_m, tile, slab0, jd.ch0 + c0, it.b, false);
+            }
+            if (dupp) {
+              float* dd = dupp + static_cast<long long>(c0) * p.x_cs;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (c0 + j < nv) *dd = r[j];
+                dd += p.x_cs;
+              }
+            }
+            if (in_range) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (c0 + 8 * i < nv) {
+                  uint4 h;
+                  h.x = pack_f16x2(r[8 * i + 0], r[8 * i + 1]);
+                  h.y = pack_f16x2(r[8 * i + 2], r[8 * i + 3]);
+                  h.z = pack_f16x2(r[8 * i + 4], r[8 * i + 5]);
+                  h.w = pack_f16x2(r[8 * i + 6], r[8 * i + 7]);
+                  *reinterpret_cast<uint4*>(x16row + c0 + 8 * i) = h;
+                }
+              }
+            }
+          };
+#pragma unroll 1
+          for (int i = 0; col_of(i) < jd.n; i += 2) {
+            chunk(col_of(i), bufA);
+            if (col_of(i + 2) < nv) issue(col_of(i + 2), bufA);
+            if (col_of(i + 1) < jd.n) {
+              chunk(col_of(i + 1), bufB);
+              if (col_of(i + 3) < nv) issue(col_of(i + 3), bufB);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+            else mbar_arrive(&tempty_bar[acc]);
+          }
+        } else {
+          // skip sum (wavenet.py:104,110-111 + the caller's running sum): store (first layer), reduce-add in L2, or
+          // relu(old + acc) for the last layer (wavenet.py:359)
+          const bool s_in = tau >= p.skp_t_lo && tau < p.t_hi;
+          const bool s_keep = s_in && tau >= p.skp_zero_lo;
+          const bool s_slab = (slab0 + 32 > p.skp_t_lo) && (slab0 < p.t_hi);
+          const float* old = p.skp + static_cast<long long>(it.b) * p.s_bs + static_cast<long long>(jd.ch0) * p.s_cs + tau;
+          if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
+          tc_fence_after();
+#pragma unroll 1
+          for (int c0 = half * 32; c0 < jd.n; c0 += 64) {
+            uint32_t v[32];
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = 0.0f;
+            if (p.skp_mode == 2) {
+              const float* s = old + static_cast<long long>(c0) * p.s_cs;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                o[j] = (s_keep && c0 + j < jd.n_valid) ? __ldcg(s) : 0.0f;
+                s += p.s_cs;
+              }
+            }
+            tmem_ld32(taddr + c0, v);
+            tmem_ld_wait();
+            if (s_slab) {
+              gf_stg_wait();
+              if (p.skp_mode >= 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  tile[j * 32 + lane] = s_keep ? fmaxf(__uint_as_float(v[j]) + o[j], 0.0f) : 0.0f;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tile[j * 32 + lane] = s_keep ? __uint_as_float(v[j]) : 0.0f;
+              }
+              gf_stg_flush(&p.skp_m, tile, slab0, jd.ch0 + c0, it.b, p.skp_mode == 1);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+            else mbar_arrive(&tempty_bar[acc]);
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    if (xmax > 65504.0f && p.err) atomicExch(p.err, AEWN_ERR_RANGE);   // fp16 operand copy saturated
+    if (elect_one()) tma_store_wait_all();
+    __syncwarp();
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x == 0 && *abort_flag && p.err) atomicExch(p.err, AEWN_ERR_TIMEOUT);
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (B, C, T) fp32  ->  (B, Tp, Cp) fp16 channels-last operand copy; channel `ones_ch` (if >= 0) is set to 1.0 (the bias
+// rides on it), channels in [C, Cp) other than that are written as 0.  64 channels x 32 time steps per CTA through a
+// padded shared-memory tile: reads coalesced along time, writes 128 contiguous bytes per time row.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cvt_f16_cl_kernel(const float* __restrict__ src, long long s_bs, long long s_cs,
+                                                         __half* __restrict__ dst, long long d_bs, int Cp, int C, int T,
+                                                         int ones_ch, int* err) {
+  __shared__ float tl[64][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 64;
+  const int t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows of 32
+  float m = 0.0f;
+  for (int cc = ty; cc < 64; cc += 8) {
+    const int c = c0 + cc, t = t0 + tx;
+    float v = 0.0f;
+    if (c < C && t < T) v = src[static_cast<long long>(b) * s_bs + static_cast<long long>(c) * s_cs + t];
+    if (c == ones_ch) v = 1.0f;
+    m = fmaxf(m, fabsf(v));
+    tl[cc][tx] = v;
+  }
+  __syncthreads();
+  // thread -> (time row, 8-channel group): 32 rows x 8 groups = 256 threads, one 16-byte store each
+  const int tr = threadIdx.x >> 3, g = threadIdx.x & 7;
+  const int t = t0 + tr;
+  if (t < T && c0 + 8 * g < Cp) {
+    uint4 h;
+    h.x = pack_f16x2(tl[8 * g + 0][tr], tl[8 * g + 1][tr]);
+    h.y = pack_f16x2(tl[8 * g + 2][tr], tl[8 * g + 3][tr]);
+    h.z = pack_f16x2(tl[8 * g + 4][tr], tl[8 * g + 5][tr]);
+    h.w = pack_f16x2(tl[8 * g + 6][tr], tl[8 * g + 7][tr]);
+    *reinterpret_cast<uint4*>(dst + static_cast<long long>(b) * d_bs + static_cast<long long>(t) * Cp + c0 + 8 * g) = h;
+  }
+  if (m > 65504.0f && err) atomicExch(err, AEWN_ERR_RANGE);
+}
+
+// Weight repacking into fp16 operand matrices: the aewn_copy_block table of aewn_pack_blocks with `dst` counted in
+// halves:  dst16[i*di + j] = fp16(src[i*si + j*sj]).
+__global__ void pack_blocks_f16_kernel(const aewn_copy_block* __restrict__ blocks, int n_blocks) {
+  for (int bi = blockIdx.x; bi < n_blocks; bi += gridDim.x) {
+    const aewn_copy_block b = blocks[bi];
+    __half* d = reinterpret_cast<__half*>(b.dst);
+    const long long total = static_cast<long long>(b.ni) * b.nj;
+    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+      const long long i = e / b.nj, j = e - i * b.nj;
+      d[i * b.di + j] = __float2half_rn(b.src[i * b.si + j * b.sj]);
+    }
+  }
+}
+
+static int encode_f16_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                          const cuuint32_t* box, CUtensorMapL2promotion promo, const char* what) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  if (!fn) return set_err(AEWN_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  if (!ptr || (reinterpret_cast<uintptr_t>(ptr) & 15u))
+    return set_err(AEWN_ERR_INVALID, "grcc_fwd: %s pointer null or not 16-byte aligned", what);
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims, strides_b, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(AEWN_ERR_DRIVER, "cuTensorMapEncodeTiled(%s) failed: CUresult %d", what, (int)r);
+  return AEWN_OK;
+}
+
+}  // namespace aewn
+
+using namespace aewn;
+
+extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d) return set_err(AEWN_ERR_INVALID, "grcc_fwd: null descriptor");
+  const int R = d->R, D = d->D, S = d->S, C1 = d->n_cond1;
+  if (D != 128 && D != 256) return set_err(AEWN_ERR_INVALID, "grcc_fwd: n_dil must be 128 or 256 (got %d)", D);
+  if (R < 8 || R > 1024 || (R & 7) || S < 32 || S > 1024 || (S & 31) || C1 < 1 || C1 > 1024)
+    return set_err(AEWN_ERR_INVALID, "grcc_fwd: need R %% 8 == 0, S %% 32 == 0 (R=%d S=%d C+1=%d)", R, S, C1);
+  if (d->batch <= 0 || d->t_hi <= d->t_lo || d->dil <= 0 || d->t_rows < d->t_hi)
+    return set_err(AEWN_ERR_INVALID, "grcc_fwd: bad batch / time range");
+  const int KR = (R + 63) & ~63, KC = (C1 + 63) & ~63;
+  if (d->x16_cp != KR || d->c16_cp != KC || d->w1_k != 2 * KR + KC)
+    return set_err(AEWN_ERR_INVALID, "grcc_fwd: operand pitches must be the 64-rounded channel counts (x %d/%d c %d/%d w1 %d/%d)",
+                   d->x16_cp, KR, d->c16_cp, KC, d->w1_k, 2 * KR + KC);
+  if (!d->x16 || !d->c16 || !d->w1h || !d->w2h || !d->skp || (!d->final_layer && (!d->x32 || !d->xo32 || !d->xo16)))
+    return set_err(AEWN_ERR_INVALID, "grcc_fwd: null operand / output pointer");
+  if ((d->x_cs & 3) || (d->x_bs & 3) || (d->a_cs & 3) || (d->a_bs & 3) || (d->s_cs & 3) || (d->s_bs & 3))
+    return set_err(AEWN_ERR_INVALID, "grcc_fwd: fp32 strides must be multiples of 4 elements");
+  if (d->save && (!d->th || !d->sg)) return set_err(AEWN_ERR_INVALID, "grcc_fwd: save needs th and sg");
+
+  GfParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)KR, (cuuint64_t)d->t_rows, (cuuint64_t)d->batch};
+    cuuint64_t str[2] = {(cuuint64_t)KR * 2u, (cuuint64_t)d->x16_bs * 2u};
+    cuuint32_t box[3] = {64u, 128u, 1u};
+    if ((rc = encode_f16_map(&p.xa, d->x16, 3, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "x16"))) return rc;
+    cuuint64_t dimc[3] = {(cuuint64_t)KC, (cuuint64_t)d->t_rows, (cuuint64_t)d->batch};
+    cuuint64_t strc[2] = {(cuuint64_t)KC * 2u, (cuuint64_t)d->c16_bs * 2u};
+    if ((rc = encode_f16_map(&p.ca, d->c16, 3, dimc, strc, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "c16"))) return rc;
+    cuuint64_t dw1[2] = {(cuuint64_t)d->w1_k, (cuuint64_t)(2 * D)};
+    cuuint64_t sw1[1] = {(cuuint64_t)d->w1_k * 2u};
+    cuuint32_t bw[2] = {64u, 128u};
+    if ((rc = encode_f16_map(&p.w1, d->w1h, 2, dw1, sw1, bw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w1h"))) return rc;
+    const int rows2 = (d->final_layer ? 0 : R) + S;
+    cuuint64_t dw2[2] = {(cuuint64_t)D, (cuuint64_t)rows2};
+    cuuint64_t sw2[1] = {(cuuint64_t)D * 2u};
+    if ((rc = encode_f16_map(&p.w2, d->w2h, 2, dw2, sw2, bw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w2h"))) return rc;
+  }
+  if (d->save) {
+    if ((rc = encode_out_map(&p.th_m, d->th, d->t_hi, D, d->batch, d->a_cs, d->a_bs))) return rc;
+    if ((rc = encode_out_map(&p.sg_m, d->sg, d->t_hi, D, d->batch, d->a_cs, d->a_bs))) return rc;
+  }
+  if (d->z) {
+    if ((rc = encode_out_map(&p.z_m, d->z, d->t_hi, D, d->batch, d->a_cs, d->a_bs))) return rc;
+  }
+  if (!d->final_layer) {
+    if ((rc = encode_out_map(&p.xo_m, d->xo32, d->t_hi, R, d->batch, d->x_cs, d->x_bs))) return rc;
+  }
+  if ((rc = encode_out_map(&p.skp_m, d->skp, d->t_hi, S, d->batch, d->s_cs, d->s_bs))) return rc;
+
+  int nj = 0;
+  for (int j = 0; j < D / 128; ++j) p.job[nj++] = GfJob{GF_GATE, 256 * j, 256, 128, 128 * j};
+  p.n_gate = nj;
+  if (!d->final_layer)
+    for (int c0 = 0; c0 < R; c0 += 256) {
+      const int nv = R - c0 < 256 ? R - c0 : 256;
+      p.job[nj++] = GfJob{GF_RES, c0, (nv + 15) & ~15, nv, c0};
+    }
+  const int row_s = d->final_layer ? 0 : R;
+  for (int c0 = 0; c0 < S; c0 += 256) {
+    const int nv = S - c0 < 256 ? S - c0 : 256;
+    p.job[nj++] = GfJob{GF_SKP, row_s + c0, (nv + 15) & ~15, nv, c0};
+  }
+  if (nj > GF_MAX_JOBS) return set_err(AEWN_ERR_INVALID, "grcc_fwd: too many jobs (%d)", nj);
+  p.n_jobs = nj;
+  p.kb_x = KR / 64;
+  p.kb_c = KC / 64;
+  p.kb_z = D / 64;
+  p.dil = d->dil;
+  p.x32 = d->x32;
+  p.x_bs = d->x_bs;
+  p.x_cs = d->x_cs;
+  p.dup = d->dup;
+  p.dup_toff = d->dup_toff;
+  p.dup_t_hi = d->dup_t_hi;
+  p.xo16 = reinterpret_cast<__half*>(d->xo16);
+  p.x16_bs = d->x16_bs;
+  p.x16_cp = d->x16_cp;
+  p.skp = d->skp;
+  p.s_bs = d->s_bs;
+  p.s_cs = d->s_cs;
+  p.save = d->save;
+  p.z_out = d->z != nullptr;
+  p.skp_mode = d->skp_mode;
+  p.batch = d->batch;
+  p.t_begin = d->t_lo & ~31;
+  p.n_tgroups = (d->t_hi - p.t_begin + 2 * GF_BM - 1) / (2 * GF_BM);
+  p.t_lo = d->t_lo;
+  p.t_zero_lo = d->t_zero_lo;
+  p.t_hi = d->t_hi;
+  p.skp_t_lo = d->skp_t_lo;
+  p.skp_zero_lo = d->skp_zero_lo;
+  p.err = d->err;
+  if ((p.t_lo & 3) || (p.skp_t_lo & 3)) return set_err(AEWN_ERR_INVALID, "grcc_fwd: t_lo / skp_t_lo must be multiples of 4");
+
+  const long long total = static_cast<long long>(p.batch) * p.n_tgroups;
+  int clusters = (d->max_ctas > 0 ? d->max_ctas : sm_count()) / 2;
+  if (clusters > total) clusters = static_cast<int>(total);
+  if (clusters < 1) clusters = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * 2);
+  cfg.blockDim = dim3(GF_THREADS);
+  cfg.dynamicSmemBytes = GF_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t ae = cudaFuncSetAttribute(grcc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_BYTES);
+  if (ae != cudaSuccess) return cuda_err(ae, "grcc_fwd: cudaFuncSetAttribute");
+  cudaError_t le = cudaLaunchKernelEx(&cfg, grcc_fwd_kernel, p);
+  count_launch();
+  if (le != cudaSuccess) return cuda_err(le, "grcc_fwd launch");
+  return cuda_err(cudaGetLastError(), "grcc_fwd launch");
+}
+
+extern "C" int aewn_cvt_f16_cl(const float* src, long long s_bs, long long s_cs, void* dst, long long d_bs, int Cp, int C,
+                               int T, int batch, int ones_ch, int* err, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!src || !dst || batch <= 0 || C <= 0 || T <= 0 || Cp < C || (Cp & 7) || (reinterpret_cast<uintptr_t>(dst) & 15u) ||
+      (d_bs & 7))
+    return set_err(AEWN_ERR_INVALID, "cvt_f16_cl: bad arguments");
+  dim3 grid((T + 31) / 32, (Cp + 63) / 64, batch);
+  cvt_f16_cl_kernel<<<grid, 256, 0, stream>>>(src, s_bs, s_cs, reinterpret_cast<__half*>(dst), d_bs, Cp, C, T, ones_ch, err);
+  count_launch();
+  return cuda_err(cudaGetLastError(), "cvt_f16_cl launch");
+}
+
+extern "C" int aewn_pack_blocks_f16(const aewn_copy_block* blocks_dev, int n_blocks, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!blocks_dev || n_blocks <= 0) return set_err(AEWN_ERR_INVALID, "pack_blocks_f16: bad arguments");
+  int grid = n_blocks < 148 * 8 ? n_blocks : 148 * 8;
+  pack_blocks_f16_kernel<<<grid, 256, 0, stream>>>(blocks_dev, n_blocks);
+  count_launch();
+  return cuda_err(cudaGetLastError(), "pack_blocks_f16 launch");
+}

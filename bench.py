@@ -129,7 +129,7 @@ def grcc_layer_fwd_bytes(B, R, D, S, C, T_in, d, W, train):
     n_weights = 2 * (D * R * 2) + 2 * D + 2 * D * C + S * D + R * D          # 607 744 for arch.basic
     b = 4 * B * (R * T_in + C * T_out + R * T_out + 2 * S * W) + 4 * n_weights
     if train:
-        b += 4 * B * 3 * D * T_out
+        b += 4 * B * 2 * D * T_out          # + the saved tanh and sigmoid (z is their product, not counted)
     return b
 
 
@@ -409,8 +409,9 @@ def main():
         T_in = geomS.T0
         for l, d in enumerate(geomS.dils):
             g1, g2 = times.get(f"fwd_gemm1.{l}", []), times.get(f"fwd_gemm2.{l}", [])
-            if g1 and g2:
-                l_ms = sum(g1) / len(g1) + sum(g2) / len(g2)
+            gl = times.get(f"fwd_layer.{l}", [])          # fused layer kernel: one launch per layer
+            if gl or (g1 and g2):
+                l_ms = sum(gl) / len(gl) if gl else sum(g1) / len(g1) + sum(g2) / len(g2)
                 l_bytes = grcc_layer_fwd_bytes(B, R, D, S, C, T_in, d, W, train=True)
                 fwd_ms += l_ms
                 fwd_bytes += l_bytes

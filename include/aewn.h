@@ -34,6 +34,7 @@ typedef void* aewn_stream_t; /* cudaStream_t */
 #define AEWN_ERR_INVALID (-1001)  /* bad argument (null pointer, misaligned pitch, size out of range) */
 #define AEWN_ERR_DRIVER (-1002)   /* cuTensorMapEncodeTiled / driver entry point unavailable */
 #define AEWN_ERR_TIMEOUT (-1003)  /* value written to the device error word when a bounded wait expires */
+#define AEWN_ERR_RANGE (-1004)    /* device error word: an activation left the fp16 operand range (|x| > 65504) */
 
 int aewn_version(void);
 const char* aewn_last_error_string(void);
@@ -253,6 +254,70 @@ int aewn_add_blocks(const aewn_copy_block* blocks_dev, int n_blocks, aewn_stream
 /* out = mask > 0 ? g : 0   (ReLU backward) */
 int aewn_relu_mask_bwd(const float* g, long long g_bs, long long g_cs, const float* mask, long long m_bs, long long m_cs,
                        float* out, long long o_bs, long long o_cs, int batch, int C, int T, aewn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused dilation layer, forward (GatedResidualCondConv.forward, wavenet.py:91-111) -- ONE launch per layer:
+ *
+ *   filt | gate = [Wf0 Wf1 Pf bf | Wg0 Wg1 Pg bg] . [x(t - dil); x(t); cond(t); 1]      (wavenet.py:100-101)
+ *   z = tanh(filt) * sigmoid(gate)                                                       (wavenet.py:102)
+ *   x_next(t) = Wr . z + x(t)         skip(t) (+)= Ws . z                                (wavenet.py:103-110)
+ *
+ * Tensor-core operands are FP16 copies (10-bit mantissa like TF32, round-to-nearest), accumulation is FP32 in TMEM and
+ * the residual stream x / x_next stays FP32.  Operand copies are CHANNELS-LAST:
+ *   x16  (batch, t_rows, x16_cp)  fp16, x16_cp = R rounded up to 64, pad channels zero
+ *   c16  (batch, t_rows, c16_cp)  fp16, channels [cond (n_cond1 - 1) | 1.0 | 0..], c16_cp = n_cond1 rounded up to 64
+ *   w1h  [2 D][w1_k]              fp16 K-major, rows per 128-channel block: 128 filt rows, 128 gate rows; columns
+ *                                 [tap x(t-dil) (x16_cp) | tap x(t) (x16_cp) | cond projection, bias (c16_cp)]
+ *   w2h  [(final ? 0 : R) + S][D] fp16 K-major: dil_res rows then dil_skp rows
+ * (aewn_cvt_f16_cl / aewn_pack_blocks_f16 produce them).  The kernel writes the next layer's x16 itself.  A value
+ * outside the fp16 range sets *err = AEWN_ERR_RANGE (the stored operand saturates at +-65504).
+ * Restrictions: D in {128, 256}; R % 8 == 0; S % 32 == 0; t_lo, skp_t_lo multiples of 4; fp32 strides multiples of 4.
+ * Shapes outside them run through aewn_tgemm (two launches per layer, TF32).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* x16;        /* layer input, fp16 channels-last */
+  long long x16_bs;       /* elements between batch items (x16 and xo16) */
+  int x16_cp;
+  const void* c16;
+  long long c16_bs;
+  int c16_cp;
+  int t_rows;             /* time rows of x16 / c16 / xo16 (>= t_hi) */
+  const void* w1h;
+  int w1_k;
+  const void* w2h;
+  const float* x32;       /* layer input, fp32 (batch, R, T): the residual addend */
+  float* xo32;            /* x_next fp32, same strides as x32 (unused for the final layer) */
+  long long x_bs, x_cs;
+  void* xo16;             /* x_next fp16 channels-last, same geometry as x16 */
+  float* dup;             /* optional: x_next again at time index t + dup_toff (same strides as x32), for the backward
+                             pass's TF32 weight-gradient tap when the NEXT layer's dilation is not a multiple of 4 */
+  int dup_toff, dup_t_hi;
+  float* th;              /* save != 0: tanh(filt), sigmoid(gate) (batch, D, T) for the backward pass */
+  float* sg;
+  float* z;               /* optional: z (batch, D, T) */
+  long long a_bs, a_cs;   /* strides of th / sg / z */
+  int save;
+  float* skp;             /* skip sum (batch, S, T) */
+  long long s_bs, s_cs;
+  int skp_mode;           /* 0: skp = Ws.z (first layer); 1: skp += Ws.z; 2: skp = relu(skp + Ws.z) (last layer, wavenet.py:359);
+                             3: skp = relu(Ws.z) (a one-layer stack) */
+  int batch, R, D, S;
+  int n_cond1;            /* conditioning channels + 1 (the bias channel) */
+  int dil;
+  int final_layer;        /* 1: no dil_res, no x_next (wavenet.py:36-37,105-106) */
+  int t_lo, t_zero_lo, t_hi;      /* outputs are stored on [t_lo, t_hi); values for t < t_zero_lo are written as 0 */
+  int skp_t_lo, skp_zero_lo;      /* same for the skip sum */
+  int* err;
+  int max_ctas;           /* 0 = one per SM */
+} aewn_grcc_fwd_desc;
+
+int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream);
+/* (batch, C, T) fp32 -> (batch, T, Cp) fp16 channels-last operand copy; channel ones_ch (>= 0) is written as 1.0, other
+ * channels in [C, Cp) as 0.  Cp % 8 == 0, dst 16-byte aligned, d_bs (elements between batch items) % 8 == 0. */
+int aewn_cvt_f16_cl(const float* src, long long s_bs, long long s_cs, void* dst, long long d_bs, int Cp, int C, int T,
+                    int batch, int ones_ch, int* err, aewn_stream_t stream);
+/* aewn_pack_blocks writing fp16: dst is a __half matrix, di counted in halves */
+int aewn_pack_blocks_f16(const aewn_copy_block* blocks_dev, int n_blocks, aewn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused VQ step (vqema_bn.py:133-188, vq_bn.py:38-41): nearest code per (b, n) vector of ze (B, d, N).

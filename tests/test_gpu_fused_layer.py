@@ -1,0 +1,188 @@
+"""The fused dilation-layer kernel (aewn_grcc_fwd, one launch per layer: wavenet.py:91-111) through ops.StackPlan.
+
+Tolerances.  The kernel feeds the tensor cores fp16 copies of x, cond, z and of the weights (round-to-nearest, 10-bit
+mantissa), accumulates in fp32 and keeps the residual stream in fp32.  The first test compares it with a float64
+reference that applies EXACTLY those operand roundings, so what is left is fp32 accumulation order, the ex2/rcp
+approximations of tanh / sigmoid (~1e-7 absolute) and the occasional 1-ulp flip of an fp16 rounding: 2e-4 of the
+tensor's max-abs, i.e. 25x tighter than the TF32 envelope (5e-3) the un-rounded comparisons use.  A wrong time step at
+a lead boundary, a mis-zeroed margin column or a swapped channel block is an O(1) error under this bound."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def h(t):
+    """fp16 operand rounding (round to nearest even), result kept in float64."""
+    return t.float().half().double()
+
+
+def make_params(R, D, S, Cc, dils, final_last, gen, dev):
+    params = []
+    for l, _ in enumerate(dils):
+        final = final_last and l == len(dils) - 1
+        p = {"conv_signal.weight": 0.06 * torch.randn(D, R, 2, generator=gen),
+             "conv_signal.bias": 0.1 * torch.randn(D, generator=gen),
+             "conv_gate.weight": 0.06 * torch.randn(D, R, 2, generator=gen),
+             "conv_gate.bias": 0.1 * torch.randn(D, generator=gen),
+             "proj_signal.weight": 0.1 * torch.randn(D, Cc, 1, generator=gen),
+             "proj_gate.weight": 0.1 * torch.randn(D, Cc, 1, generator=gen),
+             "dil_skp.weight": 0.08 * torch.randn(S, D, 1, generator=gen)}
+        if not final:
+            p["dil_res.weight"] = 0.08 * torch.randn(R, D, 1, generator=gen)
+        params.append({k: v.to(dev).contiguous() for k, v in p.items()})
+    return params
+
+
+def reference_stack(x0, cond, params, dils, final_last, rounded):
+    """float64 restatement of the stack on the absolute time axis (wavenet.py:91-111), optionally with the
+    kernel's fp16 operand roundings.  Returns per-layer (th, sg, x_next) and the skip sum; entries left of a layer's lead
+    are garbage by construction and are not compared."""
+    r = h if rounded else (lambda t: t.double())
+    B, R, T0 = x0.shape
+    x = x0.double()
+    c = cond.double()
+    outs, skp_sum, lead = [], 0, 0
+    RF = sum(dils)
+    for l, d in enumerate(dils):
+        p = params[l]
+        final = final_last and l == len(dils) - 1
+        lead += d
+        xs = F.pad(r(x), (d, 0))[:, :, :T0]                       # x[tau - d]
+        pre = []
+        for wk, pk, bk in (("conv_signal.weight", "proj_signal.weight", "conv_signal.bias"),
+                           ("conv_gate.weight", "proj_gate.weight", "conv_gate.bias")):
+            w = r(p[wk])
+            pre.append(torch.einsum("dr,brt->bdt", w[:, :, 0], xs) + torch.einsum("dr,brt->bdt", w[:, :, 1], r(x)) +
+                       torch.einsum("dc,bct->bdt", r(p[pk])[:, :, 0], r(c)) + r(p[bk])[None, :, None])
+        th, sg = torch.tanh(pre[0]), torch.sigmoid(pre[1])
+        z = r(th * sg)
+        skp_sum = skp_sum + torch.einsum("sd,bdt->bst", r(p["dil_skp.weight"])[:, :, 0], z)
+        x_next = None
+        if not final:
+            x_next = torch.einsum("rd,bdt->brt", r(p["dil_res.weight"])[:, :, 0], z) + x
+            x = x_next
+        outs.append((th, sg, x_next, lead))
+    return outs, skp_sum, RF
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max()) / max(float(b.abs().max()), 1e-12)
+
+
+CASES = [
+    # R, D, S, Cc, dils, T0, B, final_last      (arch.basic widths; a narrow 128-channel variant; a 512-channel one)
+    (368, 256, 256, 138, [1, 2, 4, 8, 16, 32], 63 + 700, 2, True),
+    (64, 128, 64, 20, [1, 2, 4], 7 + 300, 3, False),
+    (512, 256, 256, 138, [4, 1], 5 + 260, 1, True),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=["basic368", "narrow128", "wide512"])
+@pytest.mark.parametrize("save", [True, False], ids=["train", "infer"])
+def test_fused_stack_matches_fp16_operand_reference(case, save):
+    from aewn import ops
+    R, D, S, Cc, dils, T0, B, final_last = case
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(11)
+    params = make_params(R, D, S, Cc, dils, final_last, gen, dev)
+    x0 = torch.randn(B, R, T0, generator=gen).to(dev)
+    cond = torch.randn(B, Cc, T0, generator=gen).to(dev)
+    ops.set_fused_forward(True)
+    geom = ops.StackGeom(dils, T0, last_is_final=final_last)
+    plan = ops.StackPlan(B, R, D, S, Cc, geom, params, dev, relu_last=False)
+    assert plan.fused
+    plan.sig[0][:, :, :T0] = x0
+    for l, d in enumerate(dils):                      # the TF32 backward's pre-shifted tap of layer 0 (base layer's job)
+        if l == 0 and ops.needs_dup(d):
+            plan.xs[0][:, :, d:T0] = x0[:, :, :T0 - d]
+    plan.cond[:, :Cc, :T0] = cond
+    plan.forward(save=save)
+    ops._plans["t"] = plan
+    try:
+        ops.check_device_errors()
+    finally:
+        ops._plans.pop("t")
+    outs, skp_ref, RF = reference_stack(x0, cond, params, dils, final_last, rounded=True)
+    worst = {}
+    last_writer = max([l for l, o in enumerate(outs) if o[2] is not None], default=-1)
+    for l, (th, sg, xn, lead) in enumerate(outs):
+        if save:
+            worst[f"th{l}"] = rel(plan.th[l][:, :, lead:T0], th[:, :, lead:])
+            worst[f"sg{l}"] = rel(plan.sg[l][:, :, lead:T0], sg[:, :, lead:])
+            worst[f"z{l}"] = rel(plan.z[l][:, :, lead:T0], (th * sg)[:, :, lead:])
+            # margins: zero between the aligned-down lead and the lead (TMA boxes of the backward pass read them)
+            assert float(plan.th[l][:, :, lead & ~3:lead].abs().max() if lead & 3 else 0.0) == 0.0
+        if xn is not None:
+            worst[f"x{l + 1}"] = rel(plan.sig[l + 1][:, :, lead:T0], xn[:, :, lead:])
+            if l == last_writer:                      # the fp16 channels-last copy the next layer would read
+                got16 = plan.x16[(l + 1) % 2][:, lead:T0, :R].permute(0, 2, 1).float()
+                worst[f"x16_{l + 1}"] = rel(got16, xn[:, :, lead:])           # fp16 storage: 2^-11 relative
+                assert float(plan.x16[(l + 1) % 2][:, :, R:].abs().max() if plan.KR16 > R else 0.0) == 0.0
+            if save and l + 1 < len(dils) and ops.needs_dup(dils[l + 1]):
+                dn = dils[l + 1]
+                assert torch.equal(plan.xs[l + 1][:, :, lead + dn:T0], plan.sig[l + 1][:, :, lead:T0 - dn])
+    worst["skp"] = rel(plan.skp[:, :, RF:T0], skp_ref[:, :, RF:])
+    bad = {k: v for k, v in worst.items() if v > (1e-3 if k.startswith("x16") else 2e-4)}
+    assert not bad, (bad, worst)
+    # the un-rounded fp32 math is within the TF32-class envelope
+    outs32, skp32, _ = reference_stack(x0, cond, params, dils, final_last, rounded=False)
+    assert rel(plan.skp[:, :, RF:T0], skp32[:, :, RF:]) < 5e-3
+
+
+def test_fused_forward_agrees_with_two_launch_tf32_path_through_wavenet_step():
+    """Whole decoder train step at arch.basic widths (window 512, batch 2): fused fp16-operand forward + TF32 backward
+    vs the all-TF32 two-launch path.  The backward pass consumes what the fused forward saved (tanh, sigmoid, z, the
+    pre-shifted taps), so agreement of every gradient pins those side outputs too."""
+    import aewn
+    from aewn import ops
+    from test_gpu_fullsize import build
+
+    def run(fused):
+        ops.set_fused_forward(fused)
+        torch.manual_seed(2507)
+        wn, geo = build(512)
+        wn = wn.cuda().train()
+        g = torch.Generator().manual_seed(3)
+        B = 2
+        wav = torch.randint(0, 256, (B, geo["wav_len"]), generator=g).float().cuda()
+        lc = torch.randn(B, 64, geo["lc_len"], generator=g).cuda().requires_grad_(True)
+        spk = torch.randint(0, 40, (B,), generator=g).cuda()
+        jit = torch.arange(geo["lc_len"]).unsqueeze(0).repeat(B, 1).cuda()
+        q = wn(wav, lc, spk, jit)
+        o0, o1 = wn.wav_cond_offset
+        loss = aewn.RecLoss()(q[..., :-1], wav[:, o1 - 512:o1][..., 1:])
+        loss.backward()
+        ops.check_device_errors()
+        assert any(p.fused == fused for p in ops._plans.values())
+        return q.detach(), float(loss), {k: p.grad.clone() for k, p in wn.named_parameters()}, lc.grad.clone()
+
+    try:
+        q1, l1, g1, lc1 = run(True)
+        q0, l0, g0, lc0 = run(False)
+    finally:
+        ops.set_fused_forward(True)
+    assert rel(q1, q0) < 5e-3
+    assert abs(l1 - l0) < 2e-3
+    assert rel(lc1, lc0) < 3e-2
+    for k in g0:
+        assert rel(g1[k], g0[k]) < 3e-2, k
+
+
+def test_fp16_operand_range_overflow_is_reported():
+    """An activation beyond the fp16 range (|x| > 65504) cannot be an exact tensor-core operand: the kernel saturates the
+    copy and raises the device error word (include/aewn.h AEWN_ERR_RANGE) instead of silently computing with inf."""
+    from aewn import ops, _lib
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(1)
+    R, D, S, Cc, dils, T0, B = 64, 128, 64, 20, [1, 2], 3 + 200, 1
+    params = make_params(R, D, S, Cc, dils, True, gen, dev)
+    ops.set_fused_forward(True)
+    plan = ops.StackPlan(B, R, D, S, Cc, ops.StackGeom(dils, T0), params, dev, relu_last=False)
+    plan.sig[0][:, :, :T0] = 1.0e5 * torch.randn(B, R, T0, generator=gen).to(dev)
+    plan.forward(save=False)
+    torch.cuda.synchronize()
+    assert int(plan.err.item()) == _lib.ERR_RANGE
+    plan.err.zero_()
+    assert torch.isfinite(plan.skp).all()
