@@ -129,7 +129,7 @@ SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_
            "aewn_base_embed_fwd", "aewn_base_embed_bwd", "aewn_fill", "aewn_relu_mask_bwd",
            "aewn_vq_fwd", "aewn_vq_commit_bwd", "aewn_ema_update", "aewn_pack_blocks", "aewn_add_blocks", "aewn_nll_fwd", "aewn_nll_bwd",
            "aewn_gen_smem_bytes", "aewn_gen_max_clusters", "aewn_gen_run",
-           "aewn_grcc_fwd", "aewn_cvt_f16_cl", "aewn_pack_blocks_f16"]
+           "aewn_grcc_fwd", "aewn_cvt_f16_cl", "aewn_pack_blocks_f16", "aewn_conv1x1_f32", "aewn_conv1x1_wgrad_f32"]
 
 
 def lib():

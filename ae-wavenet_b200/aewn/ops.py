@@ -1229,6 +1229,57 @@ class _TapConvTransposeFn(torch.autograd.Function):
         return gx[:, :, :Lx].clone(), dw, db, None, None
 
 
+class _Conv1x1F32Fn(torch.autograd.Function):
+    """Bias-free 1x1 convolution in EXACT fp32 (aewn_conv1x1_f32: sequential fmaf, no tensor cores) with its two
+    gradients.  Used for the bottleneck projection in front of the nearest-code search (vqema_bn.py:131, vq_bn.py:35):
+    the code indices are index work, and TF32 operand rounding there moves codes across near-ties."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        B, K, T = x.shape
+        N = weight.shape[0]
+        xd = x.detach()
+        if xd.stride(2) != 1:
+            xd = xd.contiguous()
+        w = weight.detach().reshape(N, K).contiguous()
+        out = torch.empty(B, N, T, device=x.device)
+        L.check(L.lib().aewn_conv1x1_f32(
+            C.c_void_p(xd.data_ptr()), C.c_longlong(xd.stride(0)), C.c_longlong(xd.stride(1)), C.c_void_p(w.data_ptr()),
+            C.c_longlong(K), C.c_longlong(1), C.c_void_p(out.data_ptr()), C.c_longlong(out.stride(0)),
+            C.c_longlong(out.stride(1)), C.c_int(B), C.c_int(N), C.c_int(K), C.c_int(T), _stream()), "aewn_conv1x1_f32")
+        ctx.save_for_backward(xd, w)
+        ctx.wshape = weight.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xd, w = ctx.saved_tensors
+        B, K, T = xd.shape
+        N = w.shape[0]
+        gc = g.contiguous()
+        gx = dw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty(B, K, T, device=g.device)
+            L.check(L.lib().aewn_conv1x1_f32(
+                C.c_void_p(gc.data_ptr()), C.c_longlong(gc.stride(0)), C.c_longlong(gc.stride(1)),
+                C.c_void_p(w.data_ptr()), C.c_longlong(1), C.c_longlong(K), C.c_void_p(gx.data_ptr()),
+                C.c_longlong(gx.stride(0)), C.c_longlong(gx.stride(1)), C.c_int(B), C.c_int(K), C.c_int(N), C.c_int(T),
+                _stream()), "aewn_conv1x1_f32")
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(N, K, device=g.device)
+            L.check(L.lib().aewn_conv1x1_wgrad_f32(
+                C.c_void_p(gc.data_ptr()), C.c_longlong(gc.stride(0)), C.c_longlong(gc.stride(1)),
+                C.c_void_p(xd.data_ptr()), C.c_longlong(xd.stride(0)), C.c_longlong(xd.stride(1)),
+                C.c_void_p(dw.data_ptr()), C.c_int(B), C.c_int(N), C.c_int(K), C.c_int(T), _stream()),
+                "aewn_conv1x1_wgrad_f32")
+            dw = dw.reshape(ctx.wshape)
+        return gx, dw
+
+
+def conv1x1_f32(x, weight):
+    return _Conv1x1F32Fn.apply(x, weight)
+
+
 # Conditioning front-end (lc_conv + 4 transposed convs, ~0.5 % of the decoder FLOPs): "torch" = cuDNN through the
 # nn.Conv1d / nn.ConvTranspose1d parameter containers, "kernels" = the polyphase GEMMs above.  The kernel path is
 # parity-tested but its per-phase staging copies make the whole step ~10 % slower than cuDNN here (measured 39.5 vs

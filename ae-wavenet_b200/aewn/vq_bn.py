@@ -29,7 +29,7 @@ class VQ(nn.Module):
 
     def forward(self, z):
         _require_cuda(z)
-        ze = ops.tap_conv(z, self.linear.weight)
+        ze = ops.conv1x1_f32(z, self.linear.weight)       # exact fp32 (see vqema_bn.VQEMA.forward)
         self.ze = ze
         zq, min_dist, min_ind, ze_norm = _VQAssignFn.apply(ze, self.emb, METRIC_SQ_L2, self.ind_hist, None, None, True)
         self.min_dist = min_dist

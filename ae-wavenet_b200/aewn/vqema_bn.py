@@ -136,7 +136,7 @@ class VQEMA(nn.Module):
 
     def forward(self, z):
         _require_cuda(z)
-        ze = ops.tap_conv(z, self.linear.weight)          # 1x1 conv n_in -> d on the tcgen05 engine
+        ze = ops.conv1x1_f32(z, self.linear.weight)       # 1x1 conv n_in -> d in exact fp32: the code indices depend on it
         self.ze = ze
         train = self.training
         zq, min_dist, min_ind, ze_norm = _VQAssignFn.apply(

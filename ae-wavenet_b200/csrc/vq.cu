@@ -245,3 +245,87 @@ int aewn_ema_update(float* ema_numer, float* ema_denom, const float* z_sum, cons
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// The bottleneck's 1x1 projection (vqema_bn.py:92,131; vq_bn.py:18,35: self.linear, a bias-free Conv1d(n_in -> d, 1))
+// in EXACT fp32: sequential fmaf over the input channels, no tensor cores.  The nearest-code search that follows is an
+// index computation (north star: bit-identical indices); TF32 operand rounding of this 0.05 GFLOP product moved ~3 % of
+// the codes across near-ties, fp32 FMA arithmetic reproduces the reference's codes.
+//   out[b, n, t] = sum_k W[n * w_rs + k * w_cs] * x[b, k, t]
+// The same kernel computes the data gradient (W read transposed).  Thread = (time step, 8 output rows).
+// ---------------------------------------------------------------------------------------------------------------
+namespace aewn {
+
+__global__ void __launch_bounds__(256) conv1x1_f32_kernel(const float* __restrict__ x, long long x_bs, long long x_cs,
+                                                          const float* __restrict__ w, long long w_rs, long long w_cs,
+                                                          float* __restrict__ out, long long o_bs, long long o_cs, int N,
+                                                          int K, int T) {
+  const int b = blockIdx.z;
+  const int t = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int n0 = blockIdx.y * 64 + (threadIdx.x >> 5);     // this thread: rows n0, n0 + 8, ..., n0 + 56
+  if (t >= T) return;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  const float* xp = x + static_cast<long long>(b) * x_bs + t;
+  for (int k = 0; k < K; ++k) {
+    const float xv = xp[static_cast<long long>(k) * x_cs];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + 8 * i;
+      if (n < N) acc[i] = fmaf(__ldg(w + n * w_rs + k * w_cs), xv, acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + 8 * i;
+    if (n < N) out[static_cast<long long>(b) * o_bs + static_cast<long long>(n) * o_cs + t] = acc[i];
+  }
+}
+
+// dW[n, k] = sum_{b, t} g[b, n, t] * x[b, k, t]: one warp per output, lanes stride over time, fixed-order butterfly.
+__global__ void __launch_bounds__(256) conv1x1_wgrad_f32_kernel(const float* __restrict__ g, long long g_bs,
+                                                                long long g_cs, const float* __restrict__ x,
+                                                                long long x_bs, long long x_cs, float* __restrict__ dw,
+                                                                int N, int K, int T, int B) {
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (o >= N * K) return;
+  const int n = o / K, k = o - n * K;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.0f;
+  for (int b = 0; b < B; ++b) {
+    const float* gp = g + static_cast<long long>(b) * g_bs + static_cast<long long>(n) * g_cs;
+    const float* xp = x + static_cast<long long>(b) * x_bs + static_cast<long long>(k) * x_cs;
+    for (int t = lane; t < T; t += 32) acc = fmaf(gp[t], xp[t], acc);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) dw[o] = acc;
+}
+
+}  // namespace aewn
+
+extern "C" {
+
+int aewn_conv1x1_f32(const float* x, long long x_bs, long long x_cs, const float* w, long long w_rs, long long w_cs,
+                     float* out, long long o_bs, long long o_cs, int batch, int N, int K, int T, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !w || !out || batch <= 0 || N <= 0 || K <= 0 || T <= 0)
+    return aewn::set_err(AEWN_ERR_INVALID, "conv1x1_f32: bad arguments");
+  dim3 grid((T + 31) / 32, (N + 63) / 64, batch);
+  aewn::conv1x1_f32_kernel<<<grid, 256, 0, stream>>>(x, x_bs, x_cs, w, w_rs, w_cs, out, o_bs, o_cs, N, K, T);
+  aewn::count_launch();
+  return aewn::cuda_err(cudaGetLastError(), "conv1x1_f32 launch");
+}
+
+int aewn_conv1x1_wgrad_f32(const float* g, long long g_bs, long long g_cs, const float* x, long long x_bs, long long x_cs,
+                           float* dw, int batch, int N, int K, int T, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!g || !x || !dw || batch <= 0 || N <= 0 || K <= 0 || T <= 0)
+    return aewn::set_err(AEWN_ERR_INVALID, "conv1x1_wgrad_f32: bad arguments");
+  aewn::conv1x1_wgrad_f32_kernel<<<(N * K + 7) / 8, 256, 0, stream>>>(g, g_bs, g_cs, x, x_bs, x_cs, dw, N, K, T, batch);
+  aewn::count_launch();
+  return aewn::cuda_err(cudaGetLastError(), "conv1x1_wgrad_f32 launch");
+}
+
+}  // extern "C"

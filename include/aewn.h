@@ -329,6 +329,14 @@ int aewn_pack_blocks_f16(const aewn_copy_block* blocks_dev, int n_blocks, aewn_s
 int aewn_vq_fwd(const float* ze, long long ze_bs, long long ze_cs, const float* emb, int metric, long long* min_ind,
                 float* min_dist, float* zq, long long zq_bs, long long zq_cs, float* hist, float* z_sum, float* n_sum,
                 float* ze_norm, int batch, int d, int N, int K, aewn_stream_t stream);
+/* The bottleneck's bias-free 1x1 projection (vqema_bn.py:92,131; vq_bn.py:18,35) in exact fp32 (sequential fmaf over k, no
+ * tensor cores): out[b, n, t] = sum_k w[n * w_rs + k * w_cs] * x[b, k, t].  With (w_rs, w_cs) = (1, row pitch) it is the
+ * data gradient.  The code indices that follow are an index computation; TF32 rounding here moves codes across near-ties. */
+int aewn_conv1x1_f32(const float* x, long long x_bs, long long x_cs, const float* w, long long w_rs, long long w_cs,
+                     float* out, long long o_bs, long long o_cs, int batch, int N, int K, int T, aewn_stream_t stream);
+/* dw[n * K + k] = sum_{b,t} g[b, n, t] * x[b, k, t]  (overwrites dw; deterministic order) */
+int aewn_conv1x1_wgrad_f32(const float* g, long long g_bs, long long g_cs, const float* x, long long x_bs, long long x_cs,
+                           float* dw, int batch, int N, int K, int T, aewn_stream_t stream);
 /* g_ze (+)= g_min_dist[b,n] * d(min_dist)/d(ze)   (commitment-loss gradient) */
 int aewn_vq_commit_bwd(const float* ze, long long ze_bs, long long ze_cs, const float* emb, const long long* min_ind,
                        const float* g_min_dist, int metric, float* g_ze, long long g_bs, long long g_cs, int accumulate,

@@ -35,10 +35,12 @@ def make_params(R, D, S, Cc, dils, final_last, gen, dev):
     return params
 
 
-def reference_stack(x0, cond, params, dils, final_last, rounded):
+def reference_stack(x0, cond, params, dils, final_last, rounded, layer_inputs=None):
     """float64 restatement of the stack on the absolute time axis (wavenet.py:91-111), optionally with the
     kernel's fp16 operand roundings.  Returns per-layer (th, sg, x_next) and the skip sum; entries left of a layer's lead
-    are garbage by construction and are not compared."""
+    are garbage by construction and are not compared.  ``layer_inputs`` (the kernel's own fp32 layer inputs) makes every
+    layer an independent check: a 1-ulp flip of an fp16 operand rounding in layer l would otherwise be amplified by every
+    later layer's roundings (~2x per layer), which says nothing about layer l + 1."""
     r = h if rounded else (lambda t: t.double())
     B, R, T0 = x0.shape
     x = x0.double()
@@ -49,6 +51,8 @@ def reference_stack(x0, cond, params, dils, final_last, rounded):
         p = params[l]
         final = final_last and l == len(dils) - 1
         lead += d
+        if layer_inputs is not None:
+            x = layer_inputs[l].double()
         xs = F.pad(r(x), (d, 0))[:, :, :T0]                       # x[tau - d]
         pre = []
         for wk, pk, bk in (("conv_signal.weight", "proj_signal.weight", "conv_signal.bias"),
@@ -104,7 +108,8 @@ def test_fused_stack_matches_fp16_operand_reference(case, save):
         ops.check_device_errors()
     finally:
         ops._plans.pop("t")
-    outs, skp_ref, RF = reference_stack(x0, cond, params, dils, final_last, rounded=True)
+    outs, skp_ref, RF = reference_stack(x0, cond, params, dils, final_last, rounded=True,
+                                        layer_inputs=[plan.sig[l][:, :, :T0] for l in range(len(dils))])
     worst = {}
     last_writer = max([l for l, o in enumerate(outs) if o[2] is not None], default=-1)
     for l, (th, sg, xn, lead) in enumerate(outs):
