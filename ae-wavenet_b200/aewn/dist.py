@@ -6,6 +6,8 @@ gradients scaled by 1/world; chassis.py:187-190 xm.all_reduce of [loss, tprb] sc
 NVLink 5 / NVSwitch (backend "nccl"; "gloo" in the CPU tests).  Gradients and metrics are averaged; the EMA code
 statistics are TOTALS over all replicas, after which every rank applies the same EMA update
 (vqema_bn.py:190-195) -- identical to the single-process result up to fp32 summation order."""
+import weakref
+
 import torch
 import torch.distributed as dist
 
@@ -23,26 +25,48 @@ class FlatGradSync:
         self.n_metrics = n_metrics
         self.flat = torch.zeros(self.n_grad + self.n_z + self.n_n + n_metrics, device=dev)
         # gradients live INSIDE the flat buffer: backward writes/accumulates straight into it, no gather copy
+        self._views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self._views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self._bind(copy=False)
         if vqema is not None:
             vqema.defer_ema = True
         # fused_accumulate=True: the decoder's backward adds its weight gradients into these persistent .grad buffers
-        # with ONE launch instead of one clone + one add per parameter (ops.ACCUMULATE_INTO_GRAD).  Only for steps that
-        # run exactly one loss.backward() per forward: a caller that ALSO takes torch.autograd.grad(...) through the
-        # decoder (mfcc_inverter.py:103 before chassis.py:157) would have the weight gradients added twice, because a
-        # custom Function cannot tell which of its input gradients a particular backward call asks for.
+        # with ONE launch instead of one clone + one add per parameter.  The opt-in is recorded on THESE parameters (a
+        # weak reference to this object: it lapses when the sync object goes away) and is honoured per backward call
+        # only when that call accumulates into the parameters (ops.fused_accumulate_applies), so a caller that also
+        # takes torch.autograd.grad(...) through the decoder (mfcc_inverter.py:103 before chassis.py:157) stays correct.
         if fused_accumulate:
             from . import ops
-            ops.ACCUMULATE_INTO_GRAD = True
+            ops.mark_fused_accumulate(self.params, weakref.ref(self))
+
+    def _bind(self, copy=True):
+        """(Re-)alias every p.grad to its slice of the flat buffer.  optimizer.zero_grad() defaults to set_to_none=True
+        (the reference's loop calls it, chassis.py:151) and any `p.grad = ...` re-assignment detaches a gradient from the
+        buffer; the all-reduce would then carry stale zeros while the optimizer steps on local gradients.  A detached
+        gradient's values are copied in (copy=True) before the alias is restored."""
+        rebound = 0
+        for p, v in zip(self.params, self._views):
+            g = p.grad
+            if g is not None and g.data_ptr() == v.data_ptr() and g.shape == v.shape:
+                continue
+            if g is not None and copy:
+                v.copy_(g)
+            elif g is None and copy:
+                v.zero_()
+            p.grad = v
+            rebound += 1
+        return rebound
 
     def zero_grad(self):
+        self._bind(copy=False)
         self.flat[:self.n_grad].zero_()
 
     def sync(self, metrics=None):
         """Call after backward.  Returns the averaged metric scalars (tensor of n_metrics)."""
+        self._bind(copy=True)          # gradients that were detached from the flat buffer since zero_grad() come back in
         o = self.n_grad
         if self.vqema is not None:
             self.flat[o:o + self.n_z] = self.vqema.z_sum.reshape(-1)

@@ -293,13 +293,39 @@ def build_wgradw(acts, units, batch, err=None, tag=None, waves=1):
 
 
 # ------------------------------------------------------------------------------------------------- fused grad accumulation
-# When True (dist.FlatGradSync(..., fused_accumulate=True): a training engine that owns persistent .grad buffers and runs
-# exactly ONE loss.backward() per forward), the decoder's backward adds ALL its weight gradients into the parameters'
-# existing .grad tensors with one aewn_add_blocks launch and returns None for them -- autograd would otherwise run one
-# clone + one add kernel per parameter (~240 launches per step).  Must stay False for callers that also take
-# torch.autograd.grad(...) through the decoder (mfcc_inverter.py:103 before chassis.py:157): a custom Function cannot
-# tell which input gradients a particular backward call asks for, so the weight gradients would be added twice.
-ACCUMULATE_INTO_GRAD = False
+# Fused gradient accumulation (opt-in PER PARAMETER SET: dist.FlatGradSync(..., fused_accumulate=True) marks the
+# parameters it owns): the decoder's backward adds ALL its weight gradients into the parameters' existing .grad tensors
+# with one aewn_add_blocks launch and returns None for them -- autograd would otherwise run one clone + one add kernel
+# per parameter (~240 launches per step).  A custom Function cannot see which input gradients a particular backward
+# call asks for, but it can ask the engine: the fused path is taken only when the running graph task will execute the
+# parameters' AccumulateGrad nodes.  That is false inside torch.autograd.grad(loss, mel, retain_graph=True)
+# (mfcc_inverter.py:103) and true inside the loss.backward() that follows (chassis.py:157), so the reference's own
+# two-backward caller gets each weight gradient exactly once.  No process-global switch.
+def mark_fused_accumulate(params, owner):
+    for q in params:
+        q._aewn_fused_owner = owner
+
+
+def fused_accumulate_applies(leaves):
+    """True iff every leaf was marked by a live FlatGradSync AND the current backward pass accumulates into them."""
+    will = getattr(torch._C, "_will_engine_execute_node", None)
+    if will is None:
+        return False
+    try:
+        for q in leaves:
+            owner = getattr(q, "_aewn_fused_owner", None)
+            if owner is None or owner() is None or q.grad is None:
+                return False
+            node = getattr(q, "_aewn_acc_node", None)
+            if node is None:
+                node = q._aewn_acc_node = q.view_as(q).grad_fn.next_functions[0][0]     # the leaf's AccumulateGrad
+            if not will(node):
+                return False
+    except RuntimeError:
+        return False
+    return True
+
+
 _grad_tables = {}
 
 

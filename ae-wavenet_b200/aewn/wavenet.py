@@ -461,8 +461,10 @@ class _DecoderCoreFn(torch.autograd.Function):
         b1, b2 = ctx.post_has_bias
         views = [pviews["post1.weight"], pviews["post1.bias"] if b1 else None, pviews["post2.weight"],
                  pviews["post2.bias"] if b2 else None] + [grads[li][k] for (li, k) in ctx.keys]
-        if ops.ACCUMULATE_INTO_GRAD:
-            # training-engine mode: ONE launch adds every weight gradient into the existing .grad buffers
+        live = [leaf for v, leaf in zip(views, ctx.leaves) if v is not None]
+        if ops.fused_accumulate_applies(live):
+            # training-engine mode (FlatGradSync(fused_accumulate=True) owns these parameters and THIS backward call
+            # accumulates into them): ONE launch adds every weight gradient into the existing .grad buffers
             pairs = [(v, leaf.grad) for v, leaf in zip(views, ctx.leaves) if v is not None]
             if ops.add_into_grads(pairs):
                 return (None, g_cond[:, :, :T0].clone(), None, None, d_base.reshape(ctx.base_shape), d_bias) + \

@@ -137,29 +137,63 @@ def test_fused_rec_loss_matches_torch_log_softmax_gather():
     assert float(gq[..., -1].abs().max()) == 0.0
 
 
-def test_fused_grad_accumulation_equals_autograd_accumulation(golden_dir, monkeypatch):
-    """ops.ACCUMULATE_INTO_GRAD (the training-engine mode FlatGradSync switches on): one aewn_add_blocks launch adds every
-    weight gradient into the existing .grad buffers; must equal what autograd's per-parameter accumulation produces,
-    including accumulation over two backward passes."""
+def test_fused_grad_accumulation_equals_autograd_accumulation(golden_dir):
+    """FlatGradSync(fused_accumulate=True) marks ITS parameters: one aewn_add_blocks launch adds every weight gradient into
+    the existing .grad buffers; must equal what autograd's per-parameter accumulation produces, including accumulation
+    over two steps.  A second same-config model that never opted in keeps autograd's path (no process-global switch),
+    and the reference's own two-backward caller (autograd.grad w.r.t. the conditioning with retain_graph, then
+    loss.backward(): mfcc_inverter.py:103 + chassis.py:157) gets every weight gradient exactly ONCE."""
     import aewn
-    from aewn import ops
+    from aewn import ops, _lib
+    from aewn.dist import FlatGradSync
     g = torch.load(os.path.join(golden_dir, "wavenet_small.pt"))
-    wn = build_wavenet(g)
-    wav, lc = g["wav"].cuda(), g["lc"].cuda()
+    wav = g["wav"].cuda()
     t0, t1 = g["geo"]["trim_dec_out"]
 
-    def run(flag):
-        monkeypatch.setattr(ops, "ACCUMULATE_INTO_GRAD", flag)
-        for p in wn.parameters():
-            p.grad = torch.zeros_like(p)
-        for _ in range(2):
-            quant = wn(wav, lc, g["spk"].cuda(), g["jit"].cuda())
-            aewn.RecLoss()(quant[..., :-1], wav[:, t0:t1][..., 1:]).backward()
-        ops.check_device_errors()
-        return {k: p.grad.clone() for k, p in wn.named_parameters()}
+    def step(wn, lc, two_backward=False):
+        quant = wn(wav, lc, g["spk"].cuda(), g["jit"].cuda())
+        loss = aewn.RecLoss()(quant[..., :-1], wav[:, t0:t1][..., 1:])
+        if two_backward:
+            (lc_grad,) = torch.autograd.grad(loss, lc, retain_graph=True)
+            assert rel_err(lc_grad, g["lc_grad"]) < 2e-2
+        loss.backward()
 
-    ref, got = run(False), run(True)
+    plain = build_wavenet(g)                       # autograd accumulation
+    for p in plain.parameters():
+        p.grad = torch.zeros_like(p)
+    fused = build_wavenet(g)                       # same configuration, opted in
+    sync = FlatGradSync(fused.parameters(), fused_accumulate=True)
+    sync.zero_grad()
+    n0 = _lib.launch_count()
+    for _ in range(2):
+        step(fused, g["lc"].cuda())
+    n_fused = _lib.launch_count() - n0
+    for _ in range(2):
+        step(plain, g["lc"].cuda())
+    ops.check_device_errors()
+    ref = {k: p.grad.clone() for k, p in plain.named_parameters()}
+    got = {k: p.grad.clone() for k, p in fused.named_parameters()}
     for k in ref:
         scale = max(float(ref[k].abs().max()), 1e-12)
         assert float((got[k] - ref[k]).abs().max()) <= 1e-4 * scale, k      # fp32 atomics: order differs run to run
     assert rel_err(got["conv_layers.0.conv_signal.weight"], 2 * g["grads"]["conv_layers.0.conv_signal.weight"]) < 0.15
+    for k, p in fused.named_parameters():                                   # still views of the flat buffer
+        assert p.grad.data_ptr() >= sync.flat.data_ptr() and p.grad.data_ptr() < sync.flat.data_ptr() + 4 * sync.flat.numel()
+    # the two-backward caller on the opted-in model: weight gradients of ONE step, not two
+    sync.zero_grad()
+    lc = g["lc"].cuda().requires_grad_(True)
+    step(fused, lc, two_backward=True)
+    ops.check_device_errors()
+    for k, p in fused.named_parameters():
+        scale = max(float(ref[k].abs().max()), 1e-12)
+        assert float((p.grad - 0.5 * ref[k]).abs().max()) <= 1e-3 * scale, k
+    # optimizer.zero_grad(set_to_none=True) (chassis.py:151) detaches the gradients; the next sync re-attaches them
+    for p in fused.parameters():
+        p.grad = None
+    step(fused, g["lc"].cuda())
+    sync.sync()
+    for k, p in fused.named_parameters():
+        scale = max(float(ref[k].abs().max()), 1e-12)
+        assert p.grad.data_ptr() >= sync.flat.data_ptr()
+        assert float((p.grad - 0.5 * ref[k]).abs().max()) <= 1e-3 * scale, k
+    assert n_fused > 0
