@@ -318,7 +318,8 @@ def fused_accumulate_applies(leaves):
                 return False
             node = getattr(q, "_aewn_acc_node", None)
             if node is None:
-                node = q._aewn_acc_node = q.view_as(q).grad_fn.next_functions[0][0]     # the leaf's AccumulateGrad
+                with torch.enable_grad():       # (backward runs with grad mode off: view_as would have no grad_fn)
+                    node = q._aewn_acc_node = q.view_as(q).grad_fn.next_functions[0][0]     # the leaf's AccumulateGrad
             if not will(node):
                 return False
     except RuntimeError:

