@@ -29,14 +29,14 @@ namespace aewn {
 
 constexpr int GF_BM = 128;
 constexpr int GF_KB = 64;                         // K elements per ring stage: 64 fp16 = one 128-byte swizzle row
-constexpr int GF_STAGES = 4;
+constexpr int GF_STAGES = 3;                      // 3 x 32 KB ring + 64 KB z + 64 KB staging = 224 KB
 constexpr int GF_A_BYTES = GF_BM * 128;           // 16 KB: 128 time rows x 128 B
 constexpr int GF_W_BYTES = 128 * 128;             // 16 KB: 128 weight rows x 128 B (this CTA's half of the N rows)
 constexpr int GF_STAGE_BYTES = GF_A_BYTES + GF_W_BYTES;
 constexpr int GF_MAX_D = 256;
 constexpr int GF_ZBUF_BYTES = (GF_MAX_D / GF_KB) * GF_A_BYTES;   // 64 KB: z of this CTA's 128 time rows, all D channels
-constexpr int GF_THREADS = 384;
-constexpr int GF_EPI_WARPS = 8;
+constexpr int GF_THREADS = 640;                  // 4 control warps + 16 epilogue warps
+constexpr int GF_EPI_WARPS = 16;
 constexpr int GF_STG_BYTES = GF_EPI_WARPS * 4096;
 constexpr int GF_RING_BYTES = GF_STAGES * GF_STAGE_BYTES;
 constexpr int GF_SMEM_BYTES = GF_RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES + 256 + 1024;
@@ -54,7 +54,9 @@ struct GfJob {
 
 struct GfParams {
   CUtensorMap xa, ca, w1, w2;             // operand loads (fp16)
-  CUtensorMap th_m, sg_m, z_m, xo_m, skp_m;   // fp32 (t, ch, b) outputs, box {32, 32, 1}
+  CUtensorMap th_m, sg_m, z_m, xo_m, skp_m;   // fp32 (t, ch, b) outputs, box {32 t, 16 ch, 1}
+  CUtensorMap xr_m;                          // fp32 residual source, box {128 t, 32 ch, 1}: L2 prefetch only
+  int prefetch;
   GfJob job[GF_MAX_JOBS];
   int n_jobs, n_gate;
   int kb_x, kb_c, kb_z;                   // ring stages per x tap, for cond, for z
@@ -69,7 +71,7 @@ struct GfParams {
   float* skp;
   long long s_bs, s_cs;
   int save, z_out, skp_mode;               // skp_mode: 0 store, 1 reduce-add, 2 relu(old + acc), 3 relu(acc)
-  int batch, t_begin, n_tgroups;
+  int batch, t_begin, n_tgroups, n_res;
   int t_lo, t_zero_lo, t_hi, skp_t_lo, skp_zero_lo;
   int* err;
 };
@@ -94,8 +96,22 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   return r;
 }
 
-__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+// TMEM -> registers: 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Pull one box of a tensor into L2 (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 
 struct GfItem {
@@ -111,21 +127,6 @@ __device__ __forceinline__ GfItem gf_decode(const GfParams& p, int item, int cra
   it.tau0 = it.g0 + crank * GF_BM;
   it.do_skp = it.g0 + 2 * GF_BM > p.skp_t_lo;   // decided per GROUP: both CTAs walk the same job sequence
   return it;
-}
-
-// one 4 KB staging tile per epilogue warp: [32 channels][32 time steps] fp32, element (j, lane) at j*32 + lane
-__device__ __forceinline__ void gf_stg_wait() {
-  if (elect_one()) tma_store_wait_read();
-  __syncwarp();
-}
-__device__ __forceinline__ void gf_stg_flush(const CUtensorMap* map, const float* tile, int t0, int c0, int b, bool reduce) {
-  fence_proxy_async_smem();
-  __syncwarp();
-  if (elect_one()) {
-    if (reduce) tma_reduce_add_3d(map, tile, t0, c0, b);
-    else tma_store_3d(map, tile, t0, c0, b);
-    tma_store_commit();
-  }
 }
 
 __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_constant__ GfParams p) {
@@ -189,6 +190,12 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
       const uint32_t lead_full = mapa_u32(&full_bar[0], 0);
       for (int item = cid; item < total && ok; item += n_cl) {
         const GfItem it = gf_decode(p, item, crank);
+        // the residual rows this tile's RES epilogues will add (128 time steps x R channels of x32): pull them into L2
+        // now, ~20 k cycles before the epilogue warps load them
+        if (p.prefetch && elect_one()) {
+          for (int c = 0; c < p.n_res; c += 32) tma_prefetch_l2_3d(&p.xr_m, it.tau0, c, it.b);
+        }
+        __syncwarp();
         for (int jb = 0; jb < p.n_jobs && ok; ++jb) {
           const GfJob jd = p.job[jb];
           if (jd.kind == GF_SKP && !it.do_skp) continue;
@@ -271,12 +278,32 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
       }
     }
   } else {
-    reg_alloc<232>();
-    // ===================================================== epilogue (both CTAs)
+    reg_alloc<104>();
+    // ===================================================== epilogue (both CTAs): 16 warps, 4 per TMEM lane quadrant
+    // Warp (q, h): TMEM lanes [32q, 32q+32) = time rows, a quarter of every job's columns, in chunks of 16 columns
+    // (104 registers per thread: 640 threads share the 64 K register file).  fp32 outputs go through two 2 KB half-tiles
+    // per warp ([16 channels][32 time steps], alternating: the box of store k is written while the TMA engine still reads
+    // store k-1) and leave as TMA stores / reduce-adds of {32 t, 16 ch} boxes.
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int h = (warp - 4) >> 2;
     const int row = q * 32 + lane;
-    float* tile = stg_base + (warp - 4) * 1024;
+    float* const tile2 = stg_base + (warp - 4) * 1024;
+    uint32_t stg_cur = 0;
+    auto stg_acquire = [&]() -> float* {
+      stg_cur ^= 1u;
+      if (elect_one()) tma_store_wait_read1();   // all but the latest box have been read out: the older half is free
+      __syncwarp();
+      return tile2 + stg_cur * 512 + lane;
+    };
+    auto stg_flush = [&](const CUtensorMap* map, int t0, int c0, int b, bool reduce) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        if (reduce) tma_reduce_add_3d(map, tile2 + stg_cur * 512, t0, c0, b);
+        else tma_store_3d(map, tile2 + stg_cur * 512, t0, c0, b);
+        tma_store_commit();
+      }
+    };
     const uint32_t lead_tempty = mapa_u32(&tempty_bar[0], 0);
     const uint32_t lead_zready = mapa_u32(zready_bar, 0);
     uint32_t acc = 0, acc_phase = 0;
@@ -297,18 +324,23 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
 #pragma unroll 1
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c0 = half * 32 + cc * 64;
-            uint32_t vf[32], vg[32];
-            tmem_ld32(taddr + c0, vf);
-            tmem_ld32(taddr + 128 + c0, vg);
+          for (int i = 0; i < 2; ++i) {
+            const int c0 = 32 * h + 16 * i;            // z channels [c0, c0 + 16) of this 128-channel block
+            uint32_t vf[16], vg[16];
+            tmem_ld16(taddr + c0, vf);
+            tmem_ld16(taddr + 128 + c0, vg);
             tmem_ld_wait();
+            // tanh(f) = (1 - a) / (1 + a), a = e^(-2f); sigmoid(g) = 1 / (1 + b), b = e^(-g): ONE reciprocal of
+            // (1 + a)(1 + b) serves both (3 MUFU ops per element instead of 4; the exponents are clamped so that the
+            // product stays finite: 2^60 * 2^60)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float th = keep ? fast_tanh(__uint_as_float(vf[j])) : 0.0f;
-              const float sg = keep ? fast_sigmoid(__uint_as_float(vg[j])) : 0.0f;
-              vf[j] = __float_as_uint(th);
-              vg[j] = __float_as_uint(sg);
+            for (int j = 0; j < 16; ++j) {
+              const float ea = ex2_ftz(fminf(-2.8853900817779268f * __uint_as_float(vf[j]), 60.0f));
+              const float eb = ex2_ftz(fminf(-1.4426950408889634f * __uint_as_float(vg[j]), 60.0f));
+              const float pa = 1.0f + ea, pb = 1.0f + eb;
+              const float inv = rcp_ftz(pa * pb);
+              vf[j] = __float_as_uint(keep ? (1.0f - ea) * pb * inv : 0.0f);
+              vg[j] = __float_as_uint(keep ? pa * inv : 0.0f);
             }
             // z -> fp16 -> zbuf: K-major rows of 128 B (64 channels), 16-byte chunk index XOR (row & 7) = SWIZZLE_128B
             const int ch = jd.ch0 + c0;
@@ -316,35 +348,35 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               uint8_t* zrow = zbuf + (ch >> 6) * GF_A_BYTES + row * 128;
               const int lc0 = (ch & 63) >> 3;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
+              for (int k = 0; k < 2; ++k) {
                 uint4 v;
-                v.x = pack_f16x2(__uint_as_float(vf[8 * i + 0]) * __uint_as_float(vg[8 * i + 0]),
-                                 __uint_as_float(vf[8 * i + 1]) * __uint_as_float(vg[8 * i + 1]));
-                v.y = pack_f16x2(__uint_as_float(vf[8 * i + 2]) * __uint_as_float(vg[8 * i + 2]),
-                                 __uint_as_float(vf[8 * i + 3]) * __uint_as_float(vg[8 * i + 3]));
-                v.z = pack_f16x2(__uint_as_float(vf[8 * i + 4]) * __uint_as_float(vg[8 * i + 4]),
-                                 __uint_as_float(vf[8 * i + 5]) * __uint_as_float(vg[8 * i + 5]));
-                v.w = pack_f16x2(__uint_as_float(vf[8 * i + 6]) * __uint_as_float(vg[8 * i + 6]),
-                                 __uint_as_float(vf[8 * i + 7]) * __uint_as_float(vg[8 * i + 7]));
-                *reinterpret_cast<uint4*>(zrow + (((lc0 + i) ^ (row & 7)) << 4)) = v;
+                v.x = pack_f16x2(__uint_as_float(vf[8 * k + 0]) * __uint_as_float(vg[8 * k + 0]),
+                                 __uint_as_float(vf[8 * k + 1]) * __uint_as_float(vg[8 * k + 1]));
+                v.y = pack_f16x2(__uint_as_float(vf[8 * k + 2]) * __uint_as_float(vg[8 * k + 2]),
+                                 __uint_as_float(vf[8 * k + 3]) * __uint_as_float(vg[8 * k + 3]));
+                v.z = pack_f16x2(__uint_as_float(vf[8 * k + 4]) * __uint_as_float(vg[8 * k + 4]),
+                                 __uint_as_float(vf[8 * k + 5]) * __uint_as_float(vg[8 * k + 5]));
+                v.w = pack_f16x2(__uint_as_float(vf[8 * k + 6]) * __uint_as_float(vg[8 * k + 6]),
+                                 __uint_as_float(vf[8 * k + 7]) * __uint_as_float(vg[8 * k + 7]));
+                *reinterpret_cast<uint4*>(zrow + (((lc0 + k) ^ (row & 7)) << 4)) = v;
               }
             }
             if (slab_on) {
               if (p.save) {
-                gf_stg_wait();
+                float* st = stg_acquire();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tile[j * 32 + lane] = __uint_as_float(vf[j]);
-                gf_stg_flush(&p.th_m, tile, slab0, ch, it.b, false);
-                gf_stg_wait();
+                for (int j = 0; j < 16; ++j) st[j * 32] = __uint_as_float(vf[j]);
+                stg_flush(&p.th_m, slab0, ch, it.b, false);
+                st = stg_acquire();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tile[j * 32 + lane] = __uint_as_float(vg[j]);
-                gf_stg_flush(&p.sg_m, tile, slab0, ch, it.b, false);
+                for (int j = 0; j < 16; ++j) st[j * 32] = __uint_as_float(vg[j]);
+                stg_flush(&p.sg_m, slab0, ch, it.b, false);
               }
               if (p.z_out) {
-                gf_stg_wait();
+                float* st = stg_acquire();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tile[j * 32 + lane] = __uint_as_float(vf[j]) * __uint_as_float(vg[j]);
-                gf_stg_flush(&p.z_m, tile, slab0, ch, it.b, false);
+                for (int j = 0; j < 16; ++j) st[j * 32] = __uint_as_float(vf[j]) * __uint_as_float(vg[j]);
+                stg_flush(&p.z_m, slab0, ch, it.b, false);
               }
             }
           }
@@ -352,84 +384,82 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (crank != 0) {
-              mbar_arrive_cluster_release(lead_zready);
-              mbar_arrive_cluster(lead_tempty + acc * 8u);
-            } else {
-              mbar_arrive_cluster_release(lead_zready);
-              mbar_arrive(&tempty_bar[acc]);
-            }
+            mbar_arrive_cluster(lead_zready);
+            if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+            else mbar_arrive(&tempty_bar[acc]);
           }
         } else if (jd.kind == GF_RES) {
-          // x_next = acc + x (wavenet.py:108); fp32 through the staging tile + TMA store, fp16 channels-last copy with
-          // 16-byte stores (lane = time row: 64 contiguous bytes per 32 channels), optional shifted fp32 duplicate
+          // x_next = acc + x (wavenet.py:108).  fp32 through the staging half-tiles + TMA stores; fp16 channels-last copy
+          // with 16-byte stores (lane = time row: 32 contiguous bytes per 16 channels); optional shifted fp32 duplicate.
+          // The residual rows were pulled into L2 by the producer warp's bulk prefetch at the start of the tile.
+          const int span = ((jd.n + 63) >> 6) << 4;          // columns per warp: 64 for n = 256, 32 for n = 112
+          const int cb = h * span;
+          const int ce = min(cb + span, jd.n);
+          const int nv = jd.n_valid;
           const float* xsrc = p.x32 + static_cast<long long>(it.b) * p.x_bs + static_cast<long long>(jd.ch0) * p.x_cs + tau;
           __half* x16row = p.xo16 + static_cast<long long>(it.b) * p.x16_bs + static_cast<long long>(tau) * p.x16_cp + jd.ch0;
           const int dup_t = tau + p.dup_toff;
           float* dupp = (p.dup && in_range && dup_t >= 0 && dup_t < p.dup_t_hi)
                             ? p.dup + static_cast<long long>(it.b) * p.x_bs + static_cast<long long>(jd.ch0) * p.x_cs + dup_t
                             : nullptr;
-          const int nv = jd.n_valid;
-          // sub-chunk i of this warp: columns c0(i) = 64 * (half + 2 * (i / 2)) + 32 * (i % 2)
-          float bufA[32], bufB[32];
-          auto issue = [&](int c0, float (&buf)[32]) {
-            const float* s = xsrc + static_cast<long long>(c0) * p.x_cs;
+          float bufA[16], bufB[16];
+          auto issue = [&](int c0, float (&buf)[16]) {
+            const float* sp = xsrc + static_cast<long long>(c0) * p.x_cs;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              buf[j] = (keep && c0 + j < nv) ? __ldcg(s) : 0.0f;
-              s += p.x_cs;
+            for (int j = 0; j < 16; ++j) {
+              buf[j] = (keep && c0 + j < nv) ? __ldcg(sp) : 0.0f;
+              sp += p.x_cs;
             }
           };
-          auto col_of = [&](int i) { return 64 * (half + 2 * (i >> 1)) + 32 * (i & 1); };
-          if (col_of(0) < nv) issue(col_of(0), bufA);
-          if (col_of(1) < nv) issue(col_of(1), bufB);
+          if (cb < ce) issue(cb, bufA);
+          if (cb + 16 < ce) issue(cb + 16, bufB);
           if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          auto chunk = [&](int c0, float (&buf)[32]) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c0, v);
+          auto chunk = [&](int c0, float (&buf)[16]) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
-            float r[32];
+            float r[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
               r[j] = (keep && c0 + j < nv) ? __uint_as_float(v[j]) + buf[j] : 0.0f;
               xmax = fmaxf(xmax, fabsf(r[j]));
             }
             if (slab_on) {
-              gf_stg_wait();
+              float* st = stg_acquire();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) tile[j * 32 + lane] = r[j];
-              gf_stg_flush(&p.xo_m, tile, slab0, jd.ch0 + c0, it.b, false);
+              for (int j = 0; j < 16; ++j) st[j * 32] = r[j];
+              stg_flush(&p.xo_m, slab0, jd.ch0 + c0, it.b, false);
             }
             if (dupp) {
               float* dd = dupp + static_cast<long long>(c0) * p.x_cs;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
+              for (int j = 0; j < 16; ++j) {
                 if (c0 + j < nv) *dd = r[j];
                 dd += p.x_cs;
               }
             }
             if (in_range) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (c0 + 8 * i < nv) {
-                  uint4 h;
-                  h.x = pack_f16x2(r[8 * i + 0], r[8 * i + 1]);
-                  h.y = pack_f16x2(r[8 * i + 2], r[8 * i + 3]);
-                  h.z = pack_f16x2(r[8 * i + 4], r[8 * i + 5]);
-                  h.w = pack_f16x2(r[8 * i + 6], r[8 * i + 7]);
-                  *reinterpret_cast<uint4*>(x16row + c0 + 8 * i) = h;
+              for (int k = 0; k < 2; ++k) {
+                if (c0 + 8 * k < nv) {
+                  uint4 hv;
+                  hv.x = pack_f16x2(r[8 * k + 0], r[8 * k + 1]);
+                  hv.y = pack_f16x2(r[8 * k + 2], r[8 * k + 3]);
+                  hv.z = pack_f16x2(r[8 * k + 4], r[8 * k + 5]);
+                  hv.w = pack_f16x2(r[8 * k + 6], r[8 * k + 7]);
+                  *reinterpret_cast<uint4*>(x16row + c0 + 8 * k) = hv;
                 }
               }
             }
           };
 #pragma unroll 1
-          for (int i = 0; col_of(i) < jd.n; i += 2) {
-            chunk(col_of(i), bufA);
-            if (col_of(i + 2) < nv) issue(col_of(i + 2), bufA);
-            if (col_of(i + 1) < jd.n) {
-              chunk(col_of(i + 1), bufB);
-              if (col_of(i + 3) < nv) issue(col_of(i + 3), bufB);
+          for (int c0 = cb; c0 < ce; c0 += 32) {
+            chunk(c0, bufA);
+            if (c0 + 32 < ce) issue(c0 + 32, bufA);
+            if (c0 + 16 < ce) {
+              chunk(c0 + 16, bufB);
+              if (c0 + 48 < ce) issue(c0 + 48, bufB);
             }
           }
           tc_fence_before();
@@ -441,6 +471,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         } else {
           // skip sum (wavenet.py:104,110-111 + the caller's running sum): store (first layer), reduce-add in L2, or
           // relu(old + acc) for the last layer (wavenet.py:359)
+          const int span = ((jd.n + 63) >> 6) << 4;
+          const int cb = h * span;
+          const int ce = min(cb + span, jd.n);
           const bool s_in = tau >= p.skp_t_lo && tau < p.t_hi;
           const bool s_keep = s_in && tau >= p.skp_zero_lo;
           const bool s_slab = (slab0 + 32 > p.skp_t_lo) && (slab0 < p.t_hi);
@@ -448,32 +481,31 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
 #pragma unroll 1
-          for (int c0 = half * 32; c0 < jd.n; c0 += 64) {
-            uint32_t v[32];
-            float o[32];
+          for (int c0 = cb; c0 < ce; c0 += 16) {
+            uint32_t v[16];
+            float o[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = 0.0f;
+            for (int j = 0; j < 16; ++j) o[j] = 0.0f;
             if (p.skp_mode == 2) {
-              const float* s = old + static_cast<long long>(c0) * p.s_cs;
+              const float* sp = old + static_cast<long long>(c0) * p.s_cs;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                o[j] = (s_keep && c0 + j < jd.n_valid) ? __ldcg(s) : 0.0f;
-                s += p.s_cs;
+              for (int j = 0; j < 16; ++j) {
+                o[j] = (s_keep && c0 + j < jd.n_valid) ? __ldcg(sp) : 0.0f;
+                sp += p.s_cs;
               }
             }
-            tmem_ld32(taddr + c0, v);
+            tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
             if (s_slab) {
-              gf_stg_wait();
+              float* st = stg_acquire();
               if (p.skp_mode >= 2) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  tile[j * 32 + lane] = s_keep ? fmaxf(__uint_as_float(v[j]) + o[j], 0.0f) : 0.0f;
+                for (int j = 0; j < 16; ++j) st[j * 32] = s_keep ? fmaxf(__uint_as_float(v[j]) + o[j], 0.0f) : 0.0f;
               } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tile[j * 32 + lane] = s_keep ? __uint_as_float(v[j]) : 0.0f;
+                for (int j = 0; j < 16; ++j) st[j * 32] = s_keep ? __uint_as_float(v[j]) : 0.0f;
               }
-              gf_stg_flush(&p.skp_m, tile, slab0, jd.ch0 + c0, it.b, p.skp_mode == 1);
+              stg_flush(&p.skp_m, slab0, jd.ch0 + c0, it.b, p.skp_mode == 1);
             }
           }
           tc_fence_before();
@@ -619,16 +651,20 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
     if ((rc = encode_f16_map(&p.w2, d->w2h, 2, dw2, sw2, bw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w2h"))) return rc;
   }
   if (d->save) {
-    if ((rc = encode_out_map(&p.th_m, d->th, d->t_hi, D, d->batch, d->a_cs, d->a_bs))) return rc;
-    if ((rc = encode_out_map(&p.sg_m, d->sg, d->t_hi, D, d->batch, d->a_cs, d->a_bs))) return rc;
+    if ((rc = encode_out_map(&p.th_m, d->th, d->t_hi, D, d->batch, d->a_cs, d->a_bs, 16))) return rc;
+    if ((rc = encode_out_map(&p.sg_m, d->sg, d->t_hi, D, d->batch, d->a_cs, d->a_bs, 16))) return rc;
   }
   if (d->z) {
-    if ((rc = encode_out_map(&p.z_m, d->z, d->t_hi, D, d->batch, d->a_cs, d->a_bs))) return rc;
+    if ((rc = encode_out_map(&p.z_m, d->z, d->t_hi, D, d->batch, d->a_cs, d->a_bs, 16))) return rc;
   }
   if (!d->final_layer) {
-    if ((rc = encode_out_map(&p.xo_m, d->xo32, d->t_hi, R, d->batch, d->x_cs, d->x_bs))) return rc;
+    if ((rc = encode_out_map(&p.xo_m, d->xo32, d->t_hi, R, d->batch, d->x_cs, d->x_bs, 16))) return rc;
+    if ((rc = encode_out_map(&p.xr_m, const_cast<float*>(d->x32), d->t_hi, R, d->batch, d->x_cs, d->x_bs, 32, 128))) return rc;
+    static const int pf = []() { const char* e = getenv("AEWN_GF_PREFETCH"); return e ? atoi(e) : 1; }();
+    p.prefetch = pf;
+    p.n_res = R;
   }
-  if ((rc = encode_out_map(&p.skp_m, d->skp, d->t_hi, S, d->batch, d->s_cs, d->s_bs))) return rc;
+  if ((rc = encode_out_map(&p.skp_m, d->skp, d->t_hi, S, d->batch, d->s_cs, d->s_bs, 16))) return rc;
 
   int nj = 0;
   for (int j = 0; j < D / 128; ++j) p.job[nj++] = GfJob{GF_GATE, 256 * j, 256, 128, 128 * j};

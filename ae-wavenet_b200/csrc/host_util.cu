@@ -89,14 +89,14 @@ int encode_act_map(CUtensorMap* map, const aewn_act& a, int box_rows, CUtensorMa
 }
 
 int encode_out_map(CUtensorMap* map, float* ptr, int t_extent, int channels, int batch, long long row_pitch,
-                   long long batch_stride) {
+                   long long batch_stride, int box_rows, int box_t) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_err(AEWN_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(t_extent), static_cast<cuuint64_t>(channels),
                         static_cast<cuuint64_t>(batch)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_pitch) * 4u, static_cast<cuuint64_t>(batch_stride) * 4u};
   if (strides[1] < strides[0] * dims[1]) strides[1] = strides[0] * dims[1];
-  cuuint32_t box[3] = {32u, 32u, 1u};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_t), static_cast<cuuint32_t>(box_rows), 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

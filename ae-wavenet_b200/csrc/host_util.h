@@ -20,9 +20,10 @@ int sm_count();
 // 3-D fp32 activation map over (time, channel, batch); box = {32 time, box_rows channels, 1}.
 // swizzle: CU_TENSOR_MAP_SWIZZLE_128B (K-major operand) or CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (MN-major tf32).
 int encode_act_map(CUtensorMap* map, const aewn_act& a, int box_rows, CUtensorMapSwizzle swz);
-// 3-D fp32 OUTPUT map over (time, channel, batch) for TMA stores / reduce-adds; box = {32 time, 32 channels, 1}, no swizzle.
+// 3-D fp32 OUTPUT map over (time, channel, batch) for TMA stores / reduce-adds (and L2 prefetches); box = {box_t time,
+// box_rows channels, 1}, no swizzle.
 int encode_out_map(CUtensorMap* map, float* ptr, int t_extent, int channels, int batch, long long row_pitch,
-                   long long batch_stride);
+                   long long batch_stride, int box_rows = 32, int box_t = 32);
 // 2-D K-major weight map [rows][kpad]; box = {32 k, box_rows}.
 int encode_w_map(CUtensorMap* map, const float* w, int rows, int kpad, int box_rows);
 
