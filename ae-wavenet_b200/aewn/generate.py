@@ -224,14 +224,17 @@ _plans = {}
 
 
 def get_plan(wn, n_rep):
-    """Plans are cached per module and invalidated when any parameter is modified in place or re-assigned."""
-    ver = tuple((p.data_ptr(), p._version) for p in wn.parameters())
+    """Plans (descriptors, workspaces) are cached per module and parameter storage.  The packed weight stream is REBUILT
+    from the live parameters on every call (a few hundred small copies, ~ms, against thousands of generated samples):
+    an optimizer step or `p.data.copy_()` between two generations changes the weights without bumping `p._version`."""
+    ptrs = tuple(p.data_ptr() for p in wn.parameters())
     key = (id(wn), int(n_rep))
     hit = _plans.get(key)
-    if hit is not None and hit[0] == ver:
+    if hit is not None and hit[0] == ptrs:
+        hit[1]._pack(wn)
         return hit[1]
     if len(_plans) > 4:
-        _plans.clear()
+        _plans.pop(next(iter(_plans)))
     plan = GenPlan(wn, n_rep)
-    _plans[key] = (ver, plan)
+    _plans[key] = (ptrs, plan)
     return plan

@@ -6,6 +6,7 @@ Time axis convention ("absolute time"): all activations of one deco
 on ONE time axis tau in [0, T0); layer l (dilation d_l) produces valid values for tau >= lead_l = sum_{j<=l} d_j and
 reads x[tau - d_l] and x[tau] (wavenet.py:100: Conv1d is a cross-correlation, tap 0 <-> x[t], tap 1 <-> x[t+d]).
 """
+import collections
 import ctypes as C
 import os
 
@@ -979,20 +980,23 @@ class PostPlan:
         return bw["views"]
 
 
-_plans = {}
+_plans = collections.OrderedDict()
+MAX_PLANS = int(os.environ.get("AEWN_MAX_PLANS", "4"))
 
 
 def get_plan(B, R, D, S, Cc, geom, params, device, relu_last):
-    """params: list (per layer) of dicts of the live parameter tensors."""
-    key = (B, R, D, S, Cc, geom.key(), str(device), bool(relu_last))
+    """params: list (per layer) of dicts of the live parameter tensors.  Plans are cached per (configuration, parameter
+    set) in a small LRU: two same-shaped models, or a train window alternating with an eval window, each keep their
+    workspace; the least recently used plan is dropped when a new one is needed (its memory returns to PyTorch's
+    caching allocator -- no empty_cache(), which would fail inside a CUDA-graph capture)."""
+    key = (B, R, D, S, Cc, geom.key(), str(device), bool(relu_last), StackPlan._ptrs(params), FUSED_FWD)
     plan = _plans.get(key)
-    if plan is not None and not plan.matches(params):
-        plan = None                                  # parameters were re-allocated (e.g. .to(device)): rebuild
-    if plan is None:
-        if len(_plans) >= 2:                         # bound the cache: configurations rarely alternate
-            _plans.clear()
-            torch.cuda.empty_cache()
-        plan = _plans[key] = StackPlan(B, R, D, S, Cc, geom, params, device, relu_last)
+    if plan is not None:
+        _plans.move_to_end(key)
+        return plan
+    while len(_plans) >= max(1, MAX_PLANS):
+        _plans.popitem(last=False)
+    plan = _plans[key] = StackPlan(B, R, D, S, Cc, geom, params, device, relu_last)
     return plan
 
 
@@ -1005,7 +1009,7 @@ def check_device_errors():
         if e != 0:
             w.zero_()
             raise RuntimeError(f"aewn: device-side error word = {e} "
-                               f"({'bounded wait timed out' if e == L.ERR_TIMEOUT else 'invalid input'})")
+                               f"({'bounded wait timed out' if e == L.ERR_TIMEOUT else 'activation outside the fp16 operand range of the fused layer kernel' if e == L.ERR_RANGE else 'invalid input'})")
 
 
 # ------------------------------------------------------------------------------------------------- generic convs

@@ -419,13 +419,22 @@ class _DecoderCoreFn(torch.autograd.Function):
                 L.C.c_longlong(plan.sig[0].stride(1)), L.C.c_void_p(dup.data_ptr() if dup is not None else None),
                 L.C.c_int(d0), L.C.c_int(T0), L.C.c_int(B), L.C.c_int(R), L.C.c_int(Q), L.C.c_int(T0),
                 L.C.c_void_p(plan.err.data_ptr()), ops._stream()), "aewn_base_embed_fwd")
-            plan.forward(save=True)
+            # under torch.no_grad() (or with nothing upstream requiring a gradient) nothing is kept for a backward pass:
+            # the layers run in inference mode (no tanh / sigmoid / z writes: SURVEY.md 8d's inference byte count)
+            save = any(ctx.needs_input_grad)
+            plan.forward(save=save)
             pw = {"post1.weight": p1w, "post1.bias": p1b if p1b.numel() else None, "post2.weight": p2w,
                   "post2.bias": p2b if p2b.numel() else None}
             post = getattr(plan, "post", None)
             if post is None or not post.matches(pw):
                 post = plan.post = ops.PostPlan(plan, pw)
-            out = post.forward()[:, :, geom.RF:T0]       # (B, Q, W) view of a fresh (B, Q, Tp) buffer
+            logits = post.forward()
+            # a device-side fault (bounded wait expired, mu-law code outside [0, Q), activation outside the fp16 operand
+            # range) must not go unnoticed until somebody calls ops.check_device_errors(): poison ONE logit, so that the
+            # loss of this step is NaN (two 1-element kernels, no synchronisation, capturable)
+            logits[0, 0, geom.RF:geom.RF + 1] += torch.where(plan.err != 0, float("nan"), 0.0).to(logits.dtype)
+            out = logits[:, :, geom.RF:T0]               # (B, Q, W) view of a fresh (B, Q, Tp) buffer
+        ctx.saved_for_bwd = save
         ctx.post = post
         ctx.post_has_bias = (p1b.numel() > 0, p2b.numel() > 0)
         ctx.plan, ctx.keys = plan, keys
