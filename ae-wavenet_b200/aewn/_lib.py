@@ -95,7 +95,7 @@ class GrccFwdDesc(C.Structure):
                 ("batch", C.c_int), ("R", C.c_int), ("D", C.c_int), ("S", C.c_int), ("n_cond1", C.c_int),
                 ("dil", C.c_int), ("final_layer", C.c_int), ("t_lo", C.c_int), ("t_zero_lo", C.c_int),
                 ("t_hi", C.c_int), ("skp_t_lo", C.c_int), ("skp_zero_lo", C.c_int), ("err", C.c_void_p),
-                ("max_ctas", C.c_int)]
+                ("max_ctas", C.c_int), ("dbg_clock", C.c_void_p)]
 
 
 GEN_MAX_LAYERS = 64

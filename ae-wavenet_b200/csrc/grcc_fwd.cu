@@ -74,6 +74,7 @@ struct GfParams {
   int batch, t_begin, n_tgroups, n_res;
   int t_lo, t_zero_lo, t_hi, skp_t_lo, skp_zero_lo;
   int* err;
+  long long* dbg_clock;   // optional: cluster 0 / CTA 0 stamps its first items (profiles/gf_phase_clock.py)
 };
 
 __device__ __forceinline__ void umma_f16_ss_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -237,6 +238,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           for (int jb = 0; jb < p.n_jobs && ok; ++jb) {
             const GfJob jd = p.job[jb];
             if (jd.kind == GF_SKP && !it.do_skp) continue;
+            const bool stamp = p.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && lane == 0;
+            long long* ck = p.dbg_clock + ((item / n_cl) * GF_MAX_JOBS + jb) * 3;
+            if (stamp) ck[0] = clock64();
             if (!mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) { ok = false; break; }
             if (jd.kind != GF_GATE && !z_waited) {
               // every epilogue warp of the pair has written its z columns of this tile (generic proxy -> fence -> arrive)
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               z_waited = true;
             }
             tc_fence_after();
+            if (stamp) ck[1] = clock64();
             const uint32_t d_tmem = tmem_base + acc * 256u;
             const uint32_t idesc = make_idesc_f16(2 * GF_BM, jd.n);
             const int nst = jd.kind == GF_GATE ? g1_stages : p.kb_z;
@@ -267,6 +272,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             if (!ok) break;
             if (elect_one()) umma_commit_pair(&tfull_bar[acc], 0x3);
             __syncwarp();
+            if (stamp) ck[2] = clock64();
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
           }
           // a tile whose skip job was skipped still has to consume the z phase (the epilogues always arrive)
@@ -320,9 +326,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         const GfJob jd = p.job[jb];
         if (jd.kind == GF_SKP && !it.do_skp) continue;
         const uint32_t taddr = tmem_base + acc * 256u + (static_cast<uint32_t>(q * 32) << 16);
+        const bool stamp = p.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && warp == 4 && lane == 0;
+        long long* ck = p.dbg_clock + 4 * GF_MAX_JOBS * 3 + ((item / n_cl) * GF_MAX_JOBS + jb) * 3;
+        if (stamp) ck[0] = clock64();
         if (jd.kind == GF_GATE) {
           if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
+          if (stamp) ck[1] = clock64();
 #pragma unroll 1
           for (int i = 0; i < 2; ++i) {
             const int c0 = 32 * h + 16 * i;            // z channels [c0, c0 + 16) of this 128-channel block
@@ -415,6 +425,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           if (cb + 16 < ce) issue(cb + 16, bufB);
           if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
+          if (stamp) ck[1] = clock64();
           auto chunk = [&](int c0, float (&buf)[16]) {
             uint32_t v[16];
             tmem_ld16(taddr + c0, v);
@@ -480,6 +491,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           const float* old = p.skp + static_cast<long long>(it.b) * p.s_bs + static_cast<long long>(jd.ch0) * p.s_cs + tau;
           if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
+          if (stamp) ck[1] = clock64();
 #pragma unroll 1
           for (int c0 = cb; c0 < ce; c0 += 16) {
             uint32_t v[16];
@@ -515,6 +527,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             else mbar_arrive(&tempty_bar[acc]);
           }
         }
+        if (stamp) ck[2] = clock64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -709,6 +722,7 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   p.skp_t_lo = d->skp_t_lo;
   p.skp_zero_lo = d->skp_zero_lo;
   p.err = d->err;
+  p.dbg_clock = d->dbg_clock;
   if ((p.t_lo & 3) || (p.skp_t_lo & 3)) return set_err(AEWN_ERR_INVALID, "grcc_fwd: t_lo / skp_t_lo must be multiples of 4");
 
   const long long total = static_cast<long long>(p.batch) * p.n_tgroups;

@@ -309,6 +309,8 @@ typedef struct {
   int skp_t_lo, skp_zero_lo;      /* same for the skip sum */
   int* err;
   int max_ctas;           /* 0 = one per SM */
+  long long* dbg_clock;   /* optional (profiling): 2 x 4 x 8 x 3 clock64() stamps of cluster 0's first four tiles --
+                             [MMA issuer | epilogue warp 0][tile][job][job seen, operands/accumulator ready, done] */
 } aewn_grcc_fwd_desc;
 
 int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream);
