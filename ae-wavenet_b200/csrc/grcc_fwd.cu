@@ -29,7 +29,7 @@ namespace aewn {
 
 constexpr int GF_BM = 128;
 constexpr int GF_KB = 64;                         // K elements per ring stage: 64 fp16 = one 128-byte swizzle row
-constexpr int GF_STAGES = 3;                      // 3 x 32 KB ring + 64 KB z + 64 KB staging = 224 KB
+constexpr int GF_MAX_STAGES = 4;                  // ring 3 x 32 KB + two 2 KB staging half-tiles per epilogue warp, or 4 x 32 KB + one
 constexpr int GF_A_BYTES = GF_BM * 128;           // 16 KB: 128 time rows x 128 B
 constexpr int GF_W_BYTES = 128 * 128;             // 16 KB: 128 weight rows x 128 B (this CTA's half of the N rows)
 constexpr int GF_STAGE_BYTES = GF_A_BYTES + GF_W_BYTES;
@@ -37,9 +37,8 @@ constexpr int GF_MAX_D = 256;
 constexpr int GF_ZBUF_BYTES = (GF_MAX_D / GF_KB) * GF_A_BYTES;   // 64 KB: z of this CTA's 128 time rows, all D channels
 constexpr int GF_THREADS = 640;                  // 4 control warps + 16 epilogue warps
 constexpr int GF_EPI_WARPS = 16;
-constexpr int GF_STG_BYTES = GF_EPI_WARPS * 4096;
-constexpr int GF_RING_BYTES = GF_STAGES * GF_STAGE_BYTES;
-constexpr int GF_SMEM_BYTES = GF_RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES + 256 + 1024;
+constexpr int GF_POOL_BYTES = 3 * GF_STAGE_BYTES + GF_EPI_WARPS * 4096;   // ring + staging: 160 KB in either split
+constexpr int GF_SMEM_BYTES = GF_POOL_BYTES + GF_ZBUF_BYTES + 256 + 512 + 1024;   // + barriers + GfHot + alignment slack
 constexpr int GF_MAX_JOBS = 8;
 
 enum { GF_GATE = 0, GF_RES = 1, GF_SKP = 2 };
@@ -52,11 +51,10 @@ struct GfJob {
   int ch0;       // first output channel (GATE: first z channel)
 };
 
-struct GfParams {
-  CUtensorMap xa, ca, w1, w2;             // operand loads (fp16)
-  CUtensorMap th_m, sg_m, z_m, xo_m, skp_m;   // fp32 (t, ch, b) outputs, box {32 t, 16 ch, 1}
-  CUtensorMap xr_m;                          // fp32 residual source, box {128 t, 32 ch, 1}: L2 prefetch only
-  int prefetch;
+// Scalars and the job table: copied to shared memory at kernel start.  Read from the kernel parameter space they cost an
+// LDC per use (the job table is indexed at run time), and ncu attributed ~17 % of the epilogue warps' samples to
+// instructions waiting for those constant loads.
+struct GfHot {
   GfJob job[GF_MAX_JOBS];
   int n_jobs, n_gate;
   int kb_x, kb_c, kb_z;                   // ring stages per x tap, for cond, for z
@@ -73,8 +71,17 @@ struct GfParams {
   int save, z_out, skp_mode;               // skp_mode: 0 store, 1 reduce-add, 2 relu(old + acc), 3 relu(acc)
   int batch, t_begin, n_tgroups, n_res;
   int t_lo, t_zero_lo, t_hi, skp_t_lo, skp_zero_lo;
+  int prefetch;
   int* err;
   long long* dbg_clock;   // optional: cluster 0 / CTA 0 stamps its first items (profiles/gf_phase_clock.py)
+};
+static_assert(sizeof(GfHot) % 8 == 0 && sizeof(GfHot) <= 512, "GfHot is copied to shared memory as 64-bit words");
+
+struct GfParams {
+  CUtensorMap xa, ca, w1, w2;             // operand loads (fp16)
+  CUtensorMap th_m, sg_m, z_m, xo_m, skp_m;   // fp32 (t, ch, b) outputs, box {32 t, 16 ch, 1}
+  CUtensorMap xr_m;                          // fp32 residual source, box {128 t, 32 ch, 1}: L2 prefetch only
+  GfHot hot;
 };
 
 __device__ __forceinline__ void umma_f16_ss_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -120,7 +127,7 @@ struct GfItem {
   bool do_skp;
 };
 
-__device__ __forceinline__ GfItem gf_decode(const GfParams& p, int item, int crank) {
+__device__ __forceinline__ GfItem gf_decode(const GfHot& p, int item, int crank) {
   GfItem it;
   const int tg = item % p.n_tgroups;
   it.b = item / p.n_tgroups;
@@ -130,26 +137,35 @@ __device__ __forceinline__ GfItem gf_decode(const GfParams& p, int item, int cra
   return it;
 }
 
+template <int STAGES>
 __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_constant__ GfParams p) {
+  constexpr int HALVES = STAGES == 3 ? 2 : 1;                 // staging half-tiles per epilogue warp
+  constexpr int RING_BYTES = STAGES * GF_STAGE_BYTES;
+  constexpr int STG_BYTES = GF_EPI_WARPS * 2048 * HALVES;
+  static_assert(RING_BYTES + STG_BYTES == GF_POOL_BYTES, "both splits use the same shared memory");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* zbuf = smem + GF_RING_BYTES;
-  float* stg_base = reinterpret_cast<float*>(smem + GF_RING_BYTES + GF_ZBUF_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GF_RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES);
-  uint64_t* empty_bar = full_bar + GF_STAGES;
-  uint64_t* tfull_bar = empty_bar + GF_STAGES;
+  uint8_t* zbuf = smem + RING_BYTES;
+  float* stg_base = reinterpret_cast<float*>(smem + RING_BYTES + GF_ZBUF_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_BYTES + GF_ZBUF_BYTES + STG_BYTES);
+  uint64_t* empty_bar = full_bar + GF_MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + GF_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* zready_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zready_bar + 1);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  GfHot* hot_s = reinterpret_cast<GfHot*>(smem + RING_BYTES + GF_ZBUF_BYTES + STG_BYTES + 256);
+  if (threadIdx.x < sizeof(GfHot) / 8)
+    reinterpret_cast<unsigned long long*>(hot_s)[threadIdx.x] = reinterpret_cast<const unsigned long long*>(&p.hot)[threadIdx.x];
+  const GfHot& hp = *hot_s;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     *abort_flag = 0;
-    for (int i = 0; i < GF_STAGES; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);    // leader: its own arrive.expect_tx; the bytes of BOTH CTAs complete on it
       mbar_init(&empty_bar[i], 1);   // the leader's cta_group::2 commit releases the stage in both CTAs
     }
@@ -157,7 +173,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * GF_EPI_WARPS);   // on the leader: the epilogue warps of both CTAs
     }
-    mbar_init(zready_bar, 2 * GF_EPI_WARPS * p.n_gate);   // every epilogue warp of the pair, once per gate job
+    mbar_init(zready_bar, 2 * GF_EPI_WARPS * p.hot.n_gate);   // every epilogue warp of the pair, once per gate job
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -179,28 +195,28 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
   const int crank = static_cast<int>(cluster_ctarank());
   const int cid = blockIdx.x >> 1;
   const int n_cl = gridDim.x >> 1;
-  const int total = p.batch * p.n_tgroups;
-  const int g1_stages = 2 * p.kb_x + p.kb_c;
+  const int total = hp.batch * hp.n_tgroups;
+  const int g1_stages = 2 * hp.kb_x + hp.kb_c;
 
   if (warp < 4) {
-    reg_dealloc<40>();
+    reg_dealloc<56>();   // 128 x 56 + 512 x 104 = 60416 <= 640 x 96 (the CTA's launch allocation)
     if (warp == 0) {
       // ===================================================== TMA producer (both CTAs)
       uint32_t stage = 0, phase = 0;
       bool ok = true;
       const uint32_t lead_full = mapa_u32(&full_bar[0], 0);
       for (int item = cid; item < total && ok; item += n_cl) {
-        const GfItem it = gf_decode(p, item, crank);
+        const GfItem it = gf_decode(hp, item, crank);
         // the residual rows this tile's RES epilogues will add (128 time steps x R channels of x32): pull them into L2
         // now, ~20 k cycles before the epilogue warps load them
-        if (p.prefetch && elect_one()) {
-          for (int c = 0; c < p.n_res; c += 32) tma_prefetch_l2_3d(&p.xr_m, it.tau0, c, it.b);
+        if (hp.prefetch && elect_one()) {
+          for (int c = 0; c < hp.n_res; c += 32) tma_prefetch_l2_3d(&p.xr_m, it.tau0, c, it.b);
         }
         __syncwarp();
-        for (int jb = 0; jb < p.n_jobs && ok; ++jb) {
-          const GfJob jd = p.job[jb];
+        for (int jb = 0; jb < hp.n_jobs && ok; ++jb) {
+          const GfJob jd = hp.job[jb];
           if (jd.kind == GF_SKP && !it.do_skp) continue;
-          const int nst = jd.kind == GF_GATE ? g1_stages : p.kb_z;
+          const int nst = jd.kind == GF_GATE ? g1_stages : hp.kb_z;
           for (int s = 0; s < nst; ++s) {
             if (!mbar_wait_warp(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
             if (elect_one()) {
@@ -209,9 +225,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               const uint32_t fb = lead_full + stage * 8u;
               if (jd.kind == GF_GATE) {
                 if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * GF_STAGE_BYTES);
-                if (s < p.kb_x) tma_load_3d_pair(sa, &p.xa, fb, s * GF_KB, it.tau0 - p.dil, it.b);
-                else if (s < 2 * p.kb_x) tma_load_3d_pair(sa, &p.xa, fb, (s - p.kb_x) * GF_KB, it.tau0, it.b);
-                else tma_load_3d_pair(sa, &p.ca, fb, (s - 2 * p.kb_x) * GF_KB, it.tau0, it.b);
+                if (s < hp.kb_x) tma_load_3d_pair(sa, &p.xa, fb, s * GF_KB, it.tau0 - hp.dil, it.b);
+                else if (s < 2 * hp.kb_x) tma_load_3d_pair(sa, &p.xa, fb, (s - hp.kb_x) * GF_KB, it.tau0, it.b);
+                else tma_load_3d_pair(sa, &p.ca, fb, (s - 2 * hp.kb_x) * GF_KB, it.tau0, it.b);
                 tma_load_2d_pair(sw, &p.w1, fb, s * GF_KB, jd.w_row + crank * 128);
               } else {
                 // CTA r stages W2 rows [r * n/2, (r+1) * n/2) of the job (a 128-row box; the MMA reads n/2 of them)
@@ -220,7 +236,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               }
             }
             __syncwarp();
-            if (++stage == GF_STAGES) { stage = 0; phase ^= 1u; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -233,13 +249,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         const uint32_t ring = smem_u32(smem);
         const uint32_t z16_0 = (smem_u32(zbuf) >> 4) & 0x3FFFu;
         for (int item = cid; item < total && ok; item += n_cl) {
-          const GfItem it = gf_decode(p, item, crank);
+          const GfItem it = gf_decode(hp, item, crank);
           bool z_waited = false;
-          for (int jb = 0; jb < p.n_jobs && ok; ++jb) {
-            const GfJob jd = p.job[jb];
+          for (int jb = 0; jb < hp.n_jobs && ok; ++jb) {
+            const GfJob jd = hp.job[jb];
             if (jd.kind == GF_SKP && !it.do_skp) continue;
-            const bool stamp = p.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && lane == 0;
-            long long* ck = p.dbg_clock + ((item / n_cl) * GF_MAX_JOBS + jb) * 3;
+            const bool stamp = hp.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && lane == 0;
+            long long* ck = hp.dbg_clock + ((item / n_cl) * GF_MAX_JOBS + jb) * 3;
             if (stamp) ck[0] = clock64();
             if (!mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) { ok = false; break; }
             if (jd.kind != GF_GATE && !z_waited) {
@@ -252,7 +268,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             if (stamp) ck[1] = clock64();
             const uint32_t d_tmem = tmem_base + acc * 256u;
             const uint32_t idesc = make_idesc_f16(2 * GF_BM, jd.n);
-            const int nst = jd.kind == GF_GATE ? g1_stages : p.kb_z;
+            const int nst = jd.kind == GF_GATE ? g1_stages : hp.kb_z;
             for (int s = 0; s < nst; ++s) {
               if (!mbar_wait_warp(&full_bar[stage], phase, abort_flag)) { ok = false; break; }
               tc_fence_after();
@@ -267,7 +283,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 umma_commit_pair(&empty_bar[stage], 0x3);
               }
               __syncwarp();
-              if (++stage == GF_STAGES) { stage = 0; phase ^= 1u; }
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
             if (!ok) break;
             if (elect_one()) umma_commit_pair(&tfull_bar[acc], 0x3);
@@ -293,11 +309,15 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
     const int q = warp & 3;
     const int h = (warp - 4) >> 2;
     const int row = q * 32 + lane;
-    float* const tile2 = stg_base + (warp - 4) * 1024;
+    float* const tile2 = stg_base + (warp - 4) * 512 * HALVES;
     uint32_t stg_cur = 0;
     auto stg_acquire = [&]() -> float* {
-      stg_cur ^= 1u;
-      if (elect_one()) tma_store_wait_read1();   // all but the latest box have been read out: the older half is free
+      if (HALVES == 2) {
+        stg_cur ^= 1u;
+        if (elect_one()) tma_store_wait_read1();   // all but the latest box have been read out: the older half is free
+      } else {
+        if (elect_one()) tma_store_wait_read();
+      }
       __syncwarp();
       return tile2 + stg_cur * 512 + lane;
     };
@@ -316,18 +336,18 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
     float xmax = 0.0f;
     bool ok = true;
     for (int item = cid; item < total && ok; item += n_cl) {
-      const GfItem it = gf_decode(p, item, crank);
+      const GfItem it = gf_decode(hp, item, crank);
       const int tau = it.tau0 + row;
       const int slab0 = it.tau0 + q * 32;
-      const bool in_range = tau >= p.t_lo && tau < p.t_hi;
-      const bool keep = in_range && tau >= p.t_zero_lo;
-      const bool slab_on = (slab0 + 32 > p.t_lo) && (slab0 < p.t_hi);
-      for (int jb = 0; jb < p.n_jobs && ok; ++jb) {
-        const GfJob jd = p.job[jb];
+      const bool in_range = tau >= hp.t_lo && tau < hp.t_hi;
+      const bool keep = in_range && tau >= hp.t_zero_lo;
+      const bool slab_on = (slab0 + 32 > hp.t_lo) && (slab0 < hp.t_hi);
+      for (int jb = 0; jb < hp.n_jobs && ok; ++jb) {
+        const GfJob jd = hp.job[jb];
         if (jd.kind == GF_SKP && !it.do_skp) continue;
         const uint32_t taddr = tmem_base + acc * 256u + (static_cast<uint32_t>(q * 32) << 16);
-        const bool stamp = p.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && warp == 4 && lane == 0;
-        long long* ck = p.dbg_clock + 4 * GF_MAX_JOBS * 3 + ((item / n_cl) * GF_MAX_JOBS + jb) * 3;
+        const bool stamp = hp.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && warp == 4 && lane == 0;
+        long long* ck = hp.dbg_clock + 4 * GF_MAX_JOBS * 3 + ((item / n_cl) * GF_MAX_JOBS + jb) * 3;
         if (stamp) ck[0] = clock64();
         if (jd.kind == GF_GATE) {
           if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
@@ -372,7 +392,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               }
             }
             if (slab_on) {
-              if (p.save) {
+              if (hp.save) {
                 float* st = stg_acquire();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) st[j * 32] = __uint_as_float(vf[j]);
@@ -382,7 +402,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 for (int j = 0; j < 16; ++j) st[j * 32] = __uint_as_float(vg[j]);
                 stg_flush(&p.sg_m, slab0, ch, it.b, false);
               }
-              if (p.z_out) {
+              if (hp.z_out) {
                 float* st = stg_acquire();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) st[j * 32] = __uint_as_float(vf[j]) * __uint_as_float(vg[j]);
@@ -406,19 +426,19 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           const int cb = h * span;
           const int ce = min(cb + span, jd.n);
           const int nv = jd.n_valid;
-          const float* xsrc = p.x32 + static_cast<long long>(it.b) * p.x_bs + static_cast<long long>(jd.ch0) * p.x_cs + tau;
-          __half* x16row = p.xo16 + static_cast<long long>(it.b) * p.x16_bs + static_cast<long long>(tau) * p.x16_cp + jd.ch0;
-          const int dup_t = tau + p.dup_toff;
-          float* dupp = (p.dup && in_range && dup_t >= 0 && dup_t < p.dup_t_hi)
-                            ? p.dup + static_cast<long long>(it.b) * p.x_bs + static_cast<long long>(jd.ch0) * p.x_cs + dup_t
+          const float* xsrc = hp.x32 + static_cast<long long>(it.b) * hp.x_bs + static_cast<long long>(jd.ch0) * hp.x_cs + tau;
+          __half* x16row = hp.xo16 + static_cast<long long>(it.b) * hp.x16_bs + static_cast<long long>(tau) * hp.x16_cp + jd.ch0;
+          const int dup_t = tau + hp.dup_toff;
+          float* dupp = (hp.dup && in_range && dup_t >= 0 && dup_t < hp.dup_t_hi)
+                            ? hp.dup + static_cast<long long>(it.b) * hp.x_bs + static_cast<long long>(jd.ch0) * hp.x_cs + dup_t
                             : nullptr;
           float bufA[16], bufB[16];
           auto issue = [&](int c0, float (&buf)[16]) {
-            const float* sp = xsrc + static_cast<long long>(c0) * p.x_cs;
+            const float* sp = xsrc + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               buf[j] = (keep && c0 + j < nv) ? __ldcg(sp) : 0.0f;
-              sp += p.x_cs;
+              sp += hp.x_cs;
             }
           };
           if (cb < ce) issue(cb, bufA);
@@ -443,11 +463,11 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               stg_flush(&p.xo_m, slab0, jd.ch0 + c0, it.b, false);
             }
             if (dupp) {
-              float* dd = dupp + static_cast<long long>(c0) * p.x_cs;
+              float* dd = dupp + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 if (c0 + j < nv) *dd = r[j];
-                dd += p.x_cs;
+                dd += hp.x_cs;
               }
             }
             if (in_range) {
@@ -485,10 +505,10 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           const int span = ((jd.n + 63) >> 6) << 4;
           const int cb = h * span;
           const int ce = min(cb + span, jd.n);
-          const bool s_in = tau >= p.skp_t_lo && tau < p.t_hi;
-          const bool s_keep = s_in && tau >= p.skp_zero_lo;
-          const bool s_slab = (slab0 + 32 > p.skp_t_lo) && (slab0 < p.t_hi);
-          const float* old = p.skp + static_cast<long long>(it.b) * p.s_bs + static_cast<long long>(jd.ch0) * p.s_cs + tau;
+          const bool s_in = tau >= hp.skp_t_lo && tau < hp.t_hi;
+          const bool s_keep = s_in && tau >= hp.skp_zero_lo;
+          const bool s_slab = (slab0 + 32 > hp.skp_t_lo) && (slab0 < hp.t_hi);
+          const float* old = hp.skp + static_cast<long long>(it.b) * hp.s_bs + static_cast<long long>(jd.ch0) * hp.s_cs + tau;
           if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
           if (stamp) ck[1] = clock64();
@@ -498,26 +518,26 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             float o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] = 0.0f;
-            if (p.skp_mode == 2) {
-              const float* sp = old + static_cast<long long>(c0) * p.s_cs;
+            if (hp.skp_mode == 2) {
+              const float* sp = old + static_cast<long long>(c0) * hp.s_cs;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 o[j] = (s_keep && c0 + j < jd.n_valid) ? __ldcg(sp) : 0.0f;
-                sp += p.s_cs;
+                sp += hp.s_cs;
               }
             }
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
             if (s_slab) {
               float* st = stg_acquire();
-              if (p.skp_mode >= 2) {
+              if (hp.skp_mode >= 2) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) st[j * 32] = s_keep ? fmaxf(__uint_as_float(v[j]) + o[j], 0.0f) : 0.0f;
               } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) st[j * 32] = s_keep ? __uint_as_float(v[j]) : 0.0f;
               }
-              stg_flush(&p.skp_m, slab0, jd.ch0 + c0, it.b, p.skp_mode == 1);
+              stg_flush(&p.skp_m, slab0, jd.ch0 + c0, it.b, hp.skp_mode == 1);
             }
           }
           tc_fence_before();
@@ -531,7 +551,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
-    if (xmax > 65504.0f && p.err) atomicExch(p.err, AEWN_ERR_RANGE);   // fp16 operand copy saturated
+    if (xmax > 65504.0f && hp.err) atomicExch(hp.err, AEWN_ERR_RANGE);   // fp16 operand copy saturated
     if (elect_one()) tma_store_wait_all();
     __syncwarp();
   }
@@ -540,7 +560,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (threadIdx.x == 0 && *abort_flag && p.err) atomicExch(p.err, AEWN_ERR_TIMEOUT);
+  if (threadIdx.x == 0 && *abort_flag && hp.err) atomicExch(hp.err, AEWN_ERR_TIMEOUT);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
@@ -674,58 +694,62 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
     if ((rc = encode_out_map(&p.xo_m, d->xo32, d->t_hi, R, d->batch, d->x_cs, d->x_bs, 16))) return rc;
     if ((rc = encode_out_map(&p.xr_m, const_cast<float*>(d->x32), d->t_hi, R, d->batch, d->x_cs, d->x_bs, 32, 128))) return rc;
     static const int pf = []() { const char* e = getenv("AEWN_GF_PREFETCH"); return e ? atoi(e) : 1; }();
-    p.prefetch = pf;
-    p.n_res = R;
+    p.hot.prefetch = pf;
+    p.hot.n_res = R;
   }
   if ((rc = encode_out_map(&p.skp_m, d->skp, d->t_hi, S, d->batch, d->s_cs, d->s_bs, 16))) return rc;
 
   int nj = 0;
-  for (int j = 0; j < D / 128; ++j) p.job[nj++] = GfJob{GF_GATE, 256 * j, 256, 128, 128 * j};
-  p.n_gate = nj;
-  if (!d->final_layer)
-    for (int c0 = 0; c0 < R; c0 += 256) {
-      const int nv = R - c0 < 256 ? R - c0 : 256;
-      p.job[nj++] = GfJob{GF_RES, c0, (nv + 15) & ~15, nv, c0};
-    }
+  for (int j = 0; j < D / 128; ++j) p.hot.job[nj++] = GfJob{GF_GATE, 256 * j, 256, 128, 128 * j};
+  p.hot.n_gate = nj;
+  // Order of the residual / skip jobs: their epilogues are long (HBM stores) and their MMAs short, and the next tile's
+  // first gate job may start as soon as the region of the SECOND-to-last job has been drained -- so the job with the
+  // longest epilogue (a full 256-channel residual chunk) goes last, where it overlaps the next tile's gate MMAs
+  // (measured with the phase clock: 85 k -> cycles per tile with the residual chunks first).
   const int row_s = d->final_layer ? 0 : R;
   for (int c0 = 0; c0 < S; c0 += 256) {
     const int nv = S - c0 < 256 ? S - c0 : 256;
-    p.job[nj++] = GfJob{GF_SKP, row_s + c0, (nv + 15) & ~15, nv, c0};
+    p.hot.job[nj++] = GfJob{GF_SKP, row_s + c0, (nv + 15) & ~15, nv, c0};
   }
+  if (!d->final_layer)
+    for (int c0 = ((R - 1) / 256) * 256; c0 >= 0; c0 -= 256) {      // the partial chunk (if any) first
+      const int nv = R - c0 < 256 ? R - c0 : 256;
+      p.hot.job[nj++] = GfJob{GF_RES, c0, (nv + 15) & ~15, nv, c0};
+    }
   if (nj > GF_MAX_JOBS) return set_err(AEWN_ERR_INVALID, "grcc_fwd: too many jobs (%d)", nj);
-  p.n_jobs = nj;
-  p.kb_x = KR / 64;
-  p.kb_c = KC / 64;
-  p.kb_z = D / 64;
-  p.dil = d->dil;
-  p.x32 = d->x32;
-  p.x_bs = d->x_bs;
-  p.x_cs = d->x_cs;
-  p.dup = d->dup;
-  p.dup_toff = d->dup_toff;
-  p.dup_t_hi = d->dup_t_hi;
-  p.xo16 = reinterpret_cast<__half*>(d->xo16);
-  p.x16_bs = d->x16_bs;
-  p.x16_cp = d->x16_cp;
-  p.skp = d->skp;
-  p.s_bs = d->s_bs;
-  p.s_cs = d->s_cs;
-  p.save = d->save;
-  p.z_out = d->z != nullptr;
-  p.skp_mode = d->skp_mode;
-  p.batch = d->batch;
-  p.t_begin = d->t_lo & ~31;
-  p.n_tgroups = (d->t_hi - p.t_begin + 2 * GF_BM - 1) / (2 * GF_BM);
-  p.t_lo = d->t_lo;
-  p.t_zero_lo = d->t_zero_lo;
-  p.t_hi = d->t_hi;
-  p.skp_t_lo = d->skp_t_lo;
-  p.skp_zero_lo = d->skp_zero_lo;
-  p.err = d->err;
-  p.dbg_clock = d->dbg_clock;
-  if ((p.t_lo & 3) || (p.skp_t_lo & 3)) return set_err(AEWN_ERR_INVALID, "grcc_fwd: t_lo / skp_t_lo must be multiples of 4");
+  p.hot.n_jobs = nj;
+  p.hot.kb_x = KR / 64;
+  p.hot.kb_c = KC / 64;
+  p.hot.kb_z = D / 64;
+  p.hot.dil = d->dil;
+  p.hot.x32 = d->x32;
+  p.hot.x_bs = d->x_bs;
+  p.hot.x_cs = d->x_cs;
+  p.hot.dup = d->dup;
+  p.hot.dup_toff = d->dup_toff;
+  p.hot.dup_t_hi = d->dup_t_hi;
+  p.hot.xo16 = reinterpret_cast<__half*>(d->xo16);
+  p.hot.x16_bs = d->x16_bs;
+  p.hot.x16_cp = d->x16_cp;
+  p.hot.skp = d->skp;
+  p.hot.s_bs = d->s_bs;
+  p.hot.s_cs = d->s_cs;
+  p.hot.save = d->save;
+  p.hot.z_out = d->z != nullptr;
+  p.hot.skp_mode = d->skp_mode;
+  p.hot.batch = d->batch;
+  p.hot.t_begin = d->t_lo & ~31;
+  p.hot.n_tgroups = (d->t_hi - p.hot.t_begin + 2 * GF_BM - 1) / (2 * GF_BM);
+  p.hot.t_lo = d->t_lo;
+  p.hot.t_zero_lo = d->t_zero_lo;
+  p.hot.t_hi = d->t_hi;
+  p.hot.skp_t_lo = d->skp_t_lo;
+  p.hot.skp_zero_lo = d->skp_zero_lo;
+  p.hot.err = d->err;
+  p.hot.dbg_clock = d->dbg_clock;
+  if ((p.hot.t_lo & 3) || (p.hot.skp_t_lo & 3)) return set_err(AEWN_ERR_INVALID, "grcc_fwd: t_lo / skp_t_lo must be multiples of 4");
 
-  const long long total = static_cast<long long>(p.batch) * p.n_tgroups;
+  const long long total = static_cast<long long>(p.hot.batch) * p.hot.n_tgroups;
   int clusters = (d->max_ctas > 0 ? d->max_ctas : sm_count()) / 2;
   if (clusters > total) clusters = static_cast<int>(total);
   if (clusters < 1) clusters = 1;
@@ -742,9 +766,13 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t ae = cudaFuncSetAttribute(grcc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_BYTES);
+  // ring depth 3 (two staging half-tiles per epilogue warp) or 4 (one): AEWN_GF_RING=3|4 for A/B runs
+  static const int ring = []() { const char* e = getenv("AEWN_GF_RING"); return e && atoi(e) == 3 ? 3 : 4; }();
+  using KernelFn = void (*)(GfParams);
+  KernelFn fn = ring == 3 ? grcc_fwd_kernel<3> : grcc_fwd_kernel<4>;
+  cudaError_t ae = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_BYTES);
   if (ae != cudaSuccess) return cuda_err(ae, "grcc_fwd: cudaFuncSetAttribute");
-  cudaError_t le = cudaLaunchKernelEx(&cfg, grcc_fwd_kernel, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
   count_launch();
   if (le != cudaSuccess) return cuda_err(le, "grcc_fwd launch");
   return cuda_err(cudaGetLastError(), "grcc_fwd launch");

@@ -39,7 +39,7 @@ torch.cuda.synchronize()
 print(f"layer dil={dil}: {e0.elapsed_time(e1) * 1e3:.1f} us")
 c = clk.cpu().view(2, 4, 8, 3)
 t0 = int(c[c > 0].min())
-names = ["G1.0", "G1.1", "RES0", "RES1", "SKP", "-", "-", "-"]
+names = ["G1.0", "G1.1", "SKP", "RES1", "RES0", "-", "-", "-"]      # job order of arch.basic (R = 368)
 for role, rn in enumerate(("MMA issuer", "epilogue warp 0")):
     print(rn, "(cycles from first stamp: job seen | ready | done ; wait, work)")
     for tile in range(4):
