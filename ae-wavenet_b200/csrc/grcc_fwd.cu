@@ -251,16 +251,21 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         for (int item = cid; item < total && ok; item += n_cl) {
           const GfItem it = gf_decode(hp, item, crank);
           bool z_waited = false;
+          if (hp.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && lane == 0)
+            hp.dbg_clock[((item / n_cl) * GF_MAX_JOBS + 7) * 6] = clock64();      // top of the tile (slot of the unused job 7)
           for (int jb = 0; jb < hp.n_jobs && ok; ++jb) {
             const GfJob jd = hp.job[jb];
             if (jd.kind == GF_SKP && !it.do_skp) continue;
             const bool stamp = hp.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && lane == 0;
-            long long* ck = hp.dbg_clock + ((item / n_cl) * GF_MAX_JOBS + jb) * 3;
+            long long* ck = hp.dbg_clock + ((item / n_cl) * GF_MAX_JOBS + jb) * 6;
+            unsigned int w_full = 0;
             if (stamp) ck[0] = clock64();
             if (!mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) { ok = false; break; }
             if (jd.kind != GF_GATE && !z_waited) {
               // every epilogue warp of the pair has written its z columns of this tile (generic proxy -> fence -> arrive)
+              const unsigned int tz = clock();
               if (!mbar_wait_warp(zready_bar, zphase, abort_flag)) { ok = false; break; }
+              if (stamp) ck[5] = clock() - tz;
               zphase ^= 1u;
               z_waited = true;
             }
@@ -270,7 +275,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             const uint32_t idesc = make_idesc_f16(2 * GF_BM, jd.n);
             const int nst = jd.kind == GF_GATE ? g1_stages : hp.kb_z;
             for (int s = 0; s < nst; ++s) {
+              const unsigned int tf = clock();
               if (!mbar_wait_warp(&full_bar[stage], phase, abort_flag)) { ok = false; break; }
+              w_full += clock() - tf;
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t s16 = ((ring + stage * GF_STAGE_BYTES) >> 4) & 0x3FFFu;
@@ -288,7 +295,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             if (!ok) break;
             if (elect_one()) umma_commit_pair(&tfull_bar[acc], 0x3);
             __syncwarp();
-            if (stamp) ck[2] = clock64();
+            if (stamp) { ck[2] = clock64(); ck[3] = w_full; }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
           }
           // a tile whose skip job was skipped still has to consume the z phase (the epilogues always arrive)
@@ -311,7 +318,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
     const int row = q * 32 + lane;
     float* const tile2 = stg_base + (warp - 4) * 512 * HALVES;
     uint32_t stg_cur = 0;
+    unsigned int dbg_acq = 0, dbg_tm = 0, dbg_fl = 0;      // phase-clock accumulators (cycles), see dbg_clock
     auto stg_acquire = [&]() -> float* {
+      const unsigned int t_a = clock();
       if (HALVES == 2) {
         stg_cur ^= 1u;
         if (elect_one()) tma_store_wait_read1();   // all but the latest box have been read out: the older half is free
@@ -319,9 +328,11 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         if (elect_one()) tma_store_wait_read();
       }
       __syncwarp();
+      dbg_acq += clock() - t_a;
       return tile2 + stg_cur * 512 + lane;
     };
     auto stg_flush = [&](const CUtensorMap* map, int t0, int c0, int b, bool reduce) {
+      const unsigned int t_f = clock();
       fence_proxy_async_smem();
       __syncwarp();
       if (elect_one()) {
@@ -329,6 +340,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         else tma_store_3d(map, tile2 + stg_cur * 512, t0, c0, b);
         tma_store_commit();
       }
+      dbg_fl += clock() - t_f;
     };
     const uint32_t lead_tempty = mapa_u32(&tempty_bar[0], 0);
     const uint32_t lead_zready = mapa_u32(zready_bar, 0);
@@ -347,7 +359,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         if (jd.kind == GF_SKP && !it.do_skp) continue;
         const uint32_t taddr = tmem_base + acc * 256u + (static_cast<uint32_t>(q * 32) << 16);
         const bool stamp = hp.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && warp == 4 && lane == 0;
-        long long* ck = hp.dbg_clock + 4 * GF_MAX_JOBS * 3 + ((item / n_cl) * GF_MAX_JOBS + jb) * 3;
+        long long* ck = hp.dbg_clock + 4 * GF_MAX_JOBS * 6 + ((item / n_cl) * GF_MAX_JOBS + jb) * 6;
+        dbg_acq = dbg_tm = dbg_fl = 0;
         if (stamp) ck[0] = clock64();
         if (jd.kind == GF_GATE) {
           if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
@@ -357,9 +370,11 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           for (int i = 0; i < 2; ++i) {
             const int c0 = 32 * h + 16 * i;            // z channels [c0, c0 + 16) of this 128-channel block
             uint32_t vf[16], vg[16];
+            const unsigned int t_t = clock();
             tmem_ld16(taddr + c0, vf);
             tmem_ld16(taddr + 128 + c0, vg);
             tmem_ld_wait();
+            dbg_tm += clock() - t_t;
             // tanh(f) = (1 - a) / (1 + a), a = e^(-2f); sigmoid(g) = 1 / (1 + b), b = e^(-g): ONE reciprocal of
             // (1 + a)(1 + b) serves both (3 MUFU ops per element instead of 4; the exponents are clamped so that the
             // product stays finite: 2^60 * 2^60)
@@ -448,8 +463,10 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           if (stamp) ck[1] = clock64();
           auto chunk = [&](int c0, float (&buf)[16]) {
             uint32_t v[16];
+            const unsigned int t_t = clock();
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
+            dbg_tm += clock() - t_t;
             float r[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -526,8 +543,10 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 sp += hp.s_cs;
               }
             }
+            const unsigned int t_t = clock();
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
+            dbg_tm += clock() - t_t;
             if (s_slab) {
               float* st = stg_acquire();
               if (hp.skp_mode >= 2) {
@@ -547,7 +566,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             else mbar_arrive(&tempty_bar[acc]);
           }
         }
-        if (stamp) ck[2] = clock64();
+        if (stamp) { ck[2] = clock64(); ck[3] = dbg_acq; ck[4] = dbg_tm; ck[5] = dbg_fl; }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }

@@ -139,38 +139,71 @@ def grcc_layer_fwd_flops(B, R, D, S, C, T_in, d, W, K=2):
 
 
 # ------------------------------------------------------------------------------------------------- reference arm / CPU
-def cpu_port_step(B, W, steps, warmup, seed=2507):
-    """The reference's own CPU implementation of the path (oracle port of wavenet.py:323-364 + RecLoss + autograd)."""
+def port_step(B, W, steps, warmup, seed=2507, device="cpu"):
+    """The reference's own implementation of the path (oracle port of wavenet.py:323-364 + RecLoss + autograd): the same
+    ATen calls the reference modules make.  device="cpu": the CPU baseline / reference arm; device="cuda": the GPU LIBRARY
+    baseline (eager PyTorch through cuDNN on the same B200, SURVEY.md 2b / BASELINE.md 3)."""
     from oracle import torch_oracle as orc
     from aewn import geometry as vc
     import aewn
     torch.manual_seed(seed)
     with torch.device("cpu"):
         wn, geo = build_decoder(W, aewn.WaveNet, vc)
-    sd = {k: (v.clone().requires_grad_(True) if v.dtype == torch.float32 and k != "cond.eye" else v)
+    sd = {k: (v.to(device).requires_grad_(True) if v.dtype == torch.float32 and k != "cond.eye" else v.to(device))
           for k, v in wn.state_dict().items()}
     ogeo = dict(trim_ups_out=wn.trim_ups_out.tolist(), wav_cond_offset=list(wn.wav_cond_offset),
                 leads=[l.leads.tolist() for l in wn.conv_layers], n_win_batch=W, trim_dec_out=geo["trim_dec_out"])
-    wav, lc, spk, jit = synth_batch(B, geo["wav_len"], geo["lc_len"], 64, 40, 1234)
+    wav, lc, spk, jit = [t.to(device) for t in synth_batch(B, geo["wav_len"], geo["lc_len"], 64, 40, 1234)]
+    cuda = str(device).startswith("cuda")
     times = []
     for i in range(warmup + steps):
+        if cuda:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         loss, _ = orc.decoder_loss(sd, ARCH_BASIC, ogeo, wav, lc, spk, jit)
         loss.backward()
         for v in sd.values():
             if getattr(v, "grad", None) is not None:
                 v.grad = None
+        if cuda:
+            torch.cuda.synchronize()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     times.sort()
     return B * W / times[len(times) // 2], times
 
 
+def cpu_port_step(B, W, steps, warmup, seed=2507):
+    return port_step(B, W, steps, warmup, seed, "cpu")
+
+
+def gpu_library_baseline(B, W, dev, steps=3, warmup=1):
+    """Eager PyTorch / cuDNN on the same GPU, same configuration as the headline: once with the framework's default conv
+    precision (TF32) and once with IEEE fp32 convolutions.  The reference ships no CUDA kernels of its own, so this is the
+    only pre-existing Blackwell code path for its hot path."""
+    out = {}
+    prev = torch.backends.cudnn.allow_tf32
+    try:
+        for name, tf32 in (("tf32", True), ("ieee", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            try:
+                sps, times = port_step(B, W, steps, warmup, device=dev)
+                out[name] = dict(value=sps, unit=UNIT, ms_per_step=1e3 * times[len(times) // 2], steps=len(times))
+            except Exception as e:   # noqa: BLE001 -- e.g. out of memory: report, do not fail the bench
+                out[name] = dict(unavailable=f"{type(e).__name__}: {str(e)[:160]}")
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    out["what"] = (f"oracle port of the reference modules (same ATen ops: conv1d, conv_transpose1d, one_hot, tanh, sigmoid, "
+                   f"log_softmax + autograd), eager on this GPU, batch {B} x window {W}, fwd + RecLoss + bwd")
+    return out
+
+
 def pick_cpu_threads():
     """All the host threads the port can USE: oneDNN conv on a 2 x 2048 window stops scaling (and regresses badly) long
     before 128 threads, so probe a few counts with one step each and keep the fastest."""
     ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32) if c <= ncpu}) or [ncpu]
+    cands = sorted({c for c in (8, 16, 32, 64) if c <= ncpu}) or [ncpu]
     best, best_sps = cands[0], 0.0
     for c in cands:
         torch.set_num_threads(c)
@@ -181,67 +214,58 @@ def pick_cpu_threads():
     return best
 
 
+def host_mem_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:   # noqa: BLE001
+        return 0.0
+
+
 def run_reference(args, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path (the oracle port: the reference tree does not
+    exist on the bench box) on the host cores.  Runs the HEADLINE configuration (cfg2: batch 8 x window 16384, ~10-20 s per
+    step, ~45 GB of autograd state) when the host has the memory for it, 1 warm-up + min(K, 3) steps; otherwise -- and
+    always as a second key -- a bounded sample of the same network (batch 2 x window 2048)."""
     if rank != 0:
         return
     pick_cpu_threads()
-    B, W = 2, 2048                               # bounded sample of cfg2: same network, 2 x 2048-sample windows
-    sps, times = cpu_port_step(B, W, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
-    out = dict(metric=METRIC, value=sps, unit=UNIT, n_gpus=args.gpus, steps=len(times), warmup=min(args.warmup, 2),
-               ms_per_step=1e3 * sorted(times)[len(times) // 2], higher_is_better=True, scaling="weak", vs_baseline=None,
+    full = host_mem_gb() >= 96 and (os.cpu_count() or 1) >= 16 and os.environ.get("AEWN_REF_SMALL", "0") != "1"
+    sB, sW = 2, 2048
+    s_sps, s_times = cpu_port_step(sB, sW, max(1, min(args.steps, 3)), 1)
+    sample = dict(value=s_sps, unit=UNIT, global_batch=sB, window=sW, ms_per_step=1e3 * s_times[len(s_times) // 2])
+    if full:
+        B, W = 8, 16384
+        sps, times = cpu_port_step(B, W, max(1, min(args.steps, 3)), 1)
+    else:
+        B, W, sps, times = sB, sW, s_sps, s_times
+    out = dict(metric=METRIC, value=sps, unit=UNIT, n_gpus=args.gpus, steps=len(times), warmup=1,
+               ms_per_step=1e3 * times[len(times) // 2], higher_is_better=True, scaling="weak", vs_baseline=None,
                dtype="f32", data="synthetic", impl="reference",
-               config=dict(workload="WaveNet decoder par/arch.basic.json train step (fwd+RecLoss+bwd), CPU",
-                           global_batch=B, window=W),
+               config=dict(workload=f"cfg2: WaveNet decoder par/arch.basic.json train step (fwd+RecLoss+bwd), batch {B}, "
+                                    f"window {W}, CPU", global_batch=B, window=W, same_config_as_headline=full),
                cpu_baseline=dict(value=sps, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                                 sample=f"same decoder, batch {B} x window {W} (cfg2 is 8 x 16384), median step"),
+                                 sample=(f"the headline configuration itself (batch {B} x window {W}), median of "
+                                         f"{len(times)} steps after 1 warm-up" if full else
+                                         f"same decoder, batch {B} x window {W} (cfg2 is 8 x 16384; this host has "
+                                         f"{host_mem_gb():.0f} GB free / {os.cpu_count()} cores), median step")),
+               bounded_sample=sample,
                e2e=dict(value=sps, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(out), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------- our arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
-                    help="cfg2 (default, the headline): WaveNet decoder train step; cfg3: full VQ-VAE-EMA autoencoder "
-                         "train step (Encoder -> VQEMA -> WaveNet, par/arch.vqvae-ema.json), batch 16/GPU; with "
-                         "--gpus N this is cfg4 (grads + EMA statistics in ONE all-reduce); cfg5: deep decoder stress "
-                         "(30 dilation layers, 512 residual channels, window 65536, batch 2/GPU)")
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: cfg2 8, cfg3 16)")
-    ap.add_argument("--window", type=int, default=16384)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--graph-cfg3", action="store_true",
-                    help="cfg3 only: capture the VQ-VAE-EMA step too (VQEMA.static_diagnostics: unique() replaced by a "
-                         "static-shape count); default is the eager step")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-
+def bench_workload(args, workload, rank, local_rank, world, dev, light=False):
+    """One workload on this rank's GPU; returns the JSON dict on rank 0 (None elsewhere).  light=True: timing only (no
+    per-launch instrumentation, roofline, baselines) -- used for the extra cfg4 / cfg5 lines of a multi-GPU run."""
     import torch.distributed as dist
     import aewn
     from aewn import geometry as vc, ops, _lib
     from aewn.dist import FlatGradSync
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the aewn hot path has no CPU fallback; use --impl reference)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    cfg3, cfg5 = args.workload == "cfg3", args.workload == "cfg5"
-    if cfg5 and args.window == 16384:
-        args.window = 65536
-    B, W = (args.batch or (16 if cfg3 else 2 if cfg5 else 8)), args.window
+    cfg3, cfg5 = workload == "cfg3", workload == "cfg5"
+    W = args.window if not (cfg5 and args.window == 16384) else 65536
+    B = (args.batch if workload == args.workload else 0) or (16 if cfg3 else 2 if cfg5 else 8)
     arch = dict(ARCH_BASIC, n_blocks=3, n_res=512) if cfg5 else ARCH_BASIC
     torch.manual_seed(2507)                      # identical replicas (SURVEY.md 8e)
     if cfg3:
@@ -269,14 +293,15 @@ def main():
             sync.sync()                          # ONE all-reduce: grads | z_sum | n_sum | metrics, then the EMA update
             opt.step()
             return loss
-        if args.graph_cfg3:
+        graph_cfg3 = not args.eager_cfg3
+        if graph_cfg3:
             ae.bottleneck.static_diagnostics = True
     else:
         wn, geo = build_decoder(W, aewn.WaveNet, vc, arch)
         wn = wn.to(dev).train()
         model = wn
         loss_fn = aewn.RecLoss()
-        sync = FlatGradSync(wn.parameters(), fused_accumulate=True)   # one loss.backward() per step
+        sync = FlatGradSync(wn.parameters(), fused_accumulate=True)
         wav_h, lc_h, spk_h, jit_h = [t.pin_memory() for t in
                                      synth_batch(B, geo["wav_len"], geo["lc_len"], 64, 40, 1234 + rank)]
         t0w, t1w = geo["trim_dec_out"]
@@ -293,6 +318,7 @@ def main():
             sync.sync()
             opt.step()
             return loss
+        graph_cfg3 = False
     # checkpoint.py:49, par/train.basic.json:6; capturable: the step counter lives on the device (CUDA-graph replay)
     opt = torch.optim.Adam(model.parameters(), lr=2e-5, fused=True, capturable=True)
 
@@ -309,11 +335,12 @@ def main():
 
     # The public training-step API (aewn.train.GraphedStep): the step replayed as ONE CUDA graph (one GPU), or zero-grad +
     # forward + loss + backward as a graph followed by the eager NCCL all-reduce and Adam (N GPUs: collectives stay out
-    # of the capture).  Not used for the VQ-VAE step (VQEMA's unique() diagnostic has a data-dependent shape).  Falls
-    # back to eager steps if capture fails, and says so in `config`.
+    # of the capture).  The VQ-VAE step is captured with VQEMA.static_diagnostics (unique() replaced by a static-shape
+    # count; --eager-cfg3 keeps the reference's diagnostics and runs eagerly).  Falls back to eager steps if capture
+    # fails, and says so in `config`.
     eager_step, graph_note = step, "eager"
     launches_per_step = None
-    if not args.no_graph and (not cfg3 or args.graph_cfg3):
+    if not args.no_graph and (not cfg3 or graph_cfg3):
         try:
             from aewn.train import GraphedStep
             loss = None                    # drop the eager warm-up's autograd graph: its AccumulateGrad nodes are bound
@@ -364,20 +391,36 @@ def main():
     final_loss = float(loss.detach())
     ops.check_device_errors()
 
-    # ---- timed region 1b: the same K steps with a CUDA-event pair around EVERY kernel launch of ours (on the launching
-    # stream): per-kernel durations for the roofline / per-class shares.  Kept out of region 1 because ~250 extra
-    # events per step cost ~2 % of the step.
-    prof = ops.LaunchProfiler()
-    ops.set_profiler(prof)
-    barrier()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for _ in range(args.steps):
-        loss = eager_step(dwav, dlc, dspk, djit)           # eager: a graph replay cannot carry per-launch events
-    p1.record()
-    barrier()
-    ops.set_profiler(None)
-    prof_ms = p0.elapsed_time(p1) / args.steps
+    prof_ms, times, itimes = None, {}, {}
+    if not light:
+        # ---- timed region 1b: the same K steps with a CUDA-event pair around EVERY kernel launch of ours (on the
+        # launching stream): per-kernel durations for the roofline / per-class shares.  Kept out of region 1 because ~250
+        # extra events per step cost ~2 % of the step.
+        prof = ops.LaunchProfiler()
+        ops.set_profiler(prof)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(args.steps):
+            loss = eager_step(dwav, dlc, dspk, djit)           # eager: a graph replay cannot carry per-launch events
+        p1.record()
+        barrier()
+        ops.set_profiler(None)
+        prof_ms = p0.elapsed_time(p1) / args.steps
+        times = prof.times_ms()
+        # ---- region 1c: forward only, nothing kept for a backward pass (torch.no_grad(): the layers skip the tanh /
+        # sigmoid / z writes) -- the inference byte count of SURVEY.md 8d / the per-layer target of BASELINE.md 5
+        if not cfg3:
+            iprof = ops.LaunchProfiler()
+            with torch.no_grad():
+                for _ in range(2):
+                    wn(dwav, dlc, dspk, djit)
+                ops.set_profiler(iprof)
+                for _ in range(args.steps):
+                    wn(dwav, dlc, dspk, djit)
+                torch.cuda.synchronize()
+                ops.set_profiler(None)
+            itimes = iprof.times_ms()
 
     # ---- timed region 2: end to end through the public module API with HOST (pinned) inputs and a D2H loss read
     barrier()
@@ -399,39 +442,16 @@ def main():
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt[0])
 
+    out = None
     if rank == 0:
         pk = peaks()
         R, D, S, C = arch["n_res"], 256, 256, 138
-        times = prof.times_ms()
-        geomS = wn.stack_geometry(geo["dec_in_len"])
-        fwd_bytes = fwd_flops = fwd_ms = 0.0
-        per_layer_gbs = []                       # BASELINE metric, second half: achieved HBM GB/s of every layer's forward
-        T_in = geomS.T0
-        for l, d in enumerate(geomS.dils):
-            g1, g2 = times.get(f"fwd_gemm1.{l}", []), times.get(f"fwd_gemm2.{l}", [])
-            gl = times.get(f"fwd_layer.{l}", [])          # fused layer kernel: one launch per layer
-            if gl or (g1 and g2):
-                l_ms = sum(gl) / len(gl) if gl else sum(g1) / len(g1) + sum(g2) / len(g2)
-                l_bytes = grcc_layer_fwd_bytes(B, R, D, S, C, T_in, d, W, train=True)
-                fwd_ms += l_ms
-                fwd_bytes += l_bytes
-                fwd_flops += grcc_layer_fwd_flops(B, R, D, S, C, T_in, d, W)
-                per_layer_gbs.append(round(l_bytes / (l_ms * 1e-3) / 1e9, 1))
-            T_in -= d
-        gemm_ms = sum(sum(v) for v in times.values()) / args.steps
-        per_class = {}
-        for tag, v in times.items():
-            per_class[tag.split(".")[0]] = per_class.get(tag.split(".")[0], 0.0) + sum(v) / args.steps
-        hbm_ach = fwd_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None
-        tf_ach = fwd_flops / (fwd_ms * 1e-3) / 1e12 if fwd_ms else None
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tpath):
-            traffic = json.load(open(tpath)).get("grcc_layer_fwd_dram_bytes_per_launch")
+        fused = bool(getattr(next(iter(ops._plans.values()), None), "fused", False)) if ops._plans else False
         out = dict(
             metric=METRIC, value=world * B * W / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
-            dtype="tf32", data="synthetic",
+            dtype=("fp16 tensor-core operands in the forward layers (10-bit mantissa, like TF32), tf32 operands elsewhere; "
+                   "fp32 accumulation, residual stream, storage and optimizer" if fused else "tf32"), data="synthetic",
             config=dict(workload=("cfg3/cfg4: full VQ-VAE-EMA autoencoder par/arch.vqvae-ema.json train step (Encoder -> "
                                   f"VQEMA -> WaveNet), batch {B}/GPU, window {W}" if cfg3 else
                                   f"cfg5: deep decoder stress (30 dilation layers, 512 residual channels) train step, batch "
@@ -439,33 +459,157 @@ def main():
                                   f"cfg2: WaveNet decoder par/arch.basic.json train step, batch {B}/GPU, window {W}"),
                         step=("H2D(e2e only)+fwd+VQEMALoss+RecLoss+bwd+allreduce(grads|z_sum|n_sum)+EMA+Adam" if cfg3 else
                               "H2D(e2e only)+fwd+RecLoss+bwd+allreduce+Adam"), global_batch=world * B, window=W,
-                        engine_mode=ops.ENGINE_MODE, step_execution=graph_note,
+                        engine_mode=ops.ENGINE_MODE, fused_layer_forward=fused, step_execution=graph_note,
                         dec_in_len=geo["dec_in_len"], parallelism=f"dp{world}",
                         l2="activations per step ~13 GB >> 126 MB L2 (no flush needed)", seed=2507,
                         final_loss=final_loss),
-            roofline=dict(bound="hbm", achieved=hbm_ach, peak=pk["hbm_gbs"], unit="GB/s",
-                          frac=(hbm_ach / pk["hbm_gbs"]) if hbm_ach else None, traffic=traffic,
-                          kernel="tgemm_kernel: GRCC layer forward (2 launches/layer: conv+gate, res+skip), "
-                                 "algorithmic bytes per SURVEY.md 8d incl. saved activations, summed over 20 layers",
-                          ms_per_layer_fwd=fwd_ms / max(1, geomS.L), per_layer_gbs=per_layer_gbs, peak_source=pk["source"]),
-            roofline_tensor=dict(bound="tensor", achieved=tf_ach, peak=pk["bf16_tflops"], unit="TFLOP/s",
-                                 frac=(tf_ach / pk["bf16_tflops"]) if tf_ach else None,
-                                 note="TF32 operands (nominal peak = half of bf16); denominator is the measured bf16 "
-                                      "cuBLAS rate"),
-            kernel_share=dict(tcgen05_ms_per_step=gemm_ms, step_ms=ms, instrumented_step_ms=prof_ms,
-                              per_class_ms=per_class),
             clocks=clocks,
             e2e=dict(value=world * B * W / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms,
                      h2d_bytes_per_step=int(sum(t.numel() * t.element_size() for t in (wav_h, lc_h, spk_h, jit_h))),
                      d2h_bytes_per_step=4),
             gpu_launches=launches,
         )
-        if not args.no_cpu_baseline and world == 1 and not cfg3 and not cfg5:
+        if not light:
+            geomS = wn.stack_geometry(geo["dec_in_len"])
+
+            def layer_sums(tms, train):
+                tot_b = tot_f = tot_ms = 0.0
+                per = []
+                T_in = geomS.T0
+                for l, d in enumerate(geomS.dils):
+                    g1, g2 = tms.get(f"fwd_gemm1.{l}", []), tms.get(f"fwd_gemm2.{l}", [])
+                    gl = tms.get(f"fwd_layer.{l}", [])          # fused layer kernel: one launch per layer
+                    if gl or (g1 and g2):
+                        l_ms = sum(gl) / len(gl) if gl else sum(g1) / len(g1) + sum(g2) / len(g2)
+                        l_b = grcc_layer_fwd_bytes(B, R, D, S, C, T_in, d, W, train=train)
+                        tot_ms += l_ms
+                        tot_b += l_b
+                        tot_f += grcc_layer_fwd_flops(B, R, D, S, C, T_in, d, W)
+                        per.append(round(l_b / (l_ms * 1e-3) / 1e9, 1))
+                    T_in -= d
+                return tot_b, tot_f, tot_ms, per
+
+            fwd_bytes, fwd_flops, fwd_ms, per_layer_gbs = layer_sums(times, True)
+            inf_bytes, _, inf_ms, inf_gbs = layer_sums(itimes, False)
+            gemm_ms = sum(sum(v) for v in times.values()) / args.steps
+            per_class = {}
+            for tag, v in times.items():
+                per_class[tag.split(".")[0]] = per_class.get(tag.split(".")[0], 0.0) + sum(v) / args.steps
+            hbm_ach = fwd_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None
+            inf_ach = inf_bytes / (inf_ms * 1e-3) / 1e9 if inf_ms else None
+            tf_ach = fwd_flops / (fwd_ms * 1e-3) / 1e12 if fwd_ms else None
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.isfile(tpath):
+                tj = json.load(open(tpath))
+                traffic = tj.get("grcc_fwd_fused_dram_bytes_per_launch" if fused else "grcc_layer_fwd_dram_bytes_per_launch")
+            nL = max(1, geomS.L)
+            out["roofline"] = dict(
+                bound="hbm", achieved=hbm_ach, peak=pk["hbm_gbs"], unit="GB/s",
+                frac=(hbm_ach / pk["hbm_gbs"]) if hbm_ach else None, traffic=traffic,
+                kernel=("grcc_fwd_kernel: one fused launch per GRCC layer (train mode: + saved tanh, sigmoid); algorithmic "
+                        "bytes per SURVEY.md 8d (fp32 tensors: read x, cond; write x_next; RMW skip; + 2 D saved "
+                        "activations), summed over the layers" if fused else
+                        "tgemm_kernel: GRCC layer forward (2 launches/layer: conv+gate, res+skip), algorithmic bytes per "
+                        "SURVEY.md 8d incl. saved tanh/sigmoid, summed over the layers"),
+                algorithmic_bytes_per_launch=fwd_bytes / nL if fwd_bytes else None,
+                ms_per_layer_fwd=fwd_ms / nL, per_layer_gbs=per_layer_gbs,
+                frac_inference=(inf_ach / pk["hbm_gbs"]) if inf_ach else None, achieved_inference=inf_ach,
+                ms_per_layer_inference=inf_ms / nL if inf_ms else None, per_layer_gbs_inference=inf_gbs,
+                inference_note="forward only under torch.no_grad(): no saved activations; BASELINE.md 5's per-layer target "
+                               "(0.199 ms on 783.9 MB for layer 0) sits at the TF32 tensor floor (~0.19 ms under the power "
+                               "cap); the fp16-operand kernel's tensor floor is half of that",
+                peak_source=pk["source"])
+            out["roofline_tensor"] = dict(
+                bound="tensor", achieved=tf_ach, peak=pk["bf16_tflops"], unit="TFLOP/s",
+                frac=(tf_ach / pk["bf16_tflops"]) if tf_ach else None,
+                note=("fp16 operands: the measured bf16 cuBLAS rate is the like-for-like denominator" if fused else
+                      "TF32 operands: nominal peak = half of the bf16 rate, i.e. frac_of_tf32_peak = 2 x frac"),
+                frac_of_tf32_peak=None if fused or not tf_ach else 2 * tf_ach / pk["bf16_tflops"])
+            out["kernel_share"] = dict(tcgen05_ms_per_step=gemm_ms, step_ms=ms, instrumented_step_ms=prof_ms,
+                                       outside_engines_frac=max(0.0, 1.0 - gemm_ms / prof_ms) if prof_ms else None,
+                                       per_class_ms=per_class)
+    # release this workload's workspaces before the next one
+    del model, opt, sync, step, eager_step
+    ops._plans.clear()
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
+                    help="cfg2 (default, the headline): WaveNet decoder train step; cfg3: full VQ-VAE-EMA autoencoder "
+                         "train step (Encoder -> VQEMA -> WaveNet, par/arch.vqvae-ema.json), batch 16/GPU; with "
+                         "--gpus N this is cfg4 (grads + EMA statistics in ONE all-reduce); cfg5: deep decoder stress "
+                         "(30 dilation layers, 512 residual channels, window 65536, batch 2/GPU)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: cfg2 8, cfg3 16)")
+    ap.add_argument("--window", type=int, default=16384)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-PyTorch/cuDNN baseline on this GPU")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="multi-GPU runs of the default workload also time cfg4 and cfg5 (BASELINE.json's multi-GPU "
+                         "configurations) and report them under `extra`; this switch skips that")
+    ap.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--eager-cfg3", action="store_true",
+                    help="cfg3 only: keep the reference's data-dependent diagnostics (unique()) and run the step eagerly; "
+                         "default: VQEMA.static_diagnostics and the step replayed as a CUDA graph")
+    ap.add_argument("--graph-cfg3", action="store_true", help="(default now; kept for older session scripts)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the aewn hot path has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    out = bench_workload(args, args.workload, rank, local_rank, world, dev)
+    if world > 1 and args.workload == "cfg2" and not args.no_extra:
+        # BASELINE.json's multi-GPU configurations, under the same launch: cfg4 = the VQ-VAE-EMA step data-parallel with
+        # [grads | z_sum | n_sum] in one all-reduce (chassis.py:168-171,187-190; vqema_bn.py:172-195), cfg5 = the deep stack
+        extra = {}
+        for name, wl in (("cfg4", "cfg3"), ("cfg5", "cfg5")):
+            try:
+                r = bench_workload(args, wl, rank, local_rank, world, dev, light=True)
+                if rank == 0:
+                    extra[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "n_gpus", "e2e", "gpu_launches", "clocks")}
+                    extra[name]["workload"] = r["config"]["workload"]
+                    extra[name]["step_execution"] = r["config"]["step_execution"]
+            except Exception as e:   # noqa: BLE001
+                if rank == 0:
+                    extra[name] = dict(unavailable=f"{type(e).__name__}: {str(e)[:160]}")
+        if rank == 0:
+            out["extra"] = extra
+    if rank == 0:
+        cfg2 = args.workload == "cfg2"
+        if world == 1 and cfg2 and not args.no_gpu_baseline:
+            B, W = (args.batch or 8), args.window
+            out["gpu_library_baseline"] = gpu_library_baseline(B, W, dev)
+            tf = out["gpu_library_baseline"].get("tf32", {}).get("value")
+            if tf:
+                out["gpu_library_baseline"]["speedup_vs_tf32"] = out["value"] / tf
+        if not args.no_cpu_baseline and world == 1 and cfg2:
             pick_cpu_threads()
             sps, ctimes = cpu_port_step(2, 2048, 2, 1)
             out["cpu_baseline"] = dict(value=sps, unit=UNIT, cores=torch.get_num_threads(), kind="port",
                                        sample="same decoder (oracle port of wavenet.py), batch 2 x window 2048, "
-                                              "median of 2 steps after 1 warm-up")
+                                              "median of 2 steps after 1 warm-up (--impl reference runs the full "
+                                              "configuration)")
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out), flush=True)

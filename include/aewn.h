@@ -309,8 +309,10 @@ typedef struct {
   int skp_t_lo, skp_zero_lo;      /* same for the skip sum */
   int* err;
   int max_ctas;           /* 0 = one per SM */
-  long long* dbg_clock;   /* optional (profiling): 2 x 4 x 8 x 3 clock64() stamps of cluster 0's first four tiles --
-                             [MMA issuer | epilogue warp 0][tile][job][job seen, operands/accumulator ready, done] */
+  long long* dbg_clock;   /* optional (profiling): 2 x 4 x 8 x 6 values for cluster 0's first four tiles --
+                             [MMA issuer | epilogue warp 0][tile][job][clock64 at: job seen, operands / accumulator ready,
+                             done; cycles: MMA = waiting for ring stages, -, waiting for z | epilogue = acquiring staging
+                             tiles, TMEM loads, fence + TMA store issue] */
 } aewn_grcc_fwd_desc;
 
 int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream);

@@ -27,7 +27,7 @@ plan.sig[0][:, :, :T0] = torch.randn(B, R, T0, generator=gen).to(dev)
 plan.cond[:, :Cc, :T0] = torch.randn(B, Cc, T0, generator=gen).to(dev)
 for _ in range(3):
     plan.forward(save=True)
-clk = torch.zeros(2 * 4 * 8 * 3, dtype=torch.int64, device=dev)
+clk = torch.zeros(2 * 4 * 8 * 6, dtype=torch.int64, device=dev)
 kind, d, tag = plan.fwd_train[0]
 d.dbg_clock = clk.data_ptr()
 torch.cuda.synchronize()
@@ -37,14 +37,18 @@ L.check(L.lib().aewn_grcc_fwd(C.byref(d), ops._stream()), "aewn_grcc_fwd")
 e1.record()
 torch.cuda.synchronize()
 print(f"layer dil={dil}: {e0.elapsed_time(e1) * 1e3:.1f} us")
-c = clk.cpu().view(2, 4, 8, 3)
-t0 = int(c[c > 0].min())
+c = clk.cpu().view(2, 4, 8, 6)
+t0 = int(c[:, :, :, 0][c[:, :, :, 0] > 0].min())
 names = ["G1.0", "G1.1", "SKP", "RES1", "RES0", "-", "-", "-"]      # job order of arch.basic (R = 368)
 for role, rn in enumerate(("MMA issuer", "epilogue warp 0")):
     print(rn, "(cycles from first stamp: job seen | ready | done ; wait, work)")
     for tile in range(4):
         for job in range(8):
-            a, b, e = [int(v) for v in c[role, tile, job]]
+            a, b, e, x1, x2, x3 = [int(v) for v in c[role, tile, job]]
             if a == 0:
                 continue
-            print(f"  tile {tile} {names[job]:5s} {a - t0:8d} {b - t0:8d} {e - t0:8d}   wait {b - a:7d}  work {e - b:7d}")
+            if job == 7:
+                print(f"  tile {tile} top   {a - t0:8d}")
+                continue
+            aux = (f"ring-wait {x1:6d}  z-wait {x3:6d}" if role == 0 else f"stg-acquire {x1:6d}  tmem {x2:6d}  fence+store {x3:6d}")
+            print(f"  tile {tile} {names[job]:5s} {a - t0:8d} {b - t0:8d} {e - t0:8d}   wait {b - a:7d}  work {e - b:7d}   {aux}")
