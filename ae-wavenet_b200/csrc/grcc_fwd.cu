@@ -69,6 +69,8 @@ struct GfHot {
   float* skp;
   long long s_bs, s_cs;
   int save, z_out, skp_mode;               // skp_mode: 0 store, 1 reduce-add, 2 relu(old + acc), 3 relu(acc)
+  float *th, *sg, *z;                      // (B, D, Tp) saved activations (save / z_out)
+  long long a_bs, a_cs;
   int batch, t_begin, n_tgroups, n_res;
   int t_lo, t_zero_lo, t_hi, skp_t_lo, skp_zero_lo;
   int prefetch;
@@ -406,22 +408,29 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 *reinterpret_cast<uint4*>(zrow + (((lc0 + k) ^ (row & 7)) << 4)) = v;
               }
             }
-            if (slab_on) {
+            // tanh / sigmoid (/ z) for the backward pass: plain coalesced stores (lane = time step: every store
+            // instruction writes one full 128-byte line).  Through the staging tiles these were 3 TMA stores per chunk,
+            // each with its acquire / proxy fence / issue latency (~800 cycles, phase clock) in the warp's serial chain.
+            if (in_range) {
+              const long long o0 = static_cast<long long>(it.b) * hp.a_bs + static_cast<long long>(ch) * hp.a_cs + tau;
               if (hp.save) {
-                float* st = stg_acquire();
+                float* tp = hp.th + o0;
+                float* sp = hp.sg + o0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) st[j * 32] = __uint_as_float(vf[j]);
-                stg_flush(&p.th_m, slab0, ch, it.b, false);
-                st = stg_acquire();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) st[j * 32] = __uint_as_float(vg[j]);
-                stg_flush(&p.sg_m, slab0, ch, it.b, false);
+                for (int j = 0; j < 16; ++j) {
+                  *tp = __uint_as_float(vf[j]);
+                  *sp = __uint_as_float(vg[j]);
+                  tp += hp.a_cs;
+                  sp += hp.a_cs;
+                }
               }
               if (hp.z_out) {
-                float* st = stg_acquire();
+                float* zp = hp.z + o0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) st[j * 32] = __uint_as_float(vf[j]) * __uint_as_float(vg[j]);
-                stg_flush(&p.z_m, slab0, ch, it.b, false);
+                for (int j = 0; j < 16; ++j) {
+                  *zp = __uint_as_float(vf[j]) * __uint_as_float(vg[j]);
+                  zp += hp.a_cs;
+                }
               }
             }
           }
@@ -753,6 +762,11 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   p.hot.skp = d->skp;
   p.hot.s_bs = d->s_bs;
   p.hot.s_cs = d->s_cs;
+  p.hot.th = d->th;
+  p.hot.sg = d->sg;
+  p.hot.z = d->z;
+  p.hot.a_bs = d->a_bs;
+  p.hot.a_cs = d->a_cs;
   p.hot.save = d->save;
   p.hot.z_out = d->z != nullptr;
   p.hot.skp_mode = d->skp_mode;
