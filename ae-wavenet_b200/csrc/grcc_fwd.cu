@@ -60,6 +60,7 @@ struct GfHot {
   int kb_x, kb_c, kb_z;                   // ring stages per x tap, for cond, for z
   int dil;
   const float* x32;                        // residual source (B, R, Tp)
+  float* xo32;                             // x_next (B, R, Tp), same strides
   long long x_bs, x_cs;
   float* dup;                              // optional pre-shifted fp32 duplicate of x_next (backward wgrad tap, d_next % 4 != 0)
   int dup_toff, dup_t_hi;
@@ -452,6 +453,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           const int nv = jd.n_valid;
           const float* xsrc = hp.x32 + static_cast<long long>(it.b) * hp.x_bs + static_cast<long long>(jd.ch0) * hp.x_cs + tau;
           __half* x16row = hp.xo16 + static_cast<long long>(it.b) * hp.x16_bs + static_cast<long long>(tau) * hp.x16_cp + jd.ch0;
+          float* xdst = hp.xo32 + static_cast<long long>(it.b) * hp.x_bs + static_cast<long long>(jd.ch0) * hp.x_cs + tau;
           const int dup_t = tau + hp.dup_toff;
           float* dupp = (hp.dup && in_range && dup_t >= 0 && dup_t < hp.dup_t_hi)
                             ? hp.dup + static_cast<long long>(it.b) * hp.x_bs + static_cast<long long>(jd.ch0) * hp.x_cs + dup_t
@@ -482,11 +484,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               r[j] = (keep && c0 + j < nv) ? __uint_as_float(v[j]) + buf[j] : 0.0f;
               xmax = fmaxf(xmax, fabsf(r[j]));
             }
-            if (slab_on) {
-              float* st = stg_acquire();
+            if (in_range) {      // x_next fp32: plain coalesced stores (lane = time step), like tanh / sigmoid above
+              float* xo = xdst + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) st[j * 32] = r[j];
-              stg_flush(&p.xo_m, slab0, jd.ch0 + c0, it.b, false);
+              for (int j = 0; j < 16; ++j) {
+                if (c0 + j < nv) *xo = r[j];
+                xo += hp.x_cs;
+              }
             }
             if (dupp) {
               float* dd = dupp + static_cast<long long>(c0) * hp.x_cs;
@@ -751,6 +755,7 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   p.hot.kb_z = D / 64;
   p.hot.dil = d->dil;
   p.hot.x32 = d->x32;
+  p.hot.xo32 = d->xo32;
   p.hot.x_bs = d->x_bs;
   p.hot.x_cs = d->x_cs;
   p.hot.dup = d->dup;
