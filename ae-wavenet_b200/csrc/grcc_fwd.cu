@@ -75,6 +75,7 @@ struct GfHot {
   int batch, t_begin, n_tgroups, n_res;
   int t_lo, t_zero_lo, t_hi, skp_t_lo, skp_zero_lo;
   int prefetch;
+  int dbg;                                 // AEWN_GF_DBG bit mask: skip parts of the epilogues (timing experiments only)
   int* err;
   long long* dbg_clock;   // optional: cluster 0 / CTA 0 stamps its first items (profiles/gf_phase_clock.py)
 };
@@ -115,6 +116,31 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
+      : "memory");
+}
+
+// cta_group::2 loads with an L2 cache policy (createpolicy): operands that are read again soon -- the weights by every
+// CTA pair, the activation tile by the second gate job and, dil steps later, as the shifted tap -- are kept with
+// evict_last, so that the kernel's ~0.9 GB of streaming output per launch does not push them out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
+                                                      int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair_hint(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
+                                                      int c1, int c2, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
       : "memory");
 }
 
@@ -208,12 +234,20 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
       uint32_t stage = 0, phase = 0;
       bool ok = true;
       const uint32_t lead_full = mapa_u32(&full_bar[0], 0);
+      const uint64_t pol_keep = l2_policy_evict_last();
       for (int item = cid; item < total && ok; item += n_cl) {
         const GfItem it = gf_decode(hp, item, crank);
         // the residual rows this tile's RES epilogues will add (128 time steps x R channels of x32): pull them into L2
         // now, ~20 k cycles before the epilogue warps load them
-        if (hp.prefetch && elect_one()) {
+        if ((hp.prefetch & 1) && elect_one()) {
           for (int c = 0; c < hp.n_res; c += 32) tma_prefetch_l2_3d(&p.xr_m, it.tau0, c, it.b);
+        }
+        // ... and the NEXT tile's activation operand (fp16 x and conditioning rows): its first gate job otherwise waits
+        // for HBM behind a ring of only 3-4 stages (phase clock: ~1000 cycles per stage against ~570 from L2)
+        if ((hp.prefetch & 2) && item + n_cl < total && elect_one()) {
+          const GfItem nx = gf_decode(hp, item + n_cl, crank);
+          for (int kb = 0; kb < hp.kb_x; ++kb) tma_prefetch_l2_3d(&p.xa, kb * GF_KB, nx.tau0, nx.b);
+          for (int kb = 0; kb < hp.kb_c; ++kb) tma_prefetch_l2_3d(&p.ca, kb * GF_KB, nx.tau0, nx.b);
         }
         __syncwarp();
         for (int jb = 0; jb < hp.n_jobs && ok; ++jb) {
@@ -228,14 +262,14 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               const uint32_t fb = lead_full + stage * 8u;
               if (jd.kind == GF_GATE) {
                 if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * GF_STAGE_BYTES);
-                if (s < hp.kb_x) tma_load_3d_pair(sa, &p.xa, fb, s * GF_KB, it.tau0 - hp.dil, it.b);
-                else if (s < 2 * hp.kb_x) tma_load_3d_pair(sa, &p.xa, fb, (s - hp.kb_x) * GF_KB, it.tau0, it.b);
-                else tma_load_3d_pair(sa, &p.ca, fb, (s - 2 * hp.kb_x) * GF_KB, it.tau0, it.b);
-                tma_load_2d_pair(sw, &p.w1, fb, s * GF_KB, jd.w_row + crank * 128);
+                if (s < hp.kb_x) tma_load_3d_pair_hint(sa, &p.xa, fb, s * GF_KB, it.tau0 - hp.dil, it.b, pol_keep);
+                else if (s < 2 * hp.kb_x) tma_load_3d_pair_hint(sa, &p.xa, fb, (s - hp.kb_x) * GF_KB, it.tau0, it.b, pol_keep);
+                else tma_load_3d_pair_hint(sa, &p.ca, fb, (s - 2 * hp.kb_x) * GF_KB, it.tau0, it.b, pol_keep);
+                tma_load_2d_pair_hint(sw, &p.w1, fb, s * GF_KB, jd.w_row + crank * 128, pol_keep);
               } else {
                 // CTA r stages W2 rows [r * n/2, (r+1) * n/2) of the job (a 128-row box; the MMA reads n/2 of them)
                 if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * GF_W_BYTES);
-                tma_load_2d_pair(sw, &p.w2, fb, s * GF_KB, jd.w_row + crank * (jd.n >> 1));
+                tma_load_2d_pair_hint(sw, &p.w2, fb, s * GF_KB, jd.w_row + crank * (jd.n >> 1), pol_keep);
               }
             }
             __syncwarp();
@@ -322,6 +356,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
     float* const tile2 = stg_base + (warp - 4) * 512 * HALVES;
     uint32_t stg_cur = 0;
     unsigned int dbg_acq = 0, dbg_tm = 0, dbg_fl = 0;      // phase-clock accumulators (cycles), see dbg_clock
+    const int dbg = hp.dbg;
     auto stg_acquire = [&]() -> float* {
       const unsigned int t_a = clock();
       if (HALVES == 2) {
@@ -412,15 +447,15 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             // tanh / sigmoid (/ z) for the backward pass: plain coalesced stores (lane = time step: every store
             // instruction writes one full 128-byte line).  Through the staging tiles these were 3 TMA stores per chunk,
             // each with its acquire / proxy fence / issue latency (~800 cycles, phase clock) in the warp's serial chain.
-            if (in_range) {
+            if (in_range && !(dbg & 8)) {
               const long long o0 = static_cast<long long>(it.b) * hp.a_bs + static_cast<long long>(ch) * hp.a_cs + tau;
               if (hp.save) {
                 float* tp = hp.th + o0;
                 float* sp = hp.sg + o0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                  *tp = __uint_as_float(vf[j]);
-                  *sp = __uint_as_float(vg[j]);
+                  __stcs(tp, __uint_as_float(vf[j]));
+                  __stcs(sp, __uint_as_float(vg[j]));
                   tp += hp.a_cs;
                   sp += hp.a_cs;
                 }
@@ -429,7 +464,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 float* zp = hp.z + o0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                  *zp = __uint_as_float(vf[j]) * __uint_as_float(vg[j]);
+                  __stcs(zp, __uint_as_float(vf[j]) * __uint_as_float(vg[j]));
                   zp += hp.a_cs;
                 }
               }
@@ -463,7 +498,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             const float* sp = xsrc + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              buf[j] = (keep && c0 + j < nv) ? __ldcg(sp) : 0.0f;
+              buf[j] = (keep && c0 + j < nv && !(dbg & 1)) ? __ldcs(sp) : 0.0f;
               sp += hp.x_cs;
             }
           };
@@ -484,11 +519,11 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               r[j] = (keep && c0 + j < nv) ? __uint_as_float(v[j]) + buf[j] : 0.0f;
               xmax = fmaxf(xmax, fabsf(r[j]));
             }
-            if (in_range) {      // x_next fp32: plain coalesced stores (lane = time step), like tanh / sigmoid above
+            if (in_range && !(dbg & 2)) {      // x_next fp32: plain coalesced stores (lane = time step), like tanh / sigmoid above
               float* xo = xdst + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                if (c0 + j < nv) *xo = r[j];
+                if (c0 + j < nv) __stcs(xo, r[j]);
                 xo += hp.x_cs;
               }
             }
@@ -496,11 +531,11 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               float* dd = dupp + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                if (c0 + j < nv) *dd = r[j];
+                if (c0 + j < nv) __stcs(dd, r[j]);
                 dd += hp.x_cs;
               }
             }
-            if (in_range) {
+            if (in_range && !(dbg & 4)) {
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
                 if (c0 + 8 * k < nv) {
@@ -509,7 +544,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                   hv.y = pack_f16x2(r[8 * k + 2], r[8 * k + 3]);
                   hv.z = pack_f16x2(r[8 * k + 4], r[8 * k + 5]);
                   hv.w = pack_f16x2(r[8 * k + 6], r[8 * k + 7]);
-                  *reinterpret_cast<uint4*>(x16row + c0 + 8 * k) = hv;
+                  __stcs(reinterpret_cast<uint4*>(x16row + c0 + 8 * k), hv);
                 }
               }
             }
@@ -725,8 +760,10 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   if (!d->final_layer) {
     if ((rc = encode_out_map(&p.xo_m, d->xo32, d->t_hi, R, d->batch, d->x_cs, d->x_bs, 16))) return rc;
     if ((rc = encode_out_map(&p.xr_m, const_cast<float*>(d->x32), d->t_hi, R, d->batch, d->x_cs, d->x_bs, 32, 128))) return rc;
-    static const int pf = []() { const char* e = getenv("AEWN_GF_PREFETCH"); return e ? atoi(e) : 1; }();
+    static const int pf = []() { const char* e = getenv("AEWN_GF_PREFETCH"); return e ? atoi(e) : 3; }();
     p.hot.prefetch = pf;
+    static const int dbgf = []() { const char* e = getenv("AEWN_GF_DBG"); return e ? atoi(e) : 0; }();
+    p.hot.dbg = dbgf;
     p.hot.n_res = R;
   }
   if ((rc = encode_out_map(&p.skp_m, d->skp, d->t_hi, S, d->batch, d->s_cs, d->s_bs, 16))) return rc;
