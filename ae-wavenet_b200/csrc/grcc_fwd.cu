@@ -29,7 +29,8 @@ namespace aewn {
 
 constexpr int GF_BM = 128;
 constexpr int GF_KB = 64;                         // K elements per ring stage: 64 fp16 = one 128-byte swizzle row
-constexpr int GF_MAX_STAGES = 4;                  // ring 3 x 32 KB + two 2 KB staging half-tiles per epilogue warp, or 4 x 32 KB + one
+constexpr int GF_MAX_STAGES = 5;                  // ring: 5 x 32 KB (no epilogue staging: every output leaves with coalesced
+                                                  // lane = time stores / reds), or 4 x 32 KB for A/B runs
 constexpr int GF_A_BYTES = GF_BM * 128;           // 16 KB: 128 time rows x 128 B
 constexpr int GF_W_BYTES = 128 * 128;             // 16 KB: 128 weight rows x 128 B (this CTA's half of the N rows)
 constexpr int GF_STAGE_BYTES = GF_A_BYTES + GF_W_BYTES;
@@ -37,7 +38,7 @@ constexpr int GF_MAX_D = 256;
 constexpr int GF_ZBUF_BYTES = (GF_MAX_D / GF_KB) * GF_A_BYTES;   // 64 KB: z of this CTA's 128 time rows, all D channels
 constexpr int GF_THREADS = 640;                  // 4 control warps + 16 epilogue warps
 constexpr int GF_EPI_WARPS = 16;
-constexpr int GF_POOL_BYTES = 3 * GF_STAGE_BYTES + GF_EPI_WARPS * 4096;   // ring + staging: 160 KB in either split
+constexpr int GF_POOL_BYTES = GF_MAX_STAGES * GF_STAGE_BYTES;   // 160 KB
 constexpr int GF_SMEM_BYTES = GF_POOL_BYTES + GF_ZBUF_BYTES + 256 + 512 + 1024;   // + barriers + GfHot + alignment slack
 constexpr int GF_MAX_JOBS = 8;
 
@@ -168,23 +169,20 @@ __device__ __forceinline__ GfItem gf_decode(const GfHot& p, int item, int crank)
 
 template <int STAGES>
 __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_constant__ GfParams p) {
-  constexpr int HALVES = STAGES == 3 ? 2 : 1;                 // staging half-tiles per epilogue warp
-  constexpr int RING_BYTES = STAGES * GF_STAGE_BYTES;
-  constexpr int STG_BYTES = GF_EPI_WARPS * 2048 * HALVES;
-  static_assert(RING_BYTES + STG_BYTES == GF_POOL_BYTES, "both splits use the same shared memory");
+  constexpr int RING_BYTES = GF_POOL_BYTES;                   // (a shallower ring leaves its tail unused)
+  static_assert(STAGES <= GF_MAX_STAGES, "ring depth");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* zbuf = smem + RING_BYTES;
-  float* stg_base = reinterpret_cast<float*>(smem + RING_BYTES + GF_ZBUF_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_BYTES + GF_ZBUF_BYTES + STG_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_BYTES + GF_ZBUF_BYTES);
   uint64_t* empty_bar = full_bar + GF_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + GF_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* zready_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zready_bar + 1);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
-  GfHot* hot_s = reinterpret_cast<GfHot*>(smem + RING_BYTES + GF_ZBUF_BYTES + STG_BYTES + 256);
+  GfHot* hot_s = reinterpret_cast<GfHot*>(smem + RING_BYTES + GF_ZBUF_BYTES + 256);
   if (threadIdx.x < sizeof(GfHot) / 8)
     reinterpret_cast<unsigned long long*>(hot_s)[threadIdx.x] = reinterpret_cast<const unsigned long long*>(&p.hot)[threadIdx.x];
   const GfHot& hp = *hot_s;
@@ -353,33 +351,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
     const int q = warp & 3;
     const int h = (warp - 4) >> 2;
     const int row = q * 32 + lane;
-    float* const tile2 = stg_base + (warp - 4) * 512 * HALVES;
-    uint32_t stg_cur = 0;
     unsigned int dbg_acq = 0, dbg_tm = 0, dbg_fl = 0;      // phase-clock accumulators (cycles), see dbg_clock
     const int dbg = hp.dbg;
-    auto stg_acquire = [&]() -> float* {
-      const unsigned int t_a = clock();
-      if (HALVES == 2) {
-        stg_cur ^= 1u;
-        if (elect_one()) tma_store_wait_read1();   // all but the latest box have been read out: the older half is free
-      } else {
-        if (elect_one()) tma_store_wait_read();
-      }
-      __syncwarp();
-      dbg_acq += clock() - t_a;
-      return tile2 + stg_cur * 512 + lane;
-    };
-    auto stg_flush = [&](const CUtensorMap* map, int t0, int c0, int b, bool reduce) {
-      const unsigned int t_f = clock();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (elect_one()) {
-        if (reduce) tma_reduce_add_3d(map, tile2 + stg_cur * 512, t0, c0, b);
-        else tma_store_3d(map, tile2 + stg_cur * 512, t0, c0, b);
-        tma_store_commit();
-      }
-      dbg_fl += clock() - t_f;
-    };
     const uint32_t lead_tempty = mapa_u32(&tempty_bar[0], 0);
     const uint32_t lead_zready = mapa_u32(zready_bar, 0);
     uint32_t acc = 0, acc_phase = 0;
@@ -572,7 +545,6 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           const int ce = min(cb + span, jd.n);
           const bool s_in = tau >= hp.skp_t_lo && tau < hp.t_hi;
           const bool s_keep = s_in && tau >= hp.skp_zero_lo;
-          const bool s_slab = (slab0 + 32 > hp.skp_t_lo) && (slab0 < hp.t_hi);
           const float* old = hp.skp + static_cast<long long>(it.b) * hp.s_bs + static_cast<long long>(jd.ch0) * hp.s_cs + tau;
           if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
@@ -595,16 +567,22 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
             dbg_tm += clock() - t_t;
-            if (s_slab) {
-              float* st = stg_acquire();
-              if (hp.skp_mode >= 2) {
+            if (s_in) {
+              float* op = hp.skp + static_cast<long long>(it.b) * hp.s_bs + static_cast<long long>(jd.ch0 + c0) * hp.s_cs + tau;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) st[j * 32] = s_keep ? fmaxf(__uint_as_float(v[j]) + o[j], 0.0f) : 0.0f;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) st[j * 32] = s_keep ? __uint_as_float(v[j]) : 0.0f;
+              for (int j = 0; j < 16; ++j) {
+                if (c0 + j < jd.n_valid) {
+                  const float a = s_keep ? __uint_as_float(v[j]) : 0.0f;
+                  if (hp.skp_mode == 1) {
+                    if (s_keep) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(op), "f"(a) : "memory");
+                  } else if (hp.skp_mode >= 2) {
+                    *op = s_keep ? fmaxf(a + o[j], 0.0f) : 0.0f;
+                  } else {
+                    *op = a;
+                  }
+                }
+                op += hp.s_cs;
               }
-              stg_flush(&p.skp_m, slab0, jd.ch0 + c0, it.b, hp.skp_mode == 1);
             }
           }
           tc_fence_before();
@@ -760,7 +738,7 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   if (!d->final_layer) {
     if ((rc = encode_out_map(&p.xo_m, d->xo32, d->t_hi, R, d->batch, d->x_cs, d->x_bs, 16))) return rc;
     if ((rc = encode_out_map(&p.xr_m, const_cast<float*>(d->x32), d->t_hi, R, d->batch, d->x_cs, d->x_bs, 32, 128))) return rc;
-    static const int pf = []() { const char* e = getenv("AEWN_GF_PREFETCH"); return e ? atoi(e) : 3; }();
+    static const int pf = []() { const char* e = getenv("AEWN_GF_PREFETCH"); return e ? atoi(e) : 0; }();   // bit 0: residual rows, bit 1: next tile's operands. Measured SLOWER (356 -> 379 / 377 / 394 us per layer): off
     p.hot.prefetch = pf;
     static const int dbgf = []() { const char* e = getenv("AEWN_GF_DBG"); return e ? atoi(e) : 0; }();
     p.hot.dbg = dbgf;
@@ -841,10 +819,10 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  // ring depth 3 (two staging half-tiles per epilogue warp) or 4 (one): AEWN_GF_RING=3|4 for A/B runs
-  static const int ring = []() { const char* e = getenv("AEWN_GF_RING"); return e && atoi(e) == 3 ? 3 : 4; }();
+  // ring depth: 5 stages (default) or 4 (AEWN_GF_RING=4, A/B runs)
+  static const int ring = []() { const char* e = getenv("AEWN_GF_RING"); return e && atoi(e) == 4 ? 4 : 5; }();
   using KernelFn = void (*)(GfParams);
-  KernelFn fn = ring == 3 ? grcc_fwd_kernel<3> : grcc_fwd_kernel<4>;
+  KernelFn fn = ring == 4 ? grcc_fwd_kernel<4> : grcc_fwd_kernel<5>;
   cudaError_t ae = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_BYTES);
   if (ae != cudaSuccess) return cuda_err(ae, "grcc_fwd: cudaFuncSetAttribute");
   cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
