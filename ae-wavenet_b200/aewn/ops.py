@@ -474,6 +474,8 @@ class StackPlan:
         self.cond = new_buf(B, Cc + 1, Tp, device)
         self.cond[:, Cc, :] = 1.0                                            # the bias channel
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.nan_const = torch.full((1,), float("nan"), device=device)      # see _DecoderCoreFn.forward (error poison)
+        self.zero_const = torch.zeros(1, device=device)
         self.KR, self.KC, self.KD = ceil_to(R, 32), ceil_to(Cc + 1, 32), ceil_to(D, 32)
         self.KS, self.K2 = ceil_to(S, 32), ceil_to(2 * D, 32)
         self.J = (D + 127) // 128

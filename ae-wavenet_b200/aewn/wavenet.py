@@ -351,7 +351,8 @@ class WaveNet(nn.Module):
         none = wav.new_zeros(0)
         opt = lambda t: t if t is not None else none
         # base layer + 20 GRCC layers + ReLU + post1 + ReLU + post2, all on the kernel path
-        return _DecoderCoreFn.apply(wav, cond, self, keys, self.base_layer.weight, opt(self.base_layer.bias),
+        return _DecoderCoreFn.apply(wav, cond, self, keys, torch.is_grad_enabled(), self.base_layer.weight,
+                                    opt(self.base_layer.bias),
                                     self.post1.weight, opt(self.post1.bias), self.post2.weight, opt(self.post2.bias),
                                     *weights)
 
@@ -387,7 +388,7 @@ class _DecoderCoreFn(torch.autograd.Function):
     Inputs: wav (B, T_wav) float mu-law codes, cond (B, C, T0).  Output: relu(skp_sum) (B, S, W)."""
 
     @staticmethod
-    def forward(ctx, wav, cond, net, keys, base_w, base_b, p1w, p1b, p2w, p2b, *weights):
+    def forward(ctx, wav, cond, net, keys, want_grad, base_w, base_b, p1w, p1b, p2w, p2b, *weights):
         o0, o1 = net.wav_cond_offset
         T0 = o1 - o0
         B, Cc = cond.shape[0], cond.shape[1]
@@ -421,7 +422,7 @@ class _DecoderCoreFn(torch.autograd.Function):
                 L.C.c_void_p(plan.err.data_ptr()), ops._stream()), "aewn_base_embed_fwd")
             # under torch.no_grad() (or with nothing upstream requiring a gradient) nothing is kept for a backward pass:
             # the layers run in inference mode (no tanh / sigmoid / z writes: SURVEY.md 8d's inference byte count)
-            save = any(ctx.needs_input_grad)
+            save = bool(want_grad) and any(ctx.needs_input_grad)     # (needs_input_grad ignores the grad mode)
             plan.forward(save=save)
             pw = {"post1.weight": p1w, "post1.bias": p1b if p1b.numel() else None, "post2.weight": p2w,
                   "post2.bias": p2b if p2b.numel() else None}
@@ -432,7 +433,7 @@ class _DecoderCoreFn(torch.autograd.Function):
             # a device-side fault (bounded wait expired, mu-law code outside [0, Q), activation outside the fp16 operand
             # range) must not go unnoticed until somebody calls ops.check_device_errors(): poison ONE logit, so that the
             # loss of this step is NaN (two 1-element kernels, no synchronisation, capturable)
-            logits[0, 0, geom.RF:geom.RF + 1] += torch.where(plan.err != 0, float("nan"), 0.0).to(logits.dtype)
+            logits[0, 0, geom.RF:geom.RF + 1] += torch.where(plan.err != 0, plan.nan_const, plan.zero_const)
             out = logits[:, :, geom.RF:T0]               # (B, Q, W) view of a fresh (B, Q, Tp) buffer
         ctx.saved_for_bwd = save
         ctx.post = post
@@ -450,9 +451,11 @@ class _DecoderCoreFn(torch.autograd.Function):
     def backward(ctx, g_out):
         plan = ctx.plan
         geom = plan.geom
+        if not ctx.saved_for_bwd:
+            raise RuntimeError("aewn: this forward ran in inference mode (torch.no_grad()): nothing was saved for backward")
         if plan.generation != ctx.gen:
             raise RuntimeError("aewn: workspace was reused by a later forward before this backward ran "
-                               "(one in-flight forward per configuration)")
+                               "(one in-flight forward per model and configuration)")
         B, R, D, S, Cc, Q, T0 = ctx.dims
         lib = L.lib()
         # post-net backward: fills the stack's g_skp buffer (gradient w.r.t. the pre-ReLU skip sum, absolute time axis)
@@ -476,10 +479,10 @@ class _DecoderCoreFn(torch.autograd.Function):
             # accumulates into them): ONE launch adds every weight gradient into the existing .grad buffers
             pairs = [(v, leaf.grad) for v, leaf in zip(views, ctx.leaves) if v is not None]
             if ops.add_into_grads(pairs):
-                return (None, g_cond[:, :, :T0].clone(), None, None, d_base.reshape(ctx.base_shape), d_bias) + \
+                return (None, g_cond[:, :, :T0].clone(), None, None, None, d_base.reshape(ctx.base_shape), d_bias) + \
                        (None,) * len(views)
         out = tuple(v.clone() if v is not None else None for v in views)
-        return (None, g_cond[:, :, :T0].clone(), None, None, d_base.reshape(ctx.base_shape), d_bias) + out
+        return (None, g_cond[:, :, :T0].clone(), None, None, None, d_base.reshape(ctx.base_shape), d_bias) + out
 
 
 class _NLLFn(torch.autograd.Function):

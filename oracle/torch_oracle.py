@@ -6,7 +6,8 @@ is present, and against the golden vectors under tests/golden/ that oracle/make_
 reference.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import it; the product package
 never does (it has no CPU compute path at all).
 
-All tensors are CPU float32 unless noted; weights come in a flat dict keyed like the reference state_dict
+All tensors are float32 on the device of the inputs (CPU in the tests; bench.py's GPU-library baseline runs the same
+functions on cuda, i.e. eager PyTorch/cuDNN); weights come in a flat dict keyed like the reference state_dict
 (SURVEY.md 8b), e.g. ``conv_layers.3.conv_signal.weight``.
 """
 import torch
@@ -71,7 +72,7 @@ def wavenet_forward_train(sd, hp, geo, wav, lc_sparse, speaker_inds, jitter_inde
     o0, o1 = geo["wav_cond_offset"]
     wav_onehot = F.one_hot(wav.long(), hp["n_quant"]).permute(0, 2, 1).float()[:, :, o0:o1]  # :348-349
     sig = F.conv1d(wav_onehot, sd["base_layer.weight"], sd.get("base_layer.bias"))
-    skp_sum = torch.zeros(wav.shape[0], hp["n_skp"], geo["n_win_batch"])
+    skp_sum = torch.zeros(wav.shape[0], hp["n_skp"], geo["n_win_batch"], device=wav.device)
     dils = dilations(hp)
     inter = []
     for li, d in enumerate(dils):
