@@ -317,10 +317,10 @@ def fused_accumulate_applies(leaves):
             owner = getattr(q, "_aewn_fused_owner", None)
             if owner is None or owner() is None or q.grad is None:
                 return False
-            node = getattr(q, "_aewn_acc_node", None)
-            if node is None:
-                with torch.enable_grad():       # (backward runs with grad mode off: view_as would have no grad_fn)
-                    node = q._aewn_acc_node = q.view_as(q).grad_fn.next_functions[0][0]     # the leaf's AccumulateGrad
+            # (looked up per call, never cached: a cached AccumulateGrad node stays bound to the stream it was created on
+            # -- e.g. the warm-up stream -- and would put a cross-stream dependency into a later CUDA-graph capture)
+            with torch.enable_grad():           # backward runs with grad mode off: view_as would have no grad_fn
+                node = q.view_as(q).grad_fn.next_functions[0][0]     # the leaf's AccumulateGrad
             if not will(node):
                 return False
     except RuntimeError:

@@ -178,6 +178,37 @@ def golden_geometry_and_init():
     print("geometry:", {k: v.get("dec_in_len") for k, v in geo_out.items()})
 
 
+def golden_cfg1():
+    """BASELINE cfg1: the reference's UNMODIFIED mfcc_inverter.MfccInverter (hparams sets mfcc_inverter,mfcc,train ==
+    par/arch.mi.json: upsampling strides [5,4,4,2], 39 conditioning channels), batch 2, window 4096, seed 2507, through
+    MfccInverter.run (mfcc_inverter.py:89-107: forward, RecLoss, autograd.grad w.r.t. mel) on CPU.  The 13.5 M initial
+    parameters are NOT stored (54 MB): both sides build them from the same seed, pinned here by SHA-256 digests; stored
+    are the inputs, the last 64 output steps of the logits, the loss and the mel gradient."""
+    import hashlib
+    m = rh.load()
+    hps = m["hparams"].setup_hparams("mfcc_inverter,mfcc,train", dict(n_win_batch=4096, n_batch=2))
+    torch.manual_seed(2507)
+    mi = m["mfcc_inverter"].MfccInverter(hps)
+    mi.train()
+    geo = dict(wav_len=mi.enc_in_len, lc_len=mi.embed_len)
+    wav, mel, voice, jit = synth_inputs(2, geo, hps.n_lc_in, hps.n_speakers, 4321)
+    mel = mel.clone()
+    pred, target, loss = mi.run(wav, mel, voice, jit)
+    (mel_grad,) = torch.autograd.grad(loss, mel)
+    arch = {k: hps[k] for k in ("filter_sz", "n_lc_out", "lc_upsample_strides", "lc_upsample_filt_sizes", "n_res", "n_dil",
+                                "n_skp", "n_post", "n_quant", "n_blocks", "n_block_layers", "n_global_embed", "n_speakers",
+                                "bias", "n_lc_in", "mfcc_win_sz", "mfcc_hop_sz")}
+    sd = mi.wavenet.state_dict()
+    torch.save(dict(arch=arch, W=4096, wav=wav, mel=mel.detach(), voice=voice, jit=jit,
+                    trim_dec_out=mi.trim_dec_out.tolist(), wav_cond_offset=list(mi.wavenet.wav_cond_offset),
+                    dec_in_len=mi.dec_in_len, enc_in_len=mi.enc_in_len, embed_len=mi.embed_len,
+                    pred_tail=pred.detach()[:, :, -64:].clone(), loss=loss.detach(), mel_grad=mel_grad,
+                    digest={k: hashlib.sha256(v.numpy().tobytes()).hexdigest() for k, v in sd.items()
+                            if v.dtype == torch.float32}),
+               os.path.join(OUT, "cfg1_mi.pt"))
+    print("cfg1: loss", float(loss), "pred", tuple(pred.shape))
+
+
 def golden_forward_test():
     """The reference's own sampler (wavenet.py:367-531) on CPU, 2 replicas, with torch.multinomial swapped for an
     inverse-CDF draw on recorded uniforms (generator seed 99) so that the run is reproducible by any implementation.
@@ -252,6 +283,9 @@ def golden_autoencoder():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
+        golden_cfg1()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "autoencoder":
         golden_autoencoder()
         sys.exit(0)

@@ -151,3 +151,69 @@ def test_cfg5_deep_stack_window_matches_cpu_oracle():
     assert err < 8e-3, err
     ops._plans.clear()          # release the ~20 GB workspace before the next test
     torch.cuda.empty_cache()
+
+
+def test_full_size_backward_matches_cpu_oracle_on_the_trailing_window():
+    """cfg2 geometry at full length (window 16384, decoder input 18430, batch 2): the loss touches only the LAST 64 output
+    steps, so every gradient depends on the trailing RF + 64 input steps only and the CPU oracle (autograd through
+    oracle/torch_oracle.py on that window) gives the exact reference for the FULL-SIZE kernel launches: per-unit split-K
+    of the wide weight-gradient units, merged data-gradient tiles, the one-launch gradient accumulation -- all at their
+    real extents and tile counts.  Compared: every weight gradient of the first, a middle and the last dilation layer,
+    the post-net, the base layer, and the gradient w.r.t. the conditioning input lc_sparse (through the front-end)."""
+    import aewn
+    from aewn import ops
+    from oracle import torch_oracle as orc
+    torch.manual_seed(2507)
+    W, B, n_out, rf = 16384, 2, 64, 2046
+    wn, geo = build(W)
+    wn = wn.cuda().train()
+    g = torch.Generator().manual_seed(11)
+    wav = torch.randint(0, 256, (B, geo["wav_len"]), generator=g).float()
+    lc = torch.randn(B, 64, geo["lc_len"], generator=g)
+    spk = torch.randint(0, 40, (B,), generator=g)
+    jit = torch.arange(geo["lc_len"]).unsqueeze(0).repeat(B, 1)
+    gq = torch.randn(B, 256, n_out, generator=g)
+    lc_d = lc.cuda().requires_grad_(True)
+    q = wn(wav.cuda(), lc_d, spk.cuda(), jit.cuda())
+    (q[:, :, -n_out:] * gq.cuda()).sum().backward()
+    ops.check_device_errors()
+    got = {k: p.grad.detach().cpu() for k, p in wn.named_parameters()}
+    got_lc = lc_d.grad.detach().cpu()
+    # CPU oracle on the trailing window
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.dtype == torch.float32 and k != "cond.eye")
+          for k, v in wn.state_dict().items()}
+    lc_c = lc.clone().requires_grad_(True)
+    o0, o1 = wn.wav_cond_offset
+    T0 = geo["dec_in_len"]
+    leads = [l.leads.tolist() for l in wn.conv_layers]
+    cond = orc.conditioning(sd, ARCH_BASIC, lc_c, spk, jit, [0, T0])
+    s = T0 - (rf + n_out)
+    onehot = torch.nn.functional.one_hot(wav[:, o0:o1].long(), 256).permute(0, 2, 1).float()[:, :, s:]
+    sig = torch.nn.functional.conv1d(onehot, sd["base_layer.weight"], sd["base_layer.bias"])
+    c = cond[:, :, s:]
+    skp_sum = 0
+    for li, d in enumerate(orc.dilations(ARCH_BASIC)):
+        sig, skp = orc.grcc_layer(sig, c, orc.sub(sd, f"conv_layers.{li}"), d, leads[li], li == 19)
+        skp_sum = skp_sum + skp
+    post1 = torch.nn.functional.conv1d(torch.relu(skp_sum), sd["post1.weight"], sd["post1.bias"])
+    ref_q = torch.nn.functional.conv1d(torch.relu(post1), sd["post2.weight"], sd["post2.bias"])
+    assert ref_q.shape[2] == n_out
+    fwd_err = float((q[:, :, -n_out:].detach().cpu() - ref_q).abs().max()) / float(ref_q.abs().max())
+    assert fwd_err < 5e-3, fwd_err
+    (ref_q * gq).sum().backward()
+
+    def check(name, a, b, tol):
+        scale = float(b.abs().max())
+        err = float((a - b).abs().max()) / max(scale, 1e-20)
+        cos = float(a.double().flatten() @ b.double().flatten() / (a.double().norm() * b.double().norm() + 1e-300))
+        assert err < tol and cos > 0.999, (name, err, cos)
+
+    keys = [k for k in got if k.startswith(("conv_layers.0.", "conv_layers.9.", "conv_layers.19.", "post1.", "post2.",
+                                            "base_layer."))]
+    assert len(keys) >= 28
+    for k in keys:
+        check(k, got[k], sd[k].grad, 3e-2)          # TF32 operands in the backward engines, fp32 accumulation
+    for k in got:                                    # every other parameter: direction and scale
+        if k not in keys and sd[k].grad is not None and float(sd[k].grad.abs().max()) > 0:
+            check(k, got[k], sd[k].grad, 8e-2)
+    check("lc_sparse", got_lc, lc_c.grad, 5e-2)
