@@ -58,7 +58,7 @@ def test_autoencoder_small_step_matches_reference_golden(golden_dir):
         assert rel_err(getattr(bn, k), g[k]) < 5e-3, k
     (com + rec).backward()
     ops.check_device_errors()
-    assert rel_err(mels.grad, g["mel_grad"]) < 0.15 and cosine(mels.grad, g["mel_grad"]) > 0.99
+    assert rel_err(mels.grad, g["mel_grad"]) < 0.15 and cosine(mels.grad, g["mel_grad"]) > 0.995
     mods = dict(encoder=ae.encoder, bottleneck=ae.bottleneck, decoder=ae.decoder)
     worst = []
     for part, grads in g["grads"].items():
@@ -71,8 +71,10 @@ def test_autoencoder_small_step_matches_reference_golden(golden_dir):
             worst.append((rel_err(p.grad, ref), cosine(p.grad, ref), part, k))
     worst.sort(reverse=True)
     print("worst gradient errors", worst[:5])
+    # (max-abs bound: the envelope MEASURED in test_gpu_decoder.py -- cuDNN's own TF32 path against the same kind of fp32
+    # golden, times two -- lands at this order for sums of few signed terms; the direction bound is the tight one)
     for e, c, part, k in worst:
-        assert e < 0.15 and c > 0.99, (part, k, e, c)
+        assert e < 0.15 and c > 0.995, (part, k, e, c)
     fz = [float(m.frac_zero_act) for m in ae.encoder.net]
     assert max(abs(a - b) for a, b in zip(fz, g["frac_zero"])) < 2e-3
 
@@ -118,6 +120,39 @@ def test_cfg3_full_size_train_step_properties(golden_dir):
     assert rel_err(bn.z_sum, z_ref) < 1e-5
     assert rel_err(bn.ema_numer, 0.99 * numer0 + 0.01 * bn.z_sum) < 1e-6
     assert rel_err(bn.ema_denom, 0.99 * denom0 + 0.01 * bn.n_sum) < 1e-6
+    # --- oracle VALUES at the full cfg3 size (not only properties).  The encoder works on 144 mel frames, so the CPU
+    # oracle runs it for all 16 items: ze within the TF32 envelope, codes equal wherever the oracle's own decision is not
+    # a near-tie.  The decoder is checked on the trailing receptive field of item 0, conditioned on the codes the GPU
+    # step selected (wav_dec arrives pre-trimmed: wav_cond_offset = [0, dec_in_len]).
+    from oracle import torch_oracle as orc
+    sd_e = {k: v.detach().cpu() for k, v in ae.encoder.state_dict().items()}
+    enc_ref, _ = orc.encoder_forward(sd_e, mels.cpu())
+    ze_ref = torch.nn.functional.conv1d(enc_ref, bn.linear.weight.detach().cpu())
+    assert rel_err(bn.ze, ze_ref) < 5e-3
+    md_ref, ind_ref, _ = orc.vq_assign(ze_ref, bn.emb.detach().cpu(), "scaled_l2")
+    dist = orc.scaled_l2(ze_ref, bn.emb.detach().cpu())
+    top2 = dist.topk(2, dim=1, largest=False).values
+    decided = (top2[:, 1] - top2[:, 0]) > 2e-2 * top2[:, 1]
+    assert float(decided.float().mean()) > 0.5
+    assert torch.equal(bn.min_ind.cpu()[decided], ind_ref[decided])
+    sd_d = {k: v.detach().cpu() for k, v in ae.decoder.state_dict().items()}
+    T0, rf, n_out = ae.dec_in_len, 2046, 64
+    zq0 = ae.encoding_bn.detach().cpu()[0:1]
+    cond = orc.conditioning(sd_d, ARCH_VQVAE_EMA, zq0, spk.cpu()[0:1], jit.cpu()[0:1], ae.decoder.trim_ups_out.tolist())
+    assert cond.shape[2] == T0
+    s0 = T0 - (rf + n_out)
+    onehot = torch.nn.functional.one_hot(wav_dec.cpu()[0:1].long(), 256).permute(0, 2, 1).float()[:, :, s0:]
+    sig = torch.nn.functional.conv1d(onehot, sd_d["base_layer.weight"], sd_d["base_layer.bias"])
+    cw = cond[:, :, s0:]
+    skp_sum = 0
+    leads = [l.leads.tolist() for l in ae.decoder.conv_layers]
+    for li, dd in enumerate(orc.dilations(ARCH_VQVAE_EMA)):
+        sig, skp = orc.grcc_layer(sig, cw, orc.sub(sd_d, f"conv_layers.{li}"), dd, leads[li], li == 19)
+        skp_sum = skp_sum + skp
+    post1 = torch.nn.functional.conv1d(torch.relu(skp_sum), sd_d["post1.weight"], sd_d["post1.bias"])
+    ref_q = torch.nn.functional.conv1d(torch.relu(post1), sd_d["post2.weight"], sd_d["post2.bias"])
+    got_q = pred.detach()[0:1, :, -(n_out - 1):].cpu()            # pred = quant[..., :-1]
+    assert rel_err(got_q, ref_q[:, :, :-1]) < 5e-3
     # --- backward + Adam
     opt.zero_grad(set_to_none=True)
     (com + rec).backward()

