@@ -129,12 +129,14 @@ def test_cfg3_full_size_train_step_properties(golden_dir):
     enc_ref, _ = orc.encoder_forward(sd_e, mels.cpu())
     ze_ref = torch.nn.functional.conv1d(enc_ref, bn.linear.weight.detach().cpu())
     assert rel_err(bn.ze, ze_ref) < 5e-3
-    md_ref, ind_ref, _ = orc.vq_assign(ze_ref, bn.emb.detach().cpu(), "scaled_l2")
-    dist = orc.scaled_l2(ze_ref, bn.emb.detach().cpu())
-    top2 = dist.topk(2, dim=1, largest=False).values
-    decided = (top2[:, 1] - top2[:, 0]) > 2e-2 * top2[:, 1]
-    assert float(decided.float().mean()) > 0.5
-    assert torch.equal(bn.min_ind.cpu()[decided], ind_ref[decided])
+    # codes: at initialisation the scaled-L2 distances of a vector to its best codes differ by less than the TF32
+    # perturbation of ze, so index equality with the fp32 encoder is not defined; what is: the code the GPU step chose is
+    # optimal under the ORACLE's ze up to twice the largest distance perturbation the ze difference causes
+    emb_c = bn.emb.detach().cpu()
+    dist_ref = orc.scaled_l2(ze_ref, emb_c)                                  # (B, K, N)
+    delta = float((orc.scaled_l2(bn.ze.detach().cpu(), emb_c) - dist_ref).abs().max())
+    chosen = dist_ref.gather(1, bn.min_ind.cpu().unsqueeze(1)).squeeze(1)
+    assert bool((chosen - dist_ref.min(dim=1).values <= 2 * delta + 1e-7).all()) and delta < 5e-3
     sd_d = {k: v.detach().cpu() for k, v in ae.decoder.state_dict().items()}
     T0, rf, n_out = ae.dec_in_len, 2046, 64
     zq0 = ae.encoding_bn.detach().cpu()[0:1]

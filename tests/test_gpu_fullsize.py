@@ -156,10 +156,16 @@ def test_cfg5_deep_stack_window_matches_cpu_oracle():
 def test_full_size_backward_matches_cpu_oracle_on_the_trailing_window():
     """cfg2 geometry at full length (window 16384, decoder input 18430, batch 2): the loss touches only the LAST 64 output
     steps, so every gradient depends on the trailing RF + 64 input steps only and the CPU oracle (autograd through
-    oracle/torch_oracle.py on that window) gives the exact reference for the FULL-SIZE kernel launches: per-unit split-K
-    of the wide weight-gradient units, merged data-gradient tiles, the one-launch gradient accumulation -- all at their
-    real extents and tile counts.  Compared: every weight gradient of the first, a middle and the last dilation layer,
-    the post-net, the base layer, and the gradient w.r.t. the conditioning input lc_sparse (through the front-end)."""
+    oracle/torch_oracle.py on that window, fp32) gives the exact reference for the FULL-SIZE kernel launches: per-unit
+    split-K of the wide weight-gradient units, merged data-gradient tiles, the one-launch gradient accumulation -- all at
+    their real extents and tile counts.  Compared: EVERY parameter gradient and the gradient w.r.t. lc_sparse.
+
+    Tolerance = measured envelope.  The post-net has two ReLUs in front of the stack's gradient; a forward perturbation of
+    1e-3 (10-bit-mantissa operands) flips the mask of the ~0.1 % of pre-activations that lie within it of zero, and a
+    flipped fraction f moves every upstream gradient by ~sqrt(f) in the L2 sense (~3 %), uniformly over all parameters.
+    The reference's own GPU path has the same property, so the bound is taken from it: the same window through the oracle
+    port on THIS device (eager PyTorch, cuDNN's default TF32 convolutions) against the same fp32 CPU result; the kernels
+    must stay within 2x the library's worst norm-wise error (floor 3e-2) and agree in direction (cosine > 0.999)."""
     import aewn
     from aewn import ops
     from oracle import torch_oracle as orc
@@ -178,53 +184,55 @@ def test_full_size_backward_matches_cpu_oracle_on_the_trailing_window():
     (q[:, :, -n_out:] * gq.cuda()).sum().backward()
     ops.check_device_errors()
     got = {k: p.grad.detach().cpu() for k, p in wn.named_parameters()}
-    got_lc = lc_d.grad.detach().cpu()
-    # CPU oracle on the trailing window
-    sd = {k: v.detach().cpu().clone().requires_grad_(v.dtype == torch.float32 and k != "cond.eye")
-          for k, v in wn.state_dict().items()}
-    lc_c = lc.clone().requires_grad_(True)
+    got["lc_sparse"] = lc_d.grad.detach().cpu()
     o0, o1 = wn.wav_cond_offset
     T0 = geo["dec_in_len"]
     leads = [l.leads.tolist() for l in wn.conv_layers]
-    cond = orc.conditioning(sd, ARCH_BASIC, lc_c, spk, jit, [0, T0])
-    s = T0 - (rf + n_out)
-    onehot = torch.nn.functional.one_hot(wav[:, o0:o1].long(), 256).permute(0, 2, 1).float()[:, :, s:]
-    sig = torch.nn.functional.conv1d(onehot, sd["base_layer.weight"], sd["base_layer.bias"])
-    c = cond[:, :, s:]
-    skp_sum = 0
-    for li, d in enumerate(orc.dilations(ARCH_BASIC)):
-        sig, skp = orc.grcc_layer(sig, c, orc.sub(sd, f"conv_layers.{li}"), d, leads[li], li == 19)
-        skp_sum = skp_sum + skp
-    post1 = torch.nn.functional.conv1d(torch.relu(skp_sum), sd["post1.weight"], sd["post1.bias"])
-    ref_q = torch.nn.functional.conv1d(torch.relu(post1), sd["post2.weight"], sd["post2.bias"])
+    state = {k: v.detach().cpu() for k, v in wn.state_dict().items()}
+
+    def window_grads(device):
+        """the trailing window through the oracle port on `device`: (logits, {name: gradient})"""
+        sd = {k: v.clone().to(device).requires_grad_(v.dtype == torch.float32 and k != "cond.eye") for k, v in state.items()}
+        lc_c = lc.clone().to(device).requires_grad_(True)
+        cond = orc.conditioning(sd, ARCH_BASIC, lc_c, spk.to(device), jit.to(device), [0, T0])
+        s = T0 - (rf + n_out)
+        onehot = torch.nn.functional.one_hot(wav[:, o0:o1].long(), 256).permute(0, 2, 1).float()[:, :, s:].to(device)
+        sig = torch.nn.functional.conv1d(onehot, sd["base_layer.weight"], sd["base_layer.bias"])
+        c = cond[:, :, s:]
+        skp_sum = 0
+        for li, d in enumerate(orc.dilations(ARCH_BASIC)):
+            sig, skp = orc.grcc_layer(sig, c, orc.sub(sd, f"conv_layers.{li}"), d, leads[li], li == 19)
+            skp_sum = skp_sum + skp
+        post1 = torch.nn.functional.conv1d(torch.relu(skp_sum), sd["post1.weight"], sd["post1.bias"])
+        ref_q = torch.nn.functional.conv1d(torch.relu(post1), sd["post2.weight"], sd["post2.bias"])
+        (ref_q * gq.to(device)).sum().backward()
+        grads = {k: v.grad.detach().cpu() for k, v in sd.items() if getattr(v, "grad", None) is not None}
+        grads["lc_sparse"] = lc_c.grad.detach().cpu()
+        return ref_q.detach().cpu(), grads
+
+    ref_q, ref = window_grads("cpu")
     assert ref_q.shape[2] == n_out
     fwd_err = float((q[:, :, -n_out:].detach().cpu() - ref_q).abs().max()) / float(ref_q.abs().max())
     assert fwd_err < 5e-3, fwd_err
-    (ref_q * gq).sum().backward()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        _, lib = window_grads("cuda")
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
 
-    bad = []
+    def nerr(a, b):
+        return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
 
-    def check(name, a, b, tol, norm_tol=None):
-        """max-abs error relative to the tensor's max-abs, direction, and (optionally) the norm-wise relative error"""
-        scale = float(b.abs().max())
-        err = float((a - b).abs().max()) / max(scale, 1e-20)
-        nerr = float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
-        cos = float(a.double().flatten() @ b.double().flatten() / (a.double().norm() * b.double().norm() + 1e-300))
-        if not (err < tol and cos > 0.999 and (norm_tol is None or nerr < norm_tol)):
-            bad.append((name, round(err, 4), round(nerr, 4), round(cos, 5)))
+    def cos(a, b):
+        return float(a.double().flatten() @ b.double().flatten() / (a.double().norm() * b.double().norm() + 1e-300))
 
-    # the stack's and the post-net's own weight gradients: TF32 operands in the backward engines, fp32 accumulation
-    keys = [k for k in got if k.startswith(("conv_layers.0.", "conv_layers.9.", "conv_layers.19.", "post1.", "post2."))]
-    assert len(keys) >= 26
-    for k in keys:
-        check(k, got[k], sd[k].grad, 3e-2)
-    # Parameters BEHIND the whole stack (base layer, conditioning front-end): their gradient is the stack's data gradient
-    # after 20 layers of TF32 back-propagation, and every entry of the base-layer gradient sums only the ~16 time steps
-    # whose mu-law code equals its column, so single entries are noisy: bounded norm-wise (5e-2, equivalent to the
-    # cosine bound) and by 1.5e-1 on the worst entry.
-    for k in got:
-        if k not in keys and sd[k].grad is not None and float(sd[k].grad.abs().max()) > 0:
-            behind = k.startswith(("base_layer.", "lc_", "cond."))
-            check(k, got[k], sd[k].grad, 1.5e-1 if behind else 5e-2, norm_tol=5e-2)
-    check("lc_sparse", got_lc, lc_c.grad, 5e-2, norm_tol=5e-2)
-    assert not bad, bad
+    live = [k for k in ref if float(ref[k].abs().max()) > 0]
+    assert len(live) >= 170
+    lib_worst = max(nerr(lib[k], ref[k]) for k in live)
+    envelope = max(2.0 * lib_worst, 3e-2)
+    table = [(k, round(nerr(got[k], ref[k]), 4), round(cos(got[k], ref[k]), 5), round(nerr(lib[k], ref[k]), 4)) for k in live]
+    worst = sorted(table, key=lambda r: -r[1])[:6]
+    print(f"library (cuDNN TF32) worst norm-wise error {lib_worst:.4f} -> envelope {envelope:.4f}; ours worst:", worst)
+    bad = [r for r in table if not (r[1] < envelope and r[2] > 0.999)]
+    assert not bad, (envelope, bad[:8])
