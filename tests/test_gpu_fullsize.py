@@ -160,12 +160,14 @@ def test_full_size_backward_matches_cpu_oracle_on_the_trailing_window():
     split-K of the wide weight-gradient units, merged data-gradient tiles, the one-launch gradient accumulation -- all at
     their real extents and tile counts.  Compared: EVERY parameter gradient and the gradient w.r.t. lc_sparse.
 
-    Tolerance = measured envelope.  The post-net has two ReLUs in front of the stack's gradient; a forward perturbation of
-    1e-3 (10-bit-mantissa operands) flips the mask of the ~0.1 % of pre-activations that lie within it of zero, and a
-    flipped fraction f moves every upstream gradient by ~sqrt(f) in the L2 sense (~3 %), uniformly over all parameters.
-    The reference's own GPU path has the same property, so the bound is taken from it: the same window through the oracle
-    port on THIS device (eager PyTorch, cuDNN's default TF32 convolutions) against the same fp32 CPU result; the kernels
-    must stay within 2x the library's worst norm-wise error (floor 3e-2) and agree in direction (cosine > 0.999)."""
+    Tolerance.  The post-net has two ReLUs in front of the stack's gradient; a forward perturbation of 1e-3
+    (10-bit-mantissa operands) flips the mask of the ~0.1 % of pre-activations that lie within it of zero, and a flipped
+    fraction f moves every upstream gradient by ~sqrt(f) in the L2 sense -- measured 3.2-4.4 %, UNIFORM over all 180
+    tensors (first to last layer, post-net, front-end), which is the signature of that common upstream cause rather than
+    of any one kernel.  Bound: norm-wise error < 6e-2 and cosine > 0.999 for every tensor.  For scale, the same window
+    through the reference's own GPU path (the oracle port on this device: eager PyTorch, cuDNN's default TF32
+    convolutions) is measured too and printed: its worst tensor is off by 0.95 norm-wise (biases 0.1-0.5, lc_conv 0.9)
+    -- cuDNN's TF32 backward on sums with heavy cancellation -- so it cannot serve as an envelope here."""
     import aewn
     from aewn import ops
     from oracle import torch_oracle as orc
@@ -230,9 +232,9 @@ def test_full_size_backward_matches_cpu_oracle_on_the_trailing_window():
     live = [k for k in ref if float(ref[k].abs().max()) > 0]
     assert len(live) >= 170
     lib_worst = max(nerr(lib[k], ref[k]) for k in live)
-    envelope = max(2.0 * lib_worst, 3e-2)
+    envelope = 6e-2
     table = [(k, round(nerr(got[k], ref[k]), 4), round(cos(got[k], ref[k]), 5), round(nerr(lib[k], ref[k]), 4)) for k in live]
     worst = sorted(table, key=lambda r: -r[1])[:6]
-    print(f"library (cuDNN TF32) worst norm-wise error {lib_worst:.4f} -> envelope {envelope:.4f}; ours worst:", worst)
+    print(f"library (cuDNN TF32) worst norm-wise error {lib_worst:.4f}; bound {envelope:.4f}; ours worst:", worst)
     bad = [r for r in table if not (r[1] < envelope and r[2] > 0.999)]
     assert not bad, (envelope, bad[:8])
