@@ -123,7 +123,8 @@ def _wavenet_small_body(golden_dir):
     finally:
         torch.backends.cudnn.allow_tf32 = prev
     lib_errs = {k: rel_err(sd_lib[k].grad, g["grads"][k]) for k in g["grads"] if getattr(sd_lib.get(k), "grad", None) is not None}
-    envelope = max(2.0 * max(lib_errs.values()), 3e-2)
+    envelope = min(max(2.0 * max(lib_errs.values()), 3e-2), 0.15)      # (capped: see test_gpu_fullsize.py for how far the
+    #                                                                     library's TF32 backward can be off)
     errs = {k: rel_err(p.grad, g["grads"][k]) for k, p in wn.named_parameters()}
     coss = {k: cosine(p.grad, g["grads"][k]) for k, p in wn.named_parameters() if float(g["grads"][k].abs().max()) > 0}
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
