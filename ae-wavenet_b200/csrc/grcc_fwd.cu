@@ -2,24 +2,28 @@
 // tanh * sigmoid, 1x1 residual (+ x) and 1x1 skip (+= skip sum), on tcgen05 CTA pairs.
 //
 // Why a second engine next to tgemm.cu: ncu / bench arithmetic of the two-launch TF32 path showed the conv+gate launch
-// bound by operand DELIVERY -- every CTA needs 64 B/clk of operands from L2 (32 KB per 512-cycle K block) against ~42
+// bound by operand DELIVERY -- every CTA needs 64 B/clk of operands from L2 (32 KB per 512-cycle K block) against ~40
 // B/clk/SM the chip delivers with all SMs pulling -- and the res+skip launch bound by HBM while the tensor pipe idles.
 // This kernel (a) feeds the tensor cores FP16 operands (10-bit mantissa = TF32's, round-to-nearest instead of TF32's
 // truncation; FP32 accumulation in TMEM; the residual stream itself stays FP32): half the bytes per MAC, twice the MMA
 // rate; (b) reads the activations from CHANNELS-LAST fp16 copies (B, T, C): both operands are plain K-major
 // SWIZZLE_128B tiles, one contiguous 16 KB box per K block, and a dilated tap is a shift of the box's ROW coordinate, so
 // the 16-byte TMA origin rule no longer forces pre-shifted duplicates; (c) keeps z = tanh*sigmoid in shared memory as
-// the A operand of the residual/skip GEMM (it never travels to HBM unless the caller asks for it), so the HBM-bound
-// epilogues of one tile overlap the MMAs of the next job.
+// the A operand of the residual/skip GEMM (in inference mode it never travels to HBM).
 //
 // Per CTA pair and 256 time steps (128 per CTA), jobs run in a fixed order through two 256-column TMEM regions:
 //   G1.j (j < D/128): acc[t, 0:128 | 128:256] = filt | gate pre-activations of channels [128j, 128j+128)
-//                     K = [x16(t-d) | x16(t) | cond16(t), 1], 64 channels per ring stage
+//                     K = [x16(t-d) | x16(t) | cond16(t), 1], 64 channels per ring stage (5 x 32 KB ring)
 //   epilogue G1.j   : tanh, sigmoid (-> th, sg for the backward pass), z -> fp16 -> zbuf (K-major, manual 128B swizzle)
-//   RES.c           : acc = Wr[c] . z   -> x32_next = acc + x32 ; x16_next = fp16(x32_next)   (A operand = zbuf)
-//   SKP.c           : acc = Ws[c] . z   -> skip sum (TMA store / reduce-add / relu(old + acc))
-// Warp roles as in tgemm.cu: warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator, warps 4-11
-// epilogue.  All waits are bounded.
+//   SKP.c           : acc = Ws[c] . z   -> skip sum (store / red.global.add / relu(old + acc))       (A operand = zbuf)
+//   RES.c           : acc = Wr[c] . z   -> x32_next = acc + x32 ; x16_next = fp16(x32_next)
+// The residual / skip jobs come smallest-epilogue first: the next tile's first gate job may start as soon as the region
+// of the second-to-last job is drained, so the 256-channel residual chunk (the longest epilogue) goes last and overlaps
+// the next tile's gate MMAs.
+// Warps: 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-19 epilogue (16 warps, 4 per TMEM lane quadrant,
+// 16-column chunks, 104 registers).  Every output leaves the SM with plain coalesced stores (lane = time step: one
+// 128-byte line per instruction, st.global.cs); a staged TMA-store path measured slower here (acquire + proxy fence +
+// issue latency in each warp's serial chain), see profiles/r3_gf_*.  All waits are bounded.
 #include <cuda_fp16.h>
 
 #include "host_util.h"
@@ -84,7 +88,6 @@ static_assert(sizeof(GfHot) % 8 == 0 && sizeof(GfHot) <= 512, "GfHot is copied t
 
 struct GfParams {
   CUtensorMap xa, ca, w1, w2;             // operand loads (fp16)
-  CUtensorMap th_m, sg_m, z_m, xo_m, skp_m;   // fp32 (t, ch, b) outputs, box {32 t, 16 ch, 1}
   CUtensorMap xr_m;                          // fp32 residual source, box {128 t, 32 ch, 1}: L2 prefetch only
   GfHot hot;
 };
@@ -728,15 +731,7 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
     cuuint64_t sw2[1] = {(cuuint64_t)D * 2u};
     if ((rc = encode_f16_map(&p.w2, d->w2h, 2, dw2, sw2, bw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w2h"))) return rc;
   }
-  if (d->save) {
-    if ((rc = encode_out_map(&p.th_m, d->th, d->t_hi, D, d->batch, d->a_cs, d->a_bs, 16))) return rc;
-    if ((rc = encode_out_map(&p.sg_m, d->sg, d->t_hi, D, d->batch, d->a_cs, d->a_bs, 16))) return rc;
-  }
-  if (d->z) {
-    if ((rc = encode_out_map(&p.z_m, d->z, d->t_hi, D, d->batch, d->a_cs, d->a_bs, 16))) return rc;
-  }
   if (!d->final_layer) {
-    if ((rc = encode_out_map(&p.xo_m, d->xo32, d->t_hi, R, d->batch, d->x_cs, d->x_bs, 16))) return rc;
     if ((rc = encode_out_map(&p.xr_m, const_cast<float*>(d->x32), d->t_hi, R, d->batch, d->x_cs, d->x_bs, 32, 128))) return rc;
     static const int pf = []() { const char* e = getenv("AEWN_GF_PREFETCH"); return e ? atoi(e) : 0; }();   // bit 0: residual rows, bit 1: next tile's operands. Measured SLOWER (356 -> 379 / 377 / 394 us per layer): off
     p.hot.prefetch = pf;
@@ -744,7 +739,6 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
     p.hot.dbg = dbgf;
     p.hot.n_res = R;
   }
-  if ((rc = encode_out_map(&p.skp_m, d->skp, d->t_hi, S, d->batch, d->s_cs, d->s_bs, 16))) return rc;
 
   int nj = 0;
   for (int j = 0; j < D / 128; ++j) p.hot.job[nj++] = GfJob{GF_GATE, 256 * j, 256, 128, 128 * j};

@@ -25,7 +25,8 @@ for p in (ROOT, os.path.join(ROOT, "ae-wavenet_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: stdout carries ONE JSON line
+os.environ.setdefault("NCCL_DEBUG", "WARN")
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / warnings go to stderr: stdout carries ONE JSON line
 
 import torch  # noqa: E402
 

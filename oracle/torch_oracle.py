@@ -205,8 +205,8 @@ def vqema_stats(ze, min_ind, k):
     """EMA statistics, vqema_bn.py:172-188: z_sum[k,:] = sum of ze vectors assigned to k, n_sum[k] = their count."""
     d = ze.shape[1]
     flat = min_ind.flatten()
-    z_sum = torch.zeros(k, d).index_add_(0, flat, ze.permute(0, 2, 1).reshape(-1, d))
-    n_sum = torch.zeros(k).index_add_(0, flat, torch.ones(flat.numel()))
+    z_sum = torch.zeros(k, d, device=ze.device).index_add_(0, flat, ze.permute(0, 2, 1).reshape(-1, d))
+    n_sum = torch.zeros(k, device=ze.device).index_add_(0, flat, torch.ones(flat.numel(), device=ze.device))
     return z_sum, n_sum
 
 
