@@ -15,15 +15,17 @@
 //   G1.j (j < D/128): acc[t, 0:128 | 128:256] = filt | gate pre-activations of channels [128j, 128j+128)
 //                     K = [x16(t-d) | x16(t) | cond16(t), 1], 64 channels per ring stage (5 x 32 KB ring)
 //   epilogue G1.j   : tanh, sigmoid (-> th, sg for the backward pass), z -> fp16 -> zbuf (K-major, manual 128B swizzle)
-//   SKP.c           : acc = Ws[c] . z   -> skip sum (store / red.global.add / relu(old + acc))       (A operand = zbuf)
+//   SKP.c           : acc = Ws[c] . z   -> skip sum (store / TMA reduce-add / relu(old + acc))          (A operand = zbuf)
 //   RES.c           : acc = Wr[c] . z   -> x32_next = acc + x32 ; x16_next = fp16(x32_next)
 // The residual / skip jobs come smallest-epilogue first: the next tile's first gate job may start as soon as the region
 // of the second-to-last job is drained, so the 256-channel residual chunk (the longest epilogue) goes last and overlaps
 // the next tile's gate MMAs.
 // Warps: 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-19 epilogue (16 warps, 4 per TMEM lane quadrant,
-// 16-column chunks, 104 registers).  Every output leaves the SM with plain coalesced stores (lane = time step: one
-// 128-byte line per instruction, st.global.cs); a staged TMA-store path measured slower here (acquire + proxy fence +
-// issue latency in each warp's serial chain), see profiles/r3_gf_*.  All waits are bounded.
+// 16-column chunks, 104 registers).  tanh / sigmoid / z / x_next leave the SM with plain coalesced stores (lane = time
+// step: one 128-byte line per instruction, st.global.cs); a staged TMA-store path measured slower here (acquire + proxy
+// fence + issue latency in each warp's serial chain).  The running skip sum keeps the TMA reduce-add (one 2 KB box per
+// 16 channels through a per-warp staging tile): red.global.add per element measured 2x slower (profiles/r3_gf_*).
+// All waits are bounded.
 #include <cuda_fp16.h>
 
 #include "host_util.h"
@@ -33,8 +35,7 @@ namespace aewn {
 
 constexpr int GF_BM = 128;
 constexpr int GF_KB = 64;                         // K elements per ring stage: 64 fp16 = one 128-byte swizzle row
-constexpr int GF_MAX_STAGES = 5;                  // ring: 5 x 32 KB (no epilogue staging: every output leaves with coalesced
-                                                  // lane = time stores / reds), or 4 x 32 KB for A/B runs
+constexpr int GF_MAX_STAGES = 4;                  // operand ring: 4 x 32 KB
 constexpr int GF_A_BYTES = GF_BM * 128;           // 16 KB: 128 time rows x 128 B
 constexpr int GF_W_BYTES = 128 * 128;             // 16 KB: 128 weight rows x 128 B (this CTA's half of the N rows)
 constexpr int GF_STAGE_BYTES = GF_A_BYTES + GF_W_BYTES;
@@ -42,7 +43,9 @@ constexpr int GF_MAX_D = 256;
 constexpr int GF_ZBUF_BYTES = (GF_MAX_D / GF_KB) * GF_A_BYTES;   // 64 KB: z of this CTA's 128 time rows, all D channels
 constexpr int GF_THREADS = 640;                  // 4 control warps + 16 epilogue warps
 constexpr int GF_EPI_WARPS = 16;
-constexpr int GF_POOL_BYTES = GF_MAX_STAGES * GF_STAGE_BYTES;   // 160 KB
+constexpr int GF_STG_BYTES = GF_EPI_WARPS * 2048;               // one [16 ch][32 t] fp32 tile per epilogue warp: the skip
+                                                                // sum's TMA reduce-add (red.global.add measured 2x slower)
+constexpr int GF_POOL_BYTES = GF_MAX_STAGES * GF_STAGE_BYTES + GF_STG_BYTES;   // 160 KB
 constexpr int GF_SMEM_BYTES = GF_POOL_BYTES + GF_ZBUF_BYTES + 256 + 512 + 1024;   // + barriers + GfHot + alignment slack
 constexpr int GF_MAX_JOBS = 8;
 
@@ -89,6 +92,7 @@ static_assert(sizeof(GfHot) % 8 == 0 && sizeof(GfHot) <= 512, "GfHot is copied t
 struct GfParams {
   CUtensorMap xa, ca, w1, w2;             // operand loads (fp16)
   CUtensorMap xr_m;                          // fp32 residual source, box {128 t, 32 ch, 1}: L2 prefetch only
+  CUtensorMap skp_m;                         // skip sum (t, ch, b), box {32 t, 16 ch, 1}: TMA reduce-add
   GfHot hot;
 };
 
@@ -172,20 +176,20 @@ __device__ __forceinline__ GfItem gf_decode(const GfHot& p, int item, int crank)
 
 template <int STAGES>
 __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_constant__ GfParams p) {
-  constexpr int RING_BYTES = GF_POOL_BYTES;                   // (a shallower ring leaves its tail unused)
+  constexpr int RING_BYTES = GF_MAX_STAGES * GF_STAGE_BYTES;
   static_assert(STAGES <= GF_MAX_STAGES, "ring depth");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* zbuf = smem + RING_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_BYTES + GF_ZBUF_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES);
   uint64_t* empty_bar = full_bar + GF_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + GF_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* zready_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zready_bar + 1);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
-  GfHot* hot_s = reinterpret_cast<GfHot*>(smem + RING_BYTES + GF_ZBUF_BYTES + 256);
+  GfHot* hot_s = reinterpret_cast<GfHot*>(smem + RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES + 256);
   if (threadIdx.x < sizeof(GfHot) / 8)
     reinterpret_cast<unsigned long long*>(hot_s)[threadIdx.x] = reinterpret_cast<const unsigned long long*>(&p.hot)[threadIdx.x];
   const GfHot& hp = *hot_s;
@@ -356,6 +360,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
     const int row = q * 32 + lane;
     unsigned int dbg_acq = 0, dbg_tm = 0, dbg_fl = 0;      // phase-clock accumulators (cycles), see dbg_clock
     const int dbg = hp.dbg;
+    float* const stg = reinterpret_cast<float*>(smem + RING_BYTES + GF_ZBUF_BYTES) + (warp - 4) * 512;
     const uint32_t lead_tempty = mapa_u32(&tempty_bar[0], 0);
     const uint32_t lead_zready = mapa_u32(zready_bar, 0);
     uint32_t acc = 0, acc_phase = 0;
@@ -570,19 +575,31 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
             dbg_tm += clock() - t_t;
-            if (s_in) {
+            if (hp.skp_mode == 1) {
+              // running skip sum: TMA reduce-add of a {32 t, 16 ch} box (the read-modify-write happens in L2)
+              if ((slab0 + 32 > hp.skp_t_lo) && (slab0 < hp.t_hi)) {
+                const unsigned int t_a = clock();
+                if (elect_one()) tma_store_wait_read();
+                __syncwarp();
+                dbg_acq += clock() - t_a;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) stg[j * 32 + lane] = s_keep ? __uint_as_float(v[j]) : 0.0f;
+                const unsigned int t_f = clock();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                  tma_reduce_add_3d(&p.skp_m, stg, slab0, jd.ch0 + c0, it.b);
+                  tma_store_commit();
+                }
+                dbg_fl += clock() - t_f;
+              }
+            } else if (s_in) {
               float* op = hp.skp + static_cast<long long>(it.b) * hp.s_bs + static_cast<long long>(jd.ch0 + c0) * hp.s_cs + tau;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 if (c0 + j < jd.n_valid) {
                   const float a = s_keep ? __uint_as_float(v[j]) : 0.0f;
-                  if (hp.skp_mode == 1) {
-                    if (s_keep) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(op), "f"(a) : "memory");
-                  } else if (hp.skp_mode >= 2) {
-                    *op = s_keep ? fmaxf(a + o[j], 0.0f) : 0.0f;
-                  } else {
-                    *op = a;
-                  }
+                  *op = hp.skp_mode >= 2 ? (s_keep ? fmaxf(a + o[j], 0.0f) : 0.0f) : a;
                 }
                 op += hp.s_cs;
               }
@@ -740,6 +757,8 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
     p.hot.n_res = R;
   }
 
+  if ((rc = encode_out_map(&p.skp_m, d->skp, d->t_hi, S, d->batch, d->s_cs, d->s_bs, 16))) return rc;
+
   int nj = 0;
   for (int j = 0; j < D / 128; ++j) p.hot.job[nj++] = GfJob{GF_GATE, 256 * j, 256, 128, 128 * j};
   p.hot.n_gate = nj;
@@ -813,10 +832,10 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  // ring depth: 5 stages (default) or 4 (AEWN_GF_RING=4, A/B runs)
-  static const int ring = []() { const char* e = getenv("AEWN_GF_RING"); return e && atoi(e) == 4 ? 4 : 5; }();
+  // ring depth: 4 stages (default) or 3 (AEWN_GF_RING=3, A/B runs)
+  static const int ring = []() { const char* e = getenv("AEWN_GF_RING"); return e && atoi(e) == 3 ? 3 : 4; }();
   using KernelFn = void (*)(GfParams);
-  KernelFn fn = ring == 4 ? grcc_fwd_kernel<4> : grcc_fwd_kernel<5>;
+  KernelFn fn = ring == 3 ? grcc_fwd_kernel<3> : grcc_fwd_kernel<4>;
   cudaError_t ae = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_BYTES);
   if (ae != cudaSuccess) return cuda_err(ae, "grcc_fwd: cudaFuncSetAttribute");
   cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);

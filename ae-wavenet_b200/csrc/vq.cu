@@ -42,78 +42,155 @@ __device__ __forceinline__ float sumsq_blk16(int d, F f) {
   return total;
 }
 
-// One CTA per (b, n) vector.
+// d == 32 (the reference's bottleneck width): the same order, fully unrolled, so that a code row can live in registers
+template <typename F>
+__device__ __forceinline__ float sumsq_blk16_d32(F f) {
+  float total = 0.0f;
+#pragma unroll
+  for (int blk = 0; blk < 2; ++blk) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float v = f(16 * blk + i);
+      acc = __fadd_rn(acc, __fmul_rn(v, v));
+    }
+    total = blk == 0 ? acc : __fadd_rn(total, acc);
+  }
+  return total;
+}
+
+// One CTA per V consecutive (b, n) vectors; the codebook streams through shared memory in tiles of 256 codes.
+//
+// Round-2 measurement (profiles/r3_vq_latency.txt): the first version -- one CTA per vector, every thread reading ITS
+// codes' rows straight from global memory (lane stride = d floats: 32 different 128-byte lines per load instruction,
+// the 512 KB codebook re-read by each of the 1040 CTAs) -- took 1.09 ms at the cfg3 shapes, SLOWER than the reference's
+// eager op sequence (0.77 ms).  Here a code tile is loaded once per CTA with coalesced reads into a padded [d][257]
+// tile (thread = code: conflict-free reads), V vectors share it, and a thread keeps its code's row in registers when
+// d == 32.  The arithmetic per (vector, code) pair -- and with it every index and distance bit -- is unchanged.
+constexpr int VQ_TILE = 256;
+
+template <int V, bool REG_E>
 __global__ void __launch_bounds__(VQ_THREADS) vq_fwd_kernel(const float* __restrict__ ze, long long ze_bs, long long ze_cs,
                                                             const float* __restrict__ emb, int metric,
                                                             long long* __restrict__ min_ind, float* __restrict__ min_dist,
                                                             float* __restrict__ zq, long long zq_bs, long long zq_cs,
                                                             float* __restrict__ hist, float* __restrict__ z_sum,
                                                             float* __restrict__ n_sum, float* __restrict__ ze_norm,
-                                                            int d, int N, int K) {
-  __shared__ float s_ze[VQ_MAX_D];
-  __shared__ float s_best[VQ_THREADS / 32];
-  __shared__ int s_idx[VQ_THREADS / 32];
-  __shared__ int s_win;
-  const int vec = blockIdx.x;
-  const int b = vec / N, n = vec - b * N;
-  const float* zp = ze + static_cast<long long>(b) * ze_bs + n;
-  for (int j = threadIdx.x; j < d; j += blockDim.x) s_ze[j] = zp[static_cast<long long>(j) * ze_cs];
+                                                            int d, int N, int K, int n_vec) {
+  extern __shared__ float vq_smem[];
+  float* s_e = vq_smem;                               // [d][VQ_TILE + 1]
+  float* s_ze = vq_smem + d * (VQ_TILE + 1);          // [V][d]
+  __shared__ float s_best[V][VQ_THREADS / 32];
+  __shared__ int s_idx[V][VQ_THREADS / 32];
+  __shared__ int s_win[V];
+  const int vec0 = blockIdx.x * V;
+  for (int i = threadIdx.x; i < V * d; i += blockDim.x) {
+    const int v = i / d, j = i - v * d;
+    const int vec = vec0 + v;
+    float x = 0.0f;
+    if (vec < n_vec) {
+      const int b = vec / N, n = vec - b * N;
+      x = ze[static_cast<long long>(b) * ze_bs + static_cast<long long>(j) * ze_cs + n];
+    }
+    s_ze[i] = x;
+  }
   __syncthreads();
 
-  float a = 0.0f;  // ||ze||
-  if (metric == 1) a = __fsqrt_rn(sumsq_blk16(d, [&](int j) { return s_ze[j]; }));
-
-  float best = INFINITY;
-  int best_k = 0x7fffffff;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const float* e = emb + static_cast<long long>(k) * d;
-    float dist = sumsq_blk16(d, [&](int j) { return __fsub_rn(s_ze[j], __ldg(e + j)); });
-    if (metric == 1) {
-      const float bn = __fsqrt_rn(sumsq_blk16(d, [&](int j) { return __ldg(e + j); }));
-      dist = __fdiv_rn(__fsqrt_rn(dist), __fadd_rn(a, bn));
-    }
-    if (dist < best) {  // strict: the first (smallest) index wins ties within a thread (k ascending)
-      best = dist;
-      best_k = k;
-    }
-  }
-  // block argmin, ties -> smaller index
+  float a[V];  // ||ze_v||
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
-    if (ob < best || (ob == best && ok < best_k)) {
-      best = ob;
-      best_k = ok;
+  for (int v = 0; v < V; ++v) {
+    const float* zv = s_ze + v * d;
+    a[v] = (metric == 1) ? __fsqrt_rn(sumsq_blk16(d, [&](int j) { return zv[j]; })) : 0.0f;
+  }
+  float best[V];
+  int best_k[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    best[v] = INFINITY;
+    best_k[v] = 0x7fffffff;
+  }
+  for (int k0 = 0; k0 < K; k0 += VQ_TILE) {
+    __syncthreads();          // the previous tile has been consumed
+    const int nk = min(VQ_TILE, K - k0);
+    const float* src = emb + static_cast<long long>(k0) * d;
+    for (int i = threadIdx.x; i < nk * d; i += blockDim.x) {      // coalesced: the tile is contiguous in memory
+      const int c = i / d, j = i - c * d;
+      s_e[j * (VQ_TILE + 1) + c] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int c = threadIdx.x;
+    if (c < nk) {
+      const int k = k0 + c;
+      float er[REG_E ? 32 : 1];
+      if (REG_E) {       // d == 32
+#pragma unroll
+        for (int j = 0; j < 32; ++j) er[j] = s_e[j * (VQ_TILE + 1) + c];
+      }
+      float bn = 0.0f;
+      if (metric == 1)
+        bn = __fsqrt_rn(REG_E ? sumsq_blk16_d32([&](int j) { return er[j]; })
+                              : sumsq_blk16(d, [&](int j) { return s_e[j * (VQ_TILE + 1) + c]; }));
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float* zv = s_ze + v * d;
+        float dist = REG_E ? sumsq_blk16_d32([&](int j) { return __fsub_rn(zv[j], er[j]); })
+                           : sumsq_blk16(d, [&](int j) { return __fsub_rn(zv[j], s_e[j * (VQ_TILE + 1) + c]); });
+        if (metric == 1) dist = __fdiv_rn(__fsqrt_rn(dist), __fadd_rn(a[v], bn));
+        if (dist < best[v]) {  // strict: the first (smallest) index wins ties within a thread (k ascending)
+          best[v] = dist;
+          best_k[v] = k;
+        }
+      }
     }
   }
-  if ((threadIdx.x & 31) == 0) {
-    s_best[threadIdx.x >> 5] = best;
-    s_idx[threadIdx.x >> 5] = best_k;
+  // block argmin per vector, ties -> smaller index
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    float bb = best[v];
+    int bk = best_k[v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, bb, o);
+      const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      if (ob < bb || (ob == bb && ok < bk)) {
+        bb = ob;
+        bk = ok;
+      }
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_best[v][threadIdx.x >> 5] = bb;
+      s_idx[v][threadIdx.x >> 5] = bk;
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float bb = s_best[0];
-    int bk = s_idx[0];
+  if (threadIdx.x < V && vec0 + static_cast<int>(threadIdx.x) < n_vec) {
+    const int v = threadIdx.x, vec = vec0 + v;
+    float bb = s_best[v][0];
+    int bk = s_idx[v][0];
     for (int w = 1; w < VQ_THREADS / 32; ++w) {
-      if (s_best[w] < bb || (s_best[w] == bb && s_idx[w] < bk)) {
-        bb = s_best[w];
-        bk = s_idx[w];
+      if (s_best[v][w] < bb || (s_best[v][w] == bb && s_idx[v][w] < bk)) {
+        bb = s_best[v][w];
+        bk = s_idx[v][w];
       }
     }
     if (bk == 0x7fffffff) bk = 0;  // all distances NaN: torch.min would return index of the first NaN; K > 0 so 0
-    s_win = bk;
+    s_win[v] = bk;
     min_ind[vec] = bk;
     min_dist[vec] = bb;
-    if (ze_norm) ze_norm[vec] = (metric == 1) ? a : __fsqrt_rn(sumsq_blk16(d, [&](int j) { return s_ze[j]; }));
+    const float* zv = s_ze + v * d;
+    if (ze_norm) ze_norm[vec] = __fsqrt_rn(sumsq_blk16(d, [&](int j) { return zv[j]; }));
     if (hist) atomicAdd(hist + bk, 1.0f);
     if (n_sum) atomicAdd(n_sum + bk, 1.0f);
   }
   __syncthreads();
-  const int win = s_win;
-  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+  for (int i = threadIdx.x; i < V * d; i += blockDim.x) {
+    const int v = i / d, j = i - v * d;
+    const int vec = vec0 + v;
+    if (vec >= n_vec) continue;
+    const int b = vec / N, n = vec - b * N;
+    const int win = s_win[v];
     zq[static_cast<long long>(b) * zq_bs + static_cast<long long>(j) * zq_cs + n] = emb[static_cast<long long>(win) * d + j];
-    if (z_sum) atomicAdd(z_sum + static_cast<long long>(win) * d + j, s_ze[j]);
+    if (z_sum) atomicAdd(z_sum + static_cast<long long>(win) * d + j, s_ze[i]);
   }
 }
 
@@ -210,8 +287,24 @@ int aewn_vq_fwd(const float* ze, long long ze_bs, long long ze_cs, const float* 
     cudaError_t e = cudaMemsetAsync(n_sum, 0, sizeof(float) * static_cast<size_t>(K), stream);
     if (e != cudaSuccess) return cuda_err(e, "vq_fwd: memset n_sum");
   }
-  vq_fwd_kernel<<<batch * N, VQ_THREADS, 0, stream>>>(ze, ze_bs, ze_cs, emb, metric, min_ind, min_dist, zq, zq_bs, zq_cs,
-                                                      hist, z_sum, n_sum, ze_norm, d, N, K);
+  // V vectors per CTA share every code tile: the largest V in {8, 4, 2, 1} that still leaves about one CTA per SM
+  const int n_vec = batch * N;
+  const int sms = sm_count();
+  const int V = n_vec >= 8 * (sms - sms / 8) ? 8 : n_vec >= 4 * (sms - sms / 8) ? 4 : n_vec >= 2 * (sms - sms / 8) ? 2 : 1;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(d) * (VQ_TILE + 1) + static_cast<size_t>(V) * d);
+  using Fn = void (*)(const float*, long long, long long, const float*, int, long long*, float*, float*, long long,
+                      long long, float*, float*, float*, float*, int, int, int, int);
+  const bool reg_e = d == 32;
+  Fn fn = V == 8 ? (reg_e ? vq_fwd_kernel<8, true> : vq_fwd_kernel<8, false>)
+          : V == 4 ? (reg_e ? vq_fwd_kernel<4, true> : vq_fwd_kernel<4, false>)
+          : V == 2 ? (reg_e ? vq_fwd_kernel<2, true> : vq_fwd_kernel<2, false>)
+                   : (reg_e ? vq_fwd_kernel<1, true> : vq_fwd_kernel<1, false>);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return cuda_err(e, "vq_fwd: cudaFuncSetAttribute");
+  }
+  fn<<<(n_vec + V - 1) / V, VQ_THREADS, smem, stream>>>(ze, ze_bs, ze_cs, emb, metric, min_ind, min_dist, zq, zq_bs, zq_cs,
+                                                        hist, z_sum, n_sum, ze_norm, d, N, K, n_vec);
   count_launch();
   return cuda_err(cudaGetLastError(), "vq_fwd launch");
 }
