@@ -425,6 +425,19 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 *reinterpret_cast<uint4*>(zrow + (((lc0 + k) ^ (row & 7)) << 4)) = v;
               }
             }
+            if (i == 1) {
+              // Both chunks' z rows are in shared memory and the accumulator has been read: release the TMEM region and
+              // signal z NOW, ahead of this chunk's global stores -- the arrivals (remote ones for the pair's second CTA)
+              // otherwise queue behind the store burst, and the MMA issuer saw its regions thousands of cycles late.
+              fence_proxy_async_smem();   // the z rows written above are read by tcgen05.mma (async proxy)
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive_cluster(lead_zready);
+                if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+                else mbar_arrive(&tempty_bar[acc]);
+              }
+            }
             // tanh / sigmoid (/ z) for the backward pass: plain coalesced stores (lane = time step: every store
             // instruction writes one full 128-byte line).  Through the staging tiles these were 3 TMA stores per chunk,
             // each with its acquire / proxy fence / issue latency (~800 cycles, phase clock) in the warp's serial chain.
@@ -450,14 +463,6 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 }
               }
             }
-          }
-          fence_proxy_async_smem();   // the z rows written above are read by tcgen05.mma (async proxy)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive_cluster(lead_zready);
-            if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
-            else mbar_arrive(&tempty_bar[acc]);
           }
         } else if (jd.kind == GF_RES) {
           // x_next = acc + x (wavenet.py:108).  fp32 through the staging half-tiles + TMA stores; fp16 channels-last copy
@@ -494,6 +499,14 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
             dbg_tm += clock() - t_t;
+            if (c0 + 16 >= ce) {      // last chunk of this warp: the accumulator is in registers, release the region now
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+                else mbar_arrive(&tempty_bar[acc]);
+              }
+            }
             float r[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -539,11 +552,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               if (c0 + 48 < ce) issue(c0 + 48, bufB);
             }
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
-            else mbar_arrive(&tempty_bar[acc]);
+          if (cb >= ce) {             // a warp without columns in this job still owes its arrival
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+              else mbar_arrive(&tempty_bar[acc]);
+            }
           }
         } else {
           // skip sum (wavenet.py:104,110-111 + the caller's running sum): store (first layer), reduce-add in L2, or
@@ -575,6 +590,14 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
             dbg_tm += clock() - t_t;
+            if (c0 + 16 >= ce) {      // last chunk: release the region before the stores
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+                else mbar_arrive(&tempty_bar[acc]);
+              }
+            }
             if (hp.skp_mode == 1) {
               // running skip sum: TMA reduce-add of a {32 t, 16 ch} box (the read-modify-write happens in L2)
               if ((slab0 + 32 > hp.skp_t_lo) && (slab0 < hp.t_hi)) {
@@ -605,11 +628,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               }
             }
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
-            else mbar_arrive(&tempty_bar[acc]);
+          if (cb >= ce) {             // a warp without columns in this job still owes its arrival
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+              else mbar_arrive(&tempty_bar[acc]);
+            }
           }
         }
         if (stamp) { ck[2] = clock64(); ck[3] = dbg_acq; ck[4] = dbg_tm; ck[5] = dbg_fl; }
