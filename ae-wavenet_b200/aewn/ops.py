@@ -467,8 +467,11 @@ class StackPlan:
         n_sig = g.L + (0 if g.last_is_final else 1)
         self.sig = [new_buf(B, R, Tp, device) for _ in range(n_sig)]       # sig[l] = input of layer l
         self.xs = {l: new_buf(B, R, Tp, device) for l in range(g.L) if needs_dup(g.dils[l])}
+        self.fused = FUSED_FWD and fused_ok(R, D, S, Cc)
+        # saved for the backward pass: tanh and sigmoid (fp32), or -- fused forward -- ONE word per element holding the two
+        # gate-derivative factors {fp16 a = sg (1 - th^2), fp16 b = th sg (1 - sg)} in `th` (half the bytes; `sg` unused)
         self.th = [new_buf(B, D, Tp, device) for _ in range(g.L)]
-        self.sg = [new_buf(B, D, Tp, device) for _ in range(g.L)]
+        self.sg = None if self.fused else [new_buf(B, D, Tp, device) for _ in range(g.L)]
         self.z = [new_buf(B, D, Tp, device) for _ in range(g.L)]
         self.skp = new_buf(B, S, Tp, device)
         self.cond = new_buf(B, Cc + 1, Tp, device)
@@ -479,7 +482,6 @@ class StackPlan:
         self.KR, self.KC, self.KD = ceil_to(R, 32), ceil_to(Cc + 1, 32), ceil_to(D, 32)
         self.KS, self.K2 = ceil_to(S, 32), ceil_to(2 * D, 32)
         self.J = (D + 127) // 128
-        self.fused = FUSED_FWD and fused_ok(R, D, S, Cc)
         if self.fused:
             # fp16 channels-last operand copies: the layer input ping-pongs between two buffers (the
             # backward pass reads the fp32 tensors), the conditioning copy is shared by all layers
@@ -614,7 +616,7 @@ class StackPlan:
                 if save and l + 1 < g.L and needs_dup(d_next):      # the backward pass's TF32 weight-gradient tap
                     d.dup, d.dup_toff, d.dup_t_hi = self.xs[l + 1].data_ptr(), d_next, T0
             if save:
-                d.th, d.sg, d.z, d.save = self.th[l].data_ptr(), self.sg[l].data_ptr(), self.z[l].data_ptr(), 1
+                d.th, d.z, d.save = self.th[l].data_ptr(), self.z[l].data_ptr(), 2       # packed derivative factors
                 d.a_bs, d.a_cs = int(self.th[l].stride(0)), int(self.th[l].stride(1))
             d.skp, d.s_bs, d.s_cs = self.skp.data_ptr(), int(self.skp.stride(0)), int(self.skp.stride(1))
             last_relu = l == g.L - 1 and self.relu_last
@@ -735,7 +737,8 @@ class StackPlan:
                 acts = [act_of(g_skp, T0)]
                 segs = [(0, 0, S, self.KR)]
             t_store = min(lop4, lo4)
-            tile = ntile(0, D, gfg, mode=L.EPI_GATE_BWD, out2=gfg[:, D:], add=self.th[l], add2=self.sg[l],
+            tile = ntile(0, D, gfg, mode=L.EPI_GATE_BWD, out2=gfg[:, D:], add=self.th[l],
+                         add2=None if self.fused else self.sg[l], flags=L.F_AB16 if self.fused else 0,
                          out3=gfs if needs_dup(d) else None, dup_toff=-d, dup_t_hi=T0,
                          t_lo=t_store, t_hi=T0, t_zero_lo=lo)
             launches += build_tgemm(acts, segs, self.w2t[l], [tile], B, t_store & ~31, T0, self.err, tag=f"bwd_gz.{l}")

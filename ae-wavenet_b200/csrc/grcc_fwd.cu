@@ -443,7 +443,19 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             // each with its acquire / proxy fence / issue latency (~800 cycles, phase clock) in the warp's serial chain.
             if (in_range && !(dbg & 8)) {
               const long long o0 = static_cast<long long>(it.b) * hp.a_bs + static_cast<long long>(ch) * hp.a_cs + tau;
-              if (hp.save) {
+              if (hp.save == 2) {
+                // what the backward pass needs from tanh / sigmoid are the two derivative factors
+                //   a = d z / d filt = sg (1 - th^2),   b = d z / d gate = th sg (1 - sg)          
+                // kept as ONE 32-bit word {fp16 a, fp16 b} per element (relative precision 2^-11, the operand precision
+                // of the backward engines): half the saved-activation bytes of fp32 tanh + sigmoid, in both passes
+                uint32_t* ap = reinterpret_cast<uint32_t*>(hp.th) + o0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float th = __uint_as_float(vf[j]), sg = __uint_as_float(vg[j]);
+                  __stcs(ap, pack_f16x2(sg * fmaf(-th, th, 1.0f), th * sg * (1.0f - sg)));
+                  ap += hp.a_cs;
+                }
+              } else if (hp.save) {
                 float* tp = hp.th + o0;
                 float* sp = hp.sg + o0;
 #pragma unroll
@@ -751,7 +763,7 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
     return set_err(AEWN_ERR_INVALID, "grcc_fwd: null operand / output pointer");
   if ((d->x_cs & 3) || (d->x_bs & 3) || (d->a_cs & 3) || (d->a_bs & 3) || (d->s_cs & 3) || (d->s_bs & 3))
     return set_err(AEWN_ERR_INVALID, "grcc_fwd: fp32 strides must be multiples of 4 elements");
-  if (d->save && (!d->th || !d->sg)) return set_err(AEWN_ERR_INVALID, "grcc_fwd: save needs th and sg");
+  if (d->save && (!d->th || (d->save != 2 && !d->sg))) return set_err(AEWN_ERR_INVALID, "grcc_fwd: save needs th (and sg)");
 
   GfParams p;
   memset(&p, 0, sizeof(p));

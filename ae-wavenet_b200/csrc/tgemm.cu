@@ -12,6 +12,8 @@
 //                               (lane = time step, so each warp store instruction writes one full 128 B line)
 // Pipelines: 4-stage smem ring (full/empty mbarriers) and a 2-stage TMEM ring (tfull/tempty), so the epilogue of
 // tile i overlaps the MMAs of tile i+1.
+#include <cuda_fp16.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -471,6 +473,7 @@ struct GateBwdCtx {
   long long add_cs, out_cs, g_delta;
   int n, n_valid;
   bool in_range, live;
+  bool ab16;          // AEWN_F_AB16: thp holds {fp16 a, fp16 b} words, the derivative factors themselves
 };
 
 __device__ __forceinline__ GateBwdCtx gbwd_ctx(const aewn_ntile& nt, int b, int tau, const CUtensorMap* omap,
@@ -492,6 +495,7 @@ __device__ __forceinline__ GateBwdCtx gbwd_ctx(const aewn_ntile& nt, int b, int 
   cx.out_cs = nt.out_cs;
   cx.n = nt.n;
   cx.n_valid = nt.n_valid;
+  cx.ab16 = (nt.flags & AEWN_F_AB16) != 0;
   return cx;
 }
 
@@ -500,6 +504,17 @@ __device__ __forceinline__ void gbwd_issue(const GateBwdCtx& cx, int c0, float (
   const float* ps = cx.sgp + static_cast<long long>(c0) * cx.add_cs;
   const int nrem = cx.n_valid - c0;
   const bool ok = cx.in_range && cx.live;
+  if (cx.ab16) {     // one word per element: th[] receives a, sg[] receives b
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const unsigned int w = (ok && j < nrem) ? __ldcs(reinterpret_cast<const unsigned int*>(pt)) : 0u;
+      const float2 ab = __half22float2(*reinterpret_cast<const __half2*>(&w));
+      th[j] = ab.x;
+      sg[j] = ab.y;
+      pt += cx.add_cs;
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     th[j] = (ok && j < nrem) ? __ldcg(pt) : 0.0f;
@@ -520,9 +535,14 @@ __device__ __forceinline__ void gbwd_chunk(const GateBwdCtx& cx, const StgOut& s
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const float gz = cx.live ? __uint_as_float(v[j]) : 0.0f;   // th, sg are 0 when !live
-    const float gs = gz * sg[j];
-    gf[j] = cx.in_range ? gs * (1.0f - th[j] * th[j]) : 0.0f;
-    gg[j] = cx.in_range ? gs * th[j] * (1.0f - sg[j]) : 0.0f;
+    if (cx.ab16) {
+      gf[j] = cx.in_range ? gz * th[j] : 0.0f;
+      gg[j] = cx.in_range ? gz * sg[j] : 0.0f;
+    } else {
+      const float gs = gz * sg[j];
+      gf[j] = cx.in_range ? gs * (1.0f - th[j] * th[j]) : 0.0f;
+      gg[j] = cx.in_range ? gs * th[j] * (1.0f - sg[j]) : 0.0f;
+    }
   }
   if (cx.omap) {   // TMA-store path (tile-uniform decision): g_f box, then g_g box, through the warp's staging tile
     if (so.slab_on) {
@@ -928,7 +948,7 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
       if (nt.n != 256 || !nt.out3 || nt.n_valid > 128)
         return set_err(AEWN_ERR_INVALID, "tgemm: GATE_FWD tile %d needs n=256, n_valid<=128 and out3", i);
     } else if (nt.mode == AEWN_EPI_GATE_BWD) {
-      if (!nt.out || !nt.out2 || !nt.add || !nt.add2)
+      if (!nt.out || !nt.out2 || !nt.add || (!nt.add2 && !(nt.flags & AEWN_F_AB16)))
         return set_err(AEWN_ERR_INVALID, "tgemm: GATE_BWD tile %d needs out, out2, add, add2", i);
     } else {
       return set_err(AEWN_ERR_INVALID, "tgemm: n-tile %d unknown mode %d", i, nt.mode);

@@ -78,6 +78,8 @@ typedef struct {
 #define AEWN_F_MASKPOS 4    /* `add` is a mask source, not an addend: value = add[b,n,t] > 0 ? value : 0 */
 #define AEWN_F_RELU_FIRST 8 /* value = max(acc + bias, 0) + add  (wave_encoder.py:39-43 order); out3 (optional)
                                receives max(acc + bias, 0), the activation mask source for the backward pass */
+#define AEWN_F_AB16 32      /* GATE_BWD: `add` holds {fp16 a, fp16 b} words (aewn_grcc_fwd, save == 2): g_filt = g_z a, g_gate = g_z b;
+                               add2 unused */
 #define AEWN_F_MERGE_NEXT 16 /* this tile and the NEXT one in ntiles[] share one accumulator: one MMA of n + n_next (<= 256)
                                 columns over their contiguous W rows, one pass over the activations.  Pair mode, LINEAR
                                 tiles; the partner must be a plain store / AEWN_F_ACCUM tile on the TMA path and its
@@ -292,7 +294,9 @@ typedef struct {
   float* dup;             /* optional: x_next again at time index t + dup_toff (same strides as x32), for the backward
                              pass's TF32 weight-gradient tap when the NEXT layer's dilation is not a multiple of 4 */
   int dup_toff, dup_t_hi;
-  float* th;              /* save != 0: tanh(filt), sigmoid(gate) (batch, D, T) for the backward pass */
+  float* th;              /* save == 1: tanh(filt), sigmoid(gate) (batch, D, T) fp32 for the backward pass;
+                             save == 2: th receives ONE 32-bit word per element = {fp16 a, fp16 b}, the derivative factors
+                             a = sg (1 - th^2), b = th sg (1 - sg) (what AEWN_EPI_GATE_BWD + AEWN_F_AB16 reads); sg unused */
   float* sg;
   float* z;               /* optional: z (batch, D, T) */
   long long a_bs, a_cs;   /* strides of th / sg / z */
