@@ -35,7 +35,8 @@ class NTile(C.Structure):
                 ("out_bs", C.c_longlong), ("out_cs", C.c_longlong), ("out_toff", C.c_int),
                 ("dup_toff", C.c_int), ("dup_t_hi", C.c_int), ("zero_count", C.c_void_p),
                 ("add", C.c_void_p), ("add2", C.c_void_p), ("add_bs", C.c_longlong), ("add_cs", C.c_longlong),
-                ("add_toff", C.c_int), ("add_t_lo", C.c_int), ("bias", C.c_void_p)]
+                ("add_toff", C.c_int), ("add_t_lo", C.c_int), ("bias", C.c_void_p),
+                ("out16", C.c_void_p), ("out16_bs", C.c_longlong), ("out16_cp", C.c_int)]
 
 
 class TGemmDesc(C.Structure):
@@ -98,6 +99,17 @@ class GrccFwdDesc(C.Structure):
                 ("max_ctas", C.c_int), ("dbg_clock", C.c_void_p)]
 
 
+class GrccDgradDesc(C.Structure):
+    """aewn_grcc_dgrad_desc: data gradient of one dilation layer on the fused-layer engine (include/aewn.h)."""
+    _fields_ = [("g16", C.c_void_p), ("g16_bs", C.c_longlong), ("g16_cp", C.c_int), ("t_rows", C.c_int),
+                ("w1t16", C.c_void_p), ("w_k", C.c_int), ("g_sig", C.c_void_p), ("gx", C.c_void_p),
+                ("x_bs", C.c_longlong), ("x_cs", C.c_longlong), ("add_t_lo", C.c_int),
+                ("g_cond", C.c_void_p), ("c_bs", C.c_longlong), ("c_cs", C.c_longlong), ("n_cond", C.c_int),
+                ("batch", C.c_int), ("R", C.c_int), ("dil", C.c_int),
+                ("t_lo", C.c_int), ("t_zero_lo", C.c_int), ("t_hi", C.c_int),
+                ("cond_t_lo", C.c_int), ("cond_zero_lo", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int)]
+
+
 GEN_MAX_LAYERS = 64
 GEN_MAX_BLOCKS = 2 * GEN_MAX_LAYERS + 2
 GEN_MAX_REP = 4
@@ -129,7 +141,8 @@ SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_
            "aewn_base_embed_fwd", "aewn_base_embed_bwd", "aewn_fill", "aewn_relu_mask_bwd",
            "aewn_vq_fwd", "aewn_vq_commit_bwd", "aewn_ema_update", "aewn_pack_blocks", "aewn_add_blocks", "aewn_nll_fwd", "aewn_nll_bwd",
            "aewn_gen_smem_bytes", "aewn_gen_max_clusters", "aewn_gen_run",
-           "aewn_grcc_fwd", "aewn_cvt_f16_cl", "aewn_pack_blocks_f16", "aewn_conv1x1_f32", "aewn_conv1x1_wgrad_f32"]
+           "aewn_grcc_fwd", "aewn_cvt_f16_cl", "aewn_pack_blocks_f16", "aewn_conv1x1_f32", "aewn_conv1x1_wgrad_f32",
+           "aewn_grcc_dgrad", "aewn_pack_blocks_bf16"]
 
 
 def lib():

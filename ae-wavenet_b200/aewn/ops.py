@@ -374,6 +374,8 @@ def run_launches(launches):
             L.check(lib.aewn_tgemm(C.byref(d), st), "aewn_tgemm")
         elif kind == "grcc":
             L.check(lib.aewn_grcc_fwd(C.byref(d), st), "aewn_grcc_fwd")
+        elif kind == "dgrad16":
+            L.check(lib.aewn_grcc_dgrad(C.byref(d), st), "aewn_grcc_dgrad")
         elif kind == "wgradw":
             L.check(lib.aewn_wgradw(C.byref(d), st), "aewn_wgradw")
         else:
@@ -482,6 +484,9 @@ class StackPlan:
         self.KR, self.KC, self.KD = ceil_to(R, 32), ceil_to(Cc + 1, 32), ceil_to(D, 32)
         self.KS, self.K2 = ceil_to(S, 32), ceil_to(2 * D, 32)
         self.J = (D + 127) // 128
+        # data gradient on the fused-layer engine (aewn_grcc_dgrad: bf16 channels-last copy of [g_f; g_g], bf16 weights)
+        self.dgrad16 = self.fused and R % 16 == 0 and Cc <= 240 and (2 * D) % 64 == 0 and \
+            os.environ.get("AEWN_DGRAD16", "1") == "1"
         if self.fused:
             # fp16 channels-last operand copies: the layer input ping-pongs between two buffers (the
             # backward pass reads the fp32 tensors), the conditioning copy is shared by all layers
@@ -506,9 +511,16 @@ class StackPlan:
         KR, KC, KD, KS, K2, J = self.KR, self.KC, self.KD, self.KS, self.K2, self.J
         KP = 2 * KR + KC
         self.w1, self.w2, self.w2t, self.w1t = [], [], [], []
-        self.w1h, self.w2h = [], []
-        blocks, hblocks = [], []
+        self.w1h, self.w2h, self.w1t16 = [], [], []
+        blocks, hblocks, bblocks = [], [], []
         fused = self.fused
+
+        def blkb(src, s_off, dst, d_row, d_col, ni, nj, si, sj):       # same table entry, bf16 destination
+            step = max(1, 8192 // max(nj, 1))
+            for r0 in range(0, ni, step):
+                bblocks.append((src.data_ptr() + 4 * (s_off + r0 * si),
+                                dst.data_ptr() + 2 * ((d_row + r0) * dst.shape[1] + d_col), min(step, ni - r0), nj, si, sj,
+                                dst.shape[1]))
 
         def blkh(src, s_off, dst, d_row, d_col, ni, nj, si, sj):       # same table entry, fp16 destination
             step = max(1, 8192 // max(nj, 1))
@@ -559,15 +571,20 @@ class StackPlan:
             else:
                 fblk(ws, 0, w2, 0, 0, S, D, D, 1)
             blk(ws, 0, w2t, 0, KR, D, S, 1, D)                                         # Ws^T
+            if self.dgrad16:
+                w1t = torch.zeros(R + Cc, 2 * K2, device=dev, dtype=torch.bfloat16)
+                tblk = blkb
+            else:
+                tblk = blk
             for h, wc in enumerate((wf, wg)):
                 for k in (0, 1):                                                       # tap k transposed
-                    blk(wc, k, w1t, 0, k * K2 + h * D, R, D, 2, 2 * R)
+                    tblk(wc, k, w1t, 0, k * K2 + h * D, R, D, 2, 2 * R)
             for h, pj in enumerate((pf, pg)):
-                blk(pj, 0, w1t, R, K2 + h * D, Cc, D, 1, Cc)                           # P^T under the unshifted block
+                tblk(pj, 0, w1t, R, K2 + h * D, Cc, D, 1, Cc)                          # P^T under the unshifted block
             (self.w1h if fused else self.w1).append(w1)
             (self.w2h if fused else self.w2).append(w2)
             self.w2t.append(w2t)
-            self.w1t.append(w1t)
+            (self.w1t16 if self.dgrad16 else self.w1t).append(w1t)
         import numpy as np
         dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("ni", "<i4"), ("nj", "<i4"), ("si", "<i8"), ("sj", "<i8"),
                        ("di", "<i8")])
@@ -578,6 +595,9 @@ class StackPlan:
         self.n_hblocks = len(hblocks)
         if hblocks:
             self.hblock_table = torch.from_numpy(np.array(hblocks, dtype=dt).view(np.uint8).reshape(-1).copy()).to(dev)
+        self.n_bblocks = len(bblocks)
+        if bblocks:
+            self.bblock_table = torch.from_numpy(np.array(bblocks, dtype=dt).view(np.uint8).reshape(-1).copy()).to(dev)
 
     def repack(self):
         L.check(L.lib().aewn_pack_blocks(C.c_void_p(self.block_table.data_ptr()), C.c_int(self.n_blocks), _stream()),
@@ -585,6 +605,9 @@ class StackPlan:
         if self.n_hblocks:
             L.check(L.lib().aewn_pack_blocks_f16(C.c_void_p(self.hblock_table.data_ptr()), C.c_int(self.n_hblocks),
                                                  _stream()), "aewn_pack_blocks_f16")
+        if self.n_bblocks:
+            L.check(L.lib().aewn_pack_blocks_bf16(C.c_void_p(self.bblock_table.data_ptr()), C.c_int(self.n_bblocks),
+                                                  _stream()), "aewn_pack_blocks_bf16")
 
     def _to_f16_cl(self, src, dst, channels):
         """(B, C, Tp) fp32 workspace -> (B, Tp, Cp) fp16 channels-last operand copy (one launch)."""
@@ -714,6 +737,8 @@ class StackPlan:
         bw = dict(gfg=new_buf(B, 2 * D, Tp, dev), gfs=new_buf(B, 2 * D, Tp, dev),
                   gx=[new_buf(B, R, Tp, dev), new_buf(B, R, Tp, dev)], g_skp=new_buf(B, S, Tp, dev),
                   g_cond=new_buf(B, Cc, Tp, dev), g_last=None if g.last_is_final else new_buf(B, R, Tp, dev))
+        if self.dgrad16:
+            bw["g16"] = torch.zeros(B, Tp, self.K2, device=dev, dtype=torch.bfloat16)     # [g_f; g_g], channels-last
         lay, total = self._grad_layout()
         flat = torch.zeros(total, device=dev)
         views = [{k: flat[o:o + int(torch.tensor(sh).prod())].view(sh) for k, (o, sh) in e.items()} for e in lay]
@@ -739,32 +764,48 @@ class StackPlan:
             t_store = min(lop4, lo4)
             tile = ntile(0, D, gfg, mode=L.EPI_GATE_BWD, out2=gfg[:, D:], add=self.th[l],
                          add2=None if self.fused else self.sg[l], flags=L.F_AB16 if self.fused else 0,
-                         out3=gfs if needs_dup(d) else None, dup_toff=-d, dup_t_hi=T0,
+                         out3=gfs if (needs_dup(d) and not self.dgrad16) else None, dup_toff=-d, dup_t_hi=T0,
                          t_lo=t_store, t_hi=T0, t_zero_lo=lo)
+            if self.dgrad16:
+                tile.out16, tile.out16_bs, tile.out16_cp = bw["g16"].data_ptr(), int(bw["g16"].stride(0)), self.K2
             launches += build_tgemm(acts, segs, self.w2t[l], [tile], B, t_store & ~31, T0, self.err, tag=f"bwd_gz.{l}")
             # (2) g_x[tau] = tap1^T gfg[tau] + tap0^T gfg[tau + d] (+ g_sig[tau]);  g_cond[tau] += P^T gfg[tau]
-            if needs_dup(d):
-                acts = [act_of(gfs, T0 - d), act_of(gfg, T0)]
-                segs = [(0, 0, 2 * D, 0), (1, 0, 2 * D, self.K2)]
-            else:
-                acts = [act_of(gfg, T0)]
-                segs = [(0, d, 2 * D, 0), (0, 0, 2 * D, self.K2)]
             gx = bw["gx"][l % 2]
-            tiles = []
-            for (c0, n) in chunks(R):
-                tiles.append(ntile(c0, n, gx[:, c0:], add=g_sig[:, c0:] if g_sig is not None else None, add_t_lo=lo,
-                                   t_lo=lop4, t_hi=T0, t_zero_lo=lo_prev))
-            cond_tiles = [ntile(R + c0, n, g_cond[:, c0:], flags=L.F_ACCUM, seg_mask=2, t_lo=lo, t_hi=T0)
-                          for (c0, n) in chunks(Cc)]
-            # The tail tile of g_x (R - 256 = 112 columns) and the g_cond tile (138 -> 144) fit ONE 256-column accumulator and
-            # their rows are adjacent in w1t: one pass over [g_f; g_g] instead of two (the cond rows hold zeros under the
-            # shifted tap block, so running them over both segments adds exact zeros).  AEWN_F_MERGE_NEXT, pair mode only.
-            tail, first = tiles[-1], cond_tiles[0]
-            if (MERGE_DGRAD_TILES and _use_pair("bwd_dgrad") and tail.n == tail.n_valid and first.n >= 32 and
-                    tail.n + first.n <= 256 and tail.w_row + tail.n == first.w_row):
-                tail.flags |= L.F_MERGE_NEXT
-            tiles += cond_tiles
-            launches += build_tgemm(acts, segs, self.w1t[l], tiles, B, lop4 & ~31, T0, self.err, tag=f"bwd_dgrad.{l}")
+            if self.dgrad16:
+                dd = L.GrccDgradDesc()
+                g16 = bw["g16"]
+                dd.g16, dd.g16_bs, dd.g16_cp, dd.t_rows = g16.data_ptr(), int(g16.stride(0)), self.K2, Tp
+                dd.w1t16, dd.w_k = self.w1t16[l].data_ptr(), 2 * self.K2
+                dd.g_sig = g_sig.data_ptr() if g_sig is not None else None
+                dd.gx, dd.x_bs, dd.x_cs, dd.add_t_lo = gx.data_ptr(), int(gx.stride(0)), int(gx.stride(1)), lo
+                dd.g_cond, dd.c_bs, dd.c_cs, dd.n_cond = g_cond.data_ptr(), int(g_cond.stride(0)), int(g_cond.stride(1)), Cc
+                dd.batch, dd.R, dd.dil = B, R, d
+                dd.t_lo, dd.t_zero_lo, dd.t_hi = lop4, lo_prev, T0
+                dd.cond_t_lo, dd.cond_zero_lo = lo & ~3, lo
+                dd.err = self.err.data_ptr()
+                launches.append(("dgrad16", dd, f"bwd_dgrad.{l}"))
+            if not self.dgrad16:
+                if needs_dup(d):
+                    acts = [act_of(gfs, T0 - d), act_of(gfg, T0)]
+                    segs = [(0, 0, 2 * D, 0), (1, 0, 2 * D, self.K2)]
+                else:
+                    acts = [act_of(gfg, T0)]
+                    segs = [(0, d, 2 * D, 0), (0, 0, 2 * D, self.K2)]
+                tiles = []
+                for (c0, n) in chunks(R):
+                    tiles.append(ntile(c0, n, gx[:, c0:], add=g_sig[:, c0:] if g_sig is not None else None, add_t_lo=lo,
+                                       t_lo=lop4, t_hi=T0, t_zero_lo=lo_prev))
+                cond_tiles = [ntile(R + c0, n, g_cond[:, c0:], flags=L.F_ACCUM, seg_mask=2, t_lo=lo, t_hi=T0)
+                              for (c0, n) in chunks(Cc)]
+                # The tail tile of g_x (R - 256 = 112 columns) and the g_cond tile (138 -> 144) fit ONE 256-column accumulator and
+                # their rows are adjacent in w1t: one pass over [g_f; g_g] instead of two (the cond rows hold zeros under the
+                # shifted tap block, so running them over both segments adds exact zeros).  AEWN_F_MERGE_NEXT, pair mode only.
+                tail, first = tiles[-1], cond_tiles[0]
+                if (MERGE_DGRAD_TILES and _use_pair("bwd_dgrad") and tail.n == tail.n_valid and first.n >= 32 and
+                        tail.n + first.n <= 256 and tail.w_row + tail.n == first.w_row):
+                    tail.flags |= L.F_MERGE_NEXT
+                tiles += cond_tiles
+                launches += build_tgemm(acts, segs, self.w1t[l], tiles, B, lop4 & ~31, T0, self.err, tag=f"bwd_dgrad.{l}")
             # (3) weight gradients of conv_signal/conv_gate/proj_signal/proj_gate (+ biases via the ones channel)
             x0_act = act_of(self.xs[l], T0) if needs_dup(d) else act_of(x, T0)
             acts = [act_of(gfg, T0), x0_act, act_of(x, T0), act_of(self.cond, T0)]

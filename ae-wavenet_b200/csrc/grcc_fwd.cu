@@ -26,6 +26,7 @@
 // fence + issue latency in each warp's serial chain).  The running skip sum keeps the TMA reduce-add (one 2 KB box per
 // 16 channels through a per-warp staging tile): red.global.add per element measured 2x slower (profiles/r3_gf_*).
 // All waits are bounded.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "host_util.h"
@@ -57,6 +58,14 @@ struct GfJob {
   int n;         // accumulator columns (MMA N)
   int n_valid;   // output channels of this job
   int ch0;       // first output channel (GATE: first z channel)
+  int a_ring;    // RES / SKP jobs: 1 = the A operand comes through the ring (segments below) instead of the z buffer
+  int split;     // RES jobs: accumulator columns >= split are reduce-added into the `skp` tensor (channel = column - split)
+};
+
+struct GfSeg {
+  int map;       // 0: xa, 1: ca
+  int shift;     // row (time) shift of the box
+  int kb;        // ring stages (64 channels each)
 };
 
 // Scalars and the job table: copied to shared memory at kernel start.  Read from the kernel parameter space they cost an
@@ -65,8 +74,11 @@ struct GfJob {
 struct GfHot {
   GfJob job[GF_MAX_JOBS];
   int n_jobs, n_gate;
-  int kb_x, kb_c, kb_z;                   // ring stages per x tap, for cond, for z
-  int dil;
+  int kb_z;                               // ring stages of a z-operand job
+  GfSeg seg[3];                           // K segments of a ring-operand job, in W column order
+  int n_segs, ring_stages;
+  int ab_bf16;                            // operands are bf16 (data-gradient variant) instead of fp16
+  int add_t_lo;                           // RES epilogue: the addend applies for t >= add_t_lo
   const float* x32;                        // residual source (B, R, Tp)
   float* xo32;                             // x_next (B, R, Tp), same strides
   long long x_bs, x_cs;
@@ -106,8 +118,9 @@ __device__ __forceinline__ void umma_f16_ss_pair(uint32_t d_tmem, uint64_t adesc
 }
 
 // kind::f16, A and B = F16 (format 0), both K-major, FP32 accumulate
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
-  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int bf16 = 0) {
+  return (1u << 4) | (static_cast<uint32_t>(bf16) << 7) | (static_cast<uint32_t>(bf16) << 10) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
@@ -207,7 +220,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * GF_EPI_WARPS);   // on the leader: the epilogue warps of both CTAs
     }
-    mbar_init(zready_bar, 2 * GF_EPI_WARPS * p.hot.n_gate);   // every epilogue warp of the pair, once per gate job
+    mbar_init(zready_bar, 2 * GF_EPI_WARPS * (p.hot.n_gate > 0 ? p.hot.n_gate : 1));   // every epilogue warp of the pair, once per gate job
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -230,7 +243,6 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
   const int cid = blockIdx.x >> 1;
   const int n_cl = gridDim.x >> 1;
   const int total = hp.batch * hp.n_tgroups;
-  const int g1_stages = 2 * hp.kb_x + hp.kb_c;
 
   if (warp < 4) {
     reg_dealloc<56>();   // 128 x 56 + 512 x 104 = 60416 <= 640 x 96 (the CTA's launch allocation)
@@ -251,26 +263,29 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         // for HBM behind a ring of only 3-4 stages (phase clock: ~1000 cycles per stage against ~570 from L2)
         if ((hp.prefetch & 2) && item + n_cl < total && elect_one()) {
           const GfItem nx = gf_decode(hp, item + n_cl, crank);
-          for (int kb = 0; kb < hp.kb_x; ++kb) tma_prefetch_l2_3d(&p.xa, kb * GF_KB, nx.tau0, nx.b);
-          for (int kb = 0; kb < hp.kb_c; ++kb) tma_prefetch_l2_3d(&p.ca, kb * GF_KB, nx.tau0, nx.b);
+          for (int si = 0; si < hp.n_segs; ++si)
+            if (hp.seg[si].shift == 0)
+              for (int kb = 0; kb < hp.seg[si].kb; ++kb)
+                tma_prefetch_l2_3d(hp.seg[si].map ? &p.ca : &p.xa, kb * GF_KB, nx.tau0, nx.b);
         }
         __syncwarp();
         for (int jb = 0; jb < hp.n_jobs && ok; ++jb) {
           const GfJob jd = hp.job[jb];
           if (jd.kind == GF_SKP && !it.do_skp) continue;
-          const int nst = jd.kind == GF_GATE ? g1_stages : hp.kb_z;
+          const bool use_ring = jd.kind == GF_GATE || jd.a_ring;
+          const int nst = use_ring ? hp.ring_stages : hp.kb_z;
+          int sgi = 0, kb = 0;                                   // current K segment / block inside it (ring-operand jobs)
           for (int s = 0; s < nst; ++s) {
             if (!mbar_wait_warp(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
             if (elect_one()) {
               uint8_t* sa = smem + stage * GF_STAGE_BYTES;
               uint8_t* sw = sa + GF_A_BYTES;
               const uint32_t fb = lead_full + stage * 8u;
-              if (jd.kind == GF_GATE) {
+              if (use_ring) {
                 if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * GF_STAGE_BYTES);
-                if (s < hp.kb_x) tma_load_3d_pair_hint(sa, &p.xa, fb, s * GF_KB, it.tau0 - hp.dil, it.b, pol_keep);
-                else if (s < 2 * hp.kb_x) tma_load_3d_pair_hint(sa, &p.xa, fb, (s - hp.kb_x) * GF_KB, it.tau0, it.b, pol_keep);
-                else tma_load_3d_pair_hint(sa, &p.ca, fb, (s - 2 * hp.kb_x) * GF_KB, it.tau0, it.b, pol_keep);
-                tma_load_2d_pair_hint(sw, &p.w1, fb, s * GF_KB, jd.w_row + crank * 128, pol_keep);
+                const GfSeg sg = hp.seg[sgi];
+                tma_load_3d_pair_hint(sa, sg.map ? &p.ca : &p.xa, fb, kb * GF_KB, it.tau0 + sg.shift, it.b, pol_keep);
+                tma_load_2d_pair_hint(sw, &p.w1, fb, s * GF_KB, jd.w_row + crank * (jd.n >> 1), pol_keep);
               } else {
                 // CTA r stages W2 rows [r * n/2, (r+1) * n/2) of the job (a 128-row box; the MMA reads n/2 of them)
                 if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * GF_W_BYTES);
@@ -278,6 +293,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               }
             }
             __syncwarp();
+            if (use_ring && ++kb == hp.seg[sgi].kb) { kb = 0; ++sgi; }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -303,7 +319,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             unsigned int w_full = 0;
             if (stamp) ck[0] = clock64();
             if (!mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1u, abort_flag)) { ok = false; break; }
-            if (jd.kind != GF_GATE && !z_waited) {
+            const bool use_ring = jd.kind == GF_GATE || jd.a_ring;
+            if (!use_ring && !z_waited) {
               // every epilogue warp of the pair has written its z columns of this tile (generic proxy -> fence -> arrive)
               const unsigned int tz = clock();
               if (!mbar_wait_warp(zready_bar, zphase, abort_flag)) { ok = false; break; }
@@ -314,8 +331,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             tc_fence_after();
             if (stamp) ck[1] = clock64();
             const uint32_t d_tmem = tmem_base + acc * 256u;
-            const uint32_t idesc = make_idesc_f16(2 * GF_BM, jd.n);
-            const int nst = jd.kind == GF_GATE ? g1_stages : hp.kb_z;
+            const uint32_t idesc = make_idesc_f16(2 * GF_BM, jd.n, hp.ab_bf16);
+            const int nst = use_ring ? hp.ring_stages : hp.kb_z;
             for (int s = 0; s < nst; ++s) {
               const unsigned int tf = clock();
               if (!mbar_wait_warp(&full_bar[stage], phase, abort_flag)) { ok = false; break; }
@@ -324,7 +341,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               if (elect_one()) {
                 const uint32_t s16 = ((ring + stage * GF_STAGE_BYTES) >> 4) & 0x3FFFu;
                 const uint32_t w16 = s16 + (GF_A_BYTES >> 4);
-                const uint32_t a16 = jd.kind == GF_GATE ? s16 : z16_0 + static_cast<uint32_t>(s) * (GF_A_BYTES >> 4);
+                const uint32_t a16 = use_ring ? s16 : z16_0 + static_cast<uint32_t>(s) * (GF_A_BYTES >> 4);
 #pragma unroll
                 for (int ks = 0; ks < GF_KB / 16; ++ks)   // K advances 16 fp16 = 32 B inside the swizzle row
                   umma_f16_ss_pair(d_tmem, desc0 + (a16 + ks * 2), desc0 + (w16 + ks * 2), idesc,
@@ -341,7 +358,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
           }
           // a tile whose skip job was skipped still has to consume the z phase (the epilogues always arrive)
-          if (ok && !z_waited) {
+          if (ok && !z_waited && hp.n_gate > 0) {
             if (!mbar_wait_warp(zready_bar, zphase, abort_flag)) { ok = false; break; }
             zphase ^= 1u;
           }
@@ -491,12 +508,15 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           float* dupp = (hp.dup && in_range && dup_t >= 0 && dup_t < hp.dup_t_hi)
                             ? hp.dup + static_cast<long long>(it.b) * hp.x_bs + static_cast<long long>(jd.ch0) * hp.x_cs + dup_t
                             : nullptr;
+          const bool add_ok = hp.x32 != nullptr && tau >= hp.add_t_lo;
+          const bool s_in = tau >= hp.skp_t_lo && tau < hp.t_hi;           // (columns >= jd.split: reduce-add part)
+          const bool s_keep = s_in && tau >= hp.skp_zero_lo;
           float bufA[16], bufB[16];
           auto issue = [&](int c0, float (&buf)[16]) {
             const float* sp = xsrc + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              buf[j] = (keep && c0 + j < nv && !(dbg & 1)) ? __ldcs(sp) : 0.0f;
+              buf[j] = (keep && add_ok && c0 + j < nv && !(dbg & 1)) ? __ldcs(sp) : 0.0f;
               sp += hp.x_cs;
             }
           };
@@ -518,6 +538,22 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
                 else mbar_arrive(&tempty_bar[acc]);
               }
+            }
+            if (c0 >= jd.split) {
+              // the reduce-add columns of a merged job (data-gradient variant: g_cond += P^T [g_f; g_g])
+              if ((slab0 + 32 > hp.skp_t_lo) && (slab0 < hp.t_hi)) {
+                if (elect_one()) tma_store_wait_read();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) stg[j * 32 + lane] = s_keep ? __uint_as_float(v[j]) : 0.0f;
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                  tma_reduce_add_3d(&p.skp_m, stg, slab0, c0 - jd.split, it.b);
+                  tma_store_commit();
+                }
+              }
+              return;
             }
             float r[16];
 #pragma unroll
@@ -541,7 +577,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 dd += hp.x_cs;
               }
             }
-            if (in_range && !(dbg & 4)) {
+            if (in_range && hp.xo16 && !(dbg & 4)) {
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
                 if (c0 + 8 * k < nv) {
@@ -653,7 +689,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
-    if (xmax > 65504.0f && hp.err) atomicExch(hp.err, AEWN_ERR_RANGE);   // fp16 operand copy saturated
+    if (xmax > 65504.0f && hp.err && hp.xo16) atomicExch(hp.err, AEWN_ERR_RANGE);   // fp16 operand copy saturated
     if (elect_one()) tma_store_wait_all();
     __syncwarp();
   }
@@ -720,8 +756,20 @@ __global__ void pack_blocks_f16_kernel(const aewn_copy_block* __restrict__ block
   }
 }
 
+__global__ void pack_blocks_bf16_kernel(const aewn_copy_block* __restrict__ blocks, int n_blocks) {
+  for (int bi = blockIdx.x; bi < n_blocks; bi += gridDim.x) {
+    const aewn_copy_block b = blocks[bi];
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(b.dst);
+    const long long total = static_cast<long long>(b.ni) * b.nj;
+    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+      const long long i = e / b.nj, j = e - i * b.nj;
+      d[i * b.di + j] = __float2bfloat16_rn(b.src[i * b.si + j * b.sj]);
+    }
+  }
+}
+
 static int encode_f16_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                          const cuuint32_t* box, CUtensorMapL2promotion promo, const char* what) {
+                          const cuuint32_t* box, CUtensorMapL2promotion promo, const char* what, bool bf16 = false) {
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -736,7 +784,8 @@ static int encode_f16_map(CUtensorMap* map, const void* ptr, int rank, const cuu
   if (!ptr || (reinterpret_cast<uintptr_t>(ptr) & 15u))
     return set_err(AEWN_ERR_INVALID, "grcc_fwd: %s pointer null or not 16-byte aligned", what);
   cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims, strides_b, box, estr,
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims,
+                  strides_b, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(AEWN_ERR_DRIVER, "cuTensorMapEncodeTiled(%s) failed: CUresult %d", what, (int)r);
   return AEWN_OK;
@@ -745,6 +794,36 @@ static int encode_f16_map(CUtensorMap* map, const void* ptr, int rank, const cuu
 }  // namespace aewn
 
 using namespace aewn;
+
+static int gf_launch(GfParams& p, int max_ctas, cudaStream_t stream, const char* what) {
+  const long long total = static_cast<long long>(p.hot.batch) * p.hot.n_tgroups;
+  int clusters = (max_ctas > 0 ? max_ctas : sm_count()) / 2;
+  if (clusters > total) clusters = static_cast<int>(total);
+  if (clusters < 1) clusters = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * 2);
+  cfg.blockDim = dim3(GF_THREADS);
+  cfg.dynamicSmemBytes = GF_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // ring depth: 4 stages (default) or 3 (AEWN_GF_RING=3, A/B runs)
+  static const int ring = []() { const char* e = getenv("AEWN_GF_RING"); return e && atoi(e) == 3 ? 3 : 4; }();
+  using KernelFn = void (*)(GfParams);
+  KernelFn fn = ring == 3 ? grcc_fwd_kernel<3> : grcc_fwd_kernel<4>;
+  cudaError_t ae = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_BYTES);
+  if (ae != cudaSuccess) return cuda_err(ae, what);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
+  count_launch();
+  if (le != cudaSuccess) return cuda_err(le, what);
+  return cuda_err(cudaGetLastError(), what);
+}
 
 extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -797,7 +876,7 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   if ((rc = encode_out_map(&p.skp_m, d->skp, d->t_hi, S, d->batch, d->s_cs, d->s_bs, 16))) return rc;
 
   int nj = 0;
-  for (int j = 0; j < D / 128; ++j) p.hot.job[nj++] = GfJob{GF_GATE, 256 * j, 256, 128, 128 * j};
+  for (int j = 0; j < D / 128; ++j) p.hot.job[nj++] = GfJob{GF_GATE, 256 * j, 256, 128, 128 * j, 1, 256};
   p.hot.n_gate = nj;
   // Order of the residual / skip jobs: their epilogues are long (HBM stores) and their MMAs short, and the next tile's
   // first gate job may start as soon as the region of the SECOND-to-last job has been drained -- so the job with the
@@ -806,19 +885,21 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   const int row_s = d->final_layer ? 0 : R;
   for (int c0 = 0; c0 < S; c0 += 256) {
     const int nv = S - c0 < 256 ? S - c0 : 256;
-    p.hot.job[nj++] = GfJob{GF_SKP, row_s + c0, (nv + 15) & ~15, nv, c0};
+    p.hot.job[nj++] = GfJob{GF_SKP, row_s + c0, (nv + 15) & ~15, nv, c0, 0, 256};
   }
   if (!d->final_layer)
     for (int c0 = ((R - 1) / 256) * 256; c0 >= 0; c0 -= 256) {      // the partial chunk (if any) first
       const int nv = R - c0 < 256 ? R - c0 : 256;
-      p.hot.job[nj++] = GfJob{GF_RES, c0, (nv + 15) & ~15, nv, c0};
+      p.hot.job[nj++] = GfJob{GF_RES, c0, (nv + 15) & ~15, nv, c0, 0, 256};
     }
   if (nj > GF_MAX_JOBS) return set_err(AEWN_ERR_INVALID, "grcc_fwd: too many jobs (%d)", nj);
   p.hot.n_jobs = nj;
-  p.hot.kb_x = KR / 64;
-  p.hot.kb_c = KC / 64;
+  p.hot.seg[0] = GfSeg{0, -d->dil, KR / 64};      // x(t - dil)
+  p.hot.seg[1] = GfSeg{0, 0, KR / 64};            // x(t)
+  p.hot.seg[2] = GfSeg{1, 0, KC / 64};            // cond(t), 1
+  p.hot.n_segs = 3;
+  p.hot.ring_stages = 2 * (KR / 64) + KC / 64;
   p.hot.kb_z = D / 64;
-  p.hot.dil = d->dil;
   p.hot.x32 = d->x32;
   p.hot.xo32 = d->xo32;
   p.hot.x_bs = d->x_bs;
@@ -852,33 +933,93 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   p.hot.dbg_clock = d->dbg_clock;
   if ((p.hot.t_lo & 3) || (p.hot.skp_t_lo & 3)) return set_err(AEWN_ERR_INVALID, "grcc_fwd: t_lo / skp_t_lo must be multiples of 4");
 
-  const long long total = static_cast<long long>(p.hot.batch) * p.hot.n_tgroups;
-  int clusters = (d->max_ctas > 0 ? d->max_ctas : sm_count()) / 2;
-  if (clusters > total) clusters = static_cast<int>(total);
-  if (clusters < 1) clusters = 1;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(clusters * 2);
-  cfg.blockDim = dim3(GF_THREADS);
-  cfg.dynamicSmemBytes = GF_SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  // ring depth: 4 stages (default) or 3 (AEWN_GF_RING=3, A/B runs)
-  static const int ring = []() { const char* e = getenv("AEWN_GF_RING"); return e && atoi(e) == 3 ? 3 : 4; }();
-  using KernelFn = void (*)(GfParams);
-  KernelFn fn = ring == 3 ? grcc_fwd_kernel<3> : grcc_fwd_kernel<4>;
-  cudaError_t ae = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_BYTES);
-  if (ae != cudaSuccess) return cuda_err(ae, "grcc_fwd: cudaFuncSetAttribute");
-  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
+  return gf_launch(p, d->max_ctas, stream, "grcc_fwd launch");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Data gradient of a dilation layer on the same engine:
+//   g_x[t] = tap1^T gfg[t] + tap0^T gfg[t + dil] (+ g_sig[t], t >= add_t_lo);     g_cond[t] += P^T gfg[t]
+// gfg = [g_f; g_g] arrives as a bf16 channels-last copy (written by the gate-derivative launch), the transposed weights
+// as a bf16 K-major matrix [R + C][2 K2] (tap0^T | tap1^T; the conditioning rows hold zeros under the shifted block).
+// Jobs: 256-channel chunks of g_x; the last, partial chunk shares its accumulator with the conditioning columns
+// (columns >= split are reduce-added into g_cond), so the operand tile is streamed twice instead of three times.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int aewn_grcc_dgrad(const aewn_grcc_dgrad_desc* d, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d) return set_err(AEWN_ERR_INVALID, "grcc_dgrad: null descriptor");
+  const int R = d->R, C = d->n_cond, K2 = d->g16_cp;
+  if (R < 16 || R > 1024 || (R & 15) || C < 1 || C > 240 || K2 < 64 || (K2 & 63) || K2 > 1024)
+    return set_err(AEWN_ERR_INVALID, "grcc_dgrad: need R %% 16 == 0, 1 <= C <= 240, g16_cp %% 64 == 0 (R=%d C=%d K2=%d)", R, C, K2);
+  if (!d->g16 || !d->w1t16 || !d->gx || !d->g_cond || d->batch <= 0 || d->t_hi <= d->t_lo || d->t_rows < d->t_hi ||
+      d->w_k != 2 * K2 || (d->t_lo & 3) || (d->cond_t_lo & 3) || (d->x_cs & 3) || (d->x_bs & 3) || (d->c_cs & 3) || (d->c_bs & 3))
+    return set_err(AEWN_ERR_INVALID, "grcc_dgrad: bad pointer / range / stride");
+  GfParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)K2, (cuuint64_t)d->t_rows, (cuuint64_t)d->batch};
+    cuuint64_t str[2] = {(cuuint64_t)K2 * 2u, (cuuint64_t)d->g16_bs * 2u};
+    cuuint32_t box[3] = {64u, 128u, 1u};
+    if ((rc = encode_f16_map(&p.xa, d->g16, 3, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "g16", true))) return rc;
+    p.ca = p.xa;
+    cuuint64_t dw[2] = {(cuuint64_t)d->w_k, (cuuint64_t)(R + C)};
+    cuuint64_t sw[1] = {(cuuint64_t)d->w_k * 2u};
+    cuuint32_t bw[2] = {64u, 128u};
+    if ((rc = encode_f16_map(&p.w1, d->w1t16, 2, dw, sw, bw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w1t16", true))) return rc;
+    p.w2 = p.w1;
+  }
+  if ((rc = encode_out_map(&p.skp_m, d->g_cond, d->t_hi, C, d->batch, d->c_cs, d->c_bs, 16))) return rc;
+  const int Cp = (C + 15) & ~15;
+  int nj = 0;
+  bool cond_done = false;
+  for (int c0 = 0; c0 < R; c0 += 256) {
+    const int nv = R - c0 < 256 ? R - c0 : 256;
+    if (nv + Cp <= 256) {      // the partial chunk takes the conditioning columns along (their W rows follow directly)
+      p.hot.job[nj++] = GfJob{GF_RES, c0, nv + Cp, nv, c0, 1, nv};
+      cond_done = true;
+    } else {
+      p.hot.job[nj++] = GfJob{GF_RES, c0, nv, nv, c0, 1, 256};
+    }
+  }
+  if (!cond_done) p.hot.job[nj++] = GfJob{GF_RES, R, Cp, 0, 0, 1, 0};
+  if (nj > GF_MAX_JOBS) return set_err(AEWN_ERR_INVALID, "grcc_dgrad: too many jobs (%d)", nj);
+  p.hot.n_jobs = nj;
+  p.hot.n_gate = 0;
+  p.hot.seg[0] = GfSeg{0, d->dil, K2 / 64};       // tap0^T block: gfg[t + dil]
+  p.hot.seg[1] = GfSeg{0, 0, K2 / 64};            // tap1^T block: gfg[t]
+  p.hot.n_segs = 2;
+  p.hot.ring_stages = 2 * (K2 / 64);
+  p.hot.kb_z = 0;
+  p.hot.ab_bf16 = 1;
+  p.hot.add_t_lo = d->add_t_lo;
+  p.hot.x32 = d->g_sig;
+  p.hot.xo32 = d->gx;
+  p.hot.x_bs = d->x_bs;
+  p.hot.x_cs = d->x_cs;
+  p.hot.skp = d->g_cond;
+  p.hot.s_bs = d->c_bs;
+  p.hot.s_cs = d->c_cs;
+  p.hot.skp_mode = 1;
+  p.hot.batch = d->batch;
+  p.hot.t_begin = d->t_lo & ~31;
+  p.hot.n_tgroups = (d->t_hi - p.hot.t_begin + 2 * GF_BM - 1) / (2 * GF_BM);
+  p.hot.n_res = R;
+  p.hot.t_lo = d->t_lo;
+  p.hot.t_zero_lo = d->t_zero_lo;
+  p.hot.t_hi = d->t_hi;
+  p.hot.skp_t_lo = d->cond_t_lo;
+  p.hot.skp_zero_lo = d->cond_zero_lo;
+  p.hot.err = d->err;
+  return gf_launch(p, d->max_ctas, stream, "grcc_dgrad launch");
+}
+
+extern "C" int aewn_pack_blocks_bf16(const aewn_copy_block* blocks_dev, int n_blocks, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!blocks_dev || n_blocks <= 0) return set_err(AEWN_ERR_INVALID, "pack_blocks_bf16: bad arguments");
+  int grid = n_blocks < 148 * 8 ? n_blocks : 148 * 8;
+  pack_blocks_bf16_kernel<<<grid, 256, 0, stream>>>(blocks_dev, n_blocks);
   count_launch();
-  if (le != cudaSuccess) return cuda_err(le, "grcc_fwd launch");
-  return cuda_err(cudaGetLastError(), "grcc_fwd launch");
+  return cuda_err(cudaGetLastError(), "pack_blocks_bf16 launch");
 }
 
 extern "C" int aewn_cvt_f16_cl(const float* src, long long s_bs, long long s_cs, void* dst, long long d_bs, int Cp, int C,

@@ -12,6 +12,7 @@
 //                               (lane = time step, so each warp store instruction writes one full 128 B line)
 // Pipelines: 4-stage smem ring (full/empty mbarriers) and a 2-stage TMEM ring (tfull/tempty), so the epilogue of
 // tile i overlaps the MMAs of tile i+1.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "host_util.h"
@@ -474,6 +475,8 @@ struct GateBwdCtx {
   int n, n_valid;
   bool in_range, live;
   bool ab16;          // AEWN_F_AB16: thp holds {fp16 a, fp16 b} words, the derivative factors themselves
+  __nv_bfloat16* g16row;   // optional bf16 channels-last copy of [g_f; g_g]: row of this lane's time step (or nullptr)
+  int g16_goff;            // channel offset of g_gate in that row
 };
 
 __device__ __forceinline__ GateBwdCtx gbwd_ctx(const aewn_ntile& nt, int b, int tau, const CUtensorMap* omap,
@@ -496,6 +499,11 @@ __device__ __forceinline__ GateBwdCtx gbwd_ctx(const aewn_ntile& nt, int b, int 
   cx.n = nt.n;
   cx.n_valid = nt.n_valid;
   cx.ab16 = (nt.flags & AEWN_F_AB16) != 0;
+  cx.g16row = (nt.out16 && cx.in_range)
+                  ? reinterpret_cast<__nv_bfloat16*>(nt.out16) + static_cast<long long>(b) * nt.out16_bs +
+                        static_cast<long long>(tau + nt.out_toff) * nt.out16_cp
+                  : nullptr;
+  cx.g16_goff = static_cast<int>((nt.out2 - nt.out) / nt.out_cs);
   return cx;
 }
 
@@ -542,6 +550,25 @@ __device__ __forceinline__ void gbwd_chunk(const GateBwdCtx& cx, const StgOut& s
       const float gs = gz * sg[j];
       gf[j] = cx.in_range ? gs * (1.0f - th[j] * th[j]) : 0.0f;
       gg[j] = cx.in_range ? gs * th[j] * (1.0f - sg[j]) : 0.0f;
+    }
+  }
+  if (cx.g16row && nrem >= 32) {
+    // bf16 channels-last copy for the 16-bit data-gradient engine (aewn_grcc_dgrad): lane = time row, 32 channels =
+    // 64 contiguous bytes per row for g_f and for g_g
+    auto pack = [](float lo, float hi) {
+      uint32_t r;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+      return r;
+    };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 a, g;
+      a.x = pack(gf[8 * i + 0], gf[8 * i + 1]); a.y = pack(gf[8 * i + 2], gf[8 * i + 3]);
+      a.z = pack(gf[8 * i + 4], gf[8 * i + 5]); a.w = pack(gf[8 * i + 6], gf[8 * i + 7]);
+      g.x = pack(gg[8 * i + 0], gg[8 * i + 1]); g.y = pack(gg[8 * i + 2], gg[8 * i + 3]);
+      g.z = pack(gg[8 * i + 4], gg[8 * i + 5]); g.w = pack(gg[8 * i + 6], gg[8 * i + 7]);
+      *reinterpret_cast<uint4*>(cx.g16row + c0 + 8 * i) = a;
+      *reinterpret_cast<uint4*>(cx.g16row + cx.g16_goff + c0 + 8 * i) = g;
     }
   }
   if (cx.omap) {   // TMA-store path (tile-uniform decision): g_f box, then g_g box, through the warp's staging tile
@@ -950,6 +977,8 @@ extern "C" int aewn_tgemm(const aewn_tgemm_desc* d, aewn_stream_t stream_) {
     } else if (nt.mode == AEWN_EPI_GATE_BWD) {
       if (!nt.out || !nt.out2 || !nt.add || (!nt.add2 && !(nt.flags & AEWN_F_AB16)))
         return set_err(AEWN_ERR_INVALID, "tgemm: GATE_BWD tile %d needs out, out2, add, add2", i);
+      if (nt.out16 && ((nt.n_valid & 31) || (nt.out16_cp & 7) || (nt.out16_bs & 7) || (reinterpret_cast<uintptr_t>(nt.out16) & 15u)))
+        return set_err(AEWN_ERR_INVALID, "tgemm: GATE_BWD tile %d: out16 needs n_valid %% 32 == 0 and 16-byte aligned rows", i);
     } else {
       return set_err(AEWN_ERR_INVALID, "tgemm: n-tile %d unknown mode %d", i, nt.mode);
     }

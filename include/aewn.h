@@ -108,6 +108,10 @@ typedef struct {
   int add_toff;
   int add_t_lo;             /* LINEAR: the addend / mask applies only for tau >= add_t_lo */
   const float* bias; /* optional, pre-offset, indexed by column */
+  void* out16;       /* GATE_BWD, optional: bf16 channels-last copy of [g_filt; g_gate], element (b, t, c) at
+                        out16[b * out16_bs + t * out16_cp + c], g_gate at channel offset (out2 - out) / out_cs */
+  long long out16_bs;
+  int out16_cp;
 } aewn_ntile;
 
 #define AEWN_CLUSTER_PAIR_MMA 102
@@ -320,6 +324,38 @@ typedef struct {
 } aewn_grcc_fwd_desc;
 
 int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream);
+/* ------------------------------------------------------------------------------------------------------------
+ * Data gradient of a dilation layer on the fused-layer engine (autograd of wavenet.py:100-101 w.r.t. x and cond):
+ *   g_x[t] = tap1^T gfg[t] + tap0^T gfg[t + dil] (+ g_sig[t] for t >= add_t_lo);     g_cond[t] += P^T gfg[t]
+ * gfg = [g_filt; g_gate] is read from a bf16 CHANNELS-LAST copy (batch, t_rows, g16_cp) that the gate-derivative launch
+ * writes (aewn_ntile.out16), the transposed weights from a bf16 K-major matrix w1t16 [R + n_cond][2 g16_cp] =
+ * [tap0^T | tap1^T] whose conditioning rows hold zeros under the shifted block (aewn_pack_blocks_bf16).  bf16 because the
+ * operands are gradients (range); accumulation and outputs are fp32.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* g16;
+  long long g16_bs;        /* elements between batch items */
+  int g16_cp;              /* channels per time row: 2 D rounded up to 64 */
+  int t_rows;
+  const void* w1t16;
+  int w_k;                 /* = 2 * g16_cp */
+  const float* g_sig;      /* optional addend (batch, R, T): gradient w.r.t. this layer's output (residual path) */
+  float* gx;               /* (batch, R, T), same strides as g_sig */
+  long long x_bs, x_cs;
+  int add_t_lo;
+  float* g_cond;           /* (batch, n_cond, T), accumulated */
+  long long c_bs, c_cs;
+  int n_cond;
+  int batch, R, dil;
+  int t_lo, t_zero_lo, t_hi;        /* g_x is stored on [t_lo, t_hi), zero below t_zero_lo */
+  int cond_t_lo, cond_zero_lo;      /* g_cond receives contributions for t >= cond_zero_lo (cond_t_lo = its 4-aligned floor) */
+  int* err;
+  int max_ctas;
+} aewn_grcc_dgrad_desc;
+
+int aewn_grcc_dgrad(const aewn_grcc_dgrad_desc* d, aewn_stream_t stream);
+int aewn_pack_blocks_bf16(const aewn_copy_block* blocks_dev, int n_blocks, aewn_stream_t stream);
+
 /* (batch, C, T) fp32 -> (batch, T, Cp) fp16 channels-last operand copy; channel ones_ch (>= 0) is written as 1.0, other
  * channels in [C, Cp) as 0.  Cp % 8 == 0, dst 16-byte aligned, d_bs (elements between batch items) % 8 == 0. */
 int aewn_cvt_f16_cl(const float* src, long long s_bs, long long s_cs, void* dst, long long d_bs, int Cp, int C, int T,
