@@ -486,7 +486,7 @@ class StackPlan:
         self.J = (D + 127) // 128
         # data gradient on the fused-layer engine (aewn_grcc_dgrad: bf16 channels-last copy of [g_f; g_g], bf16 weights)
         self.dgrad16 = self.fused and R % 16 == 0 and Cc <= 240 and (2 * D) % 64 == 0 and \
-            os.environ.get("AEWN_DGRAD16", "1") == "1"
+            os.environ.get("AEWN_DGRAD16", "0") == "1"      # measured: no faster than the TF32 launch
         if self.fused:
             # fp16 channels-last operand copies: the layer input ping-pongs between two buffers (the
             # backward pass reads the fp32 tensors), the conditioning copy is shared by all layers

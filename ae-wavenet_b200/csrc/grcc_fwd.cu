@@ -259,21 +259,23 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         if ((hp.prefetch & 1) && elect_one()) {
           for (int c = 0; c < hp.n_res; c += 32) tma_prefetch_l2_3d(&p.xr_m, it.tau0, c, it.b);
         }
-        // ... and the NEXT tile's activation operand (fp16 x and conditioning rows): its first gate job otherwise waits
-        // for HBM behind a ring of only 3-4 stages (phase clock: ~1000 cycles per stage against ~570 from L2)
-        if ((hp.prefetch & 2) && item + n_cl < total && elect_one()) {
-          const GfItem nx = gf_decode(hp, item + n_cl, crank);
-          for (int si = 0; si < hp.n_segs; ++si)
-            if (hp.seg[si].shift == 0)
-              for (int kb = 0; kb < hp.seg[si].kb; ++kb)
-                tma_prefetch_l2_3d(hp.seg[si].map ? &p.ca : &p.xa, kb * GF_KB, nx.tau0, nx.b);
-        }
         __syncwarp();
         for (int jb = 0; jb < hp.n_jobs && ok; ++jb) {
           const GfJob jd = hp.job[jb];
           if (jd.kind == GF_SKP && !it.do_skp) continue;
           const bool use_ring = jd.kind == GF_GATE || jd.a_ring;
           const int nst = use_ring ? hp.ring_stages : hp.kb_z;
+          // After the last gate job of this tile: pull the NEXT tile's HBM-fresh activation operand (fp16 x and conditioning
+          // rows at shift 0) into L2, so that its first gate job -- which otherwise waits for HBM behind a 4-stage ring
+          // (phase clock: ~1000 cycles per stage against ~570 from L2) -- finds it there.  (bit 1 of AEWN_GF_PREFETCH)
+          if ((hp.prefetch & 2) && jb == hp.n_gate && hp.n_gate > 0 && item + n_cl < total && elect_one()) {
+            const GfItem nx = gf_decode(hp, item + n_cl, crank);
+            for (int si = 0; si < hp.n_segs; ++si)
+              if (hp.seg[si].shift == 0)
+                for (int k2 = 0; k2 < hp.seg[si].kb; ++k2)
+                  tma_prefetch_l2_3d(hp.seg[si].map ? &p.ca : &p.xa, k2 * GF_KB, nx.tau0, nx.b);
+          }
+          __syncwarp();
           int sgi = 0, kb = 0;                                   // current K segment / block inside it (ring-operand jobs)
           for (int s = 0; s < nst; ++s) {
             if (!mbar_wait_warp(&empty_bar[stage], phase ^ 1u, abort_flag)) { ok = false; break; }
