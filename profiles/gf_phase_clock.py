@@ -30,6 +30,7 @@ for _ in range(3):
 clk = torch.zeros(2 * 4 * 8 * 6, dtype=torch.int64, device=dev)
 kind, d, tag = plan.fwd_train[0]
 d.dbg_clock = clk.data_ptr()
+d.max_ctas = int(os.environ.get("GF_MAX_CTAS", "0"))      # experiment: fewer CTAs -> is the limit per SM or chip-wide?
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()

@@ -23,3 +23,5 @@ for f in ("bench","bench_cfg3"):
     except Exception as e:
         print(f, "ERR", e)
 PY
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/${T}_bench_ref.json 2> $O/${T}_bench_ref.err; tail -c 300 $O/${T}_bench_ref.err; python -c "
+import json; x=json.load(open('$O/${T}_bench_ref.json')); print('reference arm:', x['value'], x['ms_per_step'], x['config'], x['cpu_baseline']['cores'])"
