@@ -42,7 +42,8 @@ constexpr int GF_W_BYTES = 128 * 128;             // 16 KB: 128 weight rows x 12
 constexpr int GF_STAGE_BYTES = GF_A_BYTES + GF_W_BYTES;
 constexpr int GF_MAX_D = 256;
 constexpr int GF_ZBUF_BYTES = (GF_MAX_D / GF_KB) * GF_A_BYTES;   // 64 KB: z of this CTA's 128 time rows, all D channels
-constexpr int GF_THREADS = 640;                  // 4 control warps + 16 epilogue warps
+constexpr int GF_CTRL_WARPS = 4;                 // 0: TMA producer, 1: MMA issuer, 2: TMEM allocator, 3: idle (one per SM sub-partition)
+constexpr int GF_THREADS = 640;                  // 4 control warps + 16 epilogue warps (see the register split below)
 constexpr int GF_EPI_WARPS = 16;
 constexpr int GF_STG_BYTES = GF_EPI_WARPS * 2048;               // one [16 ch][32 t] fp32 tile per epilogue warp: the skip
                                                                 // sum's TMA reduce-add (red.global.add measured 2x slower)
@@ -244,15 +245,19 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
   const int n_cl = gridDim.x >> 1;
   const int total = hp.batch * hp.n_tgroups;
 
-  if (warp < 4) {
-    reg_dealloc<56>();   // 128 x 56 + 512 x 104 = 60416 <= 640 x 96 (the CTA's launch allocation)
+  if (warp < GF_CTRL_WARPS) {
+    // Registers are a per-sub-partition resource (16 K each; warp w lives on sub-partition w % 4): one control warp and
+    // four epilogue warps each, 64 + 4 x 104 = 480 = 5 x 96 (the launch allocation).  The epilogue code must not
+    // spill: a local-memory load queues behind the warp's own streaming stores in the LSU and costs 2-6 k cycles in this
+    // kernel (phase clock, profiles/r3_gf_spill_*).
+    reg_dealloc<64>();
     if (warp == 0) {
       // ===================================================== TMA producer (both CTAs)
       uint32_t stage = 0, phase = 0;
       bool ok = true;
       const uint32_t lead_full = mapa_u32(&full_bar[0], 0);
       const uint64_t pol_keep = l2_policy_evict_last();
-      for (int item = cid; item < total && ok; item += n_cl) {
+      for (int item = blockIdx.x >> 1; item < total && ok; item += n_cl) {
         const GfItem it = gf_decode(hp, item, crank);
         // the residual rows this tile's RES epilogues will add (128 time steps x R channels of x32): pull them into L2
         // now, ~20 k cycles before the epilogue warps load them
@@ -308,9 +313,17 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         const uint64_t desc0 = make_smem_desc(0, 16, 1024, kLayoutSW128);   // K-major, 128B swizzle, 8-row groups 1 KB apart
         const uint32_t ring = smem_u32(smem);
         const uint32_t z16_0 = (smem_u32(zbuf) >> 4) & 0x3FFFu;
-        for (int item = cid; item < total && ok; item += n_cl) {
+        // whole-kernel stamps of cluster 0's issuer (slot [tile 3][job 6]): cycles and nanoseconds -> effective SM clock
+        long long dbg_c0 = 0, dbg_n0 = 0;
+        int dbg_items = 0;
+        if (hp.dbg_clock && blockIdx.x == 0 && lane == 0) {
+          dbg_c0 = clock64();
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_n0));
+        }
+        for (int item = blockIdx.x >> 1; item < total && ok; item += n_cl) {
           const GfItem it = gf_decode(hp, item, crank);
           bool z_waited = false;
+          ++dbg_items;
           if (hp.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && lane == 0)
             hp.dbg_clock[((item / n_cl) * GF_MAX_JOBS + 7) * 6] = clock64();      // top of the tile (slot of the unused job 7)
           for (int jb = 0; jb < hp.n_jobs && ok; ++jb) {
@@ -365,6 +378,15 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             zphase ^= 1u;
           }
         }
+        if (hp.dbg_clock && blockIdx.x == 0 && lane == 0) {
+          long long n1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n1));
+          long long* ck = hp.dbg_clock + (3 * GF_MAX_JOBS + 6) * 6;
+          ck[0] = 1;                    // marks the slot as used
+          ck[1] = clock64() - dbg_c0;   // cycles the issuer spent on its `dbg_items` tiles
+          ck[2] = n1 - dbg_n0;          // the same span in nanoseconds
+          ck[3] = dbg_items;
+        }
       }
     }
   } else {
@@ -375,44 +397,54 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
     // per warp ([16 channels][32 time steps], alternating: the box of store k is written while the TMA engine still reads
     // store k-1) and leave as TMA stores / reduce-adds of {32 t, 16 ch} boxes.
     const int q = warp & 3;
-    const int h = (warp - 4) >> 2;
+    const int h = (warp - GF_CTRL_WARPS) >> 2;
     const int row = q * 32 + lane;
-    unsigned int dbg_acq = 0, dbg_tm = 0, dbg_fl = 0;      // phase-clock accumulators (cycles), see dbg_clock
-    const int dbg = hp.dbg;
-    float* const stg = reinterpret_cast<float*>(smem + RING_BYTES + GF_ZBUF_BYTES) + (warp - 4) * 512;
-    const uint32_t lead_tempty = mapa_u32(&tempty_bar[0], 0);
-    const uint32_t lead_zready = mapa_u32(zready_bar, 0);
+#ifdef AEWN_GF_EXPERIMENTS
+    const int dbg = hp.dbg;      // timing experiments (profiles/r3_gf_epilogue_experiments.txt): epilogue parts switched off
+#else
+    constexpr int dbg = 0;
+#endif
+    float* const stg = reinterpret_cast<float*>(smem + RING_BYTES + GF_ZBUF_BYTES) + (warp - GF_CTRL_WARPS) * 512;
     uint32_t acc = 0, acc_phase = 0;
     float xmax = 0.0f;
     bool ok = true;
-    for (int item = cid; item < total && ok; item += n_cl) {
+    // The two loop counters live in shared memory, not in registers: under the 104-register budget ptxas spilled exactly
+    // these two to LOCAL memory, and a local load at a loop back-edge queues behind the warp's own streaming stores in the
+    // L1 pipeline (2-6 k cycles per job boundary in the phase clock).  Shared-memory loads do not take that path.
+    volatile int* const wst = reinterpret_cast<volatile int*>(smem + RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES + 128) +
+                              (warp - GF_CTRL_WARPS) * 2;
+    for (wst[0] = blockIdx.x >> 1; wst[0] < hp.batch * hp.n_tgroups && ok; wst[0] = wst[0] + (gridDim.x >> 1)) {
+      const int item = wst[0];
       const GfItem it = gf_decode(hp, item, crank);
       const int tau = it.tau0 + row;
       const int slab0 = it.tau0 + q * 32;
       const bool in_range = tau >= hp.t_lo && tau < hp.t_hi;
       const bool keep = in_range && tau >= hp.t_zero_lo;
       const bool slab_on = (slab0 + 32 > hp.t_lo) && (slab0 < hp.t_hi);
-      for (int jb = 0; jb < hp.n_jobs && ok; ++jb) {
+      for (wst[1] = 0; wst[1] < hp.n_jobs && ok; wst[1] = wst[1] + 1) {
+        const int jb = wst[1];
         const GfJob jd = hp.job[jb];
         if (jd.kind == GF_SKP && !it.do_skp) continue;
         const uint32_t taddr = tmem_base + acc * 256u + (static_cast<uint32_t>(q * 32) << 16);
-        const bool stamp = hp.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && warp == 4 && lane == 0;
-        long long* ck = hp.dbg_clock + 4 * GF_MAX_JOBS * 6 + ((item / n_cl) * GF_MAX_JOBS + jb) * 6;
-        dbg_acq = dbg_tm = dbg_fl = 0;
-        if (stamp) ck[0] = clock64();
+        // phase clock (profiles/gf_phase_clock.py): nothing of it stays live in registers between the stamps
+        auto stamp_at = [&](int k) {
+#ifdef AEWN_GF_PHASE_CLOCK
+          if (hp.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && warp == 4 && lane == 0)   /* (q 0, h 0) */
+            hp.dbg_clock[4 * GF_MAX_JOBS * 6 + ((item / n_cl) * GF_MAX_JOBS + jb) * 6 + k] = clock64();
+#endif
+        };
+        stamp_at(0);
         if (jd.kind == GF_GATE) {
-          if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
+          if (!mbar_wait_warp(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          if (stamp) ck[1] = clock64();
+          stamp_at(1);
 #pragma unroll 1
           for (int i = 0; i < 2; ++i) {
             const int c0 = 32 * h + 16 * i;            // z channels [c0, c0 + 16) of this 128-channel block
             uint32_t vf[16], vg[16];
-            const unsigned int t_t = clock();
             tmem_ld16(taddr + c0, vf);
             tmem_ld16(taddr + 128 + c0, vg);
             tmem_ld_wait();
-            dbg_tm += clock() - t_t;
             // tanh(f) = (1 - a) / (1 + a), a = e^(-2f); sigmoid(g) = 1 / (1 + b), b = e^(-g): ONE reciprocal of
             // (1 + a)(1 + b) serves both (3 MUFU ops per element instead of 4; the exponents are clamped so that the
             // product stays finite: 2^60 * 2^60)
@@ -452,8 +484,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               tc_fence_before();
               __syncwarp();
               if (lane == 0) {
-                mbar_arrive_cluster(lead_zready);
-                if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+                mbar_arrive_cluster(mapa_u32(zready_bar, 0));
+                if (crank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
                 else mbar_arrive(&tempty_bar[acc]);
               }
             }
@@ -503,19 +535,19 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           const int cb = h * span;
           const int ce = min(cb + span, jd.n);
           const int nv = jd.n_valid;
-          const float* xsrc = hp.x32 + static_cast<long long>(it.b) * hp.x_bs + static_cast<long long>(jd.ch0) * hp.x_cs + tau;
-          __half* x16row = hp.xo16 + static_cast<long long>(it.b) * hp.x16_bs + static_cast<long long>(tau) * hp.x16_cp + jd.ch0;
-          float* xdst = hp.xo32 + static_cast<long long>(it.b) * hp.x_bs + static_cast<long long>(jd.ch0) * hp.x_cs + tau;
+          // ONE element offset serves x32 / xo32 / dup (same strides); the pointers are rebuilt from the shared-memory copy
+          // of the parameters where they are used.  (With four live 64-bit pointers ptxas spilled five of the first
+          // sixteen prefetched residual values right after their loads: every spill store waits for its load, ~8 k
+          // cycles of serial HBM latency per job in the phase clock.)
+          const long long eoff = static_cast<long long>(it.b) * hp.x_bs + static_cast<long long>(jd.ch0) * hp.x_cs + tau;
           const int dup_t = tau + hp.dup_toff;
-          float* dupp = (hp.dup && in_range && dup_t >= 0 && dup_t < hp.dup_t_hi)
-                            ? hp.dup + static_cast<long long>(it.b) * hp.x_bs + static_cast<long long>(jd.ch0) * hp.x_cs + dup_t
-                            : nullptr;
+          const bool dup_ok = hp.dup && in_range && dup_t >= 0 && dup_t < hp.dup_t_hi;
           const bool add_ok = hp.x32 != nullptr && tau >= hp.add_t_lo;
           const bool s_in = tau >= hp.skp_t_lo && tau < hp.t_hi;           // (columns >= jd.split: reduce-add part)
           const bool s_keep = s_in && tau >= hp.skp_zero_lo;
           float bufA[16], bufB[16];
           auto issue = [&](int c0, float (&buf)[16]) {
-            const float* sp = xsrc + static_cast<long long>(c0) * hp.x_cs;
+            const float* sp = hp.x32 + eoff + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               buf[j] = (keep && add_ok && c0 + j < nv && !(dbg & 1)) ? __ldcs(sp) : 0.0f;
@@ -524,20 +556,18 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           };
           if (cb < ce) issue(cb, bufA);
           if (cb + 16 < ce) issue(cb + 16, bufB);
-          if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
+          if (!mbar_wait_warp(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          if (stamp) ck[1] = clock64();
+          stamp_at(1);
           auto chunk = [&](int c0, float (&buf)[16]) {
             uint32_t v[16];
-            const unsigned int t_t = clock();
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
-            dbg_tm += clock() - t_t;
             if (c0 + 16 >= ce) {      // last chunk of this warp: the accumulator is in registers, release the region now
               tc_fence_before();
               __syncwarp();
               if (lane == 0) {
-                if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+                if (crank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
                 else mbar_arrive(&tempty_bar[acc]);
               }
             }
@@ -564,15 +594,15 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               xmax = fmaxf(xmax, fabsf(r[j]));
             }
             if (in_range && !(dbg & 2)) {      // x_next fp32: plain coalesced stores (lane = time step), like tanh / sigmoid above
-              float* xo = xdst + static_cast<long long>(c0) * hp.x_cs;
+              float* xo = hp.xo32 + eoff + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 if (c0 + j < nv) __stcs(xo, r[j]);
                 xo += hp.x_cs;
               }
             }
-            if (dupp) {
-              float* dd = dupp + static_cast<long long>(c0) * hp.x_cs;
+            if (dup_ok) {
+              float* dd = hp.dup + eoff + hp.dup_toff + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 if (c0 + j < nv) __stcs(dd, r[j]);
@@ -580,6 +610,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               }
             }
             if (in_range && hp.xo16 && !(dbg & 4)) {
+              __half* x16row = hp.xo16 + static_cast<long long>(it.b) * hp.x16_bs + static_cast<long long>(tau) * hp.x16_cp + jd.ch0;
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
                 if (c0 + 8 * k < nv) {
@@ -606,7 +637,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+              if (crank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
               else mbar_arrive(&tempty_bar[acc]);
             }
           }
@@ -619,9 +650,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           const bool s_in = tau >= hp.skp_t_lo && tau < hp.t_hi;
           const bool s_keep = s_in && tau >= hp.skp_zero_lo;
           const float* old = hp.skp + static_cast<long long>(it.b) * hp.s_bs + static_cast<long long>(jd.ch0) * hp.s_cs + tau;
-          if (!mbar_wait(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
+          if (!mbar_wait_warp(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          if (stamp) ck[1] = clock64();
+          stamp_at(1);
 #pragma unroll 1
           for (int c0 = cb; c0 < ce; c0 += 16) {
             uint32_t v[16];
@@ -636,35 +667,29 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 sp += hp.s_cs;
               }
             }
-            const unsigned int t_t = clock();
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
-            dbg_tm += clock() - t_t;
             if (c0 + 16 >= ce) {      // last chunk: release the region before the stores
               tc_fence_before();
               __syncwarp();
               if (lane == 0) {
-                if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+                if (crank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
                 else mbar_arrive(&tempty_bar[acc]);
               }
             }
             if (hp.skp_mode == 1) {
               // running skip sum: TMA reduce-add of a {32 t, 16 ch} box (the read-modify-write happens in L2)
               if ((slab0 + 32 > hp.skp_t_lo) && (slab0 < hp.t_hi)) {
-                const unsigned int t_a = clock();
                 if (elect_one()) tma_store_wait_read();
                 __syncwarp();
-                dbg_acq += clock() - t_a;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) stg[j * 32 + lane] = s_keep ? __uint_as_float(v[j]) : 0.0f;
-                const unsigned int t_f = clock();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (elect_one()) {
                   tma_reduce_add_3d(&p.skp_m, stg, slab0, jd.ch0 + c0, it.b);
                   tma_store_commit();
                 }
-                dbg_fl += clock() - t_f;
               }
             } else if (s_in) {
               float* op = hp.skp + static_cast<long long>(it.b) * hp.s_bs + static_cast<long long>(jd.ch0 + c0) * hp.s_cs + tau;
@@ -682,12 +707,12 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if (crank != 0) mbar_arrive_cluster(lead_tempty + acc * 8u);
+              if (crank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
               else mbar_arrive(&tempty_bar[acc]);
             }
           }
         }
-        if (stamp) { ck[2] = clock64(); ck[3] = dbg_acq; ck[4] = dbg_tm; ck[5] = dbg_fl; }
+        stamp_at(2);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }

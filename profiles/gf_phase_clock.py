@@ -48,6 +48,11 @@ for role, rn in enumerate(("MMA issuer", "epilogue warp 0")):
             a, b, e, x1, x2, x3 = [int(v) for v in c[role, tile, job]]
             if a == 0:
                 continue
+            if job == 6:
+                if role == 0:
+                    print(f"  whole kernel, cluster 0: {b} cycles in {e} ns over {x1} tiles = {b / max(e, 1):.3f} GHz, "
+                          f"{b / max(x1, 1):.0f} cycles per tile")
+                continue
             if job == 7:
                 print(f"  tile {tile} top   {a - t0:8d}")
                 continue
