@@ -413,8 +413,17 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
     // L1 pipeline (2-6 k cycles per job boundary in the phase clock).  Shared-memory loads do not take that path.
     volatile int* const wst = reinterpret_cast<volatile int*>(smem + RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES + 128) +
                               (warp - GF_CTRL_WARPS) * 2;
+#ifdef AEWN_GF_PHASE_CLOCK
+    if (warp == 4 && lane == 0) *reinterpret_cast<volatile int*>(smem + RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES + 112) = -1;
+#endif
     for (wst[0] = blockIdx.x >> 1; wst[0] < hp.batch * hp.n_tgroups && ok; wst[0] = wst[0] + (gridDim.x >> 1)) {
       const int item = wst[0];
+#ifdef AEWN_GF_PHASE_CLOCK
+      if (warp == 4 && lane == 0) {
+        volatile int* tile_no = reinterpret_cast<volatile int*>(smem + RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES + 112);
+        *tile_no = *tile_no + 1;
+      }
+#endif
       const GfItem it = gf_decode(hp, item, crank);
       const int tau = it.tau0 + row;
       const int slab0 = it.tau0 + q * 32;
@@ -425,12 +434,32 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         const int jb = wst[1];
         const GfJob jd = hp.job[jb];
         if (jd.kind == GF_SKP && !it.do_skp) continue;
+        // At the tile's first job: pull the residual rows this warp's RES epilogues will add (x32[b, ch, slab]) from HBM
+        // into L2, one 128-byte line per LANE and instruction (lane = channel), ~40 k cycles before they are loaded.
+        // Unprefetched, those loads see HBM behind the write stream: 5-6 k cycles between "job seen" and the first
+        // values in the phase clock, once per RES job, on the epilogue's critical chain.
+        if (jb == 0 && (hp.prefetch & 4) && hp.x32) {
+#pragma unroll 1
+          for (int j2 = 0; j2 < hp.n_jobs; ++j2) {
+            if (hp.job[j2].kind != GF_RES || hp.job[j2].a_ring) continue;
+            const int n2 = hp.job[j2].n, nv2 = min(hp.job[j2].n_valid, hp.job[j2].split);
+            const int span2 = ((n2 + 63) >> 6) << 4;
+#pragma unroll 1
+            for (int c = h * span2 + lane; c < min(h * span2 + span2, nv2); c += 32) {
+              const float* pl = hp.x32 + static_cast<long long>(it.b) * hp.x_bs +
+                                static_cast<long long>(hp.job[j2].ch0 + c) * hp.x_cs + slab0;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
+            }
+          }
+        }
         const uint32_t taddr = tmem_base + acc * 256u + (static_cast<uint32_t>(q * 32) << 16);
         // phase clock (profiles/gf_phase_clock.py): nothing of it stays live in registers between the stamps
         auto stamp_at = [&](int k) {
 #ifdef AEWN_GF_PHASE_CLOCK
-          if (hp.dbg_clock && blockIdx.x == 0 && item < 4 * n_cl && warp == 4 && lane == 0)   /* (q 0, h 0) */
-            hp.dbg_clock[4 * GF_MAX_JOBS * 6 + ((item / n_cl) * GF_MAX_JOBS + jb) * 6 + k] = clock64();
+          // (build with -DAEWN_GF_PHASE_CLOCK; warp 4 = (q 0, h 0) of CTA 0; the tile number lives in shared memory too)
+          volatile int* tile_no = reinterpret_cast<volatile int*>(smem + RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES + 112);
+          if (hp.dbg_clock && blockIdx.x == 0 && warp == 4 && lane == 0 && *tile_no < 4)
+            hp.dbg_clock[4 * GF_MAX_JOBS * 6 + (*tile_no * GF_MAX_JOBS + wst[1]) * 6 + k] = clock64();
 #endif
         };
         stamp_at(0);
@@ -540,13 +569,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           // sixteen prefetched residual values right after their loads: every spill store waits for its load, ~8 k
           // cycles of serial HBM latency per job in the phase clock.)
           const long long eoff = static_cast<long long>(it.b) * hp.x_bs + static_cast<long long>(jd.ch0) * hp.x_cs + tau;
-          const int dup_t = tau + hp.dup_toff;
-          const bool dup_ok = hp.dup && in_range && dup_t >= 0 && dup_t < hp.dup_t_hi;
           const bool add_ok = hp.x32 != nullptr && tau >= hp.add_t_lo;
-          const bool s_in = tau >= hp.skp_t_lo && tau < hp.t_hi;           // (columns >= jd.split: reduce-add part)
-          const bool s_keep = s_in && tau >= hp.skp_zero_lo;
-          float bufA[16], bufB[16];
-          auto issue = [&](int c0, float (&buf)[16]) {
+          float buf[16];     // residual values of the NEXT chunk: loaded while the current chunk's stores are issued
+          auto issue = [&](int c0) {
             const float* sp = hp.x32 + eoff + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -554,12 +579,12 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               sp += hp.x_cs;
             }
           };
-          if (cb < ce) issue(cb, bufA);
-          if (cb + 16 < ce) issue(cb + 16, bufB);
+          if (cb < ce) issue(cb);
+          stamp_at(3);
           if (!mbar_wait_warp(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
           stamp_at(1);
-          auto chunk = [&](int c0, float (&buf)[16]) {
+          auto chunk = [&](int c0) {
             uint32_t v[16];
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
@@ -577,6 +602,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 if (elect_one()) tma_store_wait_read();
                 __syncwarp();
 #pragma unroll
+                const bool s_keep = tau >= hp.skp_t_lo && tau < hp.t_hi && tau >= hp.skp_zero_lo;
                 for (int j = 0; j < 16; ++j) stg[j * 32 + lane] = s_keep ? __uint_as_float(v[j]) : 0.0f;
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -593,6 +619,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               r[j] = (keep && c0 + j < nv) ? __uint_as_float(v[j]) + buf[j] : 0.0f;
               xmax = fmaxf(xmax, fabsf(r[j]));
             }
+            if (c0 == cb) stamp_at(4);             // first chunk: accumulator and residual values are in registers
+            if (c0 + 16 < ce) issue(c0 + 16);      // ahead of this chunk's stores in the LSU queue
             if (in_range && !(dbg & 2)) {      // x_next fp32: plain coalesced stores (lane = time step), like tanh / sigmoid above
               float* xo = hp.xo32 + eoff + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
@@ -601,7 +629,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 xo += hp.x_cs;
               }
             }
-            if (dup_ok) {
+            const int dup_t = tau + hp.dup_toff;
+            if (hp.dup && in_range && dup_t >= 0 && dup_t < hp.dup_t_hi) {
               float* dd = hp.dup + eoff + hp.dup_toff + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -611,28 +640,20 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             }
             if (in_range && hp.xo16 && !(dbg & 4)) {
               __half* x16row = hp.xo16 + static_cast<long long>(it.b) * hp.x16_bs + static_cast<long long>(tau) * hp.x16_cp + jd.ch0;
+              if (c0 < nv) {
+                // ONE 32-byte store per lane (st.global.v8: a full sector; two 16-byte stores are two half-filled
+                // sectors on the SM -> L2 write port).  Channels in [nv, c0 + 16) are zeros and land in the padding.
+                uint32_t hw[8];
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                if (c0 + 8 * k < nv) {
-                  uint4 hv;
-                  hv.x = pack_f16x2(r[8 * k + 0], r[8 * k + 1]);
-                  hv.y = pack_f16x2(r[8 * k + 2], r[8 * k + 3]);
-                  hv.z = pack_f16x2(r[8 * k + 4], r[8 * k + 5]);
-                  hv.w = pack_f16x2(r[8 * k + 6], r[8 * k + 7]);
-                  __stcs(reinterpret_cast<uint4*>(x16row + c0 + 8 * k), hv);
-                }
+                for (int k = 0; k < 8; ++k) hw[k] = pack_f16x2(r[2 * k], r[2 * k + 1]);
+                asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(x16row + c0), "r"(hw[0]),
+                             "r"(hw[1]), "r"(hw[2]), "r"(hw[3]), "r"(hw[4]), "r"(hw[5]), "r"(hw[6]), "r"(hw[7])
+                             : "memory");
               }
             }
           };
 #pragma unroll 1
-          for (int c0 = cb; c0 < ce; c0 += 32) {
-            chunk(c0, bufA);
-            if (c0 + 32 < ce) issue(c0 + 32, bufA);
-            if (c0 + 16 < ce) {
-              chunk(c0 + 16, bufB);
-              if (c0 + 48 < ce) issue(c0 + 48, bufB);
-            }
-          }
+          for (int c0 = cb; c0 < ce; c0 += 16) chunk(c0);
           if (cb >= ce) {             // a warp without columns in this job still owes its arrival
             tc_fence_before();
             __syncwarp();
@@ -893,7 +914,9 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   }
   if (!d->final_layer) {
     if ((rc = encode_out_map(&p.xr_m, const_cast<float*>(d->x32), d->t_hi, R, d->batch, d->x_cs, d->x_bs, 32, 128))) return rc;
-    static const int pf = []() { const char* e = getenv("AEWN_GF_PREFETCH"); return e ? atoi(e) : 0; }();   // bit 0: residual rows, bit 1: next tile's operands. Measured SLOWER (356 -> 379 / 377 / 394 us per layer): off
+    // bit 0: residual rows by TMA prefetch at the top of the tile, bit 1: next tile's operands (both measured SLOWER:
+    // 356 -> 379 / 377 / 394 us per layer), bit 2: residual rows by per-lane prefetch.global.L2 from the epilogue warps
+    static const int pf = []() { const char* e = getenv("AEWN_GF_PREFETCH"); return e ? atoi(e) : 0; }();
     p.hot.prefetch = pf;
     static const int dbgf = []() { const char* e = getenv("AEWN_GF_DBG"); return e ? atoi(e) : 0; }();
     p.hot.dbg = dbgf;

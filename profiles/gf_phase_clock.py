@@ -56,5 +56,6 @@ for role, rn in enumerate(("MMA issuer", "epilogue warp 0")):
             if job == 7:
                 print(f"  tile {tile} top   {a - t0:8d}")
                 continue
-            aux = (f"ring-wait {x1:6d}  z-wait {x3:6d}" if role == 0 else f"stg-acquire {x1:6d}  tmem {x2:6d}  fence+store {x3:6d}")
+            aux = (f"ring-wait {x1:6d}  z-wait {x3:6d}" if role == 0 else
+                   (f"loads issued +{x1 - a:6d}  first chunk in registers +{x2 - a:6d}" if x1 > 0 else ""))
             print(f"  tile {tile} {names[job]:5s} {a - t0:8d} {b - t0:8d} {e - t0:8d}   wait {b - a:7d}  work {e - b:7d}   {aux}")
