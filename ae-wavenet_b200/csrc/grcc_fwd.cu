@@ -188,6 +188,17 @@ __device__ __forceinline__ GfItem gf_decode(const GfHot& p, int item, int crank)
   return it;
 }
 
+// read-once global load: no L1 allocation (the L1 is ~20 KB next to 225 KB of shared memory)
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+#ifdef AEWN_GF_LDCS
+  v = __ldcs(p);
+#else
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+#endif
+  return v;
+}
+
 template <int STAGES>
 __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_constant__ GfParams p) {
   constexpr int RING_BYTES = GF_MAX_STAGES * GF_STAGE_BYTES;
@@ -241,7 +252,6 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   const int crank = static_cast<int>(cluster_ctarank());
-  const int cid = blockIdx.x >> 1;
   const int n_cl = gridDim.x >> 1;
   const int total = hp.batch * hp.n_tgroups;
 
@@ -429,16 +439,38 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
       const int slab0 = it.tau0 + q * 32;
       const bool in_range = tau >= hp.t_lo && tau < hp.t_hi;
       const bool keep = in_range && tau >= hp.t_zero_lo;
-      const bool slab_on = (slab0 + 32 > hp.t_lo) && (slab0 < hp.t_hi);
+      // Residual values (x32) of the chunk the RES epilogue will process next.  The loads run one chunk ahead, ACROSS job
+      // boundaries: the first chunk of a RES job is requested before the skip epilogue / at the last chunk of the RES job
+      // in front of it (phase clock: 5.5-8 k cycles from "job seen" to the first values when requested at the job's top).
+      float buf[16];
+      int buf_job = -1;                 // job whose first chunk `buf` holds
+      auto res_load = [&](int j2, int c0) {
+        const int nv2 = hp.job[j2].n_valid;
+        const float* sp = hp.x32 + static_cast<long long>(it.b) * hp.x_bs +
+                          static_cast<long long>(hp.job[j2].ch0 + c0) * hp.x_cs + tau;
+        const bool on = keep && hp.x32 != nullptr && tau >= hp.add_t_lo && !(dbg & 1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          buf[j] = (on && c0 + j < nv2) ? ld_stream(sp) : 0.0f;
+          sp += hp.x_cs;
+        }
+      };
+      auto res_first = [&](int j2) {    // first chunk of job j2 (a z-operand RES job), if this warp has columns in it
+        const int n2 = hp.job[j2].n;
+        const int cb2 = h * (((n2 + 63) >> 6) << 4);
+        if (cb2 < n2) res_load(j2, cb2);
+        buf_job = j2;
+      };
       for (wst[1] = 0; wst[1] < hp.n_jobs && ok; wst[1] = wst[1] + 1) {
         const int jb = wst[1];
         const GfJob jd = hp.job[jb];
         if (jd.kind == GF_SKP && !it.do_skp) continue;
-        // At the tile's first job: pull the residual rows this warp's RES epilogues will add (x32[b, ch, slab]) from HBM
-        // into L2, one 128-byte line per LANE and instruction (lane = channel), ~40 k cycles before they are loaded.
-        // Unprefetched, those loads see HBM behind the write stream: 5-6 k cycles between "job seen" and the first
-        // values in the phase clock, once per RES job, on the epilogue's critical chain.
-        if (jb == 0 && (hp.prefetch & 4) && hp.x32) {
+        // At the tile's LAST gate job: pull the residual rows this warp's RES epilogues will add (x32[b, ch, slab]) from
+        // HBM into L2, one 128-byte line per LANE and instruction (lane = channel), 15-30 k cycles before they are
+        // loaded.  Unprefetched, each 16-channel chunk of a RES epilogue waits ~4 k cycles for HBM behind the write
+        // stream.  The moment matters: the operand ring is idle now (the residual / skip GEMMs only stream weights);
+        // issued at the tile's first job the prefetch competed with the second gate job's operand feed (+7 k cycles).
+        if (jb == hp.n_gate - 1 && (hp.prefetch & 4) && hp.x32) {
 #pragma unroll 1
           for (int j2 = 0; j2 < hp.n_jobs; ++j2) {
             if (hp.job[j2].kind != GF_RES || hp.job[j2].a_ring) continue;
@@ -569,17 +601,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           // sixteen prefetched residual values right after their loads: every spill store waits for its load, ~8 k
           // cycles of serial HBM latency per job in the phase clock.)
           const long long eoff = static_cast<long long>(it.b) * hp.x_bs + static_cast<long long>(jd.ch0) * hp.x_cs + tau;
-          const bool add_ok = hp.x32 != nullptr && tau >= hp.add_t_lo;
-          float buf[16];     // residual values of the NEXT chunk: loaded while the current chunk's stores are issued
-          auto issue = [&](int c0) {
-            const float* sp = hp.x32 + eoff + static_cast<long long>(c0) * hp.x_cs;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              buf[j] = (keep && add_ok && c0 + j < nv && !(dbg & 1)) ? __ldcs(sp) : 0.0f;
-              sp += hp.x_cs;
-            }
-          };
-          if (cb < ce) issue(cb);
+          const bool nxt_res = jb + 1 < hp.n_jobs && hp.job[jb + 1].kind == GF_RES && !hp.job[jb + 1].a_ring && !jd.a_ring;
+          if (buf_job != jb) res_first(jb);
           stamp_at(3);
           if (!mbar_wait_warp(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
@@ -601,8 +624,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               if ((slab0 + 32 > hp.skp_t_lo) && (slab0 < hp.t_hi)) {
                 if (elect_one()) tma_store_wait_read();
                 __syncwarp();
-#pragma unroll
                 const bool s_keep = tau >= hp.skp_t_lo && tau < hp.t_hi && tau >= hp.skp_zero_lo;
+#pragma unroll
                 for (int j = 0; j < 16; ++j) stg[j * 32 + lane] = s_keep ? __uint_as_float(v[j]) : 0.0f;
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -620,7 +643,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               xmax = fmaxf(xmax, fabsf(r[j]));
             }
             if (c0 == cb) stamp_at(4);             // first chunk: accumulator and residual values are in registers
-            if (c0 + 16 < ce) issue(c0 + 16);      // ahead of this chunk's stores in the LSU queue
+            if (c0 + 16 < ce) res_load(jb, c0 + 16);      // ahead of this chunk's stores in the LSU queue
+            else if (nxt_res) res_first(jb + 1);
             if (in_range && !(dbg & 2)) {      // x_next fp32: plain coalesced stores (lane = time step), like tanh / sigmoid above
               float* xo = hp.xo32 + eoff + static_cast<long long>(c0) * hp.x_cs;
 #pragma unroll
@@ -654,6 +678,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           };
 #pragma unroll 1
           for (int c0 = cb; c0 < ce; c0 += 16) chunk(c0);
+          if (cb >= ce && nxt_res) res_first(jb + 1);
           if (cb >= ce) {             // a warp without columns in this job still owes its arrival
             tc_fence_before();
             __syncwarp();
@@ -671,6 +696,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
           const bool s_in = tau >= hp.skp_t_lo && tau < hp.t_hi;
           const bool s_keep = s_in && tau >= hp.skp_zero_lo;
           const float* old = hp.skp + static_cast<long long>(it.b) * hp.s_bs + static_cast<long long>(jd.ch0) * hp.s_cs + tau;
+          if (jb + 1 < hp.n_jobs && hp.job[jb + 1].kind == GF_RES && !hp.job[jb + 1].a_ring) res_first(jb + 1);
           if (!mbar_wait_warp(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
           stamp_at(1);
