@@ -680,10 +680,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   const int crank = p.cluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-  const int cid = blockIdx.x / p.cluster;            // cluster index; all CTAs of a cluster walk the same items
-  const int n_clusters = gridDim.x / p.cluster;
+  // (the item loops below rebuild their bounds from the kernel parameters: a value computed HERE, before the register
+  // split, is spilled to local memory for all three roles, and a local load in the epilogue's tile loop queues behind the
+  // warp's own stores in the LSU)
   const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1u);
-  const int total = p.batch * p.n_tgroups * p.n_heads;
 
   // Register reallocation: warps 0-3 (TMA / MMA / TMEM-alloc roles, one warpgroup) shrink to 88 registers and the 8
   // epilogue warps grow to 208, so 32-wide column chunks + prefetch buffers stay in registers
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
       uint32_t stage = 0, phase = 0;
       bool ok = true;
       const uint32_t lead_full = pair ? mapa_u32(&full_bar[0], 0) : 0u;
-      for (int item = cid; item < total && ok; item += n_clusters) {
+      for (int item = blockIdx.x / p.cluster; item < p.batch * p.n_tgroups * p.n_heads && ok; item += gridDim.x / p.cluster) {
         const TgItem it = tg_decode(p, item, crank);
         if (!it.active) continue;
         const aewn_ntile& nt = p.nt[it.ni];
@@ -765,7 +765,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
       const uint64_t adesc0 = make_smem_desc(0, p.a_lbo, p.a_sbo, kLayoutSW128Base32);
       const uint64_t bdesc0 = make_smem_desc(0, 16, 1024, kLayoutSW128);
       const uint32_t ring = smem_u32(smem);
-      for (int item = cid; item < total && ok; item += n_clusters) {
+      for (int item = blockIdx.x / p.cluster; item < p.batch * p.n_tgroups * p.n_heads && ok; item += gridDim.x / p.cluster) {
         const TgItem it = tg_decode(p, item, crank);
         if (!it.active) continue;
         const aewn_ntile& nt = p.nt[it.ni];
@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
     const int half = (warp - 4) >> 2;
     uint32_t acc = 0, acc_phase = 0;
     int stg_cur = 0;
-    for (int item = cid; item < total; item += n_clusters) {
+    for (int item = blockIdx.x / p.cluster; item < p.batch * p.n_tgroups * p.n_heads; item += gridDim.x / p.cluster) {
       const TgItem it = tg_decode(p, item, crank);
       if (!it.active) continue;
       const aewn_ntile& nt = p.nt[it.ni];
