@@ -13,18 +13,22 @@
 //
 // Per CTA pair and 256 time steps (128 per CTA), jobs run in a fixed order through two 256-column TMEM regions:
 //   G1.j (j < D/128): acc[t, 0:128 | 128:256] = filt | gate pre-activations of channels [128j, 128j+128)
-//                     K = [x16(t-d) | x16(t) | cond16(t), 1], 64 channels per ring stage (5 x 32 KB ring)
-//   epilogue G1.j   : tanh, sigmoid (-> th, sg for the backward pass), z -> fp16 -> zbuf (K-major, manual 128B swizzle)
+//                     K = [x16(t-d) | x16(t) | cond16(t), 1], 64 channels per ring stage (4 x 32 KB ring)
+//   epilogue G1.j   : tanh, sigmoid (-> packed fp16 derivative factors for the backward pass), z -> fp16 -> zbuf (K-major,
+//                     manual 128B swizzle)
 //   SKP.c           : acc = Ws[c] . z   -> skip sum (store / TMA reduce-add / relu(old + acc))          (A operand = zbuf)
 //   RES.c           : acc = Wr[c] . z   -> x32_next = acc + x32 ; x16_next = fp16(x32_next)
 // The residual / skip jobs come smallest-epilogue first: the next tile's first gate job may start as soon as the region
 // of the second-to-last job is drained, so the 256-channel residual chunk (the longest epilogue) goes last and overlaps
 // the next tile's gate MMAs.
-// Warps: 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-19 epilogue (16 warps, 4 per TMEM lane quadrant,
-// 16-column chunks, 104 registers).  tanh / sigmoid / z / x_next leave the SM with plain coalesced stores (lane = time
-// step: one 128-byte line per instruction, st.global.cs); a staged TMA-store path measured slower here (acquire + proxy
-// fence + issue latency in each warp's serial chain).  The running skip sum keeps the TMA reduce-add (one 2 KB box per
-// 16 channels through a per-warp staging tile): red.global.add per element measured 2x slower (profiles/r3_gf_*).
+// Warps: 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 3 idle, 4-19 epilogue (16 warps, 4 per TMEM lane
+// quadrant, 16-column chunks; registers per SM sub-partition: one control warp at 64 + four epilogue warps at 104).  The
+// saved activations / z / x_next leave the SM with plain coalesced stores (lane = time step: one 128-byte line per
+// instruction, st.global.cs), the fp16 copy with one 32-byte st.global.v8 per lane; a staged TMA-store path measured
+// slower here.  The running skip sum keeps the TMA reduce-add (one 2 KB box per 16 channels through a per-warp staging
+// tile): red.global.add per element measured 2x slower (profiles/r3_gf_*).
+// NO local memory in the loops: a spill is a global-memory access that queues behind the warp's own streaming stores
+// (thousands of cycles each in this kernel) -- check `-Xptxas -v` / STL, LDL in the SASS after every edit.
 // All waits are bounded.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -149,6 +153,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
                                                       int c1, uint64_t pol) {
   asm volatile(
@@ -267,6 +276,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
       bool ok = true;
       const uint32_t lead_full = mapa_u32(&full_bar[0], 0);
       const uint64_t pol_keep = l2_policy_evict_last();
+      const uint64_t pol_drop = (hp.prefetch & 16) ? l2_policy_evict_first() : pol_keep;
       for (int item = blockIdx.x >> 1; item < total && ok; item += n_cl) {
         const GfItem it = gf_decode(hp, item, crank);
         // the residual rows this tile's RES epilogues will add (128 time steps x R channels of x32): pull them into L2
@@ -301,7 +311,10 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               if (use_ring) {
                 if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * GF_STAGE_BYTES);
                 const GfSeg sg = hp.seg[sgi];
-                tma_load_3d_pair_hint(sa, sg.map ? &p.ca : &p.xa, fb, kb * GF_KB, it.tau0 + sg.shift, it.b, pol_keep);
+                // the LAST read of an activation row in this layer (last gate job, unshifted tap) may leave L2 early
+                const bool last_use = jd.kind == GF_GATE && jb == hp.n_gate - 1 && sg.map == 0 && sg.shift == 0;
+                tma_load_3d_pair_hint(sa, sg.map ? &p.ca : &p.xa, fb, kb * GF_KB, it.tau0 + sg.shift, it.b,
+                                      last_use ? pol_drop : pol_keep);
                 tma_load_2d_pair_hint(sw, &p.w1, fb, s * GF_KB, jd.w_row + crank * (jd.n >> 1), pol_keep);
               } else {
                 // CTA r stages W2 rows [r * n/2, (r+1) * n/2) of the job (a 128-row box; the MMA reads n/2 of them)
@@ -670,9 +683,14 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 uint32_t hw[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) hw[k] = pack_f16x2(r[2 * k], r[2 * k + 1]);
-                asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(x16row + c0), "r"(hw[0]),
-                             "r"(hw[1]), "r"(hw[2]), "r"(hw[3]), "r"(hw[4]), "r"(hw[5]), "r"(hw[6]), "r"(hw[7])
-                             : "memory");
+                if (hp.prefetch & 8)     // keep the next layer's operand in L2 (experiment)
+                  asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(x16row + c0),
+                               "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]), "r"(hw[4]), "r"(hw[5]), "r"(hw[6]), "r"(hw[7])
+                               : "memory");
+                else
+                  asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(x16row + c0), "r"(hw[0]),
+                               "r"(hw[1]), "r"(hw[2]), "r"(hw[3]), "r"(hw[4]), "r"(hw[5]), "r"(hw[6]), "r"(hw[7])
+                               : "memory");
               }
             }
           };
