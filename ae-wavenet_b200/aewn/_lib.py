@@ -110,6 +110,14 @@ class GrccDgradDesc(C.Structure):
                 ("cond_t_lo", C.c_int), ("cond_zero_lo", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int)]
 
 
+class MfccDesc(C.Structure):
+    """aewn_mfcc_desc: geometry and tables of the MFCC + delta kernels (include/aewn.h, csrc/loader.cu)."""
+    _fields_ = [("n_fft", C.c_int), ("hop", C.c_int), ("n_mels", C.c_int), ("n_mfcc", C.c_int),
+                ("left_pad", C.c_int), ("trim_left", C.c_int), ("n_frames_all", C.c_int), ("n_frames", C.c_int),
+                ("top_db", C.c_float), ("twiddle", C.c_void_p), ("window", C.c_void_p), ("melw", C.c_void_p),
+                ("dctm", C.c_void_p), ("sg", C.c_void_p)]
+
+
 GEN_MAX_LAYERS = 64
 GEN_MAX_BLOCKS = 2 * GEN_MAX_LAYERS + 2
 GEN_MAX_REP = 4
@@ -142,7 +150,8 @@ SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_
            "aewn_vq_fwd", "aewn_vq_commit_bwd", "aewn_ema_update", "aewn_pack_blocks", "aewn_add_blocks", "aewn_nll_fwd", "aewn_nll_bwd",
            "aewn_gen_smem_bytes", "aewn_gen_max_clusters", "aewn_gen_run",
            "aewn_grcc_fwd", "aewn_cvt_f16_cl", "aewn_pack_blocks_f16", "aewn_conv1x1_f32", "aewn_conv1x1_wgrad_f32",
-           "aewn_grcc_dgrad", "aewn_pack_blocks_bf16"]
+           "aewn_grcc_dgrad", "aewn_pack_blocks_bf16",
+           "aewn_mu_encode", "aewn_mu_decode", "aewn_jitter_indices", "aewn_mfcc"]
 
 
 def lib():

@@ -476,6 +476,41 @@ int aewn_gen_smem_bytes(const aewn_gen_desc* d);
 int aewn_gen_max_clusters(const aewn_gen_desc* d, int* n_out);
 int aewn_gen_run(const aewn_gen_desc* d, aewn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Data-loader arithmetic (csrc/loader.cu).  Replaces, on the device:
+ *   util.mu_encode_np / mu_encode_torch (util.py:62-67, 81-86), util.mu_decode_np / mu_decode_torch (util.py:70-78, 88-96),
+ *   jitter.Jitter.__call__ (jitter.py:21-33) and mfcc.ProcessWav.__call__ (mfcc.py:39-76: librosa.feature.mfcc + two
+ *   librosa.feature.delta calls on the host).
+ * ------------------------------------------------------------------------------------------------------------ */
+/* q = (sign(x) log1p(mu |x|) / log1p(mu) + 1) mu / 2 + 0.5 in fp32, mu = n_quanta - 1; torch_round = 0: truncate like
+ * numpy's astype(int32) (util.py:67), 1: round to nearest even like torch's round_() (util.py:86).  out: int32 codes */
+int aewn_mu_encode(const float* x, long long n, int n_quanta, int torch_round, int* out, aewn_stream_t stream);
+/* x = sign(a) ((1 + mu)^|a| - 1) / mu,  a = (2 q - 1) / mu - 1 */
+int aewn_mu_decode(const int* q, long long n, int n_quanta, float* out, aewn_stream_t stream);
+/* out[b, 0] = 0, out[b, 1] = 1, out[b, t] = t - 1 + #{i : cdf_i <= u[b, t - 2]}, cdf = cumsum([p, 1 - 2p, p]) (jitter.py
+ * indexes its table [p1][p1]: every step draws from that row).  u: (B, win - 2) doubles in [0, 1); out: (B, win) int64 */
+int aewn_jitter_indices(const double* u, int B, int win, double p, long long* out, aewn_stream_t stream);
+
+typedef struct {
+  int n_fft, hop, n_mels, n_mfcc;   /* mfcc.py:28-29: win_sz, hop_sz, n_mels, n_mfcc */
+  int left_pad, trim_left;          /* mfcc.py:48-50 */
+  int n_frames_all;                 /* frames librosa computes: 1 + (L + left_pad) / hop (centered, reflect-padded) */
+  int n_frames;                     /* frames kept: n_frames_all - trim_left - trim_right (>= 9) */
+  float top_db;                     /* librosa.power_to_db: 80 */
+  const double* twiddle;            /* [n_fft][2]: cos, sin of 2 pi j / n_fft */
+  const double* window;             /* [n_fft]: periodic Hann */
+  const float* melw;                /* [n_mels][n_fft/2 + 1]: librosa.filters.mel (Slaney scale, area-normalised) */
+  const float* dctm;                /* [n_mfcc][n_mels]: DCT-II, orthonormal */
+  const float* sg;                  /* [2][9][9]: Savitzky-Golay derivative rows, order 1 and 2: rows 0-3 left edge,
+                                       4 interior, 5-8 right edge (scipy savgol_filter, window 9, mode 'interp') */
+} aewn_mfcc_desc;
+
+/* wav: (B, L) samples, wav_dtype 0 = uint8, 1 = int16, 2 = int32, 3 = float32 (the dat file's snd_dtype, data.py:36-41),
+ * row pitch wav_bs elements.  work_db: B * n_mels * n_frames_all floats, work_max: B ints.  out[b, c, j]: (B, 3 n_mfcc,
+ * n_frames) with strides out_bs / out_cs = MFCC rows, then first and second derivatives (mfcc.py:72-75) */
+int aewn_mfcc(const void* wav, int wav_dtype, long long wav_bs, int B, int L, const aewn_mfcc_desc* d, float* work_db,
+              int* work_max, float* out, long long out_bs, long long out_cs, aewn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

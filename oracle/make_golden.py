@@ -282,7 +282,36 @@ def golden_autoencoder():
     json.dump(allgeo, open(path, "w"), indent=1)
 
 
+def golden_loader():
+    """Loader arithmetic from the reference's OWN functions (importable: pure numpy / torch): util.mu_encode_np,
+    util.mu_decode_np, util.mu_encode_torch, util.mu_decode_torch (util.py:62-96) and jitter.Jitter (jitter.py:3-33) under a
+    fixed numpy seed.  (mfcc.ProcessWav needs librosa, which is absent here: no MFCC golden -- see oracle/loader_oracle.py.)"""
+    sys.path.insert(0, "/root/reference")
+    import jitter as ref_jitter
+    import util as ref_util
+    rs = np.random.RandomState(7)
+    x = np.clip(rs.randn(4096) * 0.25, -1, 1).astype(np.float32)
+    x[:9] = [0.0, 1.0, -1.0, 1e-4, -1e-4, 0.5, -0.5, 0.999, -0.999]
+    q = np.arange(256, dtype=np.int32)
+    out = dict(x=torch.from_numpy(x), enc_np=torch.from_numpy(ref_util.mu_encode_np(x, 256)),
+               enc_torch=ref_util.mu_encode_torch(torch.from_numpy(x), 256),
+               dec_np=torch.from_numpy(ref_util.mu_decode_np(q, 256).astype(np.float32)),
+               dec_torch=ref_util.mu_decode_torch(torch.from_numpy(q).long(), 256), jitter=[])
+    for seed, prob, win in ((0, 0.12, 58), (3, 0.12, 117), (11, 0.3, 40)):
+        np.random.seed(seed)
+        idx = ref_jitter.Jitter(prob)(win)
+        np.random.seed(seed)
+        u = np.random.random_sample(win - 2)          # the draws Jitter.__call__ consumed
+        out["jitter"].append(dict(seed=seed, prob=prob, win=win, index=torch.from_numpy(idx.astype(np.int64)),
+                                  uniforms=torch.from_numpy(u)))
+    torch.save(out, os.path.join(OUT, "loader.pt"))
+    print("loader golden written")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "loader":
+        golden_loader()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
         golden_cfg1()
         sys.exit(0)
@@ -296,4 +325,5 @@ if __name__ == "__main__":
     golden_vq()
     golden_geometry_and_init()
     golden_autoencoder()
+    golden_loader()
     print("goldens written to", OUT)
