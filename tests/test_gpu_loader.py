@@ -36,8 +36,8 @@ def test_mu_law_codec_matches_the_reference_golden(golden_dir):
     dec = loader.mu_decode_torch(q, 256).cpu()
     assert float((dec - g["dec_torch"]).abs().max()) < 2e-6
     assert float((dec - g["dec_np"]).abs().max()) < 2e-6
-    # codec round trip on the code book: decode -> encode is the identity (util.py:62-78)
-    assert torch.equal(loader.mu_encode_np(loader.mu_decode_torch(q, 256), 256).cpu().long(), torch.arange(256))
+    # (decode -> encode is not a usable property here: the reference's decoder puts code q at (2q - 1) / mu - 1, i.e. EXACTLY
+    # on the encoder's decision point between q - 1 and q, util.py:62-78, so the round trip is decided by the last ulp)
 
 
 def test_jitter_indices_match_the_reference_draw_for_draw(golden_dir):
