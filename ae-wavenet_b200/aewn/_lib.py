@@ -36,7 +36,7 @@ class NTile(C.Structure):
                 ("dup_toff", C.c_int), ("dup_t_hi", C.c_int), ("zero_count", C.c_void_p),
                 ("add", C.c_void_p), ("add2", C.c_void_p), ("add_bs", C.c_longlong), ("add_cs", C.c_longlong),
                 ("add_toff", C.c_int), ("add_t_lo", C.c_int), ("bias", C.c_void_p),
-                ("out16", C.c_void_p), ("out16_bs", C.c_longlong), ("out16_cp", C.c_int)]
+                ("out16", C.c_void_p), ("out16_bs", C.c_longlong), ("out16_cp", C.c_int), ("out16_scale", C.c_void_p)]
 
 
 class TGemmDesc(C.Structure):
@@ -107,7 +107,8 @@ class GrccDgradDesc(C.Structure):
                 ("g_cond", C.c_void_p), ("c_bs", C.c_longlong), ("c_cs", C.c_longlong), ("n_cond", C.c_int),
                 ("batch", C.c_int), ("R", C.c_int), ("dil", C.c_int),
                 ("t_lo", C.c_int), ("t_zero_lo", C.c_int), ("t_hi", C.c_int),
-                ("cond_t_lo", C.c_int), ("cond_zero_lo", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int)]
+                ("cond_t_lo", C.c_int), ("cond_zero_lo", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int),
+                ("g_inv_scale", C.c_void_p)]
 
 
 class MfccDesc(C.Structure):
@@ -151,7 +152,7 @@ SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_
            "aewn_gen_smem_bytes", "aewn_gen_max_clusters", "aewn_gen_run",
            "aewn_grcc_fwd", "aewn_cvt_f16_cl", "aewn_pack_blocks_f16", "aewn_conv1x1_f32", "aewn_conv1x1_wgrad_f32",
            "aewn_grcc_dgrad", "aewn_pack_blocks_bf16",
-           "aewn_mu_encode", "aewn_mu_decode", "aewn_jitter_indices", "aewn_mfcc"]
+           "aewn_mu_encode", "aewn_mu_decode", "aewn_jitter_indices", "aewn_mfcc", "aewn_amax_pow2_scale"]
 
 
 def lib():

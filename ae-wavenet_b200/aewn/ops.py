@@ -376,6 +376,9 @@ def run_launches(launches):
             L.check(lib.aewn_grcc_fwd(C.byref(d), st), "aewn_grcc_fwd")
         elif kind == "dgrad16":
             L.check(lib.aewn_grcc_dgrad(C.byref(d), st), "aewn_grcc_dgrad")
+        elif kind == "amax":
+            L.check(lib.aewn_amax_pow2_scale(C.c_void_p(d[0]), C.c_longlong(d[1]), C.c_float(d[2]), C.c_void_p(d[3]),
+                                             C.c_void_p(d[4]), st), "aewn_amax_pow2_scale")
         elif kind == "wgradw":
             L.check(lib.aewn_wgradw(C.byref(d), st), "aewn_wgradw")
         else:
@@ -485,8 +488,11 @@ class StackPlan:
         self.KS, self.K2 = ceil_to(S, 32), ceil_to(2 * D, 32)
         self.J = (D + 127) // 128
         # data gradient on the fused-layer engine (aewn_grcc_dgrad: bf16 channels-last copy of [g_f; g_g], bf16 weights)
-        self.dgrad16 = self.fused and R % 16 == 0 and Cc <= 240 and (2 * D) % 64 == 0 and \
-            os.environ.get("AEWN_DGRAD16", "0") == "1"      # measured: no faster than the TF32 launch
+        # AEWN_DGRAD16: 0 = TF32 engine (default), 1 = bf16 operands, 2 = fp16 operands with a per-step power-of-two scale
+        # taken from max|g_skp| (TF32-class mantissa; overflow is reported as AEWN_ERR_RANGE) -- DESIGN.md 4.1c
+        mode16 = os.environ.get("AEWN_DGRAD16", "0")
+        self.dgrad16 = self.fused and R % 16 == 0 and Cc <= 240 and (2 * D) % 64 == 0 and mode16 in ("1", "2")
+        self.dgrad16_scaled = self.dgrad16 and mode16 == "2"
         if self.fused:
             # fp16 channels-last operand copies: the layer input ping-pongs between two buffers (the
             # backward pass reads the fp32 tensors), the conditioning copy is shared by all layers
@@ -572,8 +578,9 @@ class StackPlan:
                 fblk(ws, 0, w2, 0, 0, S, D, D, 1)
             blk(ws, 0, w2t, 0, KR, D, S, 1, D)                                         # Ws^T
             if self.dgrad16:
-                w1t = torch.zeros(R + Cc, 2 * K2, device=dev, dtype=torch.bfloat16)
-                tblk = blkb
+                w1t = torch.zeros(R + Cc, 2 * K2, device=dev,
+                                  dtype=torch.float16 if self.dgrad16_scaled else torch.bfloat16)
+                tblk = blkh if self.dgrad16_scaled else blkb
             else:
                 tblk = blk
             for h, wc in enumerate((wf, wg)):
@@ -738,7 +745,11 @@ class StackPlan:
                   gx=[new_buf(B, R, Tp, dev), new_buf(B, R, Tp, dev)], g_skp=new_buf(B, S, Tp, dev),
                   g_cond=new_buf(B, Cc, Tp, dev), g_last=None if g.last_is_final else new_buf(B, R, Tp, dev))
         if self.dgrad16:
-            bw["g16"] = torch.zeros(B, Tp, self.K2, device=dev, dtype=torch.bfloat16)     # [g_f; g_g], channels-last
+            bw["g16"] = torch.zeros(B, Tp, self.K2, device=dev,                            # [g_f; g_g], channels-last
+                                    dtype=torch.float16 if self.dgrad16_scaled else torch.bfloat16)
+            if self.dgrad16_scaled:
+                bw["gscale"] = torch.ones(2, device=dev)                   # scale, 1 / scale (aewn_amax_pow2_scale)
+                bw["gscale_work"] = torch.zeros(1, device=dev, dtype=torch.int32)
         lay, total = self._grad_layout()
         flat = torch.zeros(total, device=dev)
         views = [{k: flat[o:o + int(torch.tensor(sh).prod())].view(sh) for k, (o, sh) in e.items()} for e in lay]
@@ -746,6 +757,11 @@ class StackPlan:
         gfg, gfs, g_skp, g_cond = bw["gfg"], bw["gfs"], bw["g_skp"], bw["g_cond"]
         rf4 = g.RF & ~3
         launches = []
+        if self.dgrad16_scaled:
+            # every layer's [g_f; g_g] derives from g_skp (and the chain through g_x): its maximum sets the common scale, with
+            # 2^13 of headroom above (max|g_skp| * scale in (4, 8]) and 17 binades of normal fp16 range below
+            launches.append(("amax", (g_skp.data_ptr(), g_skp.numel(), 8.0, bw["gscale_work"].data_ptr(),
+                                      bw["gscale"].data_ptr()), "bwd_amax"))
         g_sig = bw["g_last"]                     # gradient w.r.t. the output of the layer being processed
         for l in range(g.L - 1, -1, -1):
             d = g.dils[l]
@@ -768,6 +784,8 @@ class StackPlan:
                          t_lo=t_store, t_hi=T0, t_zero_lo=lo)
             if self.dgrad16:
                 tile.out16, tile.out16_bs, tile.out16_cp = bw["g16"].data_ptr(), int(bw["g16"].stride(0)), self.K2
+                if self.dgrad16_scaled:
+                    tile.out16_scale = bw["gscale"].data_ptr()
             launches += build_tgemm(acts, segs, self.w2t[l], [tile], B, t_store & ~31, T0, self.err, tag=f"bwd_gz.{l}")
             # (2) g_x[tau] = tap1^T gfg[tau] + tap0^T gfg[tau + d] (+ g_sig[tau]);  g_cond[tau] += P^T gfg[tau]
             gx = bw["gx"][l % 2]
@@ -783,6 +801,8 @@ class StackPlan:
                 dd.t_lo, dd.t_zero_lo, dd.t_hi = lop4, lo_prev, T0
                 dd.cond_t_lo, dd.cond_zero_lo = lo & ~3, lo
                 dd.err = self.err.data_ptr()
+                if self.dgrad16_scaled:
+                    dd.g_inv_scale = bw["gscale"].data_ptr() + 4
                 launches.append(("dgrad16", dd, f"bwd_dgrad.{l}"))
             if not self.dgrad16:
                 if needs_dup(d):
@@ -1035,7 +1055,8 @@ def get_plan(B, R, D, S, Cc, geom, params, device, relu_last):
     set) in a small LRU: two same-shaped models, or a train window alternating with an eval window, each keep their
     workspace; the least recently used plan is dropped when a new one is needed (its memory returns to PyTorch's
     caching allocator -- no empty_cache(), which would fail inside a CUDA-graph capture)."""
-    key = (B, R, D, S, Cc, geom.key(), str(device), bool(relu_last), StackPlan._ptrs(params), FUSED_FWD)
+    key = (B, R, D, S, Cc, geom.key(), str(device), bool(relu_last), StackPlan._ptrs(params), FUSED_FWD,
+           os.environ.get("AEWN_DGRAD16", "0"))
     plan = _plans.get(key)
     if plan is not None:
         _plans.move_to_end(key)

@@ -103,6 +103,7 @@ struct GfHot {
   int dbg;                                 // AEWN_GF_DBG bit mask: skip parts of the epilogues (timing experiments only)
   int* err;
   long long* dbg_clock;   // optional: cluster 0 / CTA 0 stamps its first items (profiles/gf_phase_clock.py)
+  const float* out_scale; // optional (data-gradient variant with scaled fp16 operands): accumulators are multiplied by *out_scale
 };
 static_assert(sizeof(GfHot) % 8 == 0 && sizeof(GfHot) <= 512, "GfHot is copied to shared memory as 64-bit words");
 
@@ -231,7 +232,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  float* const osc_s = reinterpret_cast<float*>(smem + RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES + 116);   // accumulator scale
   if (threadIdx.x == 0) {
+    *osc_s = p.hot.out_scale ? __ldg(p.hot.out_scale) : 1.0f;
     *abort_flag = 0;
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);    // leader: its own arrive.expect_tx; the bytes of BOTH CTAs complete on it
@@ -639,7 +642,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 __syncwarp();
                 const bool s_keep = tau >= hp.skp_t_lo && tau < hp.t_hi && tau >= hp.skp_zero_lo;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) stg[j * 32 + lane] = s_keep ? __uint_as_float(v[j]) : 0.0f;
+                for (int j = 0; j < 16; ++j) stg[j * 32 + lane] = s_keep ? __uint_as_float(v[j]) * *osc_s : 0.0f;
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (elect_one()) {
@@ -650,9 +653,10 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               return;
             }
             float r[16];
+            const float osc = *osc_s;          // 1.0f except in the scaled-fp16 data-gradient variant
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              r[j] = (keep && c0 + j < nv) ? __uint_as_float(v[j]) + buf[j] : 0.0f;
+              r[j] = (keep && c0 + j < nv) ? fmaf(__uint_as_float(v[j]), osc, buf[j]) : 0.0f;
               xmax = fmaxf(xmax, fabsf(r[j]));
             }
             if (c0 == cb) stamp_at(4);             // first chunk: accumulator and residual values are in registers
@@ -1054,12 +1058,13 @@ extern "C" int aewn_grcc_dgrad(const aewn_grcc_dgrad_desc* d, aewn_stream_t stre
     cuuint64_t dims[3] = {(cuuint64_t)K2, (cuuint64_t)d->t_rows, (cuuint64_t)d->batch};
     cuuint64_t str[2] = {(cuuint64_t)K2 * 2u, (cuuint64_t)d->g16_bs * 2u};
     cuuint32_t box[3] = {64u, 128u, 1u};
-    if ((rc = encode_f16_map(&p.xa, d->g16, 3, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "g16", true))) return rc;
+    const bool bf16 = d->g_inv_scale == nullptr;
+    if ((rc = encode_f16_map(&p.xa, d->g16, 3, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "g16", bf16))) return rc;
     p.ca = p.xa;
     cuuint64_t dw[2] = {(cuuint64_t)d->w_k, (cuuint64_t)(R + C)};
     cuuint64_t sw[1] = {(cuuint64_t)d->w_k * 2u};
     cuuint32_t bw[2] = {64u, 128u};
-    if ((rc = encode_f16_map(&p.w1, d->w1t16, 2, dw, sw, bw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w1t16", true))) return rc;
+    if ((rc = encode_f16_map(&p.w1, d->w1t16, 2, dw, sw, bw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w1t16", bf16))) return rc;
     p.w2 = p.w1;
   }
   if ((rc = encode_out_map(&p.skp_m, d->g_cond, d->t_hi, C, d->batch, d->c_cs, d->c_bs, 16))) return rc;
@@ -1084,7 +1089,8 @@ extern "C" int aewn_grcc_dgrad(const aewn_grcc_dgrad_desc* d, aewn_stream_t stre
   p.hot.n_segs = 2;
   p.hot.ring_stages = 2 * (K2 / 64);
   p.hot.kb_z = 0;
-  p.hot.ab_bf16 = 1;
+  p.hot.ab_bf16 = d->g_inv_scale ? 0 : 1;
+  p.hot.out_scale = d->g_inv_scale;
   p.hot.add_t_lo = d->add_t_lo;
   p.hot.x32 = d->g_sig;
   p.hot.xo32 = d->gx;

@@ -140,6 +140,33 @@ __global__ void add_blocks_kernel(const aewn_copy_block* __restrict__ blocks, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// max|x| over n floats (bit pattern of a non-negative float orders like the float) and the power-of-two scale that puts it
+// just below `target`: scale2[0] = 2^floor(log2(target / max|x|)), scale2[1] = 1 / scale2[0]  (1, 1 for an all-zero tensor)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ work) {
+  float m = 0.0f;
+  const long long n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = x4[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, fabsf(x[(n4 << 2) + threadIdx.x]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(work, __float_as_uint(m));      // NaN never compares greater: ignored
+}
+
+__global__ void amax_finish_kernel(const unsigned int* __restrict__ work, float target, float* __restrict__ scale2) {
+  const float m = __uint_as_float(*work);
+  float s = 1.0f;
+  if (m > 0.0f && m < INFINITY) s = exp2f(floorf(log2f(target / m)));
+  if (!(s > 0.0f) || s == INFINITY) s = 1.0f;
+  scale2[0] = s;
+  scale2[1] = 1.0f / s;
+}
+
 }  // namespace aewn
 
 using namespace aewn;
@@ -323,3 +350,17 @@ int aewn_nll_bwd(const float* logits, long long x_bs, long long x_cs, const floa
 }
 
 }  // extern "C"
+
+extern "C" int aewn_amax_pow2_scale(const float* x, long long n, float target, unsigned int* work, float* scale2,
+                                    aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !work || !scale2 || n <= 0 || !(target > 0.0f) || (reinterpret_cast<uintptr_t>(x) & 15u))
+    return aewn::set_err(AEWN_ERR_INVALID, "amax_pow2_scale: bad arguments");
+  if (int rc = aewn::cuda_err(cudaMemsetAsync(work, 0, sizeof(unsigned int), stream), "amax memset")) return rc;
+  const int grid = static_cast<int>(std::min<long long>((n / 4 + 255) / 256 + 1, 148 * 8));
+  aewn::amax_kernel<<<grid, 256, 0, stream>>>(x, n, work);
+  aewn::amax_finish_kernel<<<1, 1, 0, stream>>>(work, target, scale2);
+  aewn::count_launch();
+  aewn::count_launch();
+  return aewn::cuda_err(cudaGetLastError(), "amax launch");
+}

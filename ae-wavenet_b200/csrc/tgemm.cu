@@ -475,8 +475,10 @@ struct GateBwdCtx {
   int n, n_valid;
   bool in_range, live;
   bool ab16;          // AEWN_F_AB16: thp holds {fp16 a, fp16 b} words, the derivative factors themselves
-  __nv_bfloat16* g16row;   // optional bf16 channels-last copy of [g_f; g_g]: row of this lane's time step (or nullptr)
+  __nv_bfloat16* g16row;   // optional 16-bit channels-last copy of [g_f; g_g]: row of this lane's time step (or nullptr)
   int g16_goff;            // channel offset of g_gate in that row
+  float g16_scale;         // 0: bf16 copy; else fp16(value * g16_scale), a power of two (aewn_ntile.out16_scale)
+  int* err;                // device error word (fp16 range overflow of the scaled copy)
 };
 
 __device__ __forceinline__ GateBwdCtx gbwd_ctx(const aewn_ntile& nt, int b, int tau, const CUtensorMap* omap,
@@ -504,6 +506,8 @@ __device__ __forceinline__ GateBwdCtx gbwd_ctx(const aewn_ntile& nt, int b, int 
                         static_cast<long long>(tau + nt.out_toff) * nt.out16_cp
                   : nullptr;
   cx.g16_goff = static_cast<int>((nt.out2 - nt.out) / nt.out_cs);
+  cx.g16_scale = (nt.out16 && nt.out16_scale) ? __ldg(nt.out16_scale) : 0.0f;
+  cx.err = nullptr;
   return cx;
 }
 
@@ -555,9 +559,18 @@ __device__ __forceinline__ void gbwd_chunk(const GateBwdCtx& cx, const StgOut& s
   if (cx.g16row && nrem >= 32) {
     // bf16 channels-last copy for the 16-bit data-gradient engine (aewn_grcc_dgrad): lane = time row, 32 channels =
     // 64 contiguous bytes per row for g_f and for g_g
-    auto pack = [](float lo, float hi) {
+    const float gsc = cx.g16_scale;
+    float amax = 0.0f;
+    auto pack = [&](float lo, float hi) {
       uint32_t r;
-      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+      if (gsc != 0.0f) {      // fp16 with a power-of-two scale: TF32-class mantissa, range checked
+        lo *= gsc;
+        hi *= gsc;
+        amax = fmaxf(amax, fmaxf(fabsf(lo), fabsf(hi)));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+      } else {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+      }
       return r;
     };
 #pragma unroll
@@ -570,6 +583,7 @@ __device__ __forceinline__ void gbwd_chunk(const GateBwdCtx& cx, const StgOut& s
       *reinterpret_cast<uint4*>(cx.g16row + c0 + 8 * i) = a;
       *reinterpret_cast<uint4*>(cx.g16row + cx.g16_goff + c0 + 8 * i) = g;
     }
+    if (amax > 65504.0f && cx.err) atomicExch(cx.err, AEWN_ERR_RANGE);
   }
   if (cx.omap) {   // TMA-store path (tile-uniform decision): g_f box, then g_g box, through the warp's staging tile
     if (so.slab_on) {
@@ -858,7 +872,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
           }
         }
       } else if (mode == AEWN_EPI_GATE_BWD) {
-        const GateBwdCtx gcx = gbwd_ctx(nt, it.b, tau, use_tma ? &p.o_map[it.ni][0] : nullptr, p.gg_ch_off[it.ni]);
+        GateBwdCtx gcx = gbwd_ctx(nt, it.b, tau, use_tma ? &p.o_map[it.ni][0] : nullptr, p.gg_ch_off[it.ni]);
+        gcx.err = p.err;
         float thA[32], sgA[32];
         gbwd_issue(gcx, half * 32, thA, sgA);
         ok = mbar_wait(&tfull_bar[acc], acc_phase, abort_flag);

@@ -112,6 +112,9 @@ typedef struct {
                         out16[b * out16_bs + t * out16_cp + c], g_gate at channel offset (out2 - out) / out_cs */
   long long out16_bs;
   int out16_cp;
+  const float* out16_scale; /* NULL: out16 holds bf16.  Else (device pointer to ONE float, a power of two): out16 holds
+                               fp16(value * *out16_scale); a scaled value beyond the fp16 range raises AEWN_ERR_RANGE in
+                               the descriptor's err word (see aewn_amax_pow2_scale, aewn_grcc_dgrad_desc.g_inv_scale) */
 } aewn_ntile;
 
 #define AEWN_CLUSTER_PAIR_MMA 102
@@ -351,8 +354,13 @@ typedef struct {
   int cond_t_lo, cond_zero_lo;      /* g_cond receives contributions for t >= cond_zero_lo (cond_t_lo = its 4-aligned floor) */
   int* err;
   int max_ctas;
+  const float* g_inv_scale; /* NULL: g16 and w1t16 are bf16.  Else (device pointer to one float): g16 holds
+                               fp16(gfg * scale) and w1t16 fp16 weights; the accumulators are multiplied by *g_inv_scale */
 } aewn_grcc_dgrad_desc;
 
+/* Power-of-two scale for a 16-bit copy of a gradient tensor: scale2[0] = 2^floor(log2(target / max|x|)) (1 if the tensor
+ * is all zero), scale2[1] = 1 / scale2[0].  x: n contiguous floats; work: one unsigned int.  Two tiny launches. */
+int aewn_amax_pow2_scale(const float* x, long long n, float target, unsigned int* work, float* scale2, aewn_stream_t stream);
 int aewn_grcc_dgrad(const aewn_grcc_dgrad_desc* d, aewn_stream_t stream);
 int aewn_pack_blocks_bf16(const aewn_copy_block* blocks_dev, int n_blocks, aewn_stream_t stream);
 

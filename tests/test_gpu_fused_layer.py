@@ -6,6 +6,8 @@ reference that applies EXACTLY those operand roundings, so what is left is fp32 
 approximations of tanh / sigmoid (~1e-7 absolute) and the occasional 1-ulp flip of an fp16 rounding: 2e-4 of the
 tensor's max-abs, i.e. 25x tighter than the TF32 envelope (5e-3) the un-rounded comparisons use.  A wrong time step at
 a lead boundary, a mis-zeroed margin column or a swapped channel block is an O(1) error under this bound."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -197,3 +199,83 @@ def test_fp16_operand_range_overflow_is_reported():
     assert int(plan.err.item()) == _lib.ERR_RANGE
     plan.err.zero_()
     assert torch.isfinite(plan.skp).all()
+
+
+def test_amax_pow2_scale():
+    """aewn_amax_pow2_scale: scale = 2^floor(log2(target / max|x|)), 1 for an all-zero tensor, NaNs ignored."""
+    import ctypes as C
+    from aewn import _lib, ops
+    dev = torch.device("cuda")
+    work = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = torch.zeros(2, device=dev)
+
+    def run(x, target=8.0):
+        _lib.check(_lib.lib().aewn_amax_pow2_scale(C.c_void_p(x.data_ptr()), C.c_longlong(x.numel()), C.c_float(target),
+                                                   C.c_void_p(work.data_ptr()), C.c_void_p(out.data_ptr()), ops._stream()),
+                   "aewn_amax_pow2_scale")
+        return [float(v) for v in out.cpu()]
+
+    gen = torch.Generator().manual_seed(0)
+    x = (torch.randn(1_000_003, generator=gen) * 3e-6).to(dev)
+    x[777_777] = -7.3e-5
+    s, inv = run(x)
+    assert s == 2.0 ** 16 and inv == 2.0 ** -16            # 8 / 7.3e-5 = 1.096e5 -> 2^16 = 65536; amax * s = 4.78 in (4, 8]
+    assert run(torch.zeros(4096, device=dev)) == [1.0, 1.0]
+    x[5] = float("nan")
+    assert run(x)[0] == 2.0 ** 16
+
+
+def test_data_gradient_on_the_fused_engine_bf16_and_scaled_fp16():
+    """AEWN_DGRAD16 = 1 (bf16 operands) and 2 (fp16 operands with the per-step power-of-two scale) against the default TF32
+    data gradient, whole decoder step at arch.basic widths.  Both stay inside the backward tolerance; the scaled-fp16 copy
+    carries TF32's mantissa, so it must sit closer to the TF32 result than bf16 does."""
+    import aewn
+    from aewn import ops
+    from test_gpu_fullsize import build
+
+    def run(mode):
+        os.environ["AEWN_DGRAD16"] = mode
+        ops._plans.clear()
+        torch.manual_seed(2507)
+        wn, geo = build(512)
+        wn = wn.cuda().train()
+        g = torch.Generator().manual_seed(3)
+        B = 2
+        wav = torch.randint(0, 256, (B, geo["wav_len"]), generator=g).float().cuda()
+        lc = torch.randn(B, 64, geo["lc_len"], generator=g).cuda().requires_grad_(True)
+        spk = torch.randint(0, 40, (B,), generator=g).cuda()
+        jit = torch.arange(geo["lc_len"]).unsqueeze(0).repeat(B, 1).cuda()
+        q = wn(wav, lc, spk, jit)
+        o0, o1 = wn.wav_cond_offset
+        loss = aewn.RecLoss()(q[..., :-1], wav[:, o1 - 512:o1][..., 1:])
+        loss.backward()
+        ops.check_device_errors()
+        used = [p for p in ops._plans.values()]
+        assert used and all(p.dgrad16 == (mode != "0") and p.dgrad16_scaled == (mode == "2") for p in used)
+        return {k: p.grad.double().clone() for k, p in wn.named_parameters()}, lc.grad.double().clone()
+
+    old = os.environ.get("AEWN_DGRAD16")
+    try:
+        g0, lc0 = run("0")
+        g1, lc1 = run("1")
+        g2, lc2 = run("2")
+    finally:
+        if old is None:
+            os.environ.pop("AEWN_DGRAD16", None)
+        else:
+            os.environ["AEWN_DGRAD16"] = old
+        ops._plans.clear()
+
+    def nrm(a, b):
+        return float((a - b).norm() / b.norm())
+
+    e1 = {k: nrm(g1[k], g0[k]) for k in g0}
+    e2 = {k: nrm(g2[k], g0[k]) for k in g0}
+    assert max(e1.values()) < 6e-2 and max(e2.values()) < 6e-2, (max(e1.values()), max(e2.values()))
+    assert nrm(lc1, lc0) < 6e-2 and nrm(lc2, lc0) < 6e-2
+    # the data gradient feeds every tensor upstream of the last layer: compare the two variants on the stack's weights
+    ks = [k for k in g0 if k.startswith("conv_layers.")]
+    m1 = sum(e1[k] for k in ks) / len(ks)
+    m2 = sum(e2[k] for k in ks) / len(ks)
+    print(f"mean norm-wise distance to the TF32 data gradient: bf16 {m1:.2e}, scaled fp16 {m2:.2e}")
+    assert m2 < m1
