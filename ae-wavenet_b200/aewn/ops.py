@@ -488,9 +488,10 @@ class StackPlan:
         self.KS, self.K2 = ceil_to(S, 32), ceil_to(2 * D, 32)
         self.J = (D + 127) // 128
         # data gradient on the fused-layer engine (aewn_grcc_dgrad: bf16 channels-last copy of [g_f; g_g], bf16 weights)
-        # AEWN_DGRAD16: 0 = TF32 engine (default), 1 = bf16 operands, 2 = fp16 operands with a per-step power-of-two scale
-        # taken from max|g_skp| (TF32-class mantissa; overflow is reported as AEWN_ERR_RANGE) -- DESIGN.md 4.1c
-        mode16 = os.environ.get("AEWN_DGRAD16", "0")
+        # AEWN_DGRAD16: 2 (default) = the fused-layer engine with fp16 operands and a per-step power-of-two scale taken from
+        # max|g_skp| (10-bit mantissa like TF32, round-to-nearest; overflow is reported as AEWN_ERR_RANGE), 1 = bf16 operands
+        # (no scale, 8-bit mantissa), 0 = the TF32 tgemm engine -- DESIGN.md 4.1c
+        mode16 = dgrad16_mode()
         self.dgrad16 = self.fused and R % 16 == 0 and Cc <= 240 and (2 * D) % 64 == 0 and mode16 in ("1", "2")
         self.dgrad16_scaled = self.dgrad16 and mode16 == "2"
         if self.fused:
@@ -1050,13 +1051,17 @@ _plans = collections.OrderedDict()
 MAX_PLANS = int(os.environ.get("AEWN_MAX_PLANS", "4"))
 
 
+def dgrad16_mode():
+    return os.environ.get("AEWN_DGRAD16", "2")
+
+
 def get_plan(B, R, D, S, Cc, geom, params, device, relu_last):
     """params: list (per layer) of dicts of the live parameter tensors.  Plans are cached per (configuration, parameter
     set) in a small LRU: two same-shaped models, or a train window alternating with an eval window, each keep their
     workspace; the least recently used plan is dropped when a new one is needed (its memory returns to PyTorch's
     caching allocator -- no empty_cache(), which would fail inside a CUDA-graph capture)."""
     key = (B, R, D, S, Cc, geom.key(), str(device), bool(relu_last), StackPlan._ptrs(params), FUSED_FWD,
-           os.environ.get("AEWN_DGRAD16", "0"))
+           dgrad16_mode())
     plan = _plans.get(key)
     if plan is not None:
         _plans.move_to_end(key)

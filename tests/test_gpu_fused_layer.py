@@ -226,8 +226,8 @@ def test_amax_pow2_scale():
 
 
 def test_data_gradient_on_the_fused_engine_bf16_and_scaled_fp16():
-    """AEWN_DGRAD16 = 1 (bf16 operands) and 2 (fp16 operands with the per-step power-of-two scale) against the default TF32
-    data gradient, whole decoder step at arch.basic widths.  Both stay inside the backward tolerance; the scaled-fp16 copy
+    """AEWN_DGRAD16 = 1 (bf16 operands) and 2 (the default: fp16 operands with the per-step power-of-two scale) against the
+    TF32 data gradient of the tgemm engine (0), whole decoder step at arch.basic widths.  Both stay inside the backward tolerance; the scaled-fp16 copy
     carries TF32's mantissa, so it must sit closer to the TF32 result than bf16 does."""
     import aewn
     from aewn import ops
