@@ -517,6 +517,8 @@ def bench_workload(args, workload, rank, local_rank, world, dev, light=False):
                         "tgemm_kernel: GRCC layer forward (2 launches/layer: conv+gate, res+skip), algorithmic bytes per "
                         "SURVEY.md 8d incl. saved tanh/sigmoid, summed over the layers"),
                 algorithmic_bytes_per_launch=fwd_bytes / nL if fwd_bytes else None,
+                # the same launch on the bytes it actually moves (ncu dram__bytes of one layer, profiles/traffic.json)
+                frac_on_measured_traffic=(traffic / (fwd_ms / nL * 1e-3) / 1e9 / pk["hbm_gbs"]) if (traffic and fwd_ms) else None,
                 ms_per_layer_fwd=fwd_ms / nL, per_layer_gbs=per_layer_gbs,
                 frac_inference=(inf_ach / pk["hbm_gbs"]) if inf_ach else None, achieved_inference=inf_ach,
                 ms_per_layer_inference=inf_ms / nL if inf_ms else None, per_layer_gbs_inference=inf_gbs,
