@@ -5,7 +5,7 @@ NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v
 PKG       := ae-wavenet_b200
 CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/aewn/libaewn.so
-SRCS      := $(CSRC)/host_util.cu $(CSRC)/tgemm.cu $(CSRC)/wgrad.cu $(CSRC)/wgradw.cu $(CSRC)/misc.cu $(CSRC)/vq.cu $(CSRC)/gen.cu $(CSRC)/grcc_fwd.cu $(CSRC)/loader.cu
+SRCS      := $(CSRC)/host_util.cu $(CSRC)/tgemm.cu $(CSRC)/wgrad.cu $(CSRC)/wgradw.cu $(CSRC)/misc.cu $(CSRC)/vq.cu $(CSRC)/gen.cu $(CSRC)/grcc_fwd.cu $(CSRC)/loader.cu $(CSRC)/wgradh.cu
 HDRS      := $(CSRC)/ptx.cuh $(CSRC)/host_util.h include/aewn.h
 
 all: $(LIB) probe oracle

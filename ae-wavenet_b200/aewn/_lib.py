@@ -78,6 +78,18 @@ class WGradWDesc(C.Structure):
                 ("n_units", C.c_int), ("batch", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int)]
 
 
+class Act16(C.Structure):
+    """aewn_act16: fp16 channels-last tensor (batch, t_rows, row_pitch)."""
+    _fields_ = [("ptr", C.c_void_p), ("t_rows", C.c_int), ("channels", C.c_int), ("batch", C.c_int),
+                ("row_pitch", C.c_longlong), ("batch_stride", C.c_longlong)]
+
+
+class WGradHDesc(C.Structure):
+    _fields_ = [("acts", Act16 * WGRAD_MAX_ACTS), ("n_acts", C.c_int), ("units", WGWUnit * WGW_MAX_UNITS),
+                ("n_units", C.c_int), ("batch", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int),
+                ("inv_scale", C.c_void_p)]
+
+
 class CopyBlock(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("ni", C.c_int), ("nj", C.c_int), ("si", C.c_longlong),
                 ("sj", C.c_longlong), ("di", C.c_longlong)]
@@ -152,7 +164,7 @@ SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_
            "aewn_gen_smem_bytes", "aewn_gen_max_clusters", "aewn_gen_run",
            "aewn_grcc_fwd", "aewn_cvt_f16_cl", "aewn_pack_blocks_f16", "aewn_conv1x1_f32", "aewn_conv1x1_wgrad_f32",
            "aewn_grcc_dgrad", "aewn_pack_blocks_bf16",
-           "aewn_mu_encode", "aewn_mu_decode", "aewn_jitter_indices", "aewn_mfcc", "aewn_amax_pow2_scale"]
+           "aewn_mu_encode", "aewn_mu_decode", "aewn_jitter_indices", "aewn_mfcc", "aewn_amax_pow2_scale", "aewn_wgradh"]
 
 
 def lib():

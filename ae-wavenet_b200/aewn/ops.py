@@ -293,6 +293,61 @@ def build_wgradw(acts, units, batch, err=None, tag=None, waves=1):
     return out
 
 
+def act16_of(t16, channels=None):
+    """aewn_act16 of a (B, T, Cp) fp16 channels-last tensor."""
+    a = L.Act16()
+    a.ptr = t16.data_ptr()
+    a.t_rows, a.channels, a.batch = int(t16.shape[1]), int(channels if channels is not None else t16.shape[2]), int(t16.shape[0])
+    a.row_pitch, a.batch_stride = int(t16.stride(1)), int(t16.stride(0))
+    return a
+
+
+def build_wgradh(acts16, units, batch, inv_scale_ptr, err=None, tag=None):
+    """Descriptors of one wide-unit weight gradient on fp16 channels-last operands (aewn_wgradh); units as for build_wgradw
+    (pack_wide_units), K blocks of 64 time steps."""
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    slots = sms // 2
+    out = []
+    for i in range(0, len(units), L.WGW_MAX_UNITS):
+        grp = units[i:i + L.WGW_MAX_UNITS]
+        cost = []
+        for u in grp:
+            mma = sum(2.0 * c["n"] for c in u["chunks"])                      # cycles per K block of 64: 4 x (n / 2)
+            bytes_ = 16384 + 128 * u["rows"]
+            kbs = batch * ((u["t_hi"] - u["t_lo"] + 63) // 64)
+            cost.append(max(mma, bytes_ / 45.0) * kbs)
+        tot = sum(cost)
+        share = max(1, slots // max(1, -(-len(units) // L.WGW_MAX_UNITS)))
+        splits = [max(1, int(round(share * c / tot))) for c in cost]
+        while sum(splits) > share and max(splits) > 1:
+            splits[splits.index(max(splits))] -= 1
+        d = L.WGradHDesc()
+        for j, a in enumerate(acts16):
+            d.acts[j] = a
+        d.n_acts = len(acts16)
+        for j, u in enumerate(grp):
+            w = L.WGWUnit()
+            w.g_act, w.g_row, w.m_valid = int(u["g_act"]), int(u["g_row"]), int(u["m_valid"])
+            w.t_lo, w.t_hi = int(u["t_lo"]), int(u["t_hi"])
+            kbs = batch * ((u["t_hi"] - u["t_lo"] + 63) // 64)
+            w.n_split = max(1, min(splits[j], kbs // 8))
+            w.n_chunks = len(u["chunks"])
+            for k, c in enumerate(u["chunks"]):
+                cc = L.WGWChunk()
+                cc.x_act, cc.x_row, cc.n, cc.n_valid = int(c["x_act"]), int(c["x_row"]), int(c["n"]), int(c["n_valid"])
+                cc.shift = int(c.get("shift", 0))
+                cc.out = c["out"].data_ptr() + 4 * int(c.get("out_off", 0))
+                cc.out_rs, cc.out_cs = int(c["out_rs"]), int(c["out_cs"])
+                w.chunk[k] = cc
+            d.units[j] = w
+        d.n_units = len(grp)
+        d.batch = int(batch)
+        d.err = err.data_ptr() if err is not None else None
+        d.inv_scale = inv_scale_ptr
+        out.append(("wgradh", d, tag))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------- fused grad accumulation
 # Fused gradient accumulation (opt-in PER PARAMETER SET: dist.FlatGradSync(..., fused_accumulate=True) marks the
 # parameters it owns): the decoder's backward adds ALL its weight gradients into the parameters' existing .grad tensors
@@ -381,6 +436,8 @@ def run_launches(launches):
                                              C.c_void_p(d[4]), st), "aewn_amax_pow2_scale")
         elif kind == "wgradw":
             L.check(lib.aewn_wgradw(C.byref(d), st), "aewn_wgradw")
+        elif kind == "wgradh":
+            L.check(lib.aewn_wgradh(C.byref(d), st), "aewn_wgradh")
         else:
             L.check(lib.aewn_wgrad(C.byref(d), st), "aewn_wgrad")
         _prof_end(tag, e0)

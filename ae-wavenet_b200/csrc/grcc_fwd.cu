@@ -864,8 +864,8 @@ __global__ void pack_blocks_bf16_kernel(const aewn_copy_block* __restrict__ bloc
   }
 }
 
-static int encode_f16_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                          const cuuint32_t* box, CUtensorMapL2promotion promo, const char* what, bool bf16 = false) {
+int encode_f16_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                   const cuuint32_t* box, CUtensorMapL2promotion promo, const char* what, bool bf16) {
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

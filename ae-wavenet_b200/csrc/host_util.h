@@ -24,6 +24,9 @@ int encode_act_map(CUtensorMap* map, const aewn_act& a, int box_rows, CUtensorMa
 // box_rows channels, 1}, no swizzle.
 int encode_out_map(CUtensorMap* map, float* ptr, int t_extent, int channels, int batch, long long row_pitch,
                    long long batch_stride, int box_rows = 32, int box_t = 32);
+// 16-bit (fp16 / bf16) map of rank 2 or 3, SWIZZLE_128B, inner box extent 64 elements = 128 bytes (csrc/grcc_fwd.cu)
+int encode_f16_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                   const cuuint32_t* box, CUtensorMapL2promotion promo, const char* what, bool bf16 = false);
 // 2-D K-major weight map [rows][kpad]; box = {32 k, box_rows}.
 int encode_w_map(CUtensorMap* map, const float* w, int rows, int kpad, int box_rows);
 

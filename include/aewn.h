@@ -236,6 +236,36 @@ typedef struct {
 int aewn_wgradw(const aewn_wgradw_desc* d, aewn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * The same wide-unit weight gradient on 16-bit CHANNELS-LAST operands (csrc/wgradh.cu): fp16 tensors (batch, t_rows,
+ * row_pitch) whose element (b, t, c) sits at ptr[b * batch_stride + t * row_pitch + c] -- the copies the fused layer
+ * kernels keep (x16, cond16, the scaled fp16 [g_filt; g_gate] copy).  Units and chunks as for aewn_wgradw, with x_row /
+ * g_row = first CHANNEL (multiple of 8) and shift = ANY time shift (a row coordinate: no 16-byte rule); t_lo need not be
+ * aligned.  Rows of the last 64-step K block beyond t_hi must read as zero (or lie beyond t_rows).  The partial sums are
+ * multiplied by *inv_scale (device pointer, may be NULL) before they are added to the outputs.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* ptr;        /* fp16 */
+  int t_rows;             /* time extent of the tensor (TMA zero-fills beyond) */
+  int channels;           /* channel extent, multiple of 8 (TMA zero-fills beyond) */
+  int batch;
+  long long row_pitch;    /* elements between time steps, multiple of 8 */
+  long long batch_stride; /* elements between batch items, multiple of 8 */
+} aewn_act16;
+
+typedef struct {
+  aewn_act16 acts[AEWN_WGRAD_MAX_ACTS];
+  int n_acts;
+  aewn_wgw_unit units[AEWN_WGW_MAX_UNITS];
+  int n_units;
+  int batch;
+  int* err;
+  int max_ctas;
+  const float* inv_scale;
+} aewn_wgradh_desc;
+
+int aewn_wgradh(const aewn_wgradh_desc* d, aewn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Decoder base layer (wavenet.py:348-351): one_hot(wav.long())[..., off0:off0+T] -> Conv1d(Q->R, k=1) evaluated as
  * a column gather  out[b, r, tau] = w[r, code(b, off0 + tau)] + bias[r]  (no one-hot tensor is materialised).
  * `dup` (optional) receives the same values at time index tau + dup_toff (pre-shifted copy for a dilation-1/2 tap).
