@@ -551,11 +551,15 @@ class StackPlan:
         mode16 = dgrad16_mode()
         self.dgrad16 = self.fused and R % 16 == 0 and Cc <= 240 and (2 * D) % 64 == 0 and mode16 in ("1", "2")
         self.dgrad16_scaled = self.dgrad16 and mode16 == "2"
+        # AEWN_WGRAD16 (default 1, needs the scaled fp16 gradient copy): the weight gradients of the dilated convolutions and
+        # the conditioning projections on aewn_wgradh, from the fp16 channels-last copies (x16 is then kept per layer)
+        self.wgrad16 = self.dgrad16_scaled and os.environ.get("AEWN_WGRAD16", "1") == "1"
         if self.fused:
             # fp16 channels-last operand copies: the layer input ping-pongs between two buffers (the
             # backward pass reads the fp32 tensors), the conditioning copy is shared by all layers
             self.KR16, self.KC16 = ceil_to(R, 64), ceil_to(Cc + 1, 64)
-            self.x16 = [torch.zeros(B, Tp, self.KR16, device=device, dtype=torch.float16) for _ in range(2)]
+            self.n_x16 = (g.L + 1) if self.wgrad16 else 2                  # kept per layer when the backward reads them
+            self.x16 = [torch.zeros(B, Tp, self.KR16, device=device, dtype=torch.float16) for _ in range(self.n_x16)]
             self.c16 = torch.zeros(B, Tp, self.KC16, device=device, dtype=torch.float16)
         self._build_packs(params)
         self.fwd_train = self._build_forward(save=True)
@@ -691,7 +695,7 @@ class StackPlan:
         for l, dil in enumerate(g.dils):
             final = g.is_final(l)
             lo = g.lead[l]
-            x, xin, xout = self.sig[l], self.x16[l % 2], self.x16[(l + 1) % 2]
+            x, xin, xout = self.sig[l], self.x16[l % self.n_x16], self.x16[(l + 1) % self.n_x16]
             d = L.GrccFwdDesc()
             d.x16, d.x16_bs, d.x16_cp = xin.data_ptr(), int(xin.stride(0)), self.KR16
             d.c16, d.c16_bs, d.c16_cp = self.c16.data_ptr(), int(self.c16.stride(0)), self.KC16
@@ -891,7 +895,23 @@ class StackPlan:
             mtiles = [(h, i) for h in (0, 1) for i in range((D + 127) // 128)]
             keys = ("conv_signal.weight", "conv_gate.weight")
             wide = ENGINE_MODE == "auto" and WIDE_WGRAD
-            if wide:
+            if wide and self.wgrad16:
+                # fp16 channels-last operands (aewn_wgradh): G = the scaled copy of [g_f; g_g], X = [x16(tau - d) | x16(tau) |
+                # cond16, 1]; a tap is a row shift, the K range starts at the lead itself
+                acts16 = [act16_of(bw["g16"]), act16_of(self.x16[l % self.n_x16]), act16_of(self.c16)]
+                units = []
+                for h in (0, 1):
+                    cks = []
+                    for (c0, n) in chunks(R):
+                        for tap, sh in enumerate((-d, 0)):
+                            cks.append(dict(x_act=1, x_row=c0, n_valid=n, shift=sh, out=v[keys[h]], out_off=c0 * 2 + tap,
+                                            out_rs=2 * R, out_cs=2))
+                    for (c0, n) in chunks(Cc + 1):
+                        cks.append(dict(x_act=2, x_row=c0, n_valid=n, shift=0, out=v["dpb"],
+                                        out_off=h * D * (Cc + 1) + c0, out_rs=Cc + 1, out_cs=1))
+                    units += pack_wide_units(0, h * D, D, lo, T0, cks)
+                launches += build_wgradh(acts16, units, B, bw["gscale"].data_ptr() + 4, self.err, tag=f"wgrad1.{l}")
+            elif wide:
                 # wide units (aewn_wgradw): M = the D filt (h = 0) or gate (h = 1) rows of gfg as ONE CTA pair, against
                 # [x(tau-d) | x(tau) | cond, 1] in <= 512-column units: 256 + 256, then the tails 112 + 112 + 144
                 units = []
@@ -906,6 +926,7 @@ class StackPlan:
                                         out_off=h * D * (Cc + 1) + c0, out_rs=Cc + 1, out_cs=1))
                     units += pack_wide_units(0, h * D, D, lo4, T0, cks)
                 launches += build_wgradw(acts, units, B, self.err, tag=f"wgrad1.{l}")
+            if wide:
                 # dWs, dWr with the roles swapped: M = the D rows of z (one CTA pair), columns = [g_skp | g_sig], so z
                 # is staged once per 512 gradient rows; outputs are written transposed (out_rs = 1, out_cs = D).
                 # g_skp is zero below RF (PostPlan / caller contract), so both share the K range [lead_l, T0).
@@ -1118,7 +1139,7 @@ def get_plan(B, R, D, S, Cc, geom, params, device, relu_last):
     workspace; the least recently used plan is dropped when a new one is needed (its memory returns to PyTorch's
     caching allocator -- no empty_cache(), which would fail inside a CUDA-graph capture)."""
     key = (B, R, D, S, Cc, geom.key(), str(device), bool(relu_last), StackPlan._ptrs(params), FUSED_FWD,
-           dgrad16_mode())
+           dgrad16_mode(), os.environ.get("AEWN_WGRAD16", "1"))
     plan = _plans.get(key)
     if plan is not None:
         _plans.move_to_end(key)

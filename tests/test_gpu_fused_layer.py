@@ -126,9 +126,9 @@ def test_fused_stack_matches_fp16_operand_reference(case, save):
         if xn is not None:
             worst[f"x{l + 1}"] = rel(plan.sig[l + 1][:, :, lead:T0], xn[:, :, lead:])
             if l == last_writer:                      # the fp16 channels-last copy the next layer would read
-                got16 = plan.x16[(l + 1) % 2][:, lead:T0, :R].permute(0, 2, 1).float()
+                got16 = plan.x16[(l + 1) % plan.n_x16][:, lead:T0, :R].permute(0, 2, 1).float()
                 worst[f"x16_{l + 1}"] = rel(got16, xn[:, :, lead:])           # fp16 storage: 2^-11 relative
-                assert float(plan.x16[(l + 1) % 2][:, :, R:].abs().max() if plan.KR16 > R else 0.0) == 0.0
+                assert float(plan.x16[(l + 1) % plan.n_x16][:, :, R:].abs().max() if plan.KR16 > R else 0.0) == 0.0
             if save and l + 1 < len(dils) and ops.needs_dup(dils[l + 1]):
                 dn = dils[l + 1]
                 assert torch.equal(plan.xs[l + 1][:, :, lead + dn:T0], plan.sig[l + 1][:, :, lead:T0 - dn])
@@ -233,8 +233,9 @@ def test_data_gradient_on_the_fused_engine_bf16_and_scaled_fp16():
     from aewn import ops
     from test_gpu_fullsize import build
 
-    def run(mode):
+    def run(mode, wgrad16="0"):
         os.environ["AEWN_DGRAD16"] = mode
+        os.environ["AEWN_WGRAD16"] = wgrad16
         ops._plans.clear()
         torch.manual_seed(2507)
         wn, geo = build(512)
@@ -251,19 +252,22 @@ def test_data_gradient_on_the_fused_engine_bf16_and_scaled_fp16():
         loss.backward()
         ops.check_device_errors()
         used = [p for p in ops._plans.values()]
-        assert used and all(p.dgrad16 == (mode != "0") and p.dgrad16_scaled == (mode == "2") for p in used)
+        assert used and all(p.dgrad16 == (mode != "0") and p.dgrad16_scaled == (mode == "2") and
+                            p.wgrad16 == (mode == "2" and wgrad16 == "1") for p in used)
         return {k: p.grad.double().clone() for k, p in wn.named_parameters()}, lc.grad.double().clone()
 
-    old = os.environ.get("AEWN_DGRAD16")
+    old = os.environ.get("AEWN_DGRAD16"), os.environ.get("AEWN_WGRAD16")
     try:
         g0, lc0 = run("0")
         g1, lc1 = run("1")
         g2, lc2 = run("2")
+        g3, lc3 = run("2", wgrad16="1")          # + the weight gradients on aewn_wgradh (the default build)
     finally:
-        if old is None:
-            os.environ.pop("AEWN_DGRAD16", None)
-        else:
-            os.environ["AEWN_DGRAD16"] = old
+        for k, v in zip(("AEWN_DGRAD16", "AEWN_WGRAD16"), old):
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
         ops._plans.clear()
 
     def nrm(a, b):
@@ -279,3 +283,9 @@ def test_data_gradient_on_the_fused_engine_bf16_and_scaled_fp16():
     m2 = sum(e2[k] for k in ks) / len(ks)
     print(f"mean norm-wise distance to the TF32 data gradient: bf16 {m1:.2e}, scaled fp16 {m2:.2e}")
     assert m2 < m1
+    # fp16 weight gradients: same data gradient as mode 2 (lc gradient identical), weights within TF32-class distance
+    e3 = {k: nrm(g3[k], g0[k]) for k in g0}
+    m3 = sum(e3[k] for k in ks) / len(ks)
+    print(f"  + fp16 weight gradients: {m3:.2e} (worst {max(e3[k] for k in ks):.2e})")
+    assert torch.equal(lc3, lc2)
+    assert max(e3.values()) < 6e-2 and m3 < 2e-3
