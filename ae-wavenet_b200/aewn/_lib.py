@@ -108,7 +108,8 @@ class GrccFwdDesc(C.Structure):
                 ("batch", C.c_int), ("R", C.c_int), ("D", C.c_int), ("S", C.c_int), ("n_cond1", C.c_int),
                 ("dil", C.c_int), ("final_layer", C.c_int), ("t_lo", C.c_int), ("t_zero_lo", C.c_int),
                 ("t_hi", C.c_int), ("skp_t_lo", C.c_int), ("skp_zero_lo", C.c_int), ("err", C.c_void_p),
-                ("max_ctas", C.c_int), ("dbg_clock", C.c_void_p)]
+                ("max_ctas", C.c_int), ("dbg_clock", C.c_void_p),
+                ("z16", C.c_void_p), ("z16_bs", C.c_longlong), ("z16_cp", C.c_int)]
 
 
 class GrccDgradDesc(C.Structure):
@@ -120,7 +121,7 @@ class GrccDgradDesc(C.Structure):
                 ("batch", C.c_int), ("R", C.c_int), ("dil", C.c_int),
                 ("t_lo", C.c_int), ("t_zero_lo", C.c_int), ("t_hi", C.c_int),
                 ("cond_t_lo", C.c_int), ("cond_zero_lo", C.c_int), ("err", C.c_void_p), ("max_ctas", C.c_int),
-                ("g_inv_scale", C.c_void_p)]
+                ("gx16", C.c_void_p), ("gx16_bs", C.c_longlong), ("gx16_cp", C.c_int), ("g_inv_scale", C.c_void_p)]
 
 
 class MfccDesc(C.Structure):
@@ -164,7 +165,7 @@ SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_
            "aewn_gen_smem_bytes", "aewn_gen_max_clusters", "aewn_gen_run",
            "aewn_grcc_fwd", "aewn_cvt_f16_cl", "aewn_pack_blocks_f16", "aewn_conv1x1_f32", "aewn_conv1x1_wgrad_f32",
            "aewn_grcc_dgrad", "aewn_pack_blocks_bf16",
-           "aewn_mu_encode", "aewn_mu_decode", "aewn_jitter_indices", "aewn_mfcc", "aewn_amax_pow2_scale", "aewn_wgradh"]
+           "aewn_mu_encode", "aewn_mu_decode", "aewn_jitter_indices", "aewn_mfcc", "aewn_amax_pow2_scale", "aewn_wgradh", "aewn_cvt_f16_cl_scaled"]
 
 
 def lib():

@@ -431,6 +431,10 @@ def run_launches(launches):
             L.check(lib.aewn_grcc_fwd(C.byref(d), st), "aewn_grcc_fwd")
         elif kind == "dgrad16":
             L.check(lib.aewn_grcc_dgrad(C.byref(d), st), "aewn_grcc_dgrad")
+        elif kind == "cvt16s":
+            L.check(lib.aewn_cvt_f16_cl_scaled(C.c_void_p(d[0]), C.c_longlong(d[1]), C.c_longlong(d[2]), C.c_void_p(d[3]),
+                                               C.c_longlong(d[4]), C.c_int(d[5]), C.c_int(d[6]), C.c_int(d[7]), C.c_int(d[8]),
+                                               C.c_void_p(d[9]), C.c_void_p(d[10]), st), "aewn_cvt_f16_cl_scaled")
         elif kind == "amax":
             L.check(lib.aewn_amax_pow2_scale(C.c_void_p(d[0]), C.c_longlong(d[1]), C.c_float(d[2]), C.c_void_p(d[3]),
                                              C.c_void_p(d[4]), st), "aewn_amax_pow2_scale")
@@ -530,11 +534,23 @@ class StackPlan:
         self.sig = [new_buf(B, R, Tp, device) for _ in range(n_sig)]       # sig[l] = input of layer l
         self.xs = {l: new_buf(B, R, Tp, device) for l in range(g.L) if needs_dup(g.dils[l])}
         self.fused = FUSED_FWD and fused_ok(R, D, S, Cc)
+        # AEWN_DGRAD16: 2 (default) = the fused-layer engine with fp16 operands and a per-step power-of-two scale taken from
+        # max|g_skp| (10-bit mantissa like TF32, round-to-nearest; overflow is reported as AEWN_ERR_RANGE), 1 = bf16 operands
+        # (no scale, 8-bit mantissa), 0 = the TF32 tgemm engine -- DESIGN.md 4.1c
+        mode16 = dgrad16_mode()
+        self.dgrad16 = self.fused and R % 16 == 0 and Cc <= 240 and (2 * D) % 64 == 0 and mode16 in ("1", "2")
+        self.dgrad16_scaled = self.dgrad16 and mode16 == "2"
+        # AEWN_WGRAD16 (default 1, needs the scaled fp16 gradient copy): ALL weight gradients of the stack on aewn_wgradh,
+        # from fp16 channels-last copies: x16 (then kept per layer), cond16, z16 (written by the forward instead of the fp32
+        # z), the scaled copies of [g_f; g_g], g_x and g_skp -- DESIGN.md 4.2c
+        self.wgrad16 = self.dgrad16_scaled and os.environ.get("AEWN_WGRAD16", "1") == "1" and D % 64 == 0 and \
+            g.last_is_final
         # saved for the backward pass: tanh and sigmoid (fp32), or -- fused forward -- ONE word per element holding the two
         # gate-derivative factors {fp16 a = sg (1 - th^2), fp16 b = th sg (1 - sg)} in `th` (half the bytes; `sg` unused)
         self.th = [new_buf(B, D, Tp, device) for _ in range(g.L)]
         self.sg = None if self.fused else [new_buf(B, D, Tp, device) for _ in range(g.L)]
-        self.z = [new_buf(B, D, Tp, device) for _ in range(g.L)]
+        self.z = None if self.wgrad16 else [new_buf(B, D, Tp, device) for _ in range(g.L)]
+        self.z16 = [torch.zeros(B, Tp, D, device=device, dtype=torch.float16) for _ in range(g.L)] if self.wgrad16 else None
         self.skp = new_buf(B, S, Tp, device)
         self.cond = new_buf(B, Cc + 1, Tp, device)
         self.cond[:, Cc, :] = 1.0                                            # the bias channel
@@ -544,16 +560,6 @@ class StackPlan:
         self.KR, self.KC, self.KD = ceil_to(R, 32), ceil_to(Cc + 1, 32), ceil_to(D, 32)
         self.KS, self.K2 = ceil_to(S, 32), ceil_to(2 * D, 32)
         self.J = (D + 127) // 128
-        # data gradient on the fused-layer engine (aewn_grcc_dgrad: bf16 channels-last copy of [g_f; g_g], bf16 weights)
-        # AEWN_DGRAD16: 2 (default) = the fused-layer engine with fp16 operands and a per-step power-of-two scale taken from
-        # max|g_skp| (10-bit mantissa like TF32, round-to-nearest; overflow is reported as AEWN_ERR_RANGE), 1 = bf16 operands
-        # (no scale, 8-bit mantissa), 0 = the TF32 tgemm engine -- DESIGN.md 4.1c
-        mode16 = dgrad16_mode()
-        self.dgrad16 = self.fused and R % 16 == 0 and Cc <= 240 and (2 * D) % 64 == 0 and mode16 in ("1", "2")
-        self.dgrad16_scaled = self.dgrad16 and mode16 == "2"
-        # AEWN_WGRAD16 (default 1, needs the scaled fp16 gradient copy): the weight gradients of the dilated convolutions and
-        # the conditioning projections on aewn_wgradh, from the fp16 channels-last copies (x16 is then kept per layer)
-        self.wgrad16 = self.dgrad16_scaled and os.environ.get("AEWN_WGRAD16", "1") == "1"
         if self.fused:
             # fp16 channels-last operand copies: the layer input ping-pongs between two buffers (the
             # backward pass reads the fp32 tensors), the conditioning copy is shared by all layers
@@ -708,7 +714,11 @@ class StackPlan:
                 if save and l + 1 < g.L and needs_dup(d_next):      # the backward pass's TF32 weight-gradient tap
                     d.dup, d.dup_toff, d.dup_t_hi = self.xs[l + 1].data_ptr(), d_next, T0
             if save:
-                d.th, d.z, d.save = self.th[l].data_ptr(), self.z[l].data_ptr(), 2       # packed derivative factors
+                d.th, d.save = self.th[l].data_ptr(), 2                                  # packed derivative factors
+                if self.wgrad16:
+                    d.z16, d.z16_bs, d.z16_cp = self.z16[l].data_ptr(), int(self.z16[l].stride(0)), D
+                else:
+                    d.z = self.z[l].data_ptr()
                 d.a_bs, d.a_cs = int(self.th[l].stride(0)), int(self.th[l].stride(1))
             d.skp, d.s_bs, d.s_cs = self.skp.data_ptr(), int(self.skp.stride(0)), int(self.skp.stride(1))
             last_relu = l == g.L - 1 and self.relu_last
@@ -812,6 +822,10 @@ class StackPlan:
             if self.dgrad16_scaled:
                 bw["gscale"] = torch.ones(2, device=dev)                   # scale, 1 / scale (aewn_amax_pow2_scale)
                 bw["gscale_work"] = torch.zeros(1, device=dev, dtype=torch.int32)
+            if self.wgrad16:
+                # scaled fp16 channels-last copies of the gradients the dil_skp / dil_res weight gradients contract with z
+                bw["g_skp16"] = torch.zeros(B, Tp, ceil_to(S, 64), device=dev, dtype=torch.float16)
+                bw["gx16"] = [torch.zeros(B, Tp, self.KR16, device=dev, dtype=torch.float16) for _ in range(2)]
         lay, total = self._grad_layout()
         flat = torch.zeros(total, device=dev)
         views = [{k: flat[o:o + int(torch.tensor(sh).prod())].view(sh) for k, (o, sh) in e.items()} for e in lay]
@@ -824,6 +838,11 @@ class StackPlan:
             # 2^13 of headroom above (max|g_skp| * scale in (4, 8]) and 17 binades of normal fp16 range below
             launches.append(("amax", (g_skp.data_ptr(), g_skp.numel(), 8.0, bw["gscale_work"].data_ptr(),
                                       bw["gscale"].data_ptr()), "bwd_amax"))
+            if self.wgrad16:
+                k16 = bw["g_skp16"]
+                launches.append(("cvt16s", (g_skp.data_ptr(), int(g_skp.stride(0)), int(g_skp.stride(1)), k16.data_ptr(),
+                                            int(k16.stride(0)), int(k16.shape[2]), S, T0, B, bw["gscale"].data_ptr(),
+                                            self.err.data_ptr()), "bwd_amax"))
         g_sig = bw["g_last"]                     # gradient w.r.t. the output of the layer being processed
         for l in range(g.L - 1, -1, -1):
             d = g.dils[l]
@@ -865,6 +884,9 @@ class StackPlan:
                 dd.err = self.err.data_ptr()
                 if self.dgrad16_scaled:
                     dd.g_inv_scale = bw["gscale"].data_ptr() + 4
+                if self.wgrad16 and l > 0:         # the layer below contracts this gradient with its z (dil_res)
+                    gx16 = bw["gx16"][l % 2]
+                    dd.gx16, dd.gx16_bs, dd.gx16_cp = gx16.data_ptr(), int(gx16.stride(0)), self.KR16
                 launches.append(("dgrad16", dd, f"bwd_dgrad.{l}"))
             if not self.dgrad16:
                 if needs_dup(d):
@@ -926,6 +948,20 @@ class StackPlan:
                                         out_off=h * D * (Cc + 1) + c0, out_rs=Cc + 1, out_cs=1))
                     units += pack_wide_units(0, h * D, D, lo4, T0, cks)
                 launches += build_wgradw(acts, units, B, self.err, tag=f"wgrad1.{l}")
+            if wide and self.wgrad16:
+                # dWs, dWr: M = the D channels of z16, columns = [g_skp16 | gx16 of the layer above] (both scaled); outputs
+                # transposed like the TF32 units below.  K range [lead_l, T0): g_skp16 is zero below RF.
+                acts16 = [act16_of(self.z16[l]), act16_of(bw["g_skp16"])]
+                cks = [dict(x_act=1, x_row=c0, n_valid=n, shift=0, out=v["dil_skp.weight"], out_off=c0 * D, out_rs=1,
+                            out_cs=D) for (c0, n) in chunks(S)]
+                if not final and g_sig is not None:
+                    acts16.append(act16_of(bw["gx16"][(l + 1) % 2]))
+                    cks += [dict(x_act=2, x_row=c0, n_valid=n, shift=0, out=v["dil_res.weight"], out_off=c0 * D, out_rs=1,
+                                 out_cs=D) for (c0, n) in chunks(R)]
+                launches += build_wgradh(acts16, pack_wide_units(0, 0, D, lo, T0, cks), B, bw["gscale"].data_ptr() + 4,
+                                         self.err, tag=f"wgrad2.{l}")
+                g_sig = gx
+                continue
             if wide:
                 # dWs, dWr with the roles swapped: M = the D rows of z (one CTA pair), columns = [g_skp | g_sig], so z
                 # is staged once per 512 gradient rows; outputs are written transposed (out_rs = 1, out_cs = D).

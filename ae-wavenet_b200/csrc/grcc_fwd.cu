@@ -52,7 +52,7 @@ constexpr int GF_EPI_WARPS = 16;
 constexpr int GF_STG_BYTES = GF_EPI_WARPS * 2048;               // one [16 ch][32 t] fp32 tile per epilogue warp: the skip
                                                                 // sum's TMA reduce-add (red.global.add measured 2x slower)
 constexpr int GF_POOL_BYTES = GF_MAX_STAGES * GF_STAGE_BYTES + GF_STG_BYTES;   // 160 KB
-constexpr int GF_SMEM_BYTES = GF_POOL_BYTES + GF_ZBUF_BYTES + 256 + 512 + 1024;   // + barriers + GfHot + alignment slack
+constexpr int GF_SMEM_BYTES = GF_POOL_BYTES + GF_ZBUF_BYTES + 256 + 640 + 1024;   // + barriers + GfHot + alignment slack
 constexpr int GF_MAX_JOBS = 8;
 
 enum { GF_GATE = 0, GF_RES = 1, GF_SKP = 2 };
@@ -104,8 +104,11 @@ struct GfHot {
   int* err;
   long long* dbg_clock;   // optional: cluster 0 / CTA 0 stamps its first items (profiles/gf_phase_clock.py)
   const float* out_scale; // optional (data-gradient variant with scaled fp16 operands): accumulators are multiplied by *out_scale
+  __half* z16;            // optional fp16 channels-last copy of z (B, Tp, z16_cp)
+  long long z16_bs;
+  int z16_cp, pad0;
 };
-static_assert(sizeof(GfHot) % 8 == 0 && sizeof(GfHot) <= 512, "GfHot is copied to shared memory as 64-bit words");
+static_assert(sizeof(GfHot) % 8 == 0 && sizeof(GfHot) <= 640, "GfHot is copied to shared memory as 64-bit words");
 
 struct GfParams {
   CUtensorMap xa, ca, w1, w2;             // operand loads (fp16)
@@ -232,9 +235,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  float* const osc_s = reinterpret_cast<float*>(smem + RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES + 116);   // accumulator scale
+  // accumulator scale / copy scale slots (the pointer is rebuilt where it is used: a value computed before the register
+  // split is spilled for every role)
+#define GF_OSC_S(smem_) reinterpret_cast<float*>((smem_) + RING_BYTES + GF_ZBUF_BYTES + GF_STG_BYTES + 116)
   if (threadIdx.x == 0) {
-    *osc_s = p.hot.out_scale ? __ldg(p.hot.out_scale) : 1.0f;
+    float* osc_s = GF_OSC_S(smem);
+    osc_s[0] = p.hot.out_scale ? __ldg(p.hot.out_scale) : 1.0f;
+    osc_s[1] = 1.0f / osc_s[0];                      // powers of two: exact (the 16-bit copy of the output is scaled back up)
     *abort_flag = 0;
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);    // leader: its own arrive.expect_tx; the bytes of BOTH CTAs complete on it
@@ -536,22 +543,16 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
             }
             // z -> fp16 -> zbuf: K-major rows of 128 B (64 channels), 16-byte chunk index XOR (row & 7) = SWIZZLE_128B
             const int ch = jd.ch0 + c0;
+            uint32_t zw[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              zw[k] = pack_f16x2(__uint_as_float(vf[2 * k]) * __uint_as_float(vg[2 * k]),
+                                 __uint_as_float(vf[2 * k + 1]) * __uint_as_float(vg[2 * k + 1]));
             {
               uint8_t* zrow = zbuf + (ch >> 6) * GF_A_BYTES + row * 128;
               const int lc0 = (ch & 63) >> 3;
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                uint4 v;
-                v.x = pack_f16x2(__uint_as_float(vf[8 * k + 0]) * __uint_as_float(vg[8 * k + 0]),
-                                 __uint_as_float(vf[8 * k + 1]) * __uint_as_float(vg[8 * k + 1]));
-                v.y = pack_f16x2(__uint_as_float(vf[8 * k + 2]) * __uint_as_float(vg[8 * k + 2]),
-                                 __uint_as_float(vf[8 * k + 3]) * __uint_as_float(vg[8 * k + 3]));
-                v.z = pack_f16x2(__uint_as_float(vf[8 * k + 4]) * __uint_as_float(vg[8 * k + 4]),
-                                 __uint_as_float(vf[8 * k + 5]) * __uint_as_float(vg[8 * k + 5]));
-                v.w = pack_f16x2(__uint_as_float(vf[8 * k + 6]) * __uint_as_float(vg[8 * k + 6]),
-                                 __uint_as_float(vf[8 * k + 7]) * __uint_as_float(vg[8 * k + 7]));
-                *reinterpret_cast<uint4*>(zrow + (((lc0 + k) ^ (row & 7)) << 4)) = v;
-              }
+              *reinterpret_cast<uint4*>(zrow + (((lc0 + 0) ^ (row & 7)) << 4)) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+              *reinterpret_cast<uint4*>(zrow + (((lc0 + 1) ^ (row & 7)) << 4)) = make_uint4(zw[4], zw[5], zw[6], zw[7]);
             }
             if (i == 1) {
               // Both chunks' z rows are in shared memory and the accumulator has been read: release the TMEM region and
@@ -565,6 +566,12 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 if (crank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
                 else mbar_arrive(&tempty_bar[acc]);
               }
+            }
+            if (hp.z16 && in_range) {      // fp16 channels-last copy of z for the weight gradients: one 32-byte store per lane
+              __half* zr = hp.z16 + static_cast<long long>(it.b) * hp.z16_bs + static_cast<long long>(tau) * hp.z16_cp + ch;
+              asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(zr), "r"(zw[0]), "r"(zw[1]),
+                           "r"(zw[2]), "r"(zw[3]), "r"(zw[4]), "r"(zw[5]), "r"(zw[6]), "r"(zw[7])
+                           : "memory");
             }
             // tanh / sigmoid (/ z) for the backward pass: plain coalesced stores (lane = time step: every store
             // instruction writes one full 128-byte line).  Through the staging tiles these were 3 TMA stores per chunk,
@@ -642,7 +649,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 __syncwarp();
                 const bool s_keep = tau >= hp.skp_t_lo && tau < hp.t_hi && tau >= hp.skp_zero_lo;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) stg[j * 32 + lane] = s_keep ? __uint_as_float(v[j]) * *osc_s : 0.0f;
+                for (int j = 0; j < 16; ++j) stg[j * 32 + lane] = s_keep ? __uint_as_float(v[j]) * GF_OSC_S(smem)[0] : 0.0f;
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (elect_one()) {
@@ -653,7 +660,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               return;
             }
             float r[16];
-            const float osc = *osc_s;          // 1.0f except in the scaled-fp16 data-gradient variant
+            const float osc = GF_OSC_S(smem)[0];   // 1.0f except in the scaled-fp16 data-gradient variant
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               r[j] = (keep && c0 + j < nv) ? fmaf(__uint_as_float(v[j]), osc, buf[j]) : 0.0f;
@@ -685,8 +692,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
                 // ONE 32-byte store per lane (st.global.v8: a full sector; two 16-byte stores are two half-filled
                 // sectors on the SM -> L2 write port).  Channels in [nv, c0 + 16) are zeros and land in the padding.
                 uint32_t hw[8];
+                const float csc = GF_OSC_S(smem)[1];   // scale of the 16-bit copy (1.0f in the forward kernel)
 #pragma unroll
-                for (int k = 0; k < 8; ++k) hw[k] = pack_f16x2(r[2 * k], r[2 * k + 1]);
+                for (int k = 0; k < 8; ++k) hw[k] = pack_f16x2(r[2 * k] * csc, r[2 * k + 1] * csc);
                 if (hp.prefetch & 8)     // keep the next layer's operand in L2 (experiment)
                   asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(x16row + c0),
                                "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]), "r"(hw[4]), "r"(hw[5]), "r"(hw[6]), "r"(hw[7])
@@ -785,7 +793,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
-    if (xmax > 65504.0f && hp.err && hp.xo16) atomicExch(hp.err, AEWN_ERR_RANGE);   // fp16 operand copy saturated
+    if (xmax * GF_OSC_S(smem)[1] > 65504.0f && hp.err && hp.xo16) atomicExch(hp.err, AEWN_ERR_RANGE);   // fp16 copy saturated
     if (elect_one()) tma_store_wait_all();
     __syncwarp();
   }
@@ -808,17 +816,18 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cvt_f16_cl_kernel(const float* __restrict__ src, long long s_bs, long long s_cs,
                                                          __half* __restrict__ dst, long long d_bs, int Cp, int C, int T,
-                                                         int ones_ch, int* err) {
+                                                         int ones_ch, int* err, const float* __restrict__ scale = nullptr) {
   __shared__ float tl[64][33];
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 64;
   const int t0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows of 32
+  const float sc = scale ? __ldg(scale) : 1.0f;
   float m = 0.0f;
   for (int cc = ty; cc < 64; cc += 8) {
     const int c = c0 + cc, t = t0 + tx;
     float v = 0.0f;
-    if (c < C && t < T) v = src[static_cast<long long>(b) * s_bs + static_cast<long long>(c) * s_cs + t];
+    if (c < C && t < T) v = src[static_cast<long long>(b) * s_bs + static_cast<long long>(c) * s_cs + t] * sc;
     if (c == ones_ch) v = 1.0f;
     m = fmaxf(m, fabsf(v));
     tl[cc][tx] = v;
@@ -1018,6 +1027,13 @@ extern "C" int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream_)
   p.hot.a_cs = d->a_cs;
   p.hot.save = d->save;
   p.hot.z_out = d->z != nullptr;
+  if (d->z16) {
+    if ((d->z16_cp & 15) || d->z16_cp < D || (d->z16_bs & 7) || (reinterpret_cast<uintptr_t>(d->z16) & 31u))
+      return set_err(AEWN_ERR_INVALID, "grcc_fwd: z16 needs z16_cp %% 16 == 0, >= D, 32-byte aligned rows");
+    p.hot.z16 = reinterpret_cast<__half*>(d->z16);
+    p.hot.z16_bs = d->z16_bs;
+    p.hot.z16_cp = d->z16_cp;
+  }
   p.hot.skp_mode = d->skp_mode;
   p.hot.batch = d->batch;
   p.hot.t_begin = d->t_lo & ~31;
@@ -1091,6 +1107,13 @@ extern "C" int aewn_grcc_dgrad(const aewn_grcc_dgrad_desc* d, aewn_stream_t stre
   p.hot.kb_z = 0;
   p.hot.ab_bf16 = d->g_inv_scale ? 0 : 1;
   p.hot.out_scale = d->g_inv_scale;
+  if (d->gx16) {
+    if (!d->g_inv_scale || (d->gx16_cp & 15) || d->gx16_cp < R || (d->gx16_bs & 7) || (reinterpret_cast<uintptr_t>(d->gx16) & 31u))
+      return set_err(AEWN_ERR_INVALID, "grcc_dgrad: gx16 needs the scaled variant, gx16_cp %% 16 == 0, >= R, 32-byte aligned rows");
+    p.hot.xo16 = reinterpret_cast<__half*>(d->gx16);
+    p.hot.x16_bs = d->gx16_bs;
+    p.hot.x16_cp = d->gx16_cp;
+  }
   p.hot.add_t_lo = d->add_t_lo;
   p.hot.x32 = d->g_sig;
   p.hot.xo32 = d->gx;
@@ -1141,4 +1164,16 @@ extern "C" int aewn_pack_blocks_f16(const aewn_copy_block* blocks_dev, int n_blo
   pack_blocks_f16_kernel<<<grid, 256, 0, stream>>>(blocks_dev, n_blocks);
   count_launch();
   return cuda_err(cudaGetLastError(), "pack_blocks_f16 launch");
+}
+
+extern "C" int aewn_cvt_f16_cl_scaled(const float* src, long long s_bs, long long s_cs, void* dst, long long d_bs, int Cp, int C,
+                                      int T, int batch, const float* scale, int* err, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!src || !dst || !scale || batch <= 0 || C <= 0 || T <= 0 || Cp < C || (Cp & 7) || (reinterpret_cast<uintptr_t>(dst) & 15u) ||
+      (d_bs & 7))
+    return set_err(AEWN_ERR_INVALID, "cvt_f16_cl_scaled: bad arguments");
+  dim3 grid((T + 31) / 32, (Cp + 63) / 64, batch);
+  cvt_f16_cl_kernel<<<grid, 256, 0, stream>>>(src, s_bs, s_cs, reinterpret_cast<__half*>(dst), d_bs, Cp, C, T, -1, err, scale);
+  count_launch();
+  return cuda_err(cudaGetLastError(), "cvt_f16_cl_scaled launch");
 }

@@ -354,6 +354,10 @@ typedef struct {
                              [MMA issuer | epilogue warp 0][tile][job][clock64 at: job seen, operands / accumulator ready,
                              done; cycles: MMA = waiting for ring stages, -, waiting for z | epilogue = acquiring staging
                              tiles, TMEM loads, fence + TMA store issue] */
+  void* z16;              /* optional: fp16 CHANNELS-LAST copy of z, element (b, t, c) at z16[b * z16_bs + t * z16_cp + c]
+                             (the weight-gradient operand of aewn_wgradh; replaces the fp32 `z` output when that is NULL) */
+  long long z16_bs;
+  int z16_cp;             /* multiple of 16 */
 } aewn_grcc_fwd_desc;
 
 int aewn_grcc_fwd(const aewn_grcc_fwd_desc* d, aewn_stream_t stream);
@@ -384,6 +388,10 @@ typedef struct {
   int cond_t_lo, cond_zero_lo;      /* g_cond receives contributions for t >= cond_zero_lo (cond_t_lo = its 4-aligned floor) */
   int* err;
   int max_ctas;
+  void* gx16;               /* optional (scaled variant only): fp16 channels-last copy of gx * scale, element (b, t, c) at
+                               gx16[b * gx16_bs + t * gx16_cp + c] -- the next layer's dil_res weight-gradient operand */
+  long long gx16_bs;
+  int gx16_cp;
   const float* g_inv_scale; /* NULL: g16 and w1t16 are bf16.  Else (device pointer to one float): g16 holds
                                fp16(gfg * scale) and w1t16 fp16 weights; the accumulators are multiplied by *g_inv_scale */
 } aewn_grcc_dgrad_desc;
@@ -396,6 +404,10 @@ int aewn_pack_blocks_bf16(const aewn_copy_block* blocks_dev, int n_blocks, aewn_
 
 /* (batch, C, T) fp32 -> (batch, T, Cp) fp16 channels-last operand copy; channel ones_ch (>= 0) is written as 1.0, other
  * channels in [C, Cp) as 0.  Cp % 8 == 0, dst 16-byte aligned, d_bs (elements between batch items) % 8 == 0. */
+/* the same copy with every value multiplied by *scale (device pointer to a power of two) first; |value * scale| > 65504
+ * saturates and raises AEWN_ERR_RANGE in *err */
+int aewn_cvt_f16_cl_scaled(const float* src, long long s_bs, long long s_cs, void* dst, long long d_bs, int Cp, int C, int T,
+                           int batch, const float* scale, int* err, aewn_stream_t stream);
 int aewn_cvt_f16_cl(const float* src, long long s_bs, long long s_cs, void* dst, long long d_bs, int Cp, int C, int T,
                     int batch, int ones_ch, int* err, aewn_stream_t stream);
 /* aewn_pack_blocks writing fp16: dst is a __half matrix, di counted in halves */
