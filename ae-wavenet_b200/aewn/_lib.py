@@ -13,7 +13,7 @@ MAX_ACTS, MAX_SEGS, MAX_NTILES = 6, 6, 4
 WGRAD_MAX_ACTS, WGRAD_MAX_ITEMS = 6, 32
 
 EPI_LINEAR, EPI_GATE_FWD, EPI_GATE_BWD = 0, 1, 2
-F_ACCUM, F_RELU, F_MASKPOS, F_RELU_FIRST, F_MERGE_NEXT, F_AB16 = 1, 2, 4, 8, 16, 32
+F_ACCUM, F_RELU, F_MASKPOS, F_RELU_FIRST, F_MERGE_NEXT, F_AB16, F_NO_OUT32 = 1, 2, 4, 8, 16, 32, 64
 ERR_TIMEOUT = -1003
 ERR_RANGE = -1004     # an activation left the fp16 operand range of the fused layer kernel
 CLUSTER_PAIR_MMA = 102   # aewn.h AEWN_CLUSTER_PAIR_MMA: 2-CTA clusters issuing cta_group::2 MMAs

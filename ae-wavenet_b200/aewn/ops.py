@@ -860,7 +860,8 @@ class StackPlan:
                 segs = [(0, 0, S, self.KR)]
             t_store = min(lop4, lo4)
             tile = ntile(0, D, gfg, mode=L.EPI_GATE_BWD, out2=gfg[:, D:], add=self.th[l],
-                         add2=None if self.fused else self.sg[l], flags=L.F_AB16 if self.fused else 0,
+                         add2=None if self.fused else self.sg[l],
+                         flags=(L.F_AB16 if self.fused else 0) | (L.F_NO_OUT32 if self.wgrad16 else 0),
                          out3=gfs if (needs_dup(d) and not self.dgrad16) else None, dup_toff=-d, dup_t_hi=T0,
                          t_lo=t_store, t_hi=T0, t_zero_lo=lo)
             if self.dgrad16:

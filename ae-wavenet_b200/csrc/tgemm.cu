@@ -478,6 +478,7 @@ struct GateBwdCtx {
   __nv_bfloat16* g16row;   // optional 16-bit channels-last copy of [g_f; g_g]: row of this lane's time step (or nullptr)
   int g16_goff;            // channel offset of g_gate in that row
   float g16_scale;         // 0: bf16 copy; else fp16(value * g16_scale), a power of two (aewn_ntile.out16_scale)
+  bool no_out32;           // AEWN_F_NO_OUT32: the fp32 g_f / g_g stores are skipped
   int* err;                // device error word (fp16 range overflow of the scaled copy)
 };
 
@@ -508,6 +509,7 @@ __device__ __forceinline__ GateBwdCtx gbwd_ctx(const aewn_ntile& nt, int b, int 
   cx.g16_goff = static_cast<int>((nt.out2 - nt.out) / nt.out_cs);
   cx.g16_scale = (nt.out16 && nt.out16_scale) ? __ldg(nt.out16_scale) : 0.0f;
   cx.err = nullptr;
+  cx.no_out32 = (nt.flags & AEWN_F_NO_OUT32) != 0 && nt.out16 != nullptr;
   return cx;
 }
 
@@ -585,7 +587,9 @@ __device__ __forceinline__ void gbwd_chunk(const GateBwdCtx& cx, const StgOut& s
     }
     if (amax > 65504.0f && cx.err) atomicExch(cx.err, AEWN_ERR_RANGE);
   }
-  if (cx.omap) {   // TMA-store path (tile-uniform decision): g_f box, then g_g box, through the warp's staging tile
+  if (cx.no_out32) {
+    // every consumer (data gradient, weight gradients) reads the 16-bit copy: no fp32 [g_f; g_g] at all
+  } else if (cx.omap) {   // TMA-store path (tile-uniform decision): g_f box, then g_g box, through the warp's staging tile
     if (so.slab_on) {
       float* st = stg_acquire(so);
 #pragma unroll

@@ -80,6 +80,7 @@ typedef struct {
                                receives max(acc + bias, 0), the activation mask source for the backward pass */
 #define AEWN_F_AB16 32      /* GATE_BWD: `add` holds {fp16 a, fp16 b} words (aewn_grcc_fwd, save == 2): g_filt = g_z a, g_gate = g_z b;
                                add2 unused */
+#define AEWN_F_NO_OUT32 64   /* GATE_BWD with out16: skip the fp32 stores of g_filt / g_gate (every consumer reads the 16-bit copy) */
 #define AEWN_F_MERGE_NEXT 16 /* this tile and the NEXT one in ntiles[] share one accumulator: one MMA of n + n_next (<= 256)
                                 columns over their contiguous W rows, one pass over the activations.  Pair mode, LINEAR
                                 tiles; the partner must be a plain store / AEWN_F_ACCUM tile on the TMA path and its
