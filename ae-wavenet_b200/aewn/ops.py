@@ -532,7 +532,6 @@ class StackPlan:
         Tp = g.Tp
         n_sig = g.L + (0 if g.last_is_final else 1)
         self.sig = [new_buf(B, R, Tp, device) for _ in range(n_sig)]       # sig[l] = input of layer l
-        self.xs = {l: new_buf(B, R, Tp, device) for l in range(g.L) if needs_dup(g.dils[l])}
         self.fused = FUSED_FWD and fused_ok(R, D, S, Cc)
         # AEWN_DGRAD16: 2 (default) = the fused-layer engine with fp16 operands and a per-step power-of-two scale taken from
         # max|g_skp| (10-bit mantissa like TF32, round-to-nearest; overflow is reported as AEWN_ERR_RANGE), 1 = bf16 operands
@@ -545,6 +544,8 @@ class StackPlan:
         # z), the scaled copies of [g_f; g_g], g_x and g_skp -- DESIGN.md 4.2c
         self.wgrad16 = self.dgrad16_scaled and os.environ.get("AEWN_WGRAD16", "1") == "1" and D % 64 == 0 and \
             g.last_is_final
+        # pre-shifted duplicates of the layer inputs for dilations 1 and 2: only the TF32 weight gradients read them
+        self.xs = {} if self.wgrad16 else {l: new_buf(B, R, Tp, device) for l in range(g.L) if needs_dup(g.dils[l])}
         # saved for the backward pass: tanh and sigmoid (fp32), or -- fused forward -- ONE word per element holding the two
         # gate-derivative factors {fp16 a = sg (1 - th^2), fp16 b = th sg (1 - sg)} in `th` (half the bytes; `sg` unused)
         self.th = [new_buf(B, D, Tp, device) for _ in range(g.L)]
@@ -711,7 +712,7 @@ class StackPlan:
             if not final:
                 d.xo32, d.xo16 = self.sig[l + 1].data_ptr(), xout.data_ptr()
                 d_next = g.dils[l + 1] if l + 1 < g.L else 4
-                if save and l + 1 < g.L and needs_dup(d_next):      # the backward pass's TF32 weight-gradient tap
+                if save and l + 1 < g.L and (l + 1) in self.xs:     # the backward pass's TF32 weight-gradient tap
                     d.dup, d.dup_toff, d.dup_t_hi = self.xs[l + 1].data_ptr(), d_next, T0
             if save:
                 d.th, d.save = self.th[l].data_ptr(), 2                                  # packed derivative factors

@@ -121,7 +121,7 @@ class _LayerFn(torch.autograd.Function):
         plan.generation += 1
         with torch.no_grad():
             plan.sig[0][:, :, :T_in] = x
-            if ops.needs_dup(d):
+            if 0 in plan.xs:
                 plan.xs[0][:, :, d:T_in] = x[:, :, :T_out]
             plan.cond[:, :Cc, d:T_in] = cond[:, :, cl:cl + T_out]
             plan.forward(save=True)
@@ -411,7 +411,7 @@ class _DecoderCoreFn(torch.autograd.Function):
         with torch.no_grad():
             plan.cond[:, :Cc, :T0] = cond
             d0 = geom.dils[0]
-            dup = plan.xs[0] if ops.needs_dup(d0) else None
+            dup = plan.xs.get(0)          # pre-shifted copy for a TF32 weight-gradient tap (absent with the fp16 engines)
             bw = base_w.detach().reshape(R, Q)
             L.check(L.lib().aewn_base_embed_fwd(
                 L.C.c_void_p(wav_c.data_ptr()), L.C.c_longlong(wav_c.stride(0)), L.C.c_int(o0),

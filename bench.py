@@ -452,8 +452,8 @@ def bench_workload(args, workload, rank, local_rank, world, dev, light=False):
             metric=METRIC, value=world * B * W / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype=("fp16 tensor-core operands (10-bit mantissa, like TF32) in the forward layers and, scaled by a per-step "
-                   "power of two, in the stack's data gradient; tf32 operands elsewhere; fp32 accumulation, residual stream, "
-                   "storage and optimizer" if fused and ops.dgrad16_mode() == "2" else
+                   "power of two, in the stack's data and weight gradients; tf32 operands elsewhere; fp32 accumulation, "
+                   "residual stream, storage and optimizer" if fused and ops.dgrad16_mode() == "2" else
                    "fp16 tensor-core operands in the forward layers (10-bit mantissa, like TF32), tf32 operands elsewhere; "
                    "fp32 accumulation, residual stream, storage and optimizer" if fused else "tf32"), data="synthetic",
             config=dict(workload=("cfg3/cfg4: full VQ-VAE-EMA autoencoder par/arch.vqvae-ema.json train step (Encoder -> "

@@ -101,7 +101,7 @@ def test_fused_stack_matches_fp16_operand_reference(case, save):
     assert plan.fused
     plan.sig[0][:, :, :T0] = x0
     for l, d in enumerate(dils):                      # the TF32 backward's pre-shifted tap of layer 0 (base layer's job)
-        if l == 0 and ops.needs_dup(d):
+        if l == 0 and 0 in plan.xs:
             plan.xs[0][:, :, d:T0] = x0[:, :, :T0 - d]
     plan.cond[:, :Cc, :T0] = cond
     plan.forward(save=save)
@@ -134,7 +134,7 @@ def test_fused_stack_matches_fp16_operand_reference(case, save):
                 got16 = plan.x16[(l + 1) % plan.n_x16][:, lead:T0, :R].permute(0, 2, 1).float()
                 worst[f"x16_{l + 1}"] = rel(got16, xn[:, :, lead:])           # fp16 storage: 2^-11 relative
                 assert float(plan.x16[(l + 1) % plan.n_x16][:, :, R:].abs().max() if plan.KR16 > R else 0.0) == 0.0
-            if save and l + 1 < len(dils) and ops.needs_dup(dils[l + 1]):
+            if save and l + 1 < len(dils) and (l + 1) in plan.xs:
                 dn = dils[l + 1]
                 assert torch.equal(plan.xs[l + 1][:, :, lead + dn:T0], plan.sig[l + 1][:, :, lead:T0 - dn])
     worst["skp"] = rel(plan.skp[:, :, RF:T0], skp_ref[:, :, RF:])

@@ -41,3 +41,9 @@ def test_backward_pair_engines_have_no_spills(tmp_path):
     used = {k: v for k, v in res.items() if "tgemm_kernelILb1ELi0E" in k or "tgemm_kernelILb1ELi2E" in k}
     assert len(used) == 2, res
     assert all(v == (0, 0) for v in used.values()), used
+
+
+@pytest.mark.skipif(shutil.which(NVCC) is None, reason="nvcc not found")
+def test_fp16_weight_gradient_engine_has_no_spills(tmp_path):
+    res = spills("wgradh.cu", tmp_path)
+    assert res and all(v == (0, 0) for v in res.values()), res
