@@ -913,9 +913,9 @@ class StackPlan:
                 tiles += cond_tiles
                 launches += build_tgemm(acts, segs, self.w1t[l], tiles, B, lop4 & ~31, T0, self.err, tag=f"bwd_dgrad.{l}")
             # (3) weight gradients of conv_signal/conv_gate/proj_signal/proj_gate (+ biases via the ones channel)
-            x0_act = act_of(self.xs[l], T0) if needs_dup(d) else act_of(x, T0)
+            x0_act = act_of(self.xs[l], T0) if l in self.xs else act_of(x, T0)     # (TF32 engines only)
             acts = [act_of(gfg, T0), x0_act, act_of(x, T0), act_of(self.cond, T0)]
-            sh0 = 0 if needs_dup(d) else -d
+            sh0 = 0 if l in self.xs else -d
             mtiles = [(h, i) for h in (0, 1) for i in range((D + 127) // 128)]
             keys = ("conv_signal.weight", "conv_gate.weight")
             wide = ENGINE_MODE == "auto" and WIDE_WGRAD
