@@ -1197,7 +1197,7 @@ def check_device_errors():
         if e != 0:
             w.zero_()
             raise RuntimeError(f"aewn: device-side error word = {e} "
-                               f"({'bounded wait timed out' if e == L.ERR_TIMEOUT else 'activation outside the fp16 operand range of the fused layer kernel' if e == L.ERR_RANGE else 'invalid input'})")
+                               f"({'bounded wait timed out' if e == L.ERR_TIMEOUT else 'an activation (forward) or a scaled gradient (backward; AEWN_DGRAD16=0 selects the TF32 engines) outside the fp16 operand range' if e == L.ERR_RANGE else 'invalid input'})")
 
 
 # ------------------------------------------------------------------------------------------------- generic convs
