@@ -562,7 +562,8 @@ class StackPlan:
         self.KS, self.K2 = ceil_to(S, 32), ceil_to(2 * D, 32)
         self.J = (D + 127) // 128
         if self.fused:
-            # fp16 channels-last operand copies: the layer input ping-pongs between two buffers (the
+            # fp16 channels-last operand copies: the layer input is kept per layer when the fp16 weight
+            # gradients read it again, else it ping-pongs between two buffers (the
             # backward pass reads the fp32 tensors), the conditioning copy is shared by all layers
             self.KR16, self.KC16 = ceil_to(R, 64), ceil_to(Cc + 1, 64)
             self.n_x16 = (g.L + 1) if self.wgrad16 else 2                  # kept per layer when the backward reads them
