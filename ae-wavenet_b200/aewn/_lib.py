@@ -132,6 +132,17 @@ class MfccDesc(C.Structure):
                 ("dctm", C.c_void_p), ("sg", C.c_void_p)]
 
 
+class GrccGzDesc(C.Structure):
+    """aewn_grcc_gz_desc: gate derivative of one dilation layer on the fused-layer engine (include/aewn.h)."""
+    _fields_ = [("gx16", C.c_void_p), ("gx16_bs", C.c_longlong), ("gx16_cp", C.c_int),
+                ("gs16", C.c_void_p), ("gs16_bs", C.c_longlong), ("gs16_cp", C.c_int), ("t_rows", C.c_int),
+                ("w2t16", C.c_void_p), ("w_k", C.c_int), ("w_koff_skp", C.c_int),
+                ("ab", C.c_void_p), ("a_bs", C.c_longlong), ("a_cs", C.c_longlong),
+                ("g16", C.c_void_p), ("g16_bs", C.c_longlong), ("g16_cp", C.c_int), ("gg_off", C.c_int),
+                ("batch", C.c_int), ("D", C.c_int), ("t_lo", C.c_int), ("t_zero_lo", C.c_int), ("t_hi", C.c_int),
+                ("err", C.c_void_p), ("max_ctas", C.c_int)]
+
+
 GEN_MAX_LAYERS = 64
 GEN_MAX_BLOCKS = 2 * GEN_MAX_LAYERS + 2
 GEN_MAX_REP = 4
@@ -165,7 +176,7 @@ SYMBOLS = ["aewn_version", "aewn_last_error_string", "aewn_launch_count", "aewn_
            "aewn_gen_smem_bytes", "aewn_gen_max_clusters", "aewn_gen_run",
            "aewn_grcc_fwd", "aewn_cvt_f16_cl", "aewn_pack_blocks_f16", "aewn_conv1x1_f32", "aewn_conv1x1_wgrad_f32",
            "aewn_grcc_dgrad", "aewn_pack_blocks_bf16",
-           "aewn_mu_encode", "aewn_mu_decode", "aewn_jitter_indices", "aewn_mfcc", "aewn_amax_pow2_scale", "aewn_wgradh", "aewn_cvt_f16_cl_scaled"]
+           "aewn_mu_encode", "aewn_mu_decode", "aewn_jitter_indices", "aewn_mfcc", "aewn_amax_pow2_scale", "aewn_wgradh", "aewn_cvt_f16_cl_scaled", "aewn_grcc_gz"]
 
 
 def lib():

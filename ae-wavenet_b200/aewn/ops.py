@@ -431,6 +431,8 @@ def run_launches(launches):
             L.check(lib.aewn_grcc_fwd(C.byref(d), st), "aewn_grcc_fwd")
         elif kind == "dgrad16":
             L.check(lib.aewn_grcc_dgrad(C.byref(d), st), "aewn_grcc_dgrad")
+        elif kind == "gz16":
+            L.check(lib.aewn_grcc_gz(C.byref(d), st), "aewn_grcc_gz")
         elif kind == "cvt16s":
             L.check(lib.aewn_cvt_f16_cl_scaled(C.c_void_p(d[0]), C.c_longlong(d[1]), C.c_longlong(d[2]), C.c_void_p(d[3]),
                                                C.c_longlong(d[4]), C.c_int(d[5]), C.c_int(d[6]), C.c_int(d[7]), C.c_int(d[8]),
@@ -544,6 +546,9 @@ class StackPlan:
         # z), the scaled copies of [g_f; g_g], g_x and g_skp -- DESIGN.md 4.2c
         self.wgrad16 = self.dgrad16_scaled and os.environ.get("AEWN_WGRAD16", "1") == "1" and D % 64 == 0 and \
             g.last_is_final
+        # AEWN_GZ16 (needs the fp16 weight-gradient copies): the gate derivative's GEMM on the fused-layer engine from the
+        # scaled fp16 copies of g_x / g_skp (aewn_grcc_gz) instead of the TF32 tgemm launch reading the fp32 tensors
+        self.gz16 = self.wgrad16 and os.environ.get("AEWN_GZ16", "0") == "1"
         # pre-shifted duplicates of the layer inputs for dilations 1 and 2: only the TF32 weight gradients read them
         self.xs = {} if self.wgrad16 else {l: new_buf(B, R, Tp, device) for l in range(g.L) if needs_dup(g.dils[l])}
         # saved for the backward pass: tanh and sigmoid (fp32), or -- fused forward -- ONE word per element holding the two
@@ -587,7 +592,7 @@ class StackPlan:
         KR, KC, KD, KS, K2, J = self.KR, self.KC, self.KD, self.KS, self.K2, self.J
         KP = 2 * KR + KC
         self.w1, self.w2, self.w2t, self.w1t = [], [], [], []
-        self.w1h, self.w2h, self.w1t16 = [], [], []
+        self.w1h, self.w2h, self.w1t16, self.w2t16 = [], [], [], []
         blocks, hblocks, bblocks = [], [], []
         fused = self.fused
 
@@ -647,6 +652,12 @@ class StackPlan:
             else:
                 fblk(ws, 0, w2, 0, 0, S, D, D, 1)
             blk(ws, 0, w2t, 0, KR, D, S, 1, D)                                         # Ws^T
+            if self.gz16:                                                              # the same two blocks in fp16
+                w2t16 = torch.zeros(D, self.KR16 + ceil_to(S, 64), device=dev, dtype=torch.float16)
+                if not final:
+                    blkh(wr, 0, w2t16, 0, 0, D, R, 1, D)
+                blkh(ws, 0, w2t16, 0, self.KR16, D, S, 1, D)
+                self.w2t16.append(w2t16)
             if self.dgrad16:
                 w1t = torch.zeros(R + Cc, 2 * K2, device=dev,
                                   dtype=torch.float16 if self.dgrad16_scaled else torch.bfloat16)
@@ -870,7 +881,22 @@ class StackPlan:
                 tile.out16, tile.out16_bs, tile.out16_cp = bw["g16"].data_ptr(), int(bw["g16"].stride(0)), self.K2
                 if self.dgrad16_scaled:
                     tile.out16_scale = bw["gscale"].data_ptr()
-            launches += build_tgemm(acts, segs, self.w2t[l], [tile], B, t_store & ~31, T0, self.err, tag=f"bwd_gz.{l}")
+            if self.gz16:
+                gz = L.GrccGzDesc()
+                if g_sig is not None:
+                    gxs = bw["gx16"][(l + 1) % 2]
+                    gz.gx16, gz.gx16_bs, gz.gx16_cp = gxs.data_ptr(), int(gxs.stride(0)), self.KR16
+                k16 = bw["g_skp16"]
+                gz.gs16, gz.gs16_bs, gz.gs16_cp, gz.t_rows = k16.data_ptr(), int(k16.stride(0)), int(k16.shape[2]), Tp
+                gz.w2t16, gz.w_k, gz.w_koff_skp = self.w2t16[l].data_ptr(), int(self.w2t16[l].shape[1]), self.KR16
+                gz.ab, gz.a_bs, gz.a_cs = self.th[l].data_ptr(), int(self.th[l].stride(0)), int(self.th[l].stride(1))
+                gz.g16, gz.g16_bs, gz.g16_cp, gz.gg_off = bw["g16"].data_ptr(), int(bw["g16"].stride(0)), self.K2, D
+                gz.batch, gz.D = B, D
+                gz.t_lo, gz.t_zero_lo, gz.t_hi = t_store, lo, T0
+                gz.err = self.err.data_ptr()
+                launches.append(("gz16", gz, f"bwd_gz.{l}"))
+            else:
+                launches += build_tgemm(acts, segs, self.w2t[l], [tile], B, t_store & ~31, T0, self.err, tag=f"bwd_gz.{l}")
             # (2) g_x[tau] = tap1^T gfg[tau] + tap0^T gfg[tau + d] (+ g_sig[tau]);  g_cond[tau] += P^T gfg[tau]
             gx = bw["gx"][l % 2]
             if self.dgrad16:
@@ -1178,7 +1204,7 @@ def get_plan(B, R, D, S, Cc, geom, params, device, relu_last):
     workspace; the least recently used plan is dropped when a new one is needed (its memory returns to PyTorch's
     caching allocator -- no empty_cache(), which would fail inside a CUDA-graph capture)."""
     key = (B, R, D, S, Cc, geom.key(), str(device), bool(relu_last), StackPlan._ptrs(params), FUSED_FWD,
-           dgrad16_mode(), os.environ.get("AEWN_WGRAD16", "1"))
+           dgrad16_mode(), os.environ.get("AEWN_WGRAD16", "1"), os.environ.get("AEWN_GZ16", "0"))
     plan = _plans.get(key)
     if plan is not None:
         _plans.move_to_end(key)

@@ -55,7 +55,7 @@ constexpr int GF_POOL_BYTES = GF_MAX_STAGES * GF_STAGE_BYTES + GF_STG_BYTES;   /
 constexpr int GF_SMEM_BYTES = GF_POOL_BYTES + GF_ZBUF_BYTES + 256 + 640 + 1024;   // + barriers + GfHot + alignment slack
 constexpr int GF_MAX_JOBS = 8;
 
-enum { GF_GATE = 0, GF_RES = 1, GF_SKP = 2 };
+enum { GF_GATE = 0, GF_RES = 1, GF_SKP = 2, GF_GZ = 3 };
 
 struct GfJob {
   int kind;
@@ -212,7 +212,14 @@ __device__ __forceinline__ float ld_stream(const float* p) {
   return v;
 }
 
-template <int STAGES>
+// KINDS: bit mask of the job kinds (1 << GF_*) this instantiation can run.  The epilogues of all kinds in ONE function
+// strain the 104-register budget of the epilogue warps (adding the gate-derivative epilogue made ptxas spill in the others);
+// the forward layer, the data gradient and the gate derivative each get their own instantiation.
+constexpr int GF_KINDS_FWD = (1 << GF_GATE) | (1 << GF_RES) | (1 << GF_SKP);
+constexpr int GF_KINDS_DGRAD = 1 << GF_RES;
+constexpr int GF_KINDS_GZ = 1 << GF_GZ;
+
+template <int STAGES, int KINDS>
 __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_constant__ GfParams p) {
   constexpr int RING_BYTES = GF_MAX_STAGES * GF_STAGE_BYTES;
   static_assert(STAGES <= GF_MAX_STAGES, "ring depth");
@@ -518,7 +525,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
 #endif
         };
         stamp_at(0);
-        if (jd.kind == GF_GATE) {
+        if ((KINDS & (1 << GF_GATE)) && jd.kind == GF_GATE) {
           if (!mbar_wait_warp(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
           stamp_at(1);
@@ -611,7 +618,71 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               }
             }
           }
-        } else if (jd.kind == GF_RES) {
+        } else if ((KINDS & (1 << GF_GZ)) && jd.kind == GF_GZ) {
+          // Gate derivative (autograd of wavenet.py:100-103): the accumulator is g_z * s (its operands are
+          // the scaled fp16 copies of g_x and g_skp); with the saved word {fp16 a, fp16 b} of the forward pass
+          // g_f = g_z a, g_g = g_z b leave as the scaled fp16 channels-last copy [g_f | g_g] every other backward engine reads.
+          const int span = ((jd.n + 63) >> 6) << 4;
+          const int cb = h * span;
+          const int ce = min(cb + span, jd.n);
+          const uint32_t* ap = reinterpret_cast<const uint32_t*>(hp.th) + static_cast<long long>(it.b) * hp.a_bs + tau;
+          uint32_t abw[16];
+          auto ld_ab = [&](int c0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              abw[j] = (keep && c0 + j < jd.n_valid) ? __ldcs(ap + static_cast<long long>(c0 + j) * hp.a_cs) : 0u;
+          };
+          if (cb < ce) ld_ab(cb);
+          if (!mbar_wait_warp(&tfull_bar[acc], acc_phase, abort_flag)) { ok = false; break; }
+          tc_fence_after();
+          stamp_at(1);
+#pragma unroll 1
+          for (int c0 = cb; c0 < ce; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
+            tmem_ld_wait();
+            if (c0 + 16 >= ce) {      // last chunk of this warp: release the region
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (crank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
+                else mbar_arrive(&tempty_bar[acc]);
+              }
+            }
+            uint32_t gfw[8], ggw[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t w0 = abw[2 * k], w1 = abw[2 * k + 1];        // {fp16 a (low half), fp16 b (high half)}
+              const float a0 = __half2float(__ushort_as_half(static_cast<unsigned short>(w0 & 0xffffu)));
+              const float b0 = __half2float(__ushort_as_half(static_cast<unsigned short>(w0 >> 16)));
+              const float a1 = __half2float(__ushort_as_half(static_cast<unsigned short>(w1 & 0xffffu)));
+              const float b1 = __half2float(__ushort_as_half(static_cast<unsigned short>(w1 >> 16)));
+              const float z0 = __uint_as_float(v[2 * k]), z1 = __uint_as_float(v[2 * k + 1]);
+              const float f0 = z0 * a0, f1 = z1 * a1, g0 = z0 * b0, g1 = z1 * b1;
+              xmax = fmaxf(xmax, fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fmaxf(fabsf(g0), fabsf(g1))));
+              gfw[k] = pack_f16x2(f0, f1);
+              ggw[k] = pack_f16x2(g0, g1);
+            }
+            if (c0 + 16 < ce) ld_ab(c0 + 16);            // ahead of this chunk's stores
+            if (in_range) {
+              __half* gr = hp.xo16 + static_cast<long long>(it.b) * hp.x16_bs + static_cast<long long>(tau) * hp.x16_cp + c0;
+              asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gr), "r"(gfw[0]), "r"(gfw[1]),
+                           "r"(gfw[2]), "r"(gfw[3]), "r"(gfw[4]), "r"(gfw[5]), "r"(gfw[6]), "r"(gfw[7])
+                           : "memory");
+              asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gr + hp.dup_toff), "r"(ggw[0]),
+                           "r"(ggw[1]), "r"(ggw[2]), "r"(ggw[3]), "r"(ggw[4]), "r"(ggw[5]), "r"(ggw[6]), "r"(ggw[7])
+                           : "memory");
+            }
+          }
+          if (cb >= ce) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (crank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
+              else mbar_arrive(&tempty_bar[acc]);
+            }
+          }
+        } else if ((KINDS & (1 << GF_RES)) && jd.kind == GF_RES) {
           // x_next = acc + x (wavenet.py:108).  fp32 through the staging half-tiles + TMA stores; fp16 channels-last copy
           // with 16-byte stores (lane = time row: 32 contiguous bytes per 16 channels); optional shifted fp32 duplicate.
           // The residual rows were pulled into L2 by the producer warp's bulk prefetch at the start of the tile.
@@ -717,7 +788,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               else mbar_arrive(&tempty_bar[acc]);
             }
           }
-        } else {
+        } else if (KINDS & (1 << GF_SKP)) {
           // skip sum (wavenet.py:104,110-111 + the caller's running sum): store (first layer), reduce-add in L2, or
           // relu(old + acc) for the last layer (wavenet.py:359)
           const int span = ((jd.n + 63) >> 6) << 4;
@@ -900,7 +971,7 @@ int encode_f16_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t
 
 using namespace aewn;
 
-static int gf_launch(GfParams& p, int max_ctas, cudaStream_t stream, const char* what) {
+static int gf_launch(GfParams& p, int max_ctas, cudaStream_t stream, const char* what, int kinds = GF_KINDS_FWD) {
   const long long total = static_cast<long long>(p.hot.batch) * p.hot.n_tgroups;
   int clusters = (max_ctas > 0 ? max_ctas : sm_count()) / 2;
   if (clusters > total) clusters = static_cast<int>(total);
@@ -921,7 +992,10 @@ static int gf_launch(GfParams& p, int max_ctas, cudaStream_t stream, const char*
   // ring depth: 4 stages (default) or 3 (AEWN_GF_RING=3, A/B runs)
   static const int ring = []() { const char* e = getenv("AEWN_GF_RING"); return e && atoi(e) == 3 ? 3 : 4; }();
   using KernelFn = void (*)(GfParams);
-  KernelFn fn = ring == 3 ? grcc_fwd_kernel<3> : grcc_fwd_kernel<4>;
+  KernelFn fn = kinds == GF_KINDS_GZ      ? grcc_fwd_kernel<4, GF_KINDS_GZ>
+                : kinds == GF_KINDS_DGRAD ? grcc_fwd_kernel<4, GF_KINDS_DGRAD>
+                : ring == 3               ? grcc_fwd_kernel<3, GF_KINDS_FWD>
+                                          : grcc_fwd_kernel<4, GF_KINDS_FWD>;
   cudaError_t ae = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_BYTES);
   if (ae != cudaSuccess) return cuda_err(ae, what);
   cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
@@ -1133,7 +1207,7 @@ extern "C" int aewn_grcc_dgrad(const aewn_grcc_dgrad_desc* d, aewn_stream_t stre
   p.hot.skp_t_lo = d->cond_t_lo;
   p.hot.skp_zero_lo = d->cond_zero_lo;
   p.hot.err = d->err;
-  return gf_launch(p, d->max_ctas, stream, "grcc_dgrad launch");
+  return gf_launch(p, d->max_ctas, stream, "grcc_dgrad launch", GF_KINDS_DGRAD);
 }
 
 extern "C" int aewn_pack_blocks_bf16(const aewn_copy_block* blocks_dev, int n_blocks, aewn_stream_t stream_) {
@@ -1176,4 +1250,66 @@ extern "C" int aewn_cvt_f16_cl_scaled(const float* src, long long s_bs, long lon
   cvt_f16_cl_kernel<<<grid, 256, 0, stream>>>(src, s_bs, s_cs, reinterpret_cast<__half*>(dst), d_bs, Cp, C, T, -1, err, scale);
   count_launch();
   return cuda_err(cudaGetLastError(), "cvt_f16_cl_scaled launch");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gate derivative on the fused-layer engine: g_z = Wr^T g_x + Ws^T g_skp from the scaled fp16 channels-last copies of
+// g_x and g_skp, then [g_f | g_g] = g_z {a, b} (saved fp16 words of the forward) stored as the scaled fp16 copy.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int aewn_grcc_gz(const aewn_grcc_gz_desc* d, aewn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d) return set_err(AEWN_ERR_INVALID, "grcc_gz: null descriptor");
+  const int D = d->D, KR = d->gx16 ? d->gx16_cp : 0, KS = d->gs16_cp;
+  if ((D != 128 && D != 256) || !d->gs16 || !d->w2t16 || !d->ab || !d->g16 || d->batch <= 0 || d->t_hi <= d->t_lo ||
+      d->t_rows < d->t_hi || (KR & 63) || (KS & 63) || KS < 64 || d->w_k < KR + KS || (d->w_k & 7) || (d->g16_cp & 15) ||
+      d->gg_off < D || d->gg_off + D > d->g16_cp || (d->gg_off & 15) || (reinterpret_cast<uintptr_t>(d->g16) & 31u) ||
+      (d->g16_bs & 7))
+    return set_err(AEWN_ERR_INVALID, "grcc_gz: bad pointer / range / stride (D=%d KR=%d KS=%d w_k=%d)", D, KR, KS, d->w_k);
+  GfParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  cuuint32_t box[3] = {64u, 128u, 1u};
+  if (d->gx16) {
+    cuuint64_t dims[3] = {(cuuint64_t)KR, (cuuint64_t)d->t_rows, (cuuint64_t)d->batch};
+    cuuint64_t str[2] = {(cuuint64_t)KR * 2u, (cuuint64_t)d->gx16_bs * 2u};
+    if ((rc = encode_f16_map(&p.xa, d->gx16, 3, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "gx16"))) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)KS, (cuuint64_t)d->t_rows, (cuuint64_t)d->batch};
+    cuuint64_t str[2] = {(cuuint64_t)KS * 2u, (cuuint64_t)d->gs16_bs * 2u};
+    if ((rc = encode_f16_map(&p.ca, d->gs16, 3, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "gs16"))) return rc;
+    if (!d->gx16) p.xa = p.ca;
+    // W2^T [D][KR | KS]: without the g_x segment the columns start at the skip block
+    const __half* w = reinterpret_cast<const __half*>(d->w2t16) + (d->gx16 ? 0 : d->w_koff_skp);
+    cuuint64_t dw[2] = {(cuuint64_t)(KR + KS), (cuuint64_t)D};
+    cuuint64_t sw[1] = {(cuuint64_t)d->w_k * 2u};
+    cuuint32_t bw[2] = {64u, 128u};
+    if ((rc = encode_f16_map(&p.w1, w, 2, dw, sw, bw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w2t16"))) return rc;
+    p.w2 = p.w1;
+  }
+  p.hot.job[0] = GfJob{GF_GZ, 0, D == 128 ? 128 : 256, D, 0, 1, 1 << 30};
+  p.hot.n_jobs = 1;
+  p.hot.n_gate = 0;
+  int ns = 0;
+  if (d->gx16) p.hot.seg[ns++] = GfSeg{0, 0, KR / 64};
+  p.hot.seg[ns++] = GfSeg{1, 0, KS / 64};
+  p.hot.n_segs = ns;
+  p.hot.ring_stages = (KR + KS) / 64;
+  p.hot.th = const_cast<float*>(reinterpret_cast<const float*>(d->ab));
+  p.hot.a_bs = d->a_bs;
+  p.hot.a_cs = d->a_cs;
+  p.hot.xo16 = reinterpret_cast<__half*>(d->g16);
+  p.hot.x16_bs = d->g16_bs;
+  p.hot.x16_cp = d->g16_cp;
+  p.hot.dup_toff = d->gg_off;                  // (reused field) channel offset of g_g inside a g16 row
+  p.hot.batch = d->batch;
+  p.hot.t_begin = d->t_lo & ~31;
+  p.hot.n_tgroups = (d->t_hi - p.hot.t_begin + 2 * GF_BM - 1) / (2 * GF_BM);
+  p.hot.t_lo = d->t_lo;
+  p.hot.t_zero_lo = d->t_zero_lo;
+  p.hot.t_hi = d->t_hi;
+  p.hot.skp_t_lo = d->t_hi;
+  p.hot.skp_zero_lo = d->t_hi;
+  p.hot.err = d->err;
+  return gf_launch(p, d->max_ctas, stream, "grcc_gz launch", GF_KINDS_GZ);
 }

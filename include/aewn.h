@@ -397,6 +397,38 @@ typedef struct {
                                fp16(gfg * scale) and w1t16 fp16 weights; the accumulators are multiplied by *g_inv_scale */
 } aewn_grcc_dgrad_desc;
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Gate derivative of a dilation layer on the fused-layer engine (autograd of wavenet.py:100-106 w.r.t. the two
+ * pre-activations):  g_z = Wr^T g_x + Ws^T g_skp,  g_filt = g_z a,  g_gate = g_z b  with the {fp16 a,
+ * fp16 b} words aewn_grcc_fwd saved (save == 2).  Operands: the SCALED fp16 channels-last copies of g_x (optional: absent
+ * for the top layer) and g_skp, fp16 weights w2t16 [D][gx16_cp | gs16_cp] (K-major).  Output: the scaled fp16
+ * channels-last copy g16 (b, t, [g_filt at c | g_gate at gg_off + c]); rows in [t_lo, t_zero_lo) are written as zeros.
+ * |value| > 65504 raises AEWN_ERR_RANGE in *err.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* gx16;        /* (batch, t_rows, gx16_cp) or NULL */
+  long long gx16_bs;
+  int gx16_cp;             /* multiple of 64 */
+  const void* gs16;        /* (batch, t_rows, gs16_cp) */
+  long long gs16_bs;
+  int gs16_cp;             /* multiple of 64 */
+  int t_rows;
+  const void* w2t16;
+  int w_k;                 /* row pitch of w2t16 (elements) */
+  int w_koff_skp;          /* first column of the Ws^T block (used when gx16 == NULL) */
+  const void* ab;          /* (batch, D, T) 32-bit words {fp16 a, fp16 b} */
+  long long a_bs, a_cs;
+  void* g16;
+  long long g16_bs;
+  int g16_cp, gg_off;
+  int batch, D;
+  int t_lo, t_zero_lo, t_hi;
+  int* err;
+  int max_ctas;
+} aewn_grcc_gz_desc;
+
+int aewn_grcc_gz(const aewn_grcc_gz_desc* d, aewn_stream_t stream);
+
 /* Power-of-two scale for a 16-bit copy of a gradient tensor: scale2[0] = 2^floor(log2(target / max|x|)) (1 if the tensor
  * is all zero), scale2[1] = 1 / scale2[0].  x: n contiguous floats; work: one unsigned int.  Two tiny launches. */
 int aewn_amax_pow2_scale(const float* x, long long n, float target, unsigned int* work, float* scale2, aewn_stream_t stream);

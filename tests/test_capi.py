@@ -27,10 +27,10 @@ def test_struct_layouts_match_header_sizes():
     import subprocess
     import tempfile
     from aewn import _lib
-    src = '#include "aewn.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", ' \
+    src = '#include "aewn.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", ' \
           'sizeof(aewn_act), sizeof(aewn_seg), sizeof(aewn_ntile), sizeof(aewn_tgemm_desc), sizeof(aewn_wgrad_item), ' \
           'sizeof(aewn_wgrad_desc), sizeof(aewn_copy_block), sizeof(aewn_gen_block), sizeof(aewn_gen_desc), ' \
-          'sizeof(aewn_wgw_chunk), sizeof(aewn_wgw_unit), sizeof(aewn_wgradw_desc), sizeof(aewn_grcc_fwd_desc), sizeof(aewn_grcc_dgrad_desc), sizeof(aewn_mfcc_desc), sizeof(aewn_act16), sizeof(aewn_wgradh_desc)); ' \
+          'sizeof(aewn_wgw_chunk), sizeof(aewn_wgw_unit), sizeof(aewn_wgradw_desc), sizeof(aewn_grcc_fwd_desc), sizeof(aewn_grcc_dgrad_desc), sizeof(aewn_mfcc_desc), sizeof(aewn_act16), sizeof(aewn_wgradh_desc), sizeof(aewn_grcc_gz_desc)); ' \
           'return 0;}\n'
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(td, "p.c"), "w").write(src)
@@ -39,7 +39,7 @@ def test_struct_layouts_match_header_sizes():
         sizes = [int(v) for v in subprocess.run([os.path.join(td, "p")], capture_output=True, text=True).stdout.split()]
     mine = [ctypes.sizeof(t) for t in (_lib.Act, _lib.Seg, _lib.NTile, _lib.TGemmDesc, _lib.WGradItem, _lib.WGradDesc,
                                        _lib.CopyBlock, _lib.GenBlock, _lib.GenDesc, _lib.WGWChunk, _lib.WGWUnit,
-                                       _lib.WGradWDesc, _lib.GrccFwdDesc, _lib.GrccDgradDesc, _lib.MfccDesc, _lib.Act16, _lib.WGradHDesc)]
+                                       _lib.WGradWDesc, _lib.GrccFwdDesc, _lib.GrccDgradDesc, _lib.MfccDesc, _lib.Act16, _lib.WGradHDesc, _lib.GrccGzDesc)]
     assert mine == sizes
 
 

@@ -238,9 +238,10 @@ def test_data_gradient_on_the_fused_engine_bf16_and_scaled_fp16():
     from aewn import ops
     from test_gpu_fullsize import build
 
-    def run(mode, wgrad16="0"):
+    def run(mode, wgrad16="0", gz16="0"):
         os.environ["AEWN_DGRAD16"] = mode
         os.environ["AEWN_WGRAD16"] = wgrad16
+        os.environ["AEWN_GZ16"] = gz16
         ops._plans.clear()
         torch.manual_seed(2507)
         wn, geo = build(512)
@@ -258,17 +259,19 @@ def test_data_gradient_on_the_fused_engine_bf16_and_scaled_fp16():
         ops.check_device_errors()
         used = [p for p in ops._plans.values()]
         assert used and all(p.dgrad16 == (mode != "0") and p.dgrad16_scaled == (mode == "2") and
-                            p.wgrad16 == (mode == "2" and wgrad16 == "1") for p in used)
+                            p.wgrad16 == (mode == "2" and wgrad16 == "1") and
+                            p.gz16 == (mode == "2" and wgrad16 == "1" and gz16 == "1") for p in used)
         return {k: p.grad.double().clone() for k, p in wn.named_parameters()}, lc.grad.double().clone()
 
-    old = os.environ.get("AEWN_DGRAD16"), os.environ.get("AEWN_WGRAD16")
+    old = os.environ.get("AEWN_DGRAD16"), os.environ.get("AEWN_WGRAD16"), os.environ.get("AEWN_GZ16")
     try:
         g0, lc0 = run("0")
         g1, lc1 = run("1")
         g2, lc2 = run("2")
-        g3, lc3 = run("2", wgrad16="1")          # + the weight gradients on aewn_wgradh (the default build)
+        g3, lc3 = run("2", wgrad16="1")          # + the weight gradients on aewn_wgradh
+        g4, lc4 = run("2", wgrad16="1", gz16="1")    # + the gate derivative's GEMM on the fused engine (aewn_grcc_gz)
     finally:
-        for k, v in zip(("AEWN_DGRAD16", "AEWN_WGRAD16"), old):
+        for k, v in zip(("AEWN_DGRAD16", "AEWN_WGRAD16", "AEWN_GZ16"), old):
             if v is None:
                 os.environ.pop(k, None)
             else:
@@ -294,6 +297,11 @@ def test_data_gradient_on_the_fused_engine_bf16_and_scaled_fp16():
     print(f"  + fp16 weight gradients: {m3:.2e} (worst {max(e3[k] for k in ks):.2e})")
     assert torch.equal(lc3, lc2)
     assert max(e3.values()) < 6e-2 and m3 < 2e-3
+    # fp16 gate derivative: g_z from fp16 copies of g_x / g_skp instead of TF32 reads of the fp32 tensors
+    e4 = {k: nrm(g4[k], g0[k]) for k in g0}
+    m4 = sum(e4[k] for k in ks) / len(ks)
+    print(f"  + fp16 gate derivative: {m4:.2e} (worst {max(e4[k] for k in ks):.2e}), lc {nrm(lc4, lc0):.2e}")
+    assert max(e4.values()) < 6e-2 and m4 < 2e-3 and nrm(lc4, lc0) < 6e-2
 
 
 def test_scaled_gradient_overflow_is_reported():
