@@ -546,9 +546,9 @@ class StackPlan:
         # z), the scaled copies of [g_f; g_g], g_x and g_skp -- DESIGN.md 4.2c
         self.wgrad16 = self.dgrad16_scaled and os.environ.get("AEWN_WGRAD16", "1") == "1" and D % 64 == 0 and \
             g.last_is_final
-        # AEWN_GZ16 (needs the fp16 weight-gradient copies): the gate derivative's GEMM on the fused-layer engine from the
+        # AEWN_GZ16 (default 1; needs the fp16 weight-gradient copies): the gate derivative's GEMM on the fused-layer engine from the
         # scaled fp16 copies of g_x / g_skp (aewn_grcc_gz) instead of the TF32 tgemm launch reading the fp32 tensors
-        self.gz16 = self.wgrad16 and os.environ.get("AEWN_GZ16", "0") == "1"
+        self.gz16 = self.wgrad16 and os.environ.get("AEWN_GZ16", "1") == "1"
         # pre-shifted duplicates of the layer inputs for dilations 1 and 2: only the TF32 weight gradients read them
         self.xs = {} if self.wgrad16 else {l: new_buf(B, R, Tp, device) for l in range(g.L) if needs_dup(g.dils[l])}
         # saved for the backward pass: tanh and sigmoid (fp32), or -- fused forward -- ONE word per element holding the two
@@ -1204,7 +1204,7 @@ def get_plan(B, R, D, S, Cc, geom, params, device, relu_last):
     workspace; the least recently used plan is dropped when a new one is needed (its memory returns to PyTorch's
     caching allocator -- no empty_cache(), which would fail inside a CUDA-graph capture)."""
     key = (B, R, D, S, Cc, geom.key(), str(device), bool(relu_last), StackPlan._ptrs(params), FUSED_FWD,
-           dgrad16_mode(), os.environ.get("AEWN_WGRAD16", "1"), os.environ.get("AEWN_GZ16", "0"))
+           dgrad16_mode(), os.environ.get("AEWN_WGRAD16", "1"), os.environ.get("AEWN_GZ16", "1"))
     plan = _plans.get(key)
     if plan is not None:
         _plans.move_to_end(key)
