@@ -659,7 +659,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) grcc_fwd_kernel(const __grid_co
               const float b1 = __half2float(__ushort_as_half(static_cast<unsigned short>(w1 >> 16)));
               const float z0 = __uint_as_float(v[2 * k]), z1 = __uint_as_float(v[2 * k + 1]);
               const float f0 = z0 * a0, f1 = z1 * a1, g0 = z0 * b0, g1 = z1 * b1;
-              xmax = fmaxf(xmax, fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fmaxf(fabsf(g0), fabsf(g1))));
+              // (NaN-aware: an inf * 0 product must not slip through a fmaxf chain)
+              if (!(fabsf(f0) <= 65504.0f) || !(fabsf(f1) <= 65504.0f) || !(fabsf(g0) <= 65504.0f) || !(fabsf(g1) <= 65504.0f))
+                xmax = INFINITY;
               gfw[k] = pack_f16x2(f0, f1);
               ggw[k] = pack_f16x2(g0, g1);
             }
