@@ -305,20 +305,20 @@ def test_data_gradient_on_the_fused_engine_bf16_and_scaled_fp16():
 
 
 def test_scaled_gradient_overflow_is_reported():
-    """The fp16 gradient copies carry max|g_skp| * s in (4, 8]: gradients that grow more than 2^13-fold on their way down the
-    stack (here: residual weights of 200x the usual size, four layers) cannot be represented and must raise AEWN_ERR_RANGE
-    instead of saturating silently; with ordinary weights the same backward leaves the error word clear.  (The weights
-    themselves and the forward activations stay far inside the fp16 range: the forward leaves the error word clear.)"""
+    """The fp16 gradient copies carry max|g_skp| * s in (4, 8]: a gradient more than 2^13 times larger than max|g_skp| (here:
+    skip weights of 1e6 times the usual size, so that g_z = Ws^T g_skp dwarfs g_skp -- and the fp16 copy of those weights
+    overflows as well) cannot be represented and must raise AEWN_ERR_RANGE instead of producing saturated or NaN gradients
+    silently; with ordinary weights the same backward leaves the error word clear.  (Residual or convolution weights cannot
+    drive this: large pre-activations saturate the gates and the gradients vanish instead.)"""
     from aewn import ops, _lib
     dev = torch.device("cuda")
-    R, D, S, Cc, dils, T0, B = 64, 128, 64, 20, [1, 2, 4, 8], 15 + 400, 1
+    R, D, S, Cc, dils, T0, B = 64, 128, 64, 20, [1, 2], 3 + 300, 1
 
-    def run(res_gain):
+    def run(skip_gain):
         gen = torch.Generator().manual_seed(2)
         params = make_params(R, D, S, Cc, dils, True, gen, dev)
         for p in params:
-            if "dil_res.weight" in p:
-                p["dil_res.weight"].mul_(res_gain)
+            p["dil_skp.weight"].mul_(skip_gain)
         ops.set_fused_forward(True)
         plan = ops.StackPlan(B, R, D, S, Cc, ops.StackGeom(dils, T0), params, dev, relu_last=False)
         assert plan.dgrad16_scaled and plan.wgrad16
@@ -326,7 +326,7 @@ def test_scaled_gradient_overflow_is_reported():
         plan.cond[:, :Cc, :T0] = torch.randn(B, Cc, T0, generator=gen).to(dev)
         plan.forward(save=True)
         torch.cuda.synchronize()
-        assert int(plan.err.item()) == 0                       # the forward pass itself is in range
+        assert int(plan.err.item()) == 0                       # the forward pass itself is in range (the skip sum is fp32)
         bw = plan.bwd()
         bw["g_skp"][:, :, plan.geom.RF:T0] = torch.randn(B, S, T0 - plan.geom.RF, generator=gen).to(dev) * 1e-5
         plan.backward()
@@ -336,4 +336,4 @@ def test_scaled_gradient_overflow_is_reported():
         return e
 
     assert run(1.0) == 0
-    assert run(200.0) == _lib.ERR_RANGE
+    assert run(1.0e6) == _lib.ERR_RANGE
