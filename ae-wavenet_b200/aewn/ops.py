@@ -545,7 +545,7 @@ class StackPlan:
         # from fp16 channels-last copies: x16 (then kept per layer), cond16, z16 (written by the forward instead of the fp32
         # z), the scaled copies of [g_f; g_g], g_x and g_skp -- DESIGN.md 4.2c
         self.wgrad16 = self.dgrad16_scaled and os.environ.get("AEWN_WGRAD16", "1") == "1" and D % 64 == 0 and \
-            g.last_is_final
+            g.last_is_final and ENGINE_MODE == "auto" and WIDE_WGRAD      # (the narrow TF32 units read the fp32 z / [g_f; g_g])
         # AEWN_GZ16 (default 1; needs the fp16 weight-gradient copies): the gate derivative's GEMM on the fused-layer engine from the
         # scaled fp16 copies of g_x / g_skp (aewn_grcc_gz) instead of the TF32 tgemm launch reading the fp32 tensors
         self.gz16 = self.wgrad16 and os.environ.get("AEWN_GZ16", "1") == "1"
@@ -1204,7 +1204,7 @@ def get_plan(B, R, D, S, Cc, geom, params, device, relu_last):
     workspace; the least recently used plan is dropped when a new one is needed (its memory returns to PyTorch's
     caching allocator -- no empty_cache(), which would fail inside a CUDA-graph capture)."""
     key = (B, R, D, S, Cc, geom.key(), str(device), bool(relu_last), StackPlan._ptrs(params), FUSED_FWD,
-           dgrad16_mode(), os.environ.get("AEWN_WGRAD16", "1"), os.environ.get("AEWN_GZ16", "1"))
+           dgrad16_mode(), os.environ.get("AEWN_WGRAD16", "1"), os.environ.get("AEWN_GZ16", "1"), ENGINE_MODE, WIDE_WGRAD)
     plan = _plans.get(key)
     if plan is not None:
         _plans.move_to_end(key)
